@@ -1,0 +1,157 @@
+/* b200xf -- C ABI of the B200-native Transformer training hot path (drop-in for kuetuofa/Transformer's
+ * TensorFlow-2 runtime on the path Transformer.call -> Train.train_step -> distributed_train).
+ *
+ * Conventions:
+ *   - extern "C", plain pointers and sizes only; device pointers are `void*`/typed pointers into CUDA memory
+ *     owned by the CALLER (the Python host allocates them as torch CUDA tensors); no entry point allocates or
+ *     synchronises unless its name says so; every launch goes to the `stream` argument (a cudaStream_t).
+ *   - return 0 on success, non-zero on error; b200xf_last_error() returns a thread-local message.
+ *   - bf16 = raw 16-bit bfloat16 storage; matrices are row-major with a leading dimension in ELEMENTS.
+ *
+ * Each entry point names the reference interface (file:line in kuetuofa/Transformer) whose TF op(s) it replaces.
+ * The reference has no FFI of its own (pure Python on TensorFlow); INTEGRATION.md shows the ctypes binding.
+ */
+#ifndef B200XF_H_
+#define B200XF_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void* b200xf_stream_t; /* cudaStream_t */
+
+const char* b200xf_last_error(void);
+int b200xf_version(void);
+/* number of kernels this library has launched on this process so far (bench.py's gpu_launches) */
+long long b200xf_launch_count(void);
+
+/* ---- dense contractions: keras Dense (Attention.py:62-64,77; point_ffn.py:5-6; Transformer.py:30) and their
+ *      reverse-mode gradients (train.py:137).  D[M,N] (+)= epi(A[M,K] . B[K,N]).
+ *      a_major / b_major: 0 = K contiguous in memory (A stored [M,K], B stored [N,K]);
+ *                         1 = M resp. N contiguous   (A stored [K,M], B stored [K,N] -- the keras kernel layout).
+ *      flags: 1 = ReLU, 2 = accumulate into fp32 D (TMA reduce-add; required for splits > 1),
+ *             4 = multiply by (aux > 0) (ReLU backward, aux bf16 [M, ld_aux]).                                   */
+int b200xf_gemm_bf16(const void* A, int64_t lda, int a_major, const void* B, int64_t ldb, int b_major, void* D,
+                     int64_t ldd, int d_is_f32, const float* bias, const void* aux, int64_t ld_aux, int flags,
+                     int splits, int64_t M, int64_t N, int64_t K, b200xf_stream_t stream);
+
+/* ---- scaled_dot_product_attention + split_heads/merge (Attention.py:3-34, 52-57, 74-76).
+ *      Q/K/V/O: bf16 token-major [B*S, ld], head h = columns [h*dk, (h+1)*dk).  lse: fp32 [B,H,Sq].
+ *      kpad: uint8 [B,Sk], 1 = key token id 0 (create_padding_mask, positionalencoding.py:25-30) or NULL;
+ *      causal: look-ahead mask (positionalencoding.py:32-34); maskf: optional float mask, element (b,q,k) at
+ *      b*mask_sb + q*mask_sq + k, contributes maskf * -1e9 (Attention.py:25-26).                                  */
+int b200xf_attn_fwd(const void* Q, int64_t ld_q, const void* K, int64_t ld_k, const void* V, int64_t ld_v, void* O,
+                    int64_t ld_o, float* lse, const uint8_t* kpad, int causal, const float* maskf, int64_t mask_sb,
+                    int64_t mask_sq, int B, int H, int Sq, int Sk, int dk, b200xf_stream_t stream);
+/*      delta: fp32 [B,H,Sq] = rowsum(dO o O) (b200xf_attn_delta); dq_acc: fp32 [B*Sq, ld_dq] ZEROED by the caller
+ *      (accumulated with red.add); dK/dV: bf16 token-major like K/V.                                             */
+int b200xf_attn_bwd(const void* Q, int64_t ld_q, const void* K, int64_t ld_k, const void* V, int64_t ld_v,
+                    const void* dO, int64_t ld_do, const float* lse, const float* delta, float* dq_acc, int64_t ld_dq,
+                    void* dK, int64_t ld_dk, void* dV, int64_t ld_dv, const uint8_t* kpad, int causal,
+                    const float* maskf, int64_t mask_sb, int64_t mask_sq, int B, int H, int Sq, int Sk, int dk,
+                    b200xf_stream_t stream);
+int b200xf_attn_delta(const void* O, int64_t ld_o, const void* dO, int64_t ld_do, float* delta, int B, int S, int H,
+                      int dk, b200xf_stream_t stream);
+/*      attention_weights (Decoder.py:75-76): P fp32 [B,H,Sq,Sk] recomputed from Q, K and lse                     */
+int b200xf_attn_probs(const void* Q, int64_t ld_q, const void* K, int64_t ld_k, const float* lse, float* P,
+                      const uint8_t* kpad, int causal, const float* maskf, int64_t mask_sb, int64_t mask_sq, int B,
+                      int H, int Sq, int Sk, int dk, b200xf_stream_t stream);
+
+/* ---- Embedding * sqrt(d) + pos_encoding[:, :S] + Dropout (Encoder.py:51-55, Decoder.py:65-69) and its gradient */
+int b200xf_embed_fwd(const int64_t* ids, const float* table, const float* pos, float* out_f32, void* out_bf16,
+                     int64_t rows, int S, int d, int64_t V, float rate, uint64_t seed, uint32_t site,
+                     b200xf_stream_t stream);
+int b200xf_embed_bwd(const int64_t* ids, const float* dx, float* dtable, int64_t rows, int d, int64_t V, float rate,
+                     uint64_t seed, uint32_t site, b200xf_stream_t stream);
+
+/* ---- Dropout + residual add + LayerNormalization(eps) (Encoder.py:22-23,26-27; Decoder.py:30-31,35-36,39-40).
+ *      y_z: in = sublayer output y, out = z = x + dropout(y) (kept for backward).                                 */
+int b200xf_residual_ln_fwd(float* y_z, const float* x, const float* gamma, const float* beta, float* out_f32,
+                           void* out_bf16, float* mean, float* rstd, int64_t rows, int d, float eps, float rate,
+                           uint64_t seed, uint32_t site, b200xf_stream_t stream);
+int b200xf_residual_ln_bwd(const float* dout, const float* z, const float* mean, const float* rstd, const float* gamma,
+                           float* dz, void* dy_sub_bf16, float* dgamma, float* dbeta, int64_t rows, int d, float rate,
+                           uint64_t seed, uint32_t site, b200xf_stream_t stream);
+
+/* ---- Train.loss_function + SparseCategoricalAccuracy (train.py:83-88, 141) and d(loss)/d(logits).
+ *      row r = (b, t) reads label labels[b*label_stride + label_offset + t] (tar[:, 1:] without a copy).
+ *      stats: double[4] += {sum of masked per-token losses, #argmax==label (all positions), #positions, #non-pad}.
+ *      dlogits (bf16 [rows, ld_d], may alias bf16 logits, may be NULL) = (softmax - onehot) * (label!=0) * inv_batch */
+int b200xf_xent(const void* logits, int logits_f32, int64_t ld, const int64_t* labels, int label_stride,
+                int label_offset, int T, void* dlogits, int64_t ld_d, float* row_loss, double* stats, int64_t rows,
+                int V, float inv_batch, b200xf_stream_t stream);
+
+/* ---- bias gradients: out[n] += sum_m X[m,n] (X bf16) */
+int b200xf_colsum_bf16(const void* X, int64_t ld, float* out, int64_t rows, int N, b200xf_stream_t stream);
+
+/* ---- keras Adam, TF form (train.py:65-66,138): m,v update; p -= alpha*m/(sqrt(v)+eps); shadow = bf16(p) (may be NULL) */
+int b200xf_adam_step(float* p, float* m, float* v, const float* g, void* shadow_bf16, int64_t n, float alpha,
+                     float beta1, float beta2, float eps, b200xf_stream_t stream);
+
+/* ---- casts / masks */
+int b200xf_cast_f32_bf16(const float* in, void* out, int64_t n, b200xf_stream_t stream);
+int b200xf_cast_bf16_f32(const void* in, float* out, int64_t n, b200xf_stream_t stream);
+int b200xf_cast_f32_bf16_strided(const float* in, void* out, int64_t rows, int d, int64_t ld_out,
+                                 b200xf_stream_t stream);
+int b200xf_pad_mask(const int64_t* ids, uint8_t* mask, int64_t n, b200xf_stream_t stream);
+
+/* ---- whole-model entry points (Transformer.call, Transformer.py:21-32; Train.train_step / test_step,
+ *      train.py:124-156).  See transformer_b200/csrc/model.cu for the parameter-arena layout.                     */
+typedef struct b200xf_model_config {
+  int32_t num_layers, d_model, num_heads, dff;
+  int32_t input_vocab_size, target_vocab_size; /* logical V (keras Embedding / final Dense sizes) */
+  int32_t max_batch, max_src_len, max_tgt_len; /* workspace is sized for these */
+  int32_t pos_rows;                            /* rows of the two positional-encoding tables */
+  float dropout_rate;
+  float ln_eps;
+} b200xf_model_config;
+
+typedef struct b200xf_model b200xf_model; /* opaque */
+
+/* bytes of (a) one parameter arena in fp32 elements and (b) the activation workspace for `cfg` */
+int64_t b200xf_model_param_count(const b200xf_model_config* cfg);
+int64_t b200xf_model_workspace_bytes(const b200xf_model_config* cfg);
+/* offset (in elements) and shape of trainable variable `index` in keras order; returns 0 while index is valid.
+ * name: e.g. "encoder/layer0/mha/wq/kernel"; rows/cols/ld describe a (possibly strided) 2-D view, cols==0 for 1-D */
+int b200xf_model_variable(const b200xf_model_config* cfg, int index, char* name, int name_cap, int64_t* offset,
+                          int64_t* rows, int64_t* cols, int64_t* ld);
+/* params/grads/adam_m/adam_v: fp32 arenas of b200xf_model_param_count elements; shadow: bf16 arena, same length;
+ * pos_in/pos_tgt: fp32 [pos_rows, d_model]; workspace: b200xf_model_workspace_bytes bytes. */
+int b200xf_model_create(const b200xf_model_config* cfg, float* params, float* grads, float* adam_m, float* adam_v,
+                        void* shadow, const float* pos_in, const float* pos_tgt, void* workspace,
+                        b200xf_model** out);
+void b200xf_model_destroy(b200xf_model* m);
+/* refresh the bf16 shadow from the fp32 params (after loading / initialising weights) */
+int b200xf_model_sync_shadow(b200xf_model* m, b200xf_stream_t stream);
+
+/* Forward.  inp int64 [B,S]; tar int64 [B, tar_stride] of which columns [tar_offset, tar_offset+T) are the decoder
+ * input.  training != 0 enables dropout (seeded by `seed`) and keeps activations for b200xf_model_backward.
+ * Optional float masks of the six-argument API (NULL = derive the canonical masks from the ids):
+ *   enc_mask/dec_mask (B,1,1,S) ; look_ahead_mask (B,1,T,T) or (1,1,T,T) (la_batch_stride 0).
+ * logits_out: NULL, or fp32 [B*T, ld_logits] to materialise final_layer outputs (Transformer.py:30).             */
+int b200xf_model_forward(b200xf_model* m, const int64_t* inp, const int64_t* tar, int tar_stride, int tar_offset,
+                         int B, int S, int T, int training, uint64_t seed, const float* enc_mask,
+                         const float* look_ahead_mask, int64_t la_batch_stride, const float* dec_mask,
+                         float* logits_out, int64_t ld_logits, b200xf_stream_t stream);
+/* loss/accuracy of the last forward against labels tar[:, label_offset : label_offset+T] (train.py:83-88,141);
+ * stats: device double[4] (see b200xf_xent), accumulated.  with_grad != 0 also leaves dlogits for backward.       */
+int b200xf_model_loss(b200xf_model* m, const int64_t* tar, int tar_stride, int label_offset, float inv_batch,
+                      double* stats, int with_grad, b200xf_stream_t stream);
+/* Backward of the last training forward+loss into the (caller-zeroed) grads arena.  stage: -1 = everything;
+ * otherwise 0 = final layer, 1 = decoder stack + target embedding, 2 = encoder stack + input embedding, so a
+ * data-parallel caller can all-reduce finished arena ranges while later stages run (distributed_train.py:59). */
+int b200xf_model_backward(b200xf_model* m, int stage, b200xf_stream_t stream);
+/* [begin,end) element range of the gradient arena that `stage` finishes */
+int b200xf_model_grad_range(const b200xf_model_config* cfg, int stage, int64_t* begin, int64_t* end);
+/* attention_weights['decoder_layer{layer+1}_block{block}'] of the last forward -> P fp32 [B,H,T,Sk] */
+int b200xf_model_attention_weights(b200xf_model* m, int layer, int block, float* P, b200xf_stream_t stream);
+/* debug/parity taps: copy an internal activation of the last forward (fp32 [rows, d_model]) -- names:
+ * "enc_embed","enc_layer{i}","dec_embed","dec_layer{i}" */
+int b200xf_model_tap(b200xf_model* m, const char* name, float* out, b200xf_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200XF_H_ */

@@ -1,0 +1,359 @@
+"""T2: every sm_100a kernel, called through the C ABI (ctypes), against a plain PyTorch fp32 reference of the same
+op on the same (bf16-rounded) inputs.  Run on a B200:  python -m pytest tests -m gpu -x -q"""
+import math
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from transformer_b200 import _lib as L  # noqa: E402
+
+
+def dev():
+    assert torch.cuda.is_available(), "gpu tests need a GPU"
+    return torch.device("cuda:0")
+
+
+def sp():
+    return L.stream_ptr()
+
+
+def rnd(shape, scale=1.0, seed=0, dtype=torch.bfloat16):
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    return (torch.randn(shape, generator=g) * scale).to(dtype).to(dev())
+
+
+def padded(rows, cols, ld, dtype, fill=float("nan")):
+    """[rows, ld] buffer whose [:, :cols] view is the matrix (ld in elements)."""
+    buf = torch.full((rows, ld), fill, dtype=dtype, device=dev())
+    return buf
+
+
+def ld_for(cols, dtype):
+    q = 8 if dtype == torch.bfloat16 else 4
+    return (cols + q - 1) // q * q
+
+
+# ------------------------------------------------------------------------------------------------
+# GEMM
+# ------------------------------------------------------------------------------------------------
+def run_gemm(M, N, K, a_major, b_major, out_f32, bias=False, relu=False, aux=False, accum=False, splits=1, seed=0):
+    A = rnd((M, K), 1.0, seed)          # logical A [M,K]
+    Bm = rnd((K, N), 1.0, seed + 1)     # logical B [K,N]
+    # storage
+    if a_major == 0:
+        lda = ld_for(K, torch.bfloat16); As = padded(M, K, lda, torch.bfloat16, 0.0); As[:, :K] = A
+    else:
+        lda = ld_for(M, torch.bfloat16); As = padded(K, M, lda, torch.bfloat16, 0.0); As[:, :M] = A.t()
+    if b_major == 0:
+        ldb = ld_for(K, torch.bfloat16); Bs = padded(N, K, ldb, torch.bfloat16, 0.0); Bs[:, :K] = Bm.t()
+    else:
+        ldb = ld_for(N, torch.bfloat16); Bs = padded(K, N, ldb, torch.bfloat16, 0.0); Bs[:, :N] = Bm
+    odt = torch.float32 if out_f32 else torch.bfloat16
+    ldd = ld_for(N, odt)
+    D = torch.full((M, ldd), 7.0, dtype=odt, device=dev())
+    ref = A.float() @ Bm.float()
+    bias_t = None
+    if bias:
+        bias_t = rnd((ldd,), 1.0, seed + 2, torch.float32)
+        ref = ref + bias_t[:N]
+    if relu:
+        ref = torch.relu(ref)
+    aux_t = None
+    ld_aux = 0
+    if aux:
+        ld_aux = ld_for(N, torch.bfloat16)
+        aux_t = rnd((M, ld_aux), 1.0, seed + 3)
+        ref = ref * (aux_t[:, :N].float() > 0)
+    flags = (1 if relu else 0) | (2 if accum else 0) | (4 if aux else 0)
+    if accum:
+        init = rnd((M, ldd), 1.0, seed + 4, torch.float32)
+        D.copy_(init)
+        ref = ref + init[:, :N]
+    L.call("b200xf_gemm_bf16", L.ptr(As), lda, a_major, L.ptr(Bs), ldb, b_major, L.ptr(D), ldd, int(out_f32),
+           L.ptr(bias_t), L.ptr(aux_t), ld_aux, flags, splits, M, N, K, sp())
+    torch.cuda.synchronize()
+    got = D[:, :N].float()
+    # untouched padding columns must keep their sentinel
+    if ldd > N and not accum:
+        assert torch.all(D[:, N:] == 7.0), "GEMM wrote outside [M,N]"
+    tol = 1e-3 * math.sqrt(K) + (2e-2 if not out_f32 else 0)
+    err = (got - ref).abs().max().item()
+    scale = ref.abs().max().item()
+    assert err <= tol * max(1.0, scale / 8), f"gemm M{M} N{N} K{K} maj{a_major}{b_major} f32={out_f32} err {err} (scale {scale})"
+    return err
+
+
+@pytest.mark.parametrize("a_major,b_major", [(0, 1), (0, 0), (1, 1), (1, 0)])
+@pytest.mark.parametrize("out_f32", [False, True])
+def test_gemm_majors_basic(a_major, b_major, out_f32):
+    run_gemm(256, 256, 128, a_major, b_major, out_f32)
+    run_gemm(128, 64, 64, a_major, b_major, out_f32)          # BN=128 path, single k-block
+
+
+@pytest.mark.parametrize("a_major,b_major", [(0, 1), (0, 0), (1, 1)])
+def test_gemm_ragged_shapes(a_major, b_major):
+    run_gemm(300, 200, 136, a_major, b_major, True)           # ragged M, N, K
+    run_gemm(643, 520, 200, a_major, b_major, False)
+    run_gemm(77, 40, 72, a_major, b_major, True)
+
+
+def test_gemm_epilogues():
+    run_gemm(384, 512, 256, 0, 1, False, bias=True, relu=True)            # FFN dense0 (point_ffn.py:5)
+    run_gemm(384, 512, 256, 0, 1, True, bias=True)                        # dense (Attention.py:77)
+    run_gemm(384, 512, 256, 0, 0, False, aux=True)                        # ReLU-backward dgrad
+    run_gemm(300, 200, 136, 0, 1, False, bias=True, relu=True)            # ragged + bias tail path
+    run_gemm(384, 256, 256, 0, 0, True, accum=True)                       # residual accumulate
+    run_gemm(256, 512, 4096, 1, 1, True, accum=True, splits=8)            # wgrad split-K
+    run_gemm(512, 2048, 3000, 1, 1, True, accum=True, splits=5)
+
+
+def test_gemm_multi_wave_persistent():
+    run_gemm(4096, 2048, 512, 0, 1, False, bias=True, relu=True)          # 512 tiles > 148 SMs: ring + TMEM double buffer
+    run_gemm(4096, 512, 2048, 0, 1, True, bias=True)
+
+
+# ------------------------------------------------------------------------------------------------
+# attention
+# ------------------------------------------------------------------------------------------------
+def ref_attention(q, k, v, mask):
+    """Attention.py:3-34 in fp32.  q,k,v: (B,H,S,dk) fp32; mask broadcastable float or None."""
+    logits = (q @ k.transpose(-1, -2)) / math.sqrt(q.shape[-1])
+    if mask is not None:
+        logits = logits + mask * -1e9
+    p = torch.softmax(logits, -1)
+    return p @ v, p, torch.logsumexp(logits, -1)
+
+
+def build_mask(B, Sq, Sk, kpad, causal):
+    m = torch.zeros(B, 1, Sq, Sk, device=dev())
+    if kpad is not None:
+        m = torch.maximum(m, kpad.float()[:, None, None, :])
+    if causal:
+        m = torch.maximum(m, 1 - torch.tril(torch.ones(Sq, Sk, device=dev())))
+    return m
+
+
+def attn_case(B, H, Sq, Sk, dk, kind, seed=0, backward=True):
+    d = H * dk
+    ldq = 3 * d
+    qkv_q = rnd((B * Sq, ldq), 1.0, seed)            # packed layout like the QKV GEMM output
+    qkv_k = qkv_q if Sq == Sk else rnd((B * Sk, ldq), 1.0, seed + 1)
+    Qs = qkv_q[:, 0:d]; Ks = qkv_k[:, d:2 * d]; Vs = qkv_k[:, 2 * d:3 * d]
+    kpad = None; causal = 0; maskf = None
+    g = torch.Generator().manual_seed(seed + 5)
+    if kind in ("pad", "causal_pad"):
+        lens = torch.randint(max(1, Sk // 2), Sk + 1, (B,), generator=g)
+        kpad = (torch.arange(Sk)[None, :] >= lens[:, None]).to(torch.uint8).to(dev())
+    if kind == "lead_pad":
+        kpad = torch.zeros(B, Sk, dtype=torch.uint8); kpad[0, :3] = 1; kpad[-1, :] = 1; kpad = kpad.to(dev())   # fully-masked rows
+    if kind == "all_pad":
+        kpad = torch.zeros(B, Sk, dtype=torch.uint8); kpad[0, :] = 1; kpad = kpad.to(dev())
+    if kind in ("causal", "causal_pad", "lead_pad"):
+        causal = 1
+    if kind == "float_mask":
+        maskf = (torch.rand(B, 1, Sq, Sk, generator=g) < 0.3).float().to(dev())
+    mask = maskf if maskf is not None else build_mask(B, Sq, Sk, kpad, causal)
+    q4 = Qs.float().reshape(B, Sq, H, dk).permute(0, 2, 1, 3).contiguous().requires_grad_(True)
+    k4 = Ks.float().reshape(B, Sk, H, dk).permute(0, 2, 1, 3).contiguous().requires_grad_(True)
+    v4 = Vs.float().reshape(B, Sk, H, dk).permute(0, 2, 1, 3).contiguous().requires_grad_(True)
+    o_ref, p_ref, lse_ref = ref_attention(q4, k4, v4, mask)
+
+    O = torch.full((B * Sq, d), float("nan"), dtype=torch.bfloat16, device=dev())
+    lse = torch.full((B, H, Sq), float("nan"), dtype=torch.float32, device=dev())
+    msb = Sq * Sk if maskf is not None else 0
+    msq = Sk if maskf is not None else 0
+    L.call("b200xf_attn_fwd", L.ptr(Qs), ldq, L.ptr(Ks), ldq, L.ptr(Vs), ldq, L.ptr(O), d, L.ptr(lse), L.ptr(kpad), causal,
+           L.ptr(maskf), msb, msq, B, H, Sq, Sk, dk, sp())
+    torch.cuda.synchronize()
+    o_got = O.float().reshape(B, Sq, H, dk).permute(0, 2, 1, 3)
+    assert torch.isfinite(o_got).all(), f"{kind}: non-finite attention output"
+    err_o = (o_got - o_ref).abs().max().item()
+    assert err_o < 3e-2, f"attn fwd {kind} B{B} H{H} Sq{Sq} Sk{Sk} dk{dk}: |dO| {err_o}"
+    # lse: for fully-masked rows fp32 absorbs ln(Sk) (-1e9 + 6 == -1e9), same as the reference's own fp32
+    err_l = ((lse - lse_ref) / lse_ref.abs().clamp(min=1)).abs().max().item()
+    assert err_l < 2e-2, f"attn fwd {kind}: lse rel err {err_l}"
+
+    # attention_weights recompute
+    P = torch.empty(B, H, Sq, Sk, dtype=torch.float32, device=dev())
+    L.call("b200xf_attn_probs", L.ptr(Qs), ldq, L.ptr(Ks), ldq, L.ptr(lse), L.ptr(P), L.ptr(kpad), causal, L.ptr(maskf), msb, msq,
+           B, H, Sq, Sk, dk, sp())
+    torch.cuda.synchronize()
+    err_p = (P - p_ref).abs().max().item()
+    assert err_p < 2e-2, f"attn probs {kind}: {err_p}"
+    if not backward:
+        return
+    dO = rnd((B * Sq, d), 1.0, seed + 9)
+    do4 = dO.float().reshape(B, Sq, H, dk).permute(0, 2, 1, 3)
+    (o_ref * do4).sum().backward()
+    delta = torch.empty(B, H, Sq, dtype=torch.float32, device=dev())
+    L.call("b200xf_attn_delta", L.ptr(O), d, L.ptr(dO), d, L.ptr(delta), B, Sq, H, dk, sp())
+    dq_acc = torch.zeros(B * Sq, d, dtype=torch.float32, device=dev())
+    dKV = torch.full((B * Sk, 2 * d), float("nan"), dtype=torch.bfloat16, device=dev())
+    dKs = dKV[:, :d]; dVs = dKV[:, d:]
+    L.call("b200xf_attn_bwd", L.ptr(Qs), ldq, L.ptr(Ks), ldq, L.ptr(Vs), ldq, L.ptr(dO), d, L.ptr(lse), L.ptr(delta), L.ptr(dq_acc), d,
+           L.ptr(dKs), 2 * d, L.ptr(dVs), 2 * d, L.ptr(kpad), causal, L.ptr(maskf), msb, msq, B, H, Sq, Sk, dk, sp())
+    torch.cuda.synchronize()
+    delta_ref = (o_ref.detach() * do4).sum(-1)
+    assert (delta - delta_ref).abs().max().item() < 0.15
+    for name, got, ref, S in (("dq", dq_acc, q4.grad, Sq), ("dk", dKs.float(), k4.grad, Sk), ("dv", dVs.float(), v4.grad, Sk)):
+        got4 = got.reshape(B, S, H, dk).permute(0, 2, 1, 3)
+        assert torch.isfinite(got4).all(), f"{kind}: non-finite {name}"
+        err = (got4 - ref).abs().max().item()
+        scale = ref.abs().max().item()
+        assert err < 4e-2 * max(1.0, scale), f"attn bwd {kind} {name} B{B} H{H} Sq{Sq} Sk{Sk} dk{dk}: err {err} (scale {scale})"
+
+
+@pytest.mark.parametrize("dk", [64, 32])
+@pytest.mark.parametrize("kind", ["none", "pad", "causal", "causal_pad"])
+def test_attention_self(dk, kind):
+    attn_case(2, 2, 256, 256, dk, kind)
+    attn_case(2, 3, 200, 200, dk, kind, seed=3)      # ragged tail
+    attn_case(3, 2, 40, 40, dk, kind, seed=5)        # single partial tile (config C1 length)
+
+
+@pytest.mark.parametrize("dk", [64, 32])
+def test_attention_long_and_cross(dk):
+    attn_case(1, 2, 640, 640, dk, "causal", seed=7)          # 5 kv tiles, odd slot count
+    attn_case(2, 2, 300, 520, dk, "pad", seed=8)             # cross attention: Sq != Sk
+    attn_case(2, 2, 130, 70, dk, "none", seed=9)
+
+
+@pytest.mark.parametrize("kind", ["lead_pad", "all_pad", "float_mask"])
+def test_attention_reference_mask_semantics(kind):
+    attn_case(2, 2, 200, 200, 64, kind, seed=11)     # fully-masked rows are uniform (never NaN); arbitrary float mask
+
+
+# ------------------------------------------------------------------------------------------------
+# elementwise / reductions
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("d", [64, 128, 512, 1024])
+def test_residual_layernorm_fwd_bwd(d):
+    rows = 333
+    y = rnd((rows, d), 1.0, 1, torch.float32); x = rnd((rows, d), 1.0, 2, torch.float32)
+    gamma = 1 + rnd((d,), 0.1, 3, torch.float32); beta = rnd((d,), 0.1, 4, torch.float32)
+    z_ref = (x + y).detach().clone().requires_grad_(True)
+    out_ref = torch.nn.functional.layer_norm(z_ref, (d,), gamma, beta, 1e-6)
+    yz = y.clone(); o32 = torch.empty_like(y); o16 = torch.empty(rows, d, dtype=torch.bfloat16, device=dev())
+    mean = torch.empty(rows, device=dev()); rstd = torch.empty(rows, device=dev())
+    L.call("b200xf_residual_ln_fwd", L.ptr(yz), L.ptr(x), L.ptr(gamma), L.ptr(beta), L.ptr(o32), L.ptr(o16), L.ptr(mean), L.ptr(rstd),
+           rows, d, 1e-6, 0.0, 0, 0, sp())
+    torch.cuda.synchronize()
+    assert (yz - z_ref).abs().max().item() < 1e-6
+    assert (o32 - out_ref).abs().max().item() < 2e-5
+    assert (o16.float() - out_ref).abs().max().item() < 3e-2
+    dout = rnd((rows, d), 1.0, 5, torch.float32)
+    out_ref.backward(dout)
+    dz = torch.empty_like(y); dy16 = torch.empty(rows, d, dtype=torch.bfloat16, device=dev())
+    dg = torch.zeros(d, device=dev()); db = torch.zeros(d, device=dev())
+    L.call("b200xf_residual_ln_bwd", L.ptr(dout), L.ptr(yz), L.ptr(mean), L.ptr(rstd), L.ptr(gamma), L.ptr(dz), L.ptr(dy16), L.ptr(dg), L.ptr(db),
+           rows, d, 0.0, 0, 0, sp())
+    torch.cuda.synchronize()
+    assert (dz - z_ref.grad).abs().max().item() < 2e-4
+    assert (dy16.float() - z_ref.grad).abs().max().item() < 3e-2
+    g_ref = (dout * (out_ref.detach() - beta) / gamma).sum(0)
+    assert (dg - g_ref).abs().max().item() < 2e-3 * max(1.0, g_ref.abs().max().item())
+    assert (db - dout.sum(0)).abs().max().item() < 2e-3
+
+
+def test_dropout_fwd_bwd_consistent():
+    rows, d, rate = 257, 512, 0.1
+    y = torch.ones(rows, d, device=dev()); x = torch.zeros(rows, d, device=dev())
+    gamma = torch.ones(d, device=dev()); beta = torch.zeros(d, device=dev())
+    yz = y.clone(); o32 = torch.empty_like(y); o16 = torch.empty(rows, d, dtype=torch.bfloat16, device=dev())
+    mean = torch.empty(rows, device=dev()); rstd = torch.empty(rows, device=dev())
+    L.call("b200xf_residual_ln_fwd", L.ptr(yz), L.ptr(x), L.ptr(gamma), L.ptr(beta), L.ptr(o32), L.ptr(o16), L.ptr(mean), L.ptr(rstd),
+           rows, d, 1e-6, rate, 1234, 7, sp())
+    torch.cuda.synchronize()
+    keep = yz != 0
+    frac = keep.float().mean().item()
+    assert abs(frac - (1 - rate)) < 0.01, frac                      # keep probability
+    assert torch.allclose(yz[keep], torch.full_like(yz[keep], 1 / (1 - rate)))    # inverted-dropout scale
+    # backward regenerates the same mask: dy_sub == dz * mask/(1-rate)
+    dout = torch.ones(rows, d, device=dev()) * torch.arange(d, device=dev())
+    dz = torch.empty_like(y); dy16 = torch.empty(rows, d, dtype=torch.bfloat16, device=dev())
+    dg = torch.zeros(d, device=dev()); db = torch.zeros(d, device=dev())
+    L.call("b200xf_residual_ln_bwd", L.ptr(dout), L.ptr(yz), L.ptr(mean), L.ptr(rstd), L.ptr(gamma), L.ptr(dz), L.ptr(dy16), L.ptr(dg), L.ptr(db),
+           rows, d, rate, 1234, 7, sp())
+    torch.cuda.synchronize()
+    want = dz * keep / (1 - rate)
+    assert (dy16.float() - want).abs().max().item() <= 0.02 * want.abs().max().item() + 1e-3
+    # a different site gives a different mask
+    yz2 = y.clone()
+    L.call("b200xf_residual_ln_fwd", L.ptr(yz2), L.ptr(x), L.ptr(gamma), L.ptr(beta), L.ptr(o32), L.ptr(o16), L.ptr(mean), L.ptr(rstd),
+           rows, d, 1e-6, rate, 1234, 8, sp())
+    torch.cuda.synchronize()
+    assert (yz2 != yz).any()
+
+
+def test_embed_fwd_bwd():
+    B, S, d, V = 5, 37, 128, 1000
+    g = torch.Generator().manual_seed(0)
+    ids = torch.randint(0, V, (B, S), generator=g).to(dev())
+    table = rnd((V, d), 0.05, 1, torch.float32); pos = rnd((64, d), 1.0, 2, torch.float32)
+    o32 = torch.empty(B * S, d, device=dev()); o16 = torch.empty(B * S, d, dtype=torch.bfloat16, device=dev())
+    L.call("b200xf_embed_fwd", L.ptr(ids), L.ptr(table), L.ptr(pos), L.ptr(o32), L.ptr(o16), B * S, S, d, V, 0.0, 0, 0, sp())
+    torch.cuda.synchronize()
+    ref = table[ids] * math.sqrt(d) + pos[:S][None]
+    assert (o32.view(B, S, d) - ref).abs().max().item() < 1e-6
+    assert (o16.float().view(B, S, d) - ref).abs().max().item() < 2e-2
+    dx = rnd((B * S, d), 1.0, 3, torch.float32)
+    dt = torch.zeros(V, d, device=dev())
+    L.call("b200xf_embed_bwd", L.ptr(ids), L.ptr(dx), L.ptr(dt), B * S, d, V, 0.0, 0, 0, sp())
+    torch.cuda.synchronize()
+    dref = torch.zeros(V, d, device=dev()).index_add_(0, ids.view(-1), dx * math.sqrt(d))
+    assert (dt - dref).abs().max().item() < 1e-3
+
+
+@pytest.mark.parametrize("logits_f32", [1, 0])
+def test_xent_loss_grad_accuracy(logits_f32):
+    B, T, V = 4, 9, 1003
+    ld = 1008
+    g = torch.Generator().manual_seed(1)
+    logits = torch.randn(B * T, ld, generator=g).to(dev()) * 3
+    tar = torch.randint(1, V, (B, T + 1), generator=g); tar[1, 5:] = 0; tar[3, 1:] = 0
+    tar = tar.to(dev())
+    real = tar[:, 1:]
+    lg = logits if logits_f32 else logits.bfloat16()
+    lref = lg[:, :V].float().view(B, T, V).clone().requires_grad_(True)
+    lse = torch.logsumexp(lref, -1)
+    per = (lse - torch.gather(lref, -1, real[..., None]).squeeze(-1)) * (real != 0)
+    loss = per.sum() / B
+    loss.backward()
+    dl = torch.full((B * T, ld), float("nan"), dtype=torch.bfloat16, device=dev())
+    stats = torch.zeros(4, dtype=torch.float64, device=dev())
+    row_loss = torch.empty(B * T, device=dev())
+    L.call("b200xf_xent", L.ptr(lg), logits_f32, ld, L.ptr(tar), T + 1, 1, T, L.ptr(dl), ld, L.ptr(row_loss), L.ptr(stats), B * T, V, 1.0 / B, sp())
+    torch.cuda.synchronize()
+    assert abs(stats[0].item() / B - loss.item()) < 1e-4 * abs(loss.item())
+    assert (row_loss.view(B, T) - per.detach()).abs().max().item() < 1e-3
+    correct = (lref.argmax(-1) == real).sum().item()
+    assert stats[1].item() == correct and stats[2].item() == B * T and stats[3].item() == (real != 0).sum().item()
+    assert (dl[:, :V].float().view(B, T, V) - lref.grad).abs().max().item() < 2e-3
+    assert torch.all(dl[:, V:] == 0)
+
+
+def test_colsum_adam_casts_padmask():
+    rows, N = 1000, 520
+    X = rnd((rows, 528), 1.0, 0)
+    out = torch.zeros(N, device=dev())
+    L.call("b200xf_colsum_bf16", L.ptr(X), 528, L.ptr(out), rows, N, sp())
+    torch.cuda.synchronize()
+    assert (out - X[:, :N].float().sum(0)).abs().max().item() < 1e-2
+    n = 4096 * 3
+    p = rnd((n,), 1.0, 1, torch.float32); m = rnd((n,), 0.1, 2, torch.float32); v = rnd((n,), 0.1, 3, torch.float32).abs()
+    g = rnd((n,), 1.0, 4, torch.float32)
+    p0, m0, v0 = p.clone(), m.clone(), v.clone()
+    sh = torch.empty(n, dtype=torch.bfloat16, device=dev())
+    alpha, b1, b2, eps = 1e-3, 0.9, 0.98, 1e-9
+    L.call("b200xf_adam_step", L.ptr(p), L.ptr(m), L.ptr(v), L.ptr(g), L.ptr(sh), n, alpha, b1, b2, eps, sp())
+    torch.cuda.synchronize()
+    m1 = b1 * m0 + (1 - b1) * g; v1 = b2 * v0 + (1 - b2) * g * g; p1 = p0 - alpha * m1 / (v1.sqrt() + eps)
+    assert (m - m1).abs().max().item() < 1e-6 and (v - v1).abs().max().item() < 1e-6 and (p - p1).abs().max().item() < 1e-6
+    assert torch.equal(sh, p.bfloat16())
+    ids = torch.tensor([[3, 0, 5, 0]], device=dev()); mask = torch.empty(4, dtype=torch.uint8, device=dev())
+    L.call("b200xf_pad_mask", L.ptr(ids), L.ptr(mask), 4, sp())
+    torch.cuda.synchronize()
+    assert mask.tolist() == [0, 1, 0, 1]

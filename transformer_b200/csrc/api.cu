@@ -1,0 +1,93 @@
+// extern "C" surface of libb200xf.so (declared in include/b200xf.h): thin forwards to the bx:: launchers.
+#include "../../include/b200xf.h"
+
+#include "common.cuh"
+#include "kernels.h"
+
+#define ST(s) reinterpret_cast<cudaStream_t>(s)
+
+extern "C" {
+
+const char* b200xf_last_error(void) { return bx::last_error(); }
+int b200xf_version(void) { return 100; }
+long long b200xf_launch_count(void) { return bx::launch_count(); }
+
+int b200xf_gemm_bf16(const void* A, int64_t lda, int a_major, const void* B, int64_t ldb, int b_major, void* D,
+                     int64_t ldd, int d_is_f32, const float* bias, const void* aux, int64_t ld_aux, int flags,
+                     int splits, int64_t M, int64_t N, int64_t K, b200xf_stream_t stream) {
+  return bx::gemm_bf16(A, lda, a_major, B, ldb, b_major, D, ldd, d_is_f32, bias, aux, ld_aux, flags, splits, M, N, K,
+                       ST(stream));
+}
+int b200xf_attn_fwd(const void* Q, int64_t ld_q, const void* K, int64_t ld_k, const void* V, int64_t ld_v, void* O,
+                    int64_t ld_o, float* lse, const uint8_t* kpad, int causal, const float* maskf, int64_t mask_sb,
+                    int64_t mask_sq, int B, int H, int Sq, int Sk, int dk, b200xf_stream_t stream) {
+  return bx::attn_fwd(Q, ld_q, K, ld_k, V, ld_v, O, ld_o, lse, kpad, causal, maskf, mask_sb, mask_sq, B, H, Sq, Sk, dk,
+                      ST(stream));
+}
+int b200xf_attn_bwd(const void* Q, int64_t ld_q, const void* K, int64_t ld_k, const void* V, int64_t ld_v,
+                    const void* dO, int64_t ld_do, const float* lse, const float* delta, float* dq_acc, int64_t ld_dq,
+                    void* dK, int64_t ld_dk, void* dV, int64_t ld_dv, const uint8_t* kpad, int causal,
+                    const float* maskf, int64_t mask_sb, int64_t mask_sq, int B, int H, int Sq, int Sk, int dk,
+                    b200xf_stream_t stream) {
+  return bx::attn_bwd(Q, ld_q, K, ld_k, V, ld_v, dO, ld_do, lse, delta, dq_acc, ld_dq, dK, ld_dk, dV, ld_dv, kpad, causal,
+                      maskf, mask_sb, mask_sq, B, H, Sq, Sk, dk, ST(stream));
+}
+int b200xf_attn_delta(const void* O, int64_t ld_o, const void* dO, int64_t ld_do, float* delta, int B, int S, int H,
+                      int dk, b200xf_stream_t stream) {
+  return bx::attn_delta(O, ld_o, dO, ld_do, delta, B, S, H, dk, ST(stream));
+}
+int b200xf_attn_probs(const void* Q, int64_t ld_q, const void* K, int64_t ld_k, const float* lse, float* P,
+                      const uint8_t* kpad, int causal, const float* maskf, int64_t mask_sb, int64_t mask_sq, int B,
+                      int H, int Sq, int Sk, int dk, b200xf_stream_t stream) {
+  return bx::attn_probs(Q, ld_q, K, ld_k, lse, P, kpad, causal, maskf, mask_sb, mask_sq, B, H, Sq, Sk, dk, ST(stream));
+}
+int b200xf_embed_fwd(const int64_t* ids, const float* table, const float* pos, float* out_f32, void* out_bf16,
+                     int64_t rows, int S, int d, int64_t V, float rate, uint64_t seed, uint32_t site,
+                     b200xf_stream_t stream) {
+  return bx::embed_fwd(reinterpret_cast<const long long*>(ids), table, pos, out_f32, out_bf16, rows, S, d, V, rate, seed,
+                       site, ST(stream));
+}
+int b200xf_embed_bwd(const int64_t* ids, const float* dx, float* dtable, int64_t rows, int d, int64_t V, float rate,
+                     uint64_t seed, uint32_t site, b200xf_stream_t stream) {
+  return bx::embed_bwd(reinterpret_cast<const long long*>(ids), dx, dtable, rows, d, V, rate, seed, site, ST(stream));
+}
+int b200xf_residual_ln_fwd(float* y_z, const float* x, const float* gamma, const float* beta, float* out_f32,
+                           void* out_bf16, float* mean, float* rstd, int64_t rows, int d, float eps, float rate,
+                           uint64_t seed, uint32_t site, b200xf_stream_t stream) {
+  return bx::residual_ln_fwd(y_z, x, gamma, beta, out_f32, out_bf16, mean, rstd, rows, d, eps, rate, seed, site,
+                             ST(stream));
+}
+int b200xf_residual_ln_bwd(const float* dout, const float* z, const float* mean, const float* rstd, const float* gamma,
+                           float* dz, void* dy_sub_bf16, float* dgamma, float* dbeta, int64_t rows, int d, float rate,
+                           uint64_t seed, uint32_t site, b200xf_stream_t stream) {
+  return bx::residual_ln_bwd(dout, z, mean, rstd, gamma, dz, dy_sub_bf16, dgamma, dbeta, rows, d, rate, seed, site,
+                             ST(stream));
+}
+int b200xf_xent(const void* logits, int logits_f32, int64_t ld, const int64_t* labels, int label_stride,
+                int label_offset, int T, void* dlogits, int64_t ld_d, float* row_loss, double* stats, int64_t rows,
+                int V, float inv_batch, b200xf_stream_t stream) {
+  return bx::xent(logits, logits_f32, ld, reinterpret_cast<const long long*>(labels), label_stride, label_offset, T,
+                  dlogits, ld_d, row_loss, stats, rows, V, inv_batch, ST(stream));
+}
+int b200xf_colsum_bf16(const void* X, int64_t ld, float* out, int64_t rows, int N, b200xf_stream_t stream) {
+  return bx::colsum_bf16(X, ld, out, rows, N, ST(stream));
+}
+int b200xf_adam_step(float* p, float* m, float* v, const float* g, void* shadow_bf16, int64_t n, float alpha,
+                     float beta1, float beta2, float eps, b200xf_stream_t stream) {
+  return bx::adam_step(p, m, v, g, shadow_bf16, n, alpha, beta1, beta2, eps, ST(stream));
+}
+int b200xf_cast_f32_bf16(const float* in, void* out, int64_t n, b200xf_stream_t stream) {
+  return bx::cast_f32_bf16(in, out, n, ST(stream));
+}
+int b200xf_cast_bf16_f32(const void* in, float* out, int64_t n, b200xf_stream_t stream) {
+  return bx::cast_bf16_f32(in, out, n, ST(stream));
+}
+int b200xf_cast_f32_bf16_strided(const float* in, void* out, int64_t rows, int d, int64_t ld_out,
+                                 b200xf_stream_t stream) {
+  return bx::cast_f32_bf16_strided(in, out, rows, d, ld_out, ST(stream));
+}
+int b200xf_pad_mask(const int64_t* ids, uint8_t* mask, int64_t n, b200xf_stream_t stream) {
+  return bx::pad_mask(reinterpret_cast<const long long*>(ids), mask, n, ST(stream));
+}
+
+}  // extern "C"

@@ -1,0 +1,717 @@
+// K2: fused flash-style scaled-dot-product attention for sm_100a, forward and backward.
+//   reference: scaled_dot_product_attention (Attention.py:3-34) inside MultiHeadAttention.call (Attention.py:59-78)
+//
+//   logits = q.k^T / sqrt(dk) + mask * (-1e9) ; P = softmax(logits) ; out = P.v
+//
+// Semantics kept from the reference: masking ADDS -1e9 (finite), so in fp32 every masked
+// logit equals -1e9 exactly and a fully-masked row is a UNIFORM distribution over all Sk keys (never NaN).
+// The canonical masks of positionalencoding.py:25-52 are derived in-kernel from compact key-padding bytes
+// (1 = key token id 0) and a causal flag; an arbitrary float mask (the six-argument API) is also accepted.
+//
+// Layout: Q/K/V are column blocks [h*dk, (h+1)*dk) of token-major bf16 matrices [B*S, ld] (the packed output of
+// the QKV projection GEMM) -- split_heads/transpose (Attention.py:52-57,74-76) never materialise.  TMA 3-D maps
+// {column, token, batch} zero-fill ragged tails.  S = Q.K^T and O = P.V run on tcgen05 (accumulators in TMEM);
+// softmax warps own one query row per thread (tcgen05.ld 32x32b).
+#include "common.cuh"
+
+namespace bx {
+
+constexpr float kLog2e = 1.4426950408889634f;
+constexpr float kMaskVal = -1e9f;
+
+struct AttnMask {
+  const uint8_t* kpad;    // [B, Sk] 1 = masked key (token id 0); may be null
+  const float* maskf;     // optional float mask, value m adds m * -1e9; element (b, q, k) at b*sb + q*sq + k
+  long long sb, sq;
+  int causal;             // 1: key index > query index is masked (look-ahead mask)
+};
+
+template <int DK>
+struct AttnCfg {
+  static constexpr uint32_t ROW_BYTES = DK * 2;
+  static constexpr uint32_t TILE_BYTES = 128 * ROW_BYTES;      // a [128 x DK] bf16 tile
+  static constexpr uint32_t SWZ = DK == 64 ? kSwz128 : kSwz64;  // swizzle span == row bytes
+  static constexpr uint32_t SBO = 8 * ROW_BYTES;               // 8-row core-matrix group
+  static constexpr uint32_t P_BYTES = 128 * 256;               // [128 x 128] bf16 as two 128-byte-wide panels
+  static constexpr uint32_t KSTEP_MN = 16 * ROW_BYTES;         // k16 step of an MN-major [rows x DK] tile
+};
+
+template <int DK>
+__device__ __forceinline__ uint32_t swz_off(uint32_t row, uint32_t chunk) {
+  return DK == 64 ? swz128_off(row, chunk) : swz64_off(row, chunk);
+}
+
+// ================================================================================================
+// forward
+// ================================================================================================
+template <int DK>
+struct FwdSmem {
+  using C = AttnCfg<DK>;
+  static constexpr uint32_t OFF_Q = 0;                                  // 2 slots
+  static constexpr uint32_t OFF_K = OFF_Q + 2 * C::TILE_BYTES;          // 2 stages
+  static constexpr uint32_t OFF_V = OFF_K + 2 * C::TILE_BYTES;          // 2 stages
+  static constexpr uint32_t OFF_P = OFF_V + 2 * C::TILE_BYTES;          // 2 slots
+  static constexpr uint32_t OFF_BAR = OFF_P + 2 * C::P_BYTES;
+  static constexpr uint32_t BYTES = OFF_BAR + 256 + 1024;
+};
+
+constexpr int ATTN_FWD_THREADS = 320;  // w0 TMA, w1 MMA(+TMEM alloc), w2-5 softmax slot 0, w6-9 softmax slot 1
+
+template <int DK>
+__global__ void __launch_bounds__(ATTN_FWD_THREADS, 1)
+attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmO,
+                float* __restrict__ lse_out, AttnMask mask, int H, int Sq, int Sk, float scale) {
+  using C = AttnCfg<DK>;
+  using L = FwdSmem<DK>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L::OFF_BAR);
+  uint64_t* q_full = bars;          // [2]
+  uint64_t* k_full = bars + 2;      // [2]
+  uint64_t* v_full = bars + 4;      // [2]
+  uint64_t* k_empty = bars + 6;     // [2]
+  uint64_t* v_empty = bars + 8;     // [2]
+  uint64_t* s_full = bars + 10;     // [2]
+  uint64_t* p_full = bars + 12;     // [2]
+  uint64_t* o_full = bars + 14;     // [2]
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 16);
+
+  const uint32_t warp = warp_idx(), lane = lane_idx();
+  const int b = blockIdx.z, h = blockIdx.y;
+  const int q0 = blockIdx.x * 256;
+  const int n_slots = (q0 + 128 < Sq) ? 2 : 1;
+  const int nkv = (Sk + 127) / 128;
+  // tiles each slot must visit.  Causal rows only see keys <= query index -- unless key 0 of this batch row is
+  // padding, in which case some rows may be fully masked and (reference semantics) attend uniformly to ALL keys.
+  int nt[2];
+  {
+    const bool lead_pad = mask.causal && mask.kpad != nullptr && mask.kpad[(long long)b * Sk] != 0;
+    for (int s = 0; s < 2; ++s) {
+      int n = nkv;
+      if (mask.causal && !lead_pad) {
+        const int last_q = min(q0 + s * 128 + 127, Sq - 1);
+        n = min(nkv, last_q / 128 + 1);
+      }
+      nt[s] = s < n_slots ? n : 0;
+    }
+  }
+  const int ntiles = max(nt[0], nt[1]);
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&tmQ); prefetch_tmap(&tmK); prefetch_tmap(&tmV); prefetch_tmap(&tmO);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&q_full[i], 1); mbar_init(&k_full[i], 1); mbar_init(&v_full[i], 1);
+      mbar_init(&k_empty[i], 1); mbar_init(&v_empty[i], 1);
+      mbar_init(&s_full[i], 1); mbar_init(&p_full[i], 128); mbar_init(&o_full[i], 1);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc<512>(tmem_ptr);
+  tcgen05_before_thread_sync();
+  __syncthreads();
+  tcgen05_after_thread_sync();
+  const uint32_t tmem_base = *tmem_ptr;
+  const uint32_t tS[2] = {tmem_base, tmem_base + 128};
+  const uint32_t tO[2] = {tmem_base + 256, tmem_base + 256 + DK};
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ===================================== TMA producer =====================================
+      for (int s = 0; s < n_slots; ++s) {
+        mbar_arrive_expect_tx(&q_full[s], C::TILE_BYTES);
+        tma_load_3d(smem + L::OFF_Q + s * C::TILE_BYTES, &tmQ, &q_full[s], h * DK, q0 + s * 128, b);
+      }
+      for (int j = 0; j < ntiles; ++j) {
+        const int st = j & 1;
+        const uint32_t ph = (j >> 1) & 1;
+        mbar_wait(&k_empty[st], ph ^ 1);
+        mbar_arrive_expect_tx(&k_full[st], C::TILE_BYTES);
+        tma_load_3d(smem + L::OFF_K + st * C::TILE_BYTES, &tmK, &k_full[st], h * DK, j * 128, b);
+        mbar_wait(&v_empty[st], ph ^ 1);
+        mbar_arrive_expect_tx(&v_full[st], C::TILE_BYTES);
+        tma_load_3d(smem + L::OFF_V + st * C::TILE_BYTES, &tmV, &v_full[st], h * DK, j * 128, b);
+      }
+    }
+  } else if (warp == 1) {
+    // ===================================== MMA issuer =====================================
+    constexpr uint32_t idescS = make_idesc_bf16(128, 128, 0, 0);   // S[q,kv] = Q (K-major) . K^T (K-major)
+    constexpr uint32_t idescO = make_idesc_bf16(128, DK, 0, 1);    // O[q,dk] = P (K-major) . V (MN-major)
+    const uint32_t sQ = smem_u32(smem + L::OFF_Q), sK = smem_u32(smem + L::OFF_K), sV = smem_u32(smem + L::OFF_V),
+                   sP = smem_u32(smem + L::OFF_P);
+    auto issue_S = [&](int s, int j) {
+      const int st = j & 1;
+      mbar_wait(&k_full[st], (j >> 1) & 1);
+      if (j == 0) mbar_wait(&q_full[s], 0);
+      tcgen05_after_thread_sync();
+      if (lane == 0) {
+#pragma unroll
+        for (int k = 0; k < DK / 16; ++k) {
+          const uint64_t ad = make_smem_desc(sQ + s * C::TILE_BYTES + k * 32, 0, C::SBO, C::SWZ);
+          const uint64_t bd = make_smem_desc(sK + st * C::TILE_BYTES + k * 32, 0, C::SBO, C::SWZ);
+          umma_f16(tS[s], ad, bd, idescS, k > 0 ? 1u : 0u);
+        }
+        umma_commit(&s_full[s]);
+        const bool last_user = (s == 1) || !(j < nt[1]);
+        if (last_user) umma_commit(&k_empty[st]);
+      }
+      __syncwarp();
+    };
+    auto issue_PV = [&](int s, int j) {
+      const int st = j & 1;
+      mbar_wait(&p_full[s], j & 1);
+      mbar_wait(&v_full[st], (j >> 1) & 1);
+      tcgen05_after_thread_sync();
+      if (lane == 0) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          const uint64_t ad = make_smem_desc(sP + s * C::P_BYTES + (k >> 2) * 16384 + (k & 3) * 32, 0, 1024, kSwz128);
+          const uint64_t bd = make_smem_desc(sV + st * C::TILE_BYTES + k * C::KSTEP_MN, C::TILE_BYTES, C::SBO, C::SWZ);
+          umma_f16(tO[s], ad, bd, idescO, k > 0 ? 1u : 0u);
+        }
+        umma_commit(&o_full[s]);
+        const bool last_user = (s == 1) || !(j < nt[1]);
+        if (last_user) umma_commit(&v_empty[st]);
+      }
+      __syncwarp();
+    };
+    for (int s = 0; s < 2; ++s)
+      if (0 < nt[s]) issue_S(s, 0);
+    for (int j = 0; j < ntiles; ++j) {
+      for (int s = 0; s < 2; ++s) {
+        if (j < nt[s]) issue_PV(s, j);
+        if (j + 1 < nt[s]) issue_S(s, j + 1);
+      }
+    }
+  } else {
+    // ===================================== softmax warps =====================================
+    const int s = (warp - 2) >> 2;               // q slot
+    const uint32_t quad = warp & 3u;             // TMEM lane quadrant
+    const uint32_t row = quad * 32u + lane;
+    const int q = q0 + s * 128 + (int)row;       // global query index
+    const int wg_tid = (int)threadIdx.x - 64 - s * 128;
+    if (s < n_slots) {
+      const uint32_t lane_sel = (quad * 32u) << 16;
+      const uint32_t sPs = smem_u32(smem + L::OFF_P + s * C::P_BYTES);
+      const float* mrow = mask.maskf ? mask.maskf + (long long)b * mask.sb + (long long)min(q, Sq - 1) * mask.sq : nullptr;
+      float m_run = -INFINITY, l_run = 0.f;
+      float acc[DK];
+#pragma unroll
+      for (int i = 0; i < DK; ++i) acc[i] = 0.f;
+
+      for (int j = 0; j < nt[s]; ++j) {
+        const int kv0 = j * 128;
+        // key flags for this tile as 4 x 32-bit ballots: bit e of word c <-> key kv0 + 32c + e
+        uint32_t padbits[4], oobbits[4];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          const int kv = kv0 + c * 32 + (int)lane;
+          const bool oob = kv >= Sk;
+          const bool pad = !oob && mask.kpad != nullptr && mask.kpad[(long long)b * Sk + kv] != 0;
+          padbits[c] = __ballot_sync(0xffffffffu, pad);
+          oobbits[c] = __ballot_sync(0xffffffffu, oob);
+        }
+        const bool diag = mask.causal && (kv0 + 127 > q0 + s * 128);   // tile touches the causal boundary
+        mbar_wait(&s_full[s], j & 1);
+        tcgen05_after_thread_sync();
+
+        auto logit = [&](float raw, uint32_t pb, uint32_t ob, int c, int e) -> float {
+          const int kv = kv0 + c * 32 + e;
+          float t = raw * scale;
+          const bool masked = ((pb >> e) & 1u) || (diag && kv > q);
+          if (masked) t = kMaskVal;
+          if (mrow != nullptr && kv < Sk) t += mrow[kv] * kMaskVal;
+          if ((ob >> e) & 1u) t = -INFINITY;
+          return t;
+        };
+        auto sel4 = [](const uint32_t (&a)[4], int c) -> uint32_t {
+          return c == 0 ? a[0] : (c == 1 ? a[1] : (c == 2 ? a[2] : a[3]));
+        };
+        // pass 1: row max
+        float m_new = m_run;
+#pragma unroll 1
+        for (int c = 0; c < 4; ++c) {
+          uint32_t r[32];
+          tmem_ld_x32(tS[s] + lane_sel + c * 32, r);
+          tmem_ld_wait();
+          const uint32_t pb = sel4(padbits, c), ob = sel4(oobbits, c);
+#pragma unroll
+          for (int e = 0; e < 32; ++e) m_new = fmaxf(m_new, logit(__uint_as_float(r[e]), pb, ob, c, e));
+        }
+        const float alpha = fast_exp2((m_run - m_new) * kLog2e);   // first tile: exp2(-inf) = 0
+        const float mb = m_new * kLog2e;
+        // pass 2: p = exp(t - m), row sum (fp32), P -> bf16 -> smem (K-major SWIZZLE_128B, two 64-key panels)
+        float rsum = 0.f;
+#pragma unroll 1
+        for (int c = 0; c < 4; ++c) {
+          uint32_t r[32];
+          tmem_ld_x32(tS[s] + lane_sel + c * 32, r);
+          tmem_ld_wait();
+          float p[32];
+          const uint32_t pb = sel4(padbits, c), ob = sel4(oobbits, c);
+#pragma unroll
+          for (int e = 0; e < 32; ++e) {
+            p[e] = fast_exp2(logit(__uint_as_float(r[e]), pb, ob, c, e) * kLog2e - mb);
+            rsum += p[e];
+          }
+          const uint32_t panel = sPs + (c >> 1) * 16384;
+#pragma unroll
+          for (int g = 0; g < 4; ++g)
+            st_shared_v4(panel + swz128_off(row, (c & 1) * 4 + g), pack_bf16x2(p[8 * g], p[8 * g + 1]),
+                         pack_bf16x2(p[8 * g + 2], p[8 * g + 3]), pack_bf16x2(p[8 * g + 4], p[8 * g + 5]),
+                         pack_bf16x2(p[8 * g + 6], p[8 * g + 7]));
+        }
+        fence_proxy_async_smem();
+        tcgen05_before_thread_sync();
+        mbar_arrive(&p_full[s]);
+        l_run = l_run * alpha + rsum;
+        m_run = m_new;
+        // accumulate this tile's P.V
+        mbar_wait(&o_full[s], j & 1);
+        tcgen05_after_thread_sync();
+#pragma unroll
+        for (int c = 0; c < DK / 32; ++c) {
+          uint32_t r[32];
+          tmem_ld_x32(tO[s] + lane_sel + c * 32, r);
+          tmem_ld_wait();
+#pragma unroll
+          for (int e = 0; e < 32; ++e) acc[c * 32 + e] = acc[c * 32 + e] * alpha + __uint_as_float(r[e]);
+        }
+        tcgen05_before_thread_sync();
+      }
+      // finalise: O = acc / l -> bf16 -> smem (reuse this slot's P buffer) -> TMA store ; lse = m + ln(l)
+      const float inv = 1.f / l_run;
+#pragma unroll
+      for (int g = 0; g < DK / 8; ++g)
+        st_shared_v4(sPs + swz_off<DK>(row, g), pack_bf16x2(acc[8 * g] * inv, acc[8 * g + 1] * inv),
+                     pack_bf16x2(acc[8 * g + 2] * inv, acc[8 * g + 3] * inv),
+                     pack_bf16x2(acc[8 * g + 4] * inv, acc[8 * g + 5] * inv),
+                     pack_bf16x2(acc[8 * g + 6] * inv, acc[8 * g + 7] * inv));
+      if (q < Sq) lse_out[((long long)b * H + h) * Sq + q] = m_run + __logf(l_run);
+      fence_proxy_async_smem();
+      named_bar_sync(1 + s, 128);
+      if (wg_tid == 0) {
+        tma_store_3d(&tmO, smem + L::OFF_P + s * C::P_BYTES, h * DK, q0 + s * 128, b);
+        tma_store_commit();
+        tma_store_wait_all<0>();
+      }
+    }
+  }
+  tcgen05_before_thread_sync();
+  __syncthreads();
+  tcgen05_after_thread_sync();
+  if (warp == 1) tmem_dealloc<512>(tmem_base);
+}
+
+// ================================================================================================
+// backward:  one CTA per (kv tile, head, batch); loops over query tiles.
+//   S^T = K.Q^T, dP^T = V.dO^T (TMEM)  ->  P^T = exp(S^T*scale - lse), dS^T = P^T o (dP^T - delta) * scale  (smem, bf16)
+//   dV += P^T.dO   dK += dS^T.Q   (TMEM accumulators over all query tiles)    dQ_tile = dS.K  -> red.add fp32
+// ================================================================================================
+template <int DK>
+struct BwdSmem {
+  using C = AttnCfg<DK>;
+  static constexpr uint32_t OFF_K = 0;
+  static constexpr uint32_t OFF_V = OFF_K + C::TILE_BYTES;
+  static constexpr uint32_t OFF_Q = OFF_V + C::TILE_BYTES;          // 2 stages
+  static constexpr uint32_t OFF_DO = OFF_Q + 2 * C::TILE_BYTES;     // 2 stages
+  static constexpr uint32_t OFF_PT = OFF_DO + 2 * C::TILE_BYTES;    // P^T   [kv 128][q 128] bf16, two panels
+  static constexpr uint32_t OFF_DST = OFF_PT + C::P_BYTES;          // dS^T
+  static constexpr uint32_t OFF_ROW = OFF_DST + C::P_BYTES;         // lse/delta: 2 buffers x (128 + 128) floats
+  static constexpr uint32_t OFF_BAR = OFF_ROW + 2 * 256 * 4;
+  static constexpr uint32_t BYTES = OFF_BAR + 256 + 1024;
+};
+
+constexpr int ATTN_BWD_THREADS = 320;  // w0 TMA, w1 MMA(+TMEM alloc), w2-9 compute (rows x 2 column halves)
+
+__device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float c, float d) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+
+template <int DK>
+__global__ void __launch_bounds__(ATTN_BWD_THREADS, 1)
+attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmdO,
+                const __grid_constant__ CUtensorMap tmdK, const __grid_constant__ CUtensorMap tmdV,
+                const float* __restrict__ lse, const float* __restrict__ delta, float* __restrict__ dq_acc,
+                long long ld_dq, AttnMask mask, int H, int Sq, int Sk, float scale) {
+  using C = AttnCfg<DK>;
+  using L = BwdSmem<DK>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L::OFF_BAR);
+  uint64_t* kv_full = bars;          // [1]
+  uint64_t* qdo_full = bars + 1;     // [2]
+  uint64_t* qdo_empty = bars + 3;    // [2]
+  uint64_t* sdp_full = bars + 5;     // [1]
+  uint64_t* pds_full = bars + 6;     // [1] count 256
+  uint64_t* dq_full = bars + 7;      // [1]
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 8);
+  float* rowbuf = reinterpret_cast<float*>(smem + L::OFF_ROW);
+
+  const uint32_t warp = warp_idx(), lane = lane_idx();
+  const int b = blockIdx.z, h = blockIdx.y, jt = blockIdx.x;
+  const int kv0 = jt * 128;
+  const int nq = (Sq + 127) / 128;
+  const bool lead_pad = mask.causal && mask.kpad != nullptr && mask.kpad[(long long)b * Sk] != 0;
+  const int i_start = (mask.causal && !lead_pad) ? min(jt, nq - 1) : 0;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&tmQ); prefetch_tmap(&tmK); prefetch_tmap(&tmV); prefetch_tmap(&tmdO);
+    prefetch_tmap(&tmdK); prefetch_tmap(&tmdV);
+    mbar_init(kv_full, 1);
+    for (int i = 0; i < 2; ++i) { mbar_init(&qdo_full[i], 1); mbar_init(&qdo_empty[i], 1); }
+    mbar_init(sdp_full, 1); mbar_init(pds_full, 256); mbar_init(dq_full, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc<512>(tmem_ptr);
+  tcgen05_before_thread_sync();
+  __syncthreads();
+  tcgen05_after_thread_sync();
+  const uint32_t tmem_base = *tmem_ptr;
+  const uint32_t tSt = tmem_base, tdPt = tmem_base + 128, tdV = tmem_base + 256, tdK = tmem_base + 256 + DK,
+                 tdQ = tmem_base + 256 + 2 * DK;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ===================================== TMA producer =====================================
+      mbar_arrive_expect_tx(kv_full, 2 * C::TILE_BYTES);
+      tma_load_3d(smem + L::OFF_K, &tmK, kv_full, h * DK, kv0, b);
+      tma_load_3d(smem + L::OFF_V, &tmV, kv_full, h * DK, kv0, b);
+      int n = 0;
+      for (int i = i_start; i < nq; ++i, ++n) {
+        const int st = n & 1;
+        mbar_wait(&qdo_empty[st], ((n >> 1) & 1) ^ 1);
+        mbar_arrive_expect_tx(&qdo_full[st], 2 * C::TILE_BYTES);
+        tma_load_3d(smem + L::OFF_Q + st * C::TILE_BYTES, &tmQ, &qdo_full[st], h * DK, i * 128, b);
+        tma_load_3d(smem + L::OFF_DO + st * C::TILE_BYTES, &tmdO, &qdo_full[st], h * DK, i * 128, b);
+      }
+    }
+  } else if (warp == 1) {
+    // ===================================== MMA issuer =====================================
+    constexpr uint32_t idescS = make_idesc_bf16(128, 128, 0, 0);    // [kv, q] = K/V (K-major) . Q/dO^T (K-major)
+    constexpr uint32_t idescKV = make_idesc_bf16(128, DK, 0, 1);    // [kv, dk] = P^T/dS^T (K-major) . dO/Q (MN-major)
+    constexpr uint32_t idescQ = make_idesc_bf16(128, DK, 1, 1);     // [q, dk]  = dS (MN-major view of dS^T) . K (MN-major)
+    const uint32_t sK = smem_u32(smem + L::OFF_K), sV = smem_u32(smem + L::OFF_V), sQ = smem_u32(smem + L::OFF_Q),
+                   sdO = smem_u32(smem + L::OFF_DO), sPt = smem_u32(smem + L::OFF_PT), sdSt = smem_u32(smem + L::OFF_DST);
+    auto issue_sdp = [&](int n) {
+      const int st = n & 1;
+      mbar_wait(&qdo_full[st], (n >> 1) & 1);
+      tcgen05_after_thread_sync();
+      if (lane == 0) {
+#pragma unroll
+        for (int k = 0; k < DK / 16; ++k) {
+          const uint64_t ad = make_smem_desc(sK + k * 32, 0, C::SBO, C::SWZ);
+          const uint64_t bd = make_smem_desc(sQ + st * C::TILE_BYTES + k * 32, 0, C::SBO, C::SWZ);
+          umma_f16(tSt, ad, bd, idescS, k > 0 ? 1u : 0u);
+        }
+#pragma unroll
+        for (int k = 0; k < DK / 16; ++k) {
+          const uint64_t ad = make_smem_desc(sV + k * 32, 0, C::SBO, C::SWZ);
+          const uint64_t bd = make_smem_desc(sdO + st * C::TILE_BYTES + k * 32, 0, C::SBO, C::SWZ);
+          umma_f16(tdPt, ad, bd, idescS, k > 0 ? 1u : 0u);
+        }
+        umma_commit(sdp_full);
+      }
+      __syncwarp();
+    };
+    mbar_wait(kv_full, 0);
+    const int ntile = nq - i_start;
+    issue_sdp(0);
+    for (int n = 0; n < ntile; ++n) {
+      const int st = n & 1;
+      mbar_wait(pds_full, n & 1);
+      tcgen05_after_thread_sync();
+      if (lane == 0) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {   // dV += P^T . dO     (K = 128 queries)
+          const uint64_t ad = make_smem_desc(sPt + (k >> 2) * 16384 + (k & 3) * 32, 0, 1024, kSwz128);
+          const uint64_t bd = make_smem_desc(sdO + st * C::TILE_BYTES + k * C::KSTEP_MN, C::TILE_BYTES, C::SBO, C::SWZ);
+          umma_f16(tdV, ad, bd, idescKV, (n > 0 || k > 0) ? 1u : 0u);
+        }
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {   // dK += dS^T . Q
+          const uint64_t ad = make_smem_desc(sdSt + (k >> 2) * 16384 + (k & 3) * 32, 0, 1024, kSwz128);
+          const uint64_t bd = make_smem_desc(sQ + st * C::TILE_BYTES + k * C::KSTEP_MN, C::TILE_BYTES, C::SBO, C::SWZ);
+          umma_f16(tdK, ad, bd, idescKV, (n > 0 || k > 0) ? 1u : 0u);
+        }
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {   // dQ = dS . K        (K = 128 keys; A = MN-major view of dS^T)
+          const uint64_t ad = make_smem_desc(sdSt + k * 2048, 16384, 1024, kSwz128);
+          const uint64_t bd = make_smem_desc(sK + k * C::KSTEP_MN, C::TILE_BYTES, C::SBO, C::SWZ);
+          umma_f16(tdQ, ad, bd, idescQ, k > 0 ? 1u : 0u);
+        }
+        umma_commit(&qdo_empty[st]);
+        umma_commit(dq_full);
+      }
+      __syncwarp();
+      if (n + 1 < ntile) issue_sdp(n + 1);
+    }
+  } else {
+    // ===================================== compute warps =====================================
+    const int cw = (int)warp - 2;                 // 0..7
+    const uint32_t quad = warp & 3u;
+    const int half = cw >> 2;                     // which 64 query columns / which dk half this warp owns
+    const uint32_t row = quad * 32u + lane;       // kv row (S^T, dV, dK) or q row (dQ)
+    const uint32_t lane_sel = (quad * 32u) << 16;
+    const int ctid = (int)threadIdx.x - 64;       // 0..255
+    const int kv = kv0 + (int)row;
+    const bool kv_valid = kv < Sk;
+    const bool kv_pad = kv_valid && mask.kpad != nullptr && mask.kpad[(long long)b * Sk + kv] != 0;
+    const uint32_t sPt = smem_u32(smem + L::OFF_PT), sdSt = smem_u32(smem + L::OFF_DST);
+    const float sl2 = scale * kLog2e;
+    const float inv_sk = 1.f / (float)Sk;
+    int n = 0;
+    for (int i = i_start; i < nq; ++i, ++n) {
+      const int qt0 = i * 128;
+      float* rb = rowbuf + (n & 1) * 256;
+      {  // stage lse / delta of this query tile (lse = +inf for out-of-range queries -> p = 0)
+        const int qq = qt0 + (ctid & 127);
+        const long long off = ((long long)b * H + h) * Sq + qq;
+        if (ctid < 128) rb[ctid] = qq < Sq ? lse[off] * kLog2e : INFINITY;
+        else rb[ctid] = qq < Sq ? delta[off] : 0.f;
+      }
+      named_bar_sync(1, 256);
+      const bool diag = mask.causal && (qt0 < kv0 + 128);   // tile touches the causal boundary (some q < kv)
+      mbar_wait(sdp_full, n & 1);
+      tcgen05_after_thread_sync();
+#pragma unroll 1
+      for (int c = 0; c < 2; ++c) {
+        const int col0 = half * 64 + c * 32;
+        uint32_t rs[32], rp[32];
+        tmem_ld_x32(tSt + lane_sel + col0, rs);
+        tmem_ld_x32(tdPt + lane_sel + col0, rp);
+        tmem_ld_wait();
+        float p[32], ds[32];
+#pragma unroll
+        for (int e = 0; e < 32; ++e) {
+          const int qi = qt0 + col0 + e;
+          float t2 = __uint_as_float(rs[e]) * sl2;                        // logit * log2(e)
+          const bool masked = kv_pad || (diag && kv > qi);
+          if (masked) t2 = kMaskVal * kLog2e;
+          if (mask.maskf != nullptr && kv_valid && qi < Sq)
+            t2 += mask.maskf[(long long)b * mask.sb + (long long)qi * mask.sq + kv] * (kMaskVal * kLog2e);
+          const float l2 = rb[col0 + e];
+          float pe = fast_exp2(t2 - l2);
+          if (l2 < -1e8f) pe *= inv_sk;     // fully-masked query row: lse == -1e9 in fp32 (ln Sk absorbed) -> uniform 1/Sk
+          if (!kv_valid) pe = 0.f;
+          p[e] = pe;
+          ds[e] = pe * (__uint_as_float(rp[e]) - rb[128 + col0 + e]) * scale;
+        }
+        const uint32_t po = half * 16384;
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          const uint32_t off = po + swz128_off(row, c * 4 + g);
+          st_shared_v4(sPt + off, pack_bf16x2(p[8 * g], p[8 * g + 1]), pack_bf16x2(p[8 * g + 2], p[8 * g + 3]),
+                       pack_bf16x2(p[8 * g + 4], p[8 * g + 5]), pack_bf16x2(p[8 * g + 6], p[8 * g + 7]));
+          st_shared_v4(sdSt + off, pack_bf16x2(ds[8 * g], ds[8 * g + 1]), pack_bf16x2(ds[8 * g + 2], ds[8 * g + 3]),
+                       pack_bf16x2(ds[8 * g + 4], ds[8 * g + 5]), pack_bf16x2(ds[8 * g + 6], ds[8 * g + 7]));
+        }
+      }
+      fence_proxy_async_smem();
+      tcgen05_before_thread_sync();
+      mbar_arrive(pds_full);
+      // dQ tile: row = query, this warp's half of the dk columns -> fp32 red.add into the accumulator
+      mbar_wait(dq_full, n & 1);
+      tcgen05_after_thread_sync();
+      {
+        constexpr int HC = DK / 2;
+        const int qi = qt0 + (int)row;
+        float* dst = dq_acc + ((long long)b * Sq + qi) * ld_dq + h * DK + half * HC;
+        if (HC == 32) {
+          uint32_t r[32];
+          tmem_ld_x32(tdQ + lane_sel + half * HC, r);
+          tmem_ld_wait();
+          if (qi < Sq) {
+#pragma unroll
+            for (int g = 0; g < 8; ++g)
+              red_add_v4(dst + 4 * g, __uint_as_float(r[4 * g]), __uint_as_float(r[4 * g + 1]),
+                         __uint_as_float(r[4 * g + 2]), __uint_as_float(r[4 * g + 3]));
+          }
+        } else {
+          uint32_t r[16];
+          tmem_ld_x16(tdQ + lane_sel + half * HC, r);
+          tmem_ld_wait();
+          if (qi < Sq) {
+#pragma unroll
+            for (int g = 0; g < 4; ++g)
+              red_add_v4(dst + 4 * g, __uint_as_float(r[4 * g]), __uint_as_float(r[4 * g + 1]),
+                         __uint_as_float(r[4 * g + 2]), __uint_as_float(r[4 * g + 3]));
+          }
+        }
+      }
+      tcgen05_before_thread_sync();
+    }
+    // epilogue: dV, dK (TMEM) -> bf16 -> smem (reuse P^T / dS^T buffers) -> TMA store
+    {
+      constexpr int HC = DK / 2;
+      float v[HC], k[HC];
+      if (HC == 32) {
+        uint32_t r[32];
+        tmem_ld_x32(tdV + lane_sel + half * HC, r); tmem_ld_wait();
+#pragma unroll
+        for (int e = 0; e < HC; ++e) v[e] = __uint_as_float(r[e]);
+        tmem_ld_x32(tdK + lane_sel + half * HC, r); tmem_ld_wait();
+#pragma unroll
+        for (int e = 0; e < HC; ++e) k[e] = __uint_as_float(r[e]);
+      } else {
+        uint32_t r[16];
+        tmem_ld_x16(tdV + lane_sel + half * HC, r); tmem_ld_wait();
+#pragma unroll
+        for (int e = 0; e < HC; ++e) v[e] = __uint_as_float(r[e]);
+        tmem_ld_x16(tdK + lane_sel + half * HC, r); tmem_ld_wait();
+#pragma unroll
+        for (int e = 0; e < HC; ++e) k[e] = __uint_as_float(r[e]);
+      }
+#pragma unroll
+      for (int g = 0; g < HC / 8; ++g) {
+        const uint32_t off = swz_off<DK>(row, half * (HC / 8) + g);
+        st_shared_v4(sPt + off, pack_bf16x2(v[8 * g], v[8 * g + 1]), pack_bf16x2(v[8 * g + 2], v[8 * g + 3]),
+                     pack_bf16x2(v[8 * g + 4], v[8 * g + 5]), pack_bf16x2(v[8 * g + 6], v[8 * g + 7]));
+        st_shared_v4(sdSt + off, pack_bf16x2(k[8 * g], k[8 * g + 1]), pack_bf16x2(k[8 * g + 2], k[8 * g + 3]),
+                     pack_bf16x2(k[8 * g + 4], k[8 * g + 5]), pack_bf16x2(k[8 * g + 6], k[8 * g + 7]));
+      }
+      fence_proxy_async_smem();
+      named_bar_sync(1, 256);
+      if (ctid == 0) {
+        tma_store_3d(&tmdV, smem + L::OFF_PT, h * DK, kv0, b);
+        tma_store_3d(&tmdK, smem + L::OFF_DST, h * DK, kv0, b);
+        tma_store_commit();
+        tma_store_wait_all<0>();
+      }
+    }
+  }
+  tcgen05_before_thread_sync();
+  __syncthreads();
+  tcgen05_after_thread_sync();
+  if (warp == 1) tmem_dealloc<512>(tmem_base);
+}
+
+// ================================================================================================
+// attention-weights materialisation (Decoder.py:75-76 returns them; train_step discards them): recompute
+// P[b,h,q,:] = exp(logit - lse) from Q, K and the forward's lse.  Inspection/parity path, plain SIMT.
+// ================================================================================================
+__global__ void __launch_bounds__(128)
+attn_probs_kernel(const __nv_bfloat16* __restrict__ Q, long long ld_q, const __nv_bfloat16* __restrict__ K, long long ld_k,
+                  const float* __restrict__ lse, float* __restrict__ P, AttnMask mask, int H, int Sq, int Sk, int dk,
+                  float scale) {
+  const int q = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
+  __shared__ float qs[128];
+  const __nv_bfloat16* qp = Q + ((long long)b * Sq + q) * ld_q + h * dk;
+  for (int c = threadIdx.x; c < dk; c += blockDim.x) qs[c] = __bfloat162float(qp[c]);
+  __syncthreads();
+  const float l = lse[((long long)b * H + h) * Sq + q];
+  float* out = P + (((long long)b * H + h) * Sq + q) * Sk;
+  for (int k = threadIdx.x; k < Sk; k += blockDim.x) {
+    const __nv_bfloat16* kp = K + ((long long)b * Sk + k) * ld_k + h * dk;
+    float s = 0.f;
+    for (int c = 0; c < dk; c += 2) {
+      const float2 f = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(kp + c));
+      s += qs[c] * f.x + qs[c + 1] * f.y;
+    }
+    float t = s * scale;
+    const bool masked = (mask.kpad != nullptr && mask.kpad[(long long)b * Sk + k] != 0) || (mask.causal && k > q);
+    if (masked) t = kMaskVal;
+    if (mask.maskf != nullptr) t += mask.maskf[(long long)b * mask.sb + (long long)q * mask.sq + k] * kMaskVal;
+    float pe = __expf(t - l);
+    if (l < -1e8f) pe *= 1.f / (float)Sk;   // fully-masked row (see attn_bwd_kernel)
+    out[k] = pe;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// host launchers
+// ------------------------------------------------------------------------------------------------
+template <int DK>
+static int attn_fwd_launch(const void* Q, long long ld_q, const void* K, long long ld_k, const void* V, long long ld_v,
+                           void* O, long long ld_o, float* lse, const AttnMask& mask, int B, int H, int Sq, int Sk,
+                           cudaStream_t st) {
+  using L = FwdSmem<DK>;
+  const int swz = DK * 2;
+  CUtensorMap tmQ, tmK, tmV, tmO;
+  int rc;
+  if ((rc = encode_tmap_3d(&tmQ, 0, Q, (uint64_t)H * DK, Sq, B, ld_q, (uint64_t)Sq * ld_q, DK, 128, 1, swz))) return rc;
+  if ((rc = encode_tmap_3d(&tmK, 0, K, (uint64_t)H * DK, Sk, B, ld_k, (uint64_t)Sk * ld_k, DK, 128, 1, swz))) return rc;
+  if ((rc = encode_tmap_3d(&tmV, 0, V, (uint64_t)H * DK, Sk, B, ld_v, (uint64_t)Sk * ld_v, DK, 128, 1, swz))) return rc;
+  if ((rc = encode_tmap_3d(&tmO, 0, O, (uint64_t)H * DK, Sq, B, ld_o, (uint64_t)Sq * ld_o, DK, 128, 1, swz))) return rc;
+  auto kern = attn_fwd_kernel<DK>;
+  static bool attr_done = false;
+  if (!attr_done) {
+    BX_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::BYTES));
+    attr_done = true;
+  }
+  dim3 grid((Sq + 255) / 256, H, B);
+  kern<<<grid, ATTN_FWD_THREADS, L::BYTES, st>>>(tmQ, tmK, tmV, tmO, lse, mask, H, Sq, Sk, 1.f / sqrtf((float)DK));
+  BX_POST_LAUNCH();
+  return 0;
+}
+
+template <int DK>
+static int attn_bwd_launch(const void* Q, long long ld_q, const void* K, long long ld_k, const void* V, long long ld_v,
+                           const void* dO, long long ld_do, const float* lse, const float* delta, float* dq_acc,
+                           long long ld_dq, void* dK, long long ld_dk, void* dV, long long ld_dv, const AttnMask& mask,
+                           int B, int H, int Sq, int Sk, cudaStream_t st) {
+  using L = BwdSmem<DK>;
+  const int swz = DK * 2;
+  CUtensorMap tmQ, tmK, tmV, tmdO, tmdK, tmdV;
+  int rc;
+  if ((rc = encode_tmap_3d(&tmQ, 0, Q, (uint64_t)H * DK, Sq, B, ld_q, (uint64_t)Sq * ld_q, DK, 128, 1, swz))) return rc;
+  if ((rc = encode_tmap_3d(&tmK, 0, K, (uint64_t)H * DK, Sk, B, ld_k, (uint64_t)Sk * ld_k, DK, 128, 1, swz))) return rc;
+  if ((rc = encode_tmap_3d(&tmV, 0, V, (uint64_t)H * DK, Sk, B, ld_v, (uint64_t)Sk * ld_v, DK, 128, 1, swz))) return rc;
+  if ((rc = encode_tmap_3d(&tmdO, 0, dO, (uint64_t)H * DK, Sq, B, ld_do, (uint64_t)Sq * ld_do, DK, 128, 1, swz))) return rc;
+  if ((rc = encode_tmap_3d(&tmdK, 0, dK, (uint64_t)H * DK, Sk, B, ld_dk, (uint64_t)Sk * ld_dk, DK, 128, 1, swz))) return rc;
+  if ((rc = encode_tmap_3d(&tmdV, 0, dV, (uint64_t)H * DK, Sk, B, ld_dv, (uint64_t)Sk * ld_dv, DK, 128, 1, swz))) return rc;
+  auto kern = attn_bwd_kernel<DK>;
+  static bool attr_done = false;
+  if (!attr_done) {
+    BX_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::BYTES));
+    attr_done = true;
+  }
+  dim3 grid((Sk + 127) / 128, H, B);
+  kern<<<grid, ATTN_BWD_THREADS, L::BYTES, st>>>(tmQ, tmK, tmV, tmdO, tmdK, tmdV, lse, delta, dq_acc, ld_dq, mask, H, Sq,
+                                                 Sk, 1.f / sqrtf((float)DK));
+  BX_POST_LAUNCH();
+  return 0;
+}
+
+static int check_attn_args(int B, int H, int Sq, int Sk, int dk, int causal) {
+  BX_REQUIRE(dk == 32 || dk == 64, "attention: head depth %d unsupported (32 or 64)", dk);
+  BX_REQUIRE(B > 0 && H > 0 && Sq > 0 && Sk > 0 && B < 65536 && H < 65536, "attention: bad shape");
+  BX_REQUIRE(!causal || Sq == Sk, "attention: causal (look-ahead) mask needs Sq == Sk");
+  return 0;
+}
+
+int attn_fwd(const void* Q, long long ld_q, const void* K, long long ld_k, const void* V, long long ld_v, void* O,
+             long long ld_o, float* lse, const uint8_t* kpad, int causal, const float* maskf, long long mask_sb,
+             long long mask_sq, int B, int H, int Sq, int Sk, int dk, cudaStream_t st) {
+  if (int rc = check_attn_args(B, H, Sq, Sk, dk, causal)) return rc;
+  AttnMask m{kpad, maskf, mask_sb, mask_sq, causal};
+  return dk == 64 ? attn_fwd_launch<64>(Q, ld_q, K, ld_k, V, ld_v, O, ld_o, lse, m, B, H, Sq, Sk, st)
+                  : attn_fwd_launch<32>(Q, ld_q, K, ld_k, V, ld_v, O, ld_o, lse, m, B, H, Sq, Sk, st);
+}
+
+int attn_bwd(const void* Q, long long ld_q, const void* K, long long ld_k, const void* V, long long ld_v, const void* dO,
+             long long ld_do, const float* lse, const float* delta, float* dq_acc, long long ld_dq, void* dK,
+             long long ld_dk, void* dV, long long ld_dv, const uint8_t* kpad, int causal, const float* maskf,
+             long long mask_sb, long long mask_sq, int B, int H, int Sq, int Sk, int dk, cudaStream_t st) {
+  if (int rc = check_attn_args(B, H, Sq, Sk, dk, causal)) return rc;
+  BX_REQUIRE(ld_dq % 4 == 0 && (reinterpret_cast<uintptr_t>(dq_acc) & 15) == 0, "attention: dq accumulator alignment");
+  AttnMask m{kpad, maskf, mask_sb, mask_sq, causal};
+  return dk == 64 ? attn_bwd_launch<64>(Q, ld_q, K, ld_k, V, ld_v, dO, ld_do, lse, delta, dq_acc, ld_dq, dK, ld_dk, dV,
+                                        ld_dv, m, B, H, Sq, Sk, st)
+                  : attn_bwd_launch<32>(Q, ld_q, K, ld_k, V, ld_v, dO, ld_do, lse, delta, dq_acc, ld_dq, dK, ld_dk, dV,
+                                        ld_dv, m, B, H, Sq, Sk, st);
+}
+
+int attn_probs(const void* Q, long long ld_q, const void* K, long long ld_k, const float* lse, float* P,
+               const uint8_t* kpad, int causal, const float* maskf, long long mask_sb, long long mask_sq, int B, int H,
+               int Sq, int Sk, int dk, cudaStream_t st) {
+  BX_REQUIRE(dk <= 128 && dk % 2 == 0, "attn_probs: dk %d unsupported", dk);
+  AttnMask m{kpad, maskf, mask_sb, mask_sq, causal};
+  attn_probs_kernel<<<dim3(Sq, H, B), 128, 0, st>>>((const __nv_bfloat16*)Q, ld_q, (const __nv_bfloat16*)K, ld_k, lse, P, m,
+                                                    H, Sq, Sk, dk, 1.f / sqrtf((float)dk));
+  BX_POST_LAUNCH();
+  return 0;
+}
+
+}  // namespace bx

@@ -1,0 +1,545 @@
+// HBM-bound kernels of the training step: embedding (+pos-enc, dropout), dropout+residual+LayerNorm fwd/bwd,
+// softmax-cross-entropy (+ its gradient, accuracy counters), column sums (bias grads), fused Adam (+bf16 shadow),
+// casts and masks.  All vectorised 16-byte accesses, fp32 math.  Reference call sites are cited per kernel.
+#include "common.cuh"
+
+namespace bx {
+
+// ------------------------------------------------------------------------------------------------
+// counter-based dropout RNG (Philox-4x32-10); keep-mask regenerated in backward from (seed, site, element)
+// keras Dropout semantics: keep w.p. 1-rate, scale kept by 1/(1-rate).
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint4 philox4x32_10(uint4 ctr, uint2 key) {
+  constexpr uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
+#pragma unroll
+  for (int i = 0; i < 10; ++i) {
+    const uint32_t hi0 = __umulhi(M0, ctr.x), lo0 = M0 * ctr.x;
+    const uint32_t hi1 = __umulhi(M1, ctr.z), lo1 = M1 * ctr.z;
+    ctr = make_uint4(hi1 ^ ctr.y ^ key.x, lo1, hi0 ^ ctr.w ^ key.y, lo0);
+    key.x += W0;
+    key.y += W1;
+  }
+  return ctr;
+}
+// keep-scale factors for the 4 consecutive elements starting at flat element index `idx4*4`
+__device__ __forceinline__ float4 dropout_scale4(unsigned long long seed, uint32_t site, unsigned long long idx4,
+                                                 float rate) {
+  const uint4 r = philox4x32_10(make_uint4((uint32_t)idx4, (uint32_t)(idx4 >> 32), site, 0u),
+                                make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)));
+  const float inv = 1.f / (1.f - rate);
+  const float s = 2.3283064365386963e-10f;  // 2^-32
+  return make_float4((r.x * s >= rate) ? inv : 0.f, (r.y * s >= rate) ? inv : 0.f, (r.z * s >= rate) ? inv : 0.f,
+                     (r.w * s >= rate) ? inv : 0.f);
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+// ------------------------------------------------------------------------------------------------
+// K6  embedding * sqrt(d) + pos_encoding[:, :S] (+ dropout)      Encoder.py:51-55, Decoder.py:65-69
+//   ids int64 [rows] (rows = B*S), table fp32 [V, d], pos fp32 [P, d]  ->  x fp32 [rows, d] and bf16 copy
+// ------------------------------------------------------------------------------------------------
+__global__ void embed_fwd_kernel(const long long* __restrict__ ids, const float* __restrict__ table,
+                                 const float* __restrict__ pos, float* __restrict__ out_f32,
+                                 __nv_bfloat16* __restrict__ out_bf16, long long rows, int S, int d, long long V,
+                                 float scale, float rate, unsigned long long seed, uint32_t site) {
+  const int d4 = d >> 2;
+  const long long total = rows * d4;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long r = i / d4;
+    const int c4 = (int)(i - r * d4);
+    long long id = ids[r];
+    id = id < 0 ? 0 : (id >= V ? V - 1 : id);
+    const float4 e = __ldg(reinterpret_cast<const float4*>(table + id * d) + c4);
+    const float4 p = __ldg(reinterpret_cast<const float4*>(pos + (r % S) * (long long)d) + c4);
+    float4 o = make_float4(e.x * scale + p.x, e.y * scale + p.y, e.z * scale + p.z, e.w * scale + p.w);
+    if (rate > 0.f) {
+      const float4 k = dropout_scale4(seed, site, (unsigned long long)i, rate);
+      o.x *= k.x; o.y *= k.y; o.z *= k.z; o.w *= k.w;
+    }
+    reinterpret_cast<float4*>(out_f32)[i] = o;
+    reinterpret_cast<uint2*>(out_bf16)[i] = make_uint2(pack_bf16x2(o.x, o.y), pack_bf16x2(o.z, o.w));
+  }
+}
+
+// backward: dTable[id] += dx * sqrt(d) * dropmask   (dense-equivalent IndexedSlices sum, Appendix A.8)
+__global__ void embed_bwd_kernel(const long long* __restrict__ ids, const float* __restrict__ dx,
+                                 float* __restrict__ dtable, long long rows, int d, long long V, float scale,
+                                 float rate, unsigned long long seed, uint32_t site) {
+  const int d4 = d >> 2;
+  const long long total = rows * d4;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long r = i / d4;
+    const int c4 = (int)(i - r * d4);
+    long long id = ids[r];
+    id = id < 0 ? 0 : (id >= V ? V - 1 : id);
+    float4 g = reinterpret_cast<const float4*>(dx)[i];
+    if (rate > 0.f) {
+      const float4 k = dropout_scale4(seed, site, (unsigned long long)i, rate);
+      g.x *= k.x; g.y *= k.y; g.z *= k.z; g.w *= k.w;
+    }
+    float* dst = dtable + id * d + c4 * 4;
+    atomicAdd(dst + 0, g.x * scale);
+    atomicAdd(dst + 1, g.y * scale);
+    atomicAdd(dst + 2, g.z * scale);
+    atomicAdd(dst + 3, g.w * scale);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K3/K4 epilogue (stand-alone form) + K5:  z = x + dropout(y);  out = LayerNorm(z)   (eps 1e-6, biased var)
+//   Encoder.py:22-23,26-27  Decoder.py:30-31,35-36,39-40 ; LN formula SURVEY Appendix A.4
+//   one warp per row; NV = ceil(d/128) float4 per lane kept in registers.
+//   y (fp32, sublayer output) is overwritten in place by z (kept for backward).
+// ------------------------------------------------------------------------------------------------
+template <int NV>
+__global__ void __launch_bounds__(256)
+residual_ln_fwd_kernel(float* __restrict__ y_z, const float* __restrict__ x, const float* __restrict__ gamma,
+                       const float* __restrict__ beta, float* __restrict__ out_f32,
+                       __nv_bfloat16* __restrict__ out_bf16, float* __restrict__ mean_out,
+                       float* __restrict__ rstd_out, long long rows, int d, float eps, float rate,
+                       unsigned long long seed, uint32_t site) {
+  const int lane = threadIdx.x & 31;
+  const long long warp_global = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
+  const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+  const int d4 = d >> 2;
+  for (long long r = warp_global; r < rows; r += nwarps) {
+    float4 z[NV];
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int c4 = lane + 32 * i;
+      z[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (c4 < d4) {
+        const long long idx = r * d4 + c4;
+        float4 yv = reinterpret_cast<const float4*>(y_z)[idx];
+        const float4 xv = reinterpret_cast<const float4*>(x)[idx];
+        if (rate > 0.f) {
+          const float4 k = dropout_scale4(seed, site, (unsigned long long)idx, rate);
+          yv.x *= k.x; yv.y *= k.y; yv.z *= k.z; yv.w *= k.w;
+        }
+        z[i] = make_float4(xv.x + yv.x, xv.y + yv.y, xv.z + yv.z, xv.w + yv.w);
+        reinterpret_cast<float4*>(y_z)[idx] = z[i];
+        s += z[i].x + z[i].y + z[i].z + z[i].w;
+      }
+    }
+    const float mean = warp_sum(s) / d;
+    float v = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      if (lane + 32 * i < d4) {
+        const float a = z[i].x - mean, b = z[i].y - mean, c = z[i].z - mean, e = z[i].w - mean;
+        v += a * a + b * b + c * c + e * e;
+      }
+    }
+    const float rstd = rsqrtf(warp_sum(v) / d + eps);
+    if (lane == 0) { mean_out[r] = mean; rstd_out[r] = rstd; }
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int c4 = lane + 32 * i;
+      if (c4 < d4) {
+        const float4 g = __ldg(reinterpret_cast<const float4*>(gamma) + c4);
+        const float4 b = __ldg(reinterpret_cast<const float4*>(beta) + c4);
+        float4 o;
+        o.x = (z[i].x - mean) * rstd * g.x + b.x;
+        o.y = (z[i].y - mean) * rstd * g.y + b.y;
+        o.z = (z[i].z - mean) * rstd * g.z + b.z;
+        o.w = (z[i].w - mean) * rstd * g.w + b.w;
+        const long long idx = r * d4 + c4;
+        reinterpret_cast<float4*>(out_f32)[idx] = o;
+        reinterpret_cast<uint2*>(out_bf16)[idx] = make_uint2(pack_bf16x2(o.x, o.y), pack_bf16x2(o.z, o.w));
+      }
+    }
+  }
+}
+
+// backward of out = LN(z), z = x + dropout(y):
+//   dz = rstd * (g*dy - mean(g*dy) - xhat * mean(g*dy*xhat))            (fp32, gradient to the residual input x)
+//   dy_sub = dz * dropmask/(1-rate)                                      (bf16, gradient to the sublayer output)
+//   dgamma += sum_rows dy*xhat ; dbeta += sum_rows dy                    (block partials -> atomicAdd)
+template <int NV>
+__global__ void __launch_bounds__(256)
+residual_ln_bwd_kernel(const float* __restrict__ dout, const float* __restrict__ z, const float* __restrict__ mean_in,
+                       const float* __restrict__ rstd_in, const float* __restrict__ gamma, float* __restrict__ dz,
+                       __nv_bfloat16* __restrict__ dy_sub, float* __restrict__ dgamma, float* __restrict__ dbeta,
+                       long long rows, int d, float rate, unsigned long long seed, uint32_t site) {
+  extern __shared__ float red[];  // [2][warps][d]   (dgamma partials, dbeta partials)
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  const long long warp_global = (long long)blockIdx.x * nw + wib;
+  const long long nwarps = (long long)gridDim.x * nw;
+  const int d4 = d >> 2;
+  float4 ag[NV], ab[NV];
+#pragma unroll
+  for (int i = 0; i < NV; ++i) { ag[i] = make_float4(0, 0, 0, 0); ab[i] = make_float4(0, 0, 0, 0); }
+  for (long long r = warp_global; r < rows; r += nwarps) {
+    const float mean = mean_in[r], rstd = rstd_in[r];
+    float4 xh[NV], gd[NV];
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int c4 = lane + 32 * i;
+      xh[i] = make_float4(0, 0, 0, 0); gd[i] = make_float4(0, 0, 0, 0);
+      if (c4 < d4) {
+        const long long idx = r * d4 + c4;
+        const float4 dyv = reinterpret_cast<const float4*>(dout)[idx];
+        const float4 zv = reinterpret_cast<const float4*>(z)[idx];
+        const float4 g = __ldg(reinterpret_cast<const float4*>(gamma) + c4);
+        xh[i] = make_float4((zv.x - mean) * rstd, (zv.y - mean) * rstd, (zv.z - mean) * rstd, (zv.w - mean) * rstd);
+        gd[i] = make_float4(g.x * dyv.x, g.y * dyv.y, g.z * dyv.z, g.w * dyv.w);
+        s1 += gd[i].x + gd[i].y + gd[i].z + gd[i].w;
+        s2 += gd[i].x * xh[i].x + gd[i].y * xh[i].y + gd[i].z * xh[i].z + gd[i].w * xh[i].w;
+        ag[i].x += dyv.x * xh[i].x; ag[i].y += dyv.y * xh[i].y; ag[i].z += dyv.z * xh[i].z; ag[i].w += dyv.w * xh[i].w;
+        ab[i].x += dyv.x; ab[i].y += dyv.y; ab[i].z += dyv.z; ab[i].w += dyv.w;
+      }
+    }
+    const float m1 = warp_sum(s1) / d, m2 = warp_sum(s2) / d;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int c4 = lane + 32 * i;
+      if (c4 < d4) {
+        const long long idx = r * d4 + c4;
+        float4 o;
+        o.x = rstd * (gd[i].x - m1 - xh[i].x * m2);
+        o.y = rstd * (gd[i].y - m1 - xh[i].y * m2);
+        o.z = rstd * (gd[i].z - m1 - xh[i].z * m2);
+        o.w = rstd * (gd[i].w - m1 - xh[i].w * m2);
+        reinterpret_cast<float4*>(dz)[idx] = o;
+        if (rate > 0.f) {
+          const float4 k = dropout_scale4(seed, site, (unsigned long long)idx, rate);
+          o.x *= k.x; o.y *= k.y; o.z *= k.z; o.w *= k.w;
+        }
+        reinterpret_cast<uint2*>(dy_sub)[idx] = make_uint2(pack_bf16x2(o.x, o.y), pack_bf16x2(o.z, o.w));
+      }
+    }
+  }
+  // block reduction of dgamma / dbeta partials
+  float* rg = red;
+  float* rb = red + (size_t)nw * d;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int c4 = lane + 32 * i;
+    if (c4 < d4) {
+      reinterpret_cast<float4*>(rg + (size_t)wib * d)[c4] = ag[i];
+      reinterpret_cast<float4*>(rb + (size_t)wib * d)[c4] = ab[i];
+    }
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < d; c += blockDim.x) {
+    float sg = 0.f, sb = 0.f;
+    for (int w = 0; w < nw; ++w) { sg += rg[(size_t)w * d + c]; sb += rb[(size_t)w * d + c]; }
+    atomicAdd(dgamma + c, sg);
+    atomicAdd(dbeta + c, sb);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K7 (stand-alone form): masked sparse softmax cross-entropy over materialised logits + its gradient
+//   train.py:83-88 (loss = sum_{real!=0} (lse - logit[real]) / batch_size), train.py:141 (accuracy over ALL
+//   positions incl. pads), gradient (softmax - onehot) * mask / batch_size  (SURVEY Appendix A.7).
+//   one CTA per row; logits bf16 or fp32 [rows, ld], V valid columns; dlogits bf16 [rows, ld_d] (may alias
+//   a bf16 logits buffer).  stats: double[0] loss_sum, [1] correct, [2] positions, [3] nonpad
+// ------------------------------------------------------------------------------------------------
+template <typename T>
+__device__ __forceinline__ float ld_logit(const T* p, long long i);
+template <>
+__device__ __forceinline__ float ld_logit<float>(const float* p, long long i) { return p[i]; }
+template <>
+__device__ __forceinline__ float ld_logit<__nv_bfloat16>(const __nv_bfloat16* p, long long i) { return __bfloat162float(p[i]); }
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+xent_kernel(const T* __restrict__ logits, long long ld, const long long* __restrict__ labels, int label_stride,
+            int label_offset, int T_len, __nv_bfloat16* __restrict__ dlogits, long long ld_d, float* __restrict__ row_loss,
+            double* __restrict__ stats, int V, float inv_batch) {
+  // labels for row r = (b, t) live at labels[b * label_stride + label_offset + t]  (tar[:, 1:] without a copy)
+  const long long r = blockIdx.x;
+  const T* row = logits + r * ld;
+  const long long b = r / T_len, t = r % T_len;
+  long long label = labels[b * label_stride + label_offset + t];
+  const bool nonpad = label != 0;
+  if (label < 0 || label >= V) label = 0;
+  __shared__ float s_m[8], s_s[8];
+  __shared__ int s_i[8];
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  // pass 1: online max / sum-exp / argmax (first index attaining the max, like tf.argmax)
+  float m = -INFINITY, s = 0.f;
+  int am = 0x7fffffff;
+  for (int c = threadIdx.x; c < V; c += blockDim.x) {
+    const float x = ld_logit<T>(row, c);
+    if (x > m) { s = s * __expf(m - x) + 1.f; m = x; am = c; }
+    else s += __expf(x - m);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float m2 = __shfl_xor_sync(0xffffffffu, m, o), s2 = __shfl_xor_sync(0xffffffffu, s, o);
+    const int a2 = __shfl_xor_sync(0xffffffffu, am, o);
+    const float mn = fmaxf(m, m2);
+    s = (m == -INFINITY ? 0.f : s * __expf(m - mn)) + (m2 == -INFINITY ? 0.f : s2 * __expf(m2 - mn));
+    am = (m2 > m || (m2 == m && a2 < am)) ? a2 : am;
+    m = mn;
+  }
+  if (lane == 0) { s_m[wib] = m; s_s[wib] = s; s_i[wib] = am; }
+  __syncthreads();
+  m = s_m[0]; s = s_s[0]; am = s_i[0];
+  for (int w = 1; w < (int)(blockDim.x >> 5); ++w) {
+    const float m2 = s_m[w], s2 = s_s[w];
+    const int a2 = s_i[w];
+    const float mn = fmaxf(m, m2);
+    s = (m == -INFINITY ? 0.f : s * __expf(m - mn)) + (m2 == -INFINITY ? 0.f : s2 * __expf(m2 - mn));
+    am = (m2 > m || (m2 == m && a2 < am)) ? a2 : am;
+    m = mn;
+  }
+  const float lse = m + __logf(s);
+  if (threadIdx.x == 0) {
+    const float loss = nonpad ? (lse - ld_logit<T>(row, label)) : 0.f;
+    if (row_loss) row_loss[r] = loss;
+    atomicAdd(&stats[0], (double)loss);
+    atomicAdd(&stats[1], (double)(am == (int)labels[b * label_stride + label_offset + t] ? 1.0 : 0.0));
+    atomicAdd(&stats[2], 1.0);
+    atomicAdd(&stats[3], nonpad ? 1.0 : 0.0);
+  }
+  if (dlogits == nullptr) return;
+  // pass 2: gradient (row re-read hits L1/L2)
+  const float gscale = nonpad ? inv_batch : 0.f;
+  __nv_bfloat16* drow = dlogits + r * ld_d;
+  for (int c = threadIdx.x; c < V; c += blockDim.x) {
+    const float x = ld_logit<T>(row, c);
+    float g = __expf(x - lse);
+    if (c == (int)label) g -= 1.f;
+    drow[c] = __float2bfloat16(g * gscale);
+  }
+  for (long long c = V + threadIdx.x; c < ld_d; c += blockDim.x) drow[c] = __float2bfloat16(0.f);  // padded columns
+}
+
+// ------------------------------------------------------------------------------------------------
+// column sums: out[n] += sum_m X[m, n]   (bias gradients = reduce of dY over tokens)
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+colsum_bf16_kernel(const __nv_bfloat16* __restrict__ X, long long ld, float* __restrict__ out, long long rows, int N,
+                   int rows_per_block) {
+  // block (bx, by): columns [bx*512, +512) (2 per thread), rows [by*rows_per_block, ...)
+  const int c = (blockIdx.x * blockDim.x + threadIdx.x) * 2;
+  if (c >= N) return;
+  const long long r0 = (long long)blockIdx.y * rows_per_block;
+  const long long r1 = r0 + rows_per_block < rows ? r0 + rows_per_block : rows;
+  float a0 = 0.f, a1 = 0.f;
+  for (long long r = r0; r < r1; ++r) {
+    const float2 f = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(X + r * ld + c));
+    a0 += f.x; a1 += f.y;
+  }
+  atomicAdd(out + c, a0);
+  if (c + 1 < N) atomicAdd(out + c + 1, a1);
+}
+
+// ------------------------------------------------------------------------------------------------
+// K8 fused Adam over the flat fp32 arena, TF form + bf16 shadow refresh
+//   m = b1 m + (1-b1) g ; v = b2 v + (1-b2) g^2 ; p -= alpha * m / (sqrt(v) + eps) ; shadow = bf16(p)
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+adam_kernel(float* __restrict__ p, float* __restrict__ m, float* __restrict__ v, const float* __restrict__ g,
+            __nv_bfloat16* __restrict__ shadow, long long n4, float alpha, float b1, float b2, float eps) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+    float4 pv = reinterpret_cast<float4*>(p)[i], mv = reinterpret_cast<float4*>(m)[i], vv = reinterpret_cast<float4*>(v)[i];
+    const float4 gv = reinterpret_cast<const float4*>(g)[i];
+#define BX_ADAM1(c)                                       \
+  mv.c = b1 * mv.c + (1.f - b1) * gv.c;                   \
+  vv.c = b2 * vv.c + (1.f - b2) * gv.c * gv.c;            \
+  pv.c -= alpha * mv.c / (sqrtf(vv.c) + eps);
+    BX_ADAM1(x) BX_ADAM1(y) BX_ADAM1(z) BX_ADAM1(w)
+#undef BX_ADAM1
+    reinterpret_cast<float4*>(p)[i] = pv;
+    reinterpret_cast<float4*>(m)[i] = mv;
+    reinterpret_cast<float4*>(v)[i] = vv;
+    if (shadow) reinterpret_cast<uint2*>(shadow)[i] = make_uint2(pack_bf16x2(pv.x, pv.y), pack_bf16x2(pv.z, pv.w));
+  }
+}
+
+__global__ void __launch_bounds__(256)
+cast_f32_bf16_kernel(const float* __restrict__ in, __nv_bfloat16* __restrict__ out, long long n4) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+    const float4 a = reinterpret_cast<const float4*>(in)[i];
+    reinterpret_cast<uint2*>(out)[i] = make_uint2(pack_bf16x2(a.x, a.y), pack_bf16x2(a.z, a.w));
+  }
+}
+__global__ void __launch_bounds__(256)
+cast_bf16_f32_kernel(const __nv_bfloat16* __restrict__ in, float* __restrict__ out, long long n) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    out[i] = __bfloat162float(in[i]);
+}
+// dQ accumulator fp32 [rows, d] -> column block [col0, col0+d) of a bf16 [rows, ld] buffer
+__global__ void __launch_bounds__(256)
+cast_f32_bf16_strided_kernel(const float* __restrict__ in, __nv_bfloat16* __restrict__ out, long long rows, int d,
+                             long long ld_out) {
+  const int d4 = d >> 2;
+  const long long total = rows * d4;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long r = i / d4;
+    const int c4 = (int)(i - r * d4);
+    const float4 a = reinterpret_cast<const float4*>(in)[i];
+    *reinterpret_cast<uint2*>(out + r * ld_out + c4 * 4) = make_uint2(pack_bf16x2(a.x, a.y), pack_bf16x2(a.z, a.w));
+  }
+}
+
+// key-padding bytes: 1 where token id == 0   (positionalencoding.py:25-30, compact form)
+__global__ void pad_mask_kernel(const long long* __restrict__ ids, uint8_t* __restrict__ mask, long long n) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    mask[i] = ids[i] == 0 ? 1 : 0;
+}
+
+// attention backward pre-pass: delta[b,h,q] = sum_c dO[b,q,h*dk+c] * O[b,q,h*dk+c]
+__global__ void __launch_bounds__(256)
+attn_delta_kernel(const __nv_bfloat16* __restrict__ O, long long ld_o, const __nv_bfloat16* __restrict__ dO,
+                  long long ld_do, float* __restrict__ delta, int B, int S, int H, int dk) {
+  // one warp per (b, q, h)
+  const int lane = threadIdx.x & 31;
+  const long long w = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
+  const long long total = (long long)B * S * H;
+  if (w >= total) return;
+  const int h = (int)(w % H);
+  const long long bq = w / H;
+  const __nv_bfloat16* o = O + bq * ld_o + h * dk;
+  const __nv_bfloat16* g = dO + bq * ld_do + h * dk;
+  float s = 0.f;
+  for (int c = lane * 2; c < dk; c += 64) {
+    const float2 a = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(o + c));
+    const float2 b = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(g + c));
+    s += a.x * b.x + a.y * b.y;
+  }
+  s = warp_sum(s);
+  if (lane == 0) {
+    const long long b = bq / S, q = bq % S;
+    delta[(b * H + h) * S + q] = s;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// host launchers
+// ------------------------------------------------------------------------------------------------
+static inline int grid_for(long long work, int threads, int max_blocks_per_sm = 8) {
+  long long b = (work + threads - 1) / threads;
+  const long long cap = (long long)sm_count() * max_blocks_per_sm;
+  if (b > cap) b = cap;
+  if (b < 1) b = 1;
+  return (int)b;
+}
+
+int embed_fwd(const long long* ids, const float* table, const float* pos, float* out_f32, void* out_bf16,
+              long long rows, int S, int d, long long V, float rate, unsigned long long seed, unsigned site,
+              cudaStream_t st) {
+  BX_REQUIRE(d % 4 == 0, "embed: d_model %% 4 != 0");
+  embed_fwd_kernel<<<grid_for(rows * (d / 4), 256), 256, 0, st>>>(ids, table, pos, out_f32, (__nv_bfloat16*)out_bf16, rows, S, d,
+                                                                 V, sqrtf((float)d), rate, seed, site);
+  BX_POST_LAUNCH();
+  return 0;
+}
+int embed_bwd(const long long* ids, const float* dx, float* dtable, long long rows, int d, long long V, float rate,
+              unsigned long long seed, unsigned site, cudaStream_t st) {
+  BX_REQUIRE(d % 4 == 0, "embed: d_model %% 4 != 0");
+  embed_bwd_kernel<<<grid_for(rows * (d / 4), 256), 256, 0, st>>>(ids, dx, dtable, rows, d, V, sqrtf((float)d), rate, seed, site);
+  BX_POST_LAUNCH();
+  return 0;
+}
+
+#define BX_LN_DISPATCH(NAME, ...)                                       \
+  if (d <= 128) NAME<1> __VA_ARGS__;                                    \
+  else if (d <= 256) NAME<2> __VA_ARGS__;                               \
+  else if (d <= 512) NAME<4> __VA_ARGS__;                               \
+  else NAME<8> __VA_ARGS__;
+
+int residual_ln_fwd(float* y_z, const float* x, const float* gamma, const float* beta, float* out_f32, void* out_bf16,
+                    float* mean, float* rstd, long long rows, int d, float eps, float rate, unsigned long long seed,
+                    unsigned site, cudaStream_t st) {
+  BX_REQUIRE(d % 4 == 0 && d <= 1024, "layernorm: need d %% 4 == 0 and d <= 1024 (got %d)", d);
+  const int grid = grid_for(rows * 32, 256);
+  BX_LN_DISPATCH(residual_ln_fwd_kernel, <<<grid, 256, 0, st>>>(y_z, x, gamma, beta, out_f32, (__nv_bfloat16*)out_bf16, mean, rstd,
+                                                               rows, d, eps, rate, seed, site))
+  BX_POST_LAUNCH();
+  return 0;
+}
+int residual_ln_bwd(const float* dout, const float* z, const float* mean, const float* rstd, const float* gamma,
+                    float* dz, void* dy_sub, float* dgamma, float* dbeta, long long rows, int d, float rate,
+                    unsigned long long seed, unsigned site, cudaStream_t st) {
+  BX_REQUIRE(d % 4 == 0 && d <= 1024, "layernorm: need d %% 4 == 0 and d <= 1024 (got %d)", d);
+  const int grid = grid_for(rows * 32, 256, 2);
+  const size_t smem = (size_t)2 * 8 * d * sizeof(float);
+  BX_LN_DISPATCH(residual_ln_bwd_kernel, <<<grid, 256, smem, st>>>(dout, z, mean, rstd, gamma, dz, (__nv_bfloat16*)dy_sub, dgamma,
+                                                                  dbeta, rows, d, rate, seed, site))
+  BX_POST_LAUNCH();
+  return 0;
+}
+
+int xent(const void* logits, int logits_f32, long long ld, const long long* labels, int label_stride, int label_offset,
+         int T_len, void* dlogits, long long ld_d, float* row_loss, double* stats, long long rows, int V, float inv_batch,
+         cudaStream_t st) {
+  BX_REQUIRE(rows > 0 && rows < (1ll << 31), "xent: bad row count");
+  if (logits_f32)
+    xent_kernel<float><<<(unsigned)rows, 256, 0, st>>>((const float*)logits, ld, labels, label_stride, label_offset, T_len,
+                                                       (__nv_bfloat16*)dlogits, ld_d, row_loss, stats, V, inv_batch);
+  else
+    xent_kernel<__nv_bfloat16><<<(unsigned)rows, 256, 0, st>>>((const __nv_bfloat16*)logits, ld, labels, label_stride,
+                                                               label_offset, T_len, (__nv_bfloat16*)dlogits, ld_d, row_loss,
+                                                               stats, V, inv_batch);
+  BX_POST_LAUNCH();
+  return 0;
+}
+
+int colsum_bf16(const void* X, long long ld, float* out, long long rows, int N, cudaStream_t st) {
+  BX_REQUIRE(ld % 2 == 0, "colsum: ld must be even");
+  const int bx_ = (N + 511) / 512;
+  long long by = (long long)sm_count() * 4 / bx_;
+  if (by < 1) by = 1;
+  int rpb = (int)((rows + by - 1) / by);
+  if (rpb < 32) rpb = 32;
+  by = (rows + rpb - 1) / rpb;
+  colsum_bf16_kernel<<<dim3(bx_, (unsigned)by), 256, 0, st>>>((const __nv_bfloat16*)X, ld, out, rows, N, rpb);
+  BX_POST_LAUNCH();
+  return 0;
+}
+
+int adam_step(float* p, float* m, float* v, const float* g, void* shadow, long long n, float alpha, float b1, float b2,
+              float eps, cudaStream_t st) {
+  BX_REQUIRE(n % 4 == 0, "adam: arena length must be a multiple of 4");
+  adam_kernel<<<grid_for(n / 4, 256), 256, 0, st>>>(p, m, v, g, (__nv_bfloat16*)shadow, n / 4, alpha, b1, b2, eps);
+  BX_POST_LAUNCH();
+  return 0;
+}
+int cast_f32_bf16(const float* in, void* out, long long n, cudaStream_t st) {
+  BX_REQUIRE(n % 4 == 0, "cast: length must be a multiple of 4");
+  cast_f32_bf16_kernel<<<grid_for(n / 4, 256), 256, 0, st>>>(in, (__nv_bfloat16*)out, n / 4);
+  BX_POST_LAUNCH();
+  return 0;
+}
+int cast_bf16_f32(const void* in, float* out, long long n, cudaStream_t st) {
+  cast_bf16_f32_kernel<<<grid_for(n, 256), 256, 0, st>>>((const __nv_bfloat16*)in, out, n);
+  BX_POST_LAUNCH();
+  return 0;
+}
+int cast_f32_bf16_strided(const float* in, void* out, long long rows, int d, long long ld_out, cudaStream_t st) {
+  BX_REQUIRE(d % 4 == 0 && ld_out % 4 == 0, "cast: d and ld must be multiples of 4");
+  cast_f32_bf16_strided_kernel<<<grid_for(rows * (d / 4), 256), 256, 0, st>>>(in, (__nv_bfloat16*)out, rows, d, ld_out);
+  BX_POST_LAUNCH();
+  return 0;
+}
+int pad_mask(const long long* ids, uint8_t* mask, long long n, cudaStream_t st) {
+  pad_mask_kernel<<<grid_for(n, 256), 256, 0, st>>>(ids, mask, n);
+  BX_POST_LAUNCH();
+  return 0;
+}
+int attn_delta(const void* O, long long ld_o, const void* dO, long long ld_do, float* delta, int B, int S, int H, int dk,
+               cudaStream_t st) {
+  const long long warps = (long long)B * S * H;
+  attn_delta_kernel<<<(unsigned)((warps * 32 + 255) / 256), 256, 0, st>>>((const __nv_bfloat16*)O, ld_o, (const __nv_bfloat16*)dO,
+                                                                          ld_do, delta, B, S, H, dk);
+  BX_POST_LAUNCH();
+  return 0;
+}
+
+}  // namespace bx

@@ -1,0 +1,316 @@
+// Persistent warp-specialised tcgen05 GEMM for sm_100a:   D[M,N] (+)= epilogue( A[M,K] . B[K,N] )
+//
+//   bf16 operands staged HBM -> smem by TMA (SWIZZLE_128B, mbarrier full/empty ring), tcgen05.mma kind::f16
+//   issued by one thread (UMMA 128 x BN x 16), fp32 accumulators double-buffered in TMEM, epilogue warps
+//   read them back with tcgen05.ld, apply bias / ReLU / ReLU-mask, and TMA-store (or TMA reduce-add for
+//   split-K / residual accumulation) through a swizzled smem staging tile.
+//
+// This one kernel serves every dense contraction on the hot path (reference call sites):
+//   forward   y = x.W + b          Attention.py:62-64,77  point_ffn.py:5-6  Transformer.py:30   (A K-major, B MN-major)
+//   dgrad     dx = dy.W^T          reverse-mode of the above (train.py:137)                     (A K-major, B K-major)
+//   wgrad     dW = x^T.dy          ditto, split-K over tokens with TMA reduce-add               (A MN-major, B MN-major)
+// Operand "major": 0 = K-major (K contiguous in memory), 1 = MN-major (M resp. N contiguous).
+#include "common.cuh"
+
+namespace bx {
+
+constexpr int GEMM_BM = 128;
+constexpr int GEMM_BK = 64;
+constexpr int GEMM_THREADS = 256;  // w0 TMA, w1 MMA, w2 TMEM alloc, w3 idle, w4-7 epilogue
+
+constexpr int GEMM_FLAG_RELU = 1;       // out = max(out, 0)
+constexpr int GEMM_FLAG_ACCUM = 2;      // D += out (TMA reduce-add; fp32 D only)
+constexpr int GEMM_FLAG_AUX_MASK = 4;   // out *= (aux[m,n] > 0)   (ReLU backward; aux bf16)
+
+template <int BN>
+struct GemmCfg {
+  static constexpr int kStages = BN == 256 ? 4 : 6;
+  static constexpr uint32_t A_BYTES = GEMM_BM * GEMM_BK * 2;
+  static constexpr uint32_t B_BYTES = BN * GEMM_BK * 2;
+  static constexpr uint32_t STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr uint32_t D_BYTES = GEMM_BM * 128;  // one 128-byte-wide staging box
+  static constexpr uint32_t OFF_D = kStages * STAGE_BYTES;
+  static constexpr uint32_t OFF_BAR = OFF_D + 2 * D_BYTES;
+  static constexpr uint32_t SMEM_BYTES = OFF_BAR + 256 + 1024;  // + alignment slack
+  static constexpr uint32_t TMEM_COLS = 2 * BN;
+};
+
+template <int MA, int MB, int BN, bool kOutF32>
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+            const __grid_constant__ CUtensorMap tmD, int M, int N, int K, int splits,
+            const float* __restrict__ bias, const __nv_bfloat16* __restrict__ aux, long long ld_aux, int flags) {
+  using Cfg = GemmCfg<BN>;
+  constexpr int kStages = Cfg::kStages;
+  constexpr int OUT_COLS = kOutF32 ? 32 : 64;  // columns per 128-byte staging row
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + Cfg::OFF_BAR);
+  uint64_t* empty_bar = full_bar + kStages;
+  uint64_t* tmem_full = empty_bar + kStages;
+  uint64_t* tmem_empty = tmem_full + 2;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+  const uint32_t warp = warp_idx();
+  const uint32_t lane = lane_idx();
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&tmA);
+    prefetch_tmap(&tmB);
+    prefetch_tmap(&tmD);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < kStages; ++i) {
+      mbar_init(&full_bar[i], 1);
+      mbar_init(&empty_bar[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tmem_full[i], 1);
+      mbar_init(&tmem_empty[i], 128);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc<Cfg::TMEM_COLS>(tmem_ptr);
+  tcgen05_before_thread_sync();
+  __syncthreads();
+  tcgen05_after_thread_sync();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  const int m_tiles = (M + GEMM_BM - 1) / GEMM_BM;
+  const int n_tiles = (N + BN - 1) / BN;
+  const int kblocks = (K + GEMM_BK - 1) / GEMM_BK;
+  const int tiles_mn = m_tiles * n_tiles;
+  const int total = tiles_mn * splits;
+
+  if (warp == 0 && lane == 0) {
+    // ===================================== TMA producer =====================================
+    uint32_t stage = 0, phase = 0;
+    for (int t = blockIdx.x; t < total; t += gridDim.x) {
+      const int split = t / tiles_mn, rem = t % tiles_mn;
+      const int m0 = (rem / n_tiles) * GEMM_BM, n0 = (rem % n_tiles) * BN;
+      const int kb0 = (int)((long long)split * kblocks / splits), kb1 = (int)((long long)(split + 1) * kblocks / splits);
+      for (int kb = kb0; kb < kb1; ++kb) {
+        mbar_wait(&empty_bar[stage], phase ^ 1);
+        uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
+        uint8_t* sb = sa + Cfg::A_BYTES;
+        mbar_arrive_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
+        const int k0 = kb * GEMM_BK;
+        if (MA == 0) {
+          tma_load_2d(sa, &tmA, &full_bar[stage], k0, m0);
+        } else {
+#pragma unroll
+          for (int p = 0; p < GEMM_BM / 64; ++p) tma_load_2d(sa + p * 8192, &tmA, &full_bar[stage], m0 + p * 64, k0);
+        }
+        if (MB == 0) {
+          tma_load_2d(sb, &tmB, &full_bar[stage], k0, n0);
+        } else {
+#pragma unroll
+          for (int p = 0; p < BN / 64; ++p) tma_load_2d(sb + p * 8192, &tmB, &full_bar[stage], n0 + p * 64, k0);
+        }
+        if (++stage == kStages) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================================== MMA issuer =====================================
+    constexpr uint32_t idesc = make_idesc_bf16(GEMM_BM, BN, MA, MB);
+    uint32_t stage = 0, phase = 0, it = 0;
+    for (int t = blockIdx.x; t < total; t += gridDim.x, ++it) {
+      const int split = t / tiles_mn;
+      const int kb0 = (int)((long long)split * kblocks / splits), kb1 = (int)((long long)(split + 1) * kblocks / splits);
+      const uint32_t acc = it & 1u, acc_phase = (it >> 1) & 1u;
+      mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+      tcgen05_after_thread_sync();
+      const uint32_t d_tmem = tmem_base + acc * BN;
+      for (int kb = kb0; kb < kb1; ++kb) {
+        mbar_wait(&full_bar[stage], phase);
+        tcgen05_after_thread_sync();
+        if (lane == 0) {
+          const uint32_t sa = smem_u32(smem + stage * Cfg::STAGE_BYTES);
+          const uint32_t sb = sa + Cfg::A_BYTES;
+#pragma unroll
+          for (int k = 0; k < GEMM_BK / 16; ++k) {
+            const uint64_t adesc = MA == 0 ? make_smem_desc(sa + k * 32, 0, 1024, kSwz128)
+                                           : make_smem_desc(sa + k * 2048, GEMM_BK * 128, 1024, kSwz128);
+            const uint64_t bdesc = MB == 0 ? make_smem_desc(sb + k * 32, 0, 1024, kSwz128)
+                                           : make_smem_desc(sb + k * 2048, GEMM_BK * 128, 1024, kSwz128);
+            umma_f16(d_tmem, adesc, bdesc, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+          }
+          umma_commit(&empty_bar[stage]);                    // frees the smem slot once these MMAs retire
+          if (kb == kb1 - 1) umma_commit(&tmem_full[acc]);   // accumulator ready for the epilogue
+        }
+        __syncwarp();
+        if (++stage == kStages) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp >= 4) {
+    // ===================================== epilogue =====================================
+    const uint32_t q = warp & 3u;                // TMEM lane quadrant this warp may access
+    const uint32_t row = q * 32u + lane;         // accumulator row owned by this thread
+    const uint32_t epi_tid = threadIdx.x - 128u;
+    const uint32_t stg_base = smem_u32(smem + Cfg::OFF_D);
+    uint32_t it = 0, buf = 0;
+    for (int t = blockIdx.x; t < total; t += gridDim.x, ++it) {
+      const int rem = t % tiles_mn;
+      const int m0 = (rem / n_tiles) * GEMM_BM, n0 = (rem % n_tiles) * BN;
+      const uint32_t acc = it & 1u, acc_phase = (it >> 1) & 1u;
+      mbar_wait(&tmem_full[acc], acc_phase);
+      tcgen05_after_thread_sync();
+      const uint32_t t_row = tmem_base + ((q * 32u) << 16) + acc * BN;
+      const long long grow = (long long)m0 + row;
+#pragma unroll 1
+      for (int c = 0; c < BN / OUT_COLS; ++c) {
+        const int nc = n0 + c * OUT_COLS;
+        if (nc >= N) break;
+        if (epi_tid == 0) tma_store_wait_read<1>();   // staging buffer `buf` no longer being read
+        named_bar_sync(1, 128);
+        float v[OUT_COLS];
+        {
+          uint32_t r[32];
+#pragma unroll
+          for (int h = 0; h < OUT_COLS / 32; ++h) {
+            tmem_ld_x32(t_row + c * OUT_COLS + h * 32, r);
+            tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[h * 32 + j] = __uint_as_float(r[j]);
+          }
+        }
+        if (bias != nullptr) {
+          if (nc + OUT_COLS <= N) {
+            const float4* b4 = reinterpret_cast<const float4*>(bias + nc);
+#pragma unroll
+            for (int j = 0; j < OUT_COLS / 4; ++j) {
+              const float4 b = __ldg(b4 + j);
+              v[4 * j + 0] += b.x; v[4 * j + 1] += b.y; v[4 * j + 2] += b.z; v[4 * j + 3] += b.w;
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < OUT_COLS; ++j)
+              if (nc + j < N) v[j] += __ldg(bias + nc + j);
+          }
+        }
+        if (flags & GEMM_FLAG_RELU) {
+#pragma unroll
+          for (int j = 0; j < OUT_COLS; ++j) v[j] = fmaxf(v[j], 0.f);
+        }
+        if ((flags & GEMM_FLAG_AUX_MASK) && grow < M) {
+          const __nv_bfloat16* ap = aux + grow * ld_aux + nc;
+          if (nc + OUT_COLS <= N) {
+#pragma unroll
+            for (int j = 0; j < OUT_COLS / 8; ++j) {
+              const uint4 a = __ldg(reinterpret_cast<const uint4*>(ap) + j);
+              const uint32_t w[4] = {a.x, a.y, a.z, a.w};
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                const float2 f = unpack_bf16x2(w[e]);
+                if (!(f.x > 0.f)) v[8 * j + 2 * e] = 0.f;
+                if (!(f.y > 0.f)) v[8 * j + 2 * e + 1] = 0.f;
+              }
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < OUT_COLS; ++j)
+              if (nc + j < N && !(__bfloat162float(ap[j]) > 0.f)) v[j] = 0.f;
+          }
+        }
+        const uint32_t stg = stg_base + buf * Cfg::D_BYTES;
+        if (kOutF32) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            st_shared_v4(stg + swz128_off(row, j), __float_as_uint(v[4 * j]), __float_as_uint(v[4 * j + 1]),
+                         __float_as_uint(v[4 * j + 2]), __float_as_uint(v[4 * j + 3]));
+        } else {
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            st_shared_v4(stg + swz128_off(row, j), pack_bf16x2(v[8 * j], v[8 * j + 1]),
+                         pack_bf16x2(v[8 * j + 2], v[8 * j + 3]), pack_bf16x2(v[8 * j + 4], v[8 * j + 5]),
+                         pack_bf16x2(v[8 * j + 6], v[8 * j + 7]));
+        }
+        fence_proxy_async_smem();
+        named_bar_sync(1, 128);
+        if (epi_tid == 0) {
+          if (flags & GEMM_FLAG_ACCUM) tma_reduce_add_2d(&tmD, smem + Cfg::OFF_D + buf * Cfg::D_BYTES, nc, m0);
+          else tma_store_2d(&tmD, smem + Cfg::OFF_D + buf * Cfg::D_BYTES, nc, m0);
+          tma_store_commit();
+        }
+        buf ^= 1u;
+      }
+      tcgen05_before_thread_sync();
+      mbar_arrive(&tmem_empty[acc]);
+    }
+    if (epi_tid == 0) tma_store_wait_all<0>();
+  }
+
+  tcgen05_before_thread_sync();
+  __syncthreads();
+  tcgen05_after_thread_sync();
+  if (warp == 2) tmem_dealloc<Cfg::TMEM_COLS>(tmem_base);
+}
+
+// ------------------------------------------------------------------------------------------------
+// host launcher
+// ------------------------------------------------------------------------------------------------
+template <int MA, int MB, int BN, bool kOutF32>
+static int launch_gemm(const void* A, long long lda, const void* B, long long ldb, void* D, long long ldd,
+                       const float* bias, const void* aux, long long ld_aux, int flags, int splits, long long M,
+                       long long N, long long K, cudaStream_t stream) {
+  using Cfg = GemmCfg<BN>;
+  CUtensorMap tmA, tmB, tmD;
+  int rc;
+  if (MA == 0) rc = encode_tmap_2d(&tmA, 0, A, K, M, lda, 64, GEMM_BM, 128);
+  else rc = encode_tmap_2d(&tmA, 0, A, M, K, lda, 64, 64, 128);
+  if (rc) return rc;
+  if (MB == 0) rc = encode_tmap_2d(&tmB, 0, B, K, N, ldb, 64, BN, 128);
+  else rc = encode_tmap_2d(&tmB, 0, B, N, K, ldb, 64, 64, 128);
+  if (rc) return rc;
+  rc = encode_tmap_2d(&tmD, kOutF32 ? 1 : 0, D, N, M, ldd, kOutF32 ? 32 : 64, GEMM_BM, 128);
+  if (rc) return rc;
+  auto kern = gemm_kernel<MA, MB, BN, kOutF32>;
+  static bool attr_done = false;
+  if (!attr_done) {
+    BX_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+    attr_done = true;
+  }
+  const long long m_tiles = (M + GEMM_BM - 1) / GEMM_BM, n_tiles = (N + BN - 1) / BN;
+  const long long total = m_tiles * n_tiles * splits;
+  const int grid = (int)(total < sm_count() ? total : sm_count());
+  kern<<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, tmD, (int)M, (int)N, (int)K, splits, bias,
+                                                        reinterpret_cast<const __nv_bfloat16*>(aux), ld_aux, flags);
+  BX_POST_LAUNCH();
+  return 0;
+}
+
+int gemm_bf16(const void* A, long long lda, int a_major, const void* B, long long ldb, int b_major, void* D,
+              long long ldd, int d_is_f32, const float* bias, const void* aux, long long ld_aux, int flags,
+              int splits, long long M, long long N, long long K, cudaStream_t stream) {
+  BX_REQUIRE(M > 0 && N > 0 && K > 0, "gemm: empty problem %lld x %lld x %lld", M, N, K);
+  BX_REQUIRE(M < (1ll << 31) && N < (1ll << 31) && K < (1ll << 31), "gemm: dimension too large");
+  const long long kblocks = (K + GEMM_BK - 1) / GEMM_BK;
+  if (splits < 1) splits = 1;
+  if (splits > kblocks) splits = (int)kblocks;
+  BX_REQUIRE(splits == 1 || ((flags & GEMM_FLAG_ACCUM) && d_is_f32), "gemm: split-K needs fp32 D with ACCUM");
+  BX_REQUIRE(!(flags & GEMM_FLAG_ACCUM) || d_is_f32, "gemm: ACCUM needs fp32 D");
+  BX_REQUIRE(!(flags & GEMM_FLAG_AUX_MASK) || aux != nullptr, "gemm: AUX_MASK without aux");
+  BX_REQUIRE(!(flags & GEMM_FLAG_AUX_MASK) || (ld_aux % 8 == 0 && (reinterpret_cast<uintptr_t>(aux) & 15) == 0),
+             "gemm: aux must be 16-byte aligned with ld %% 8 == 0");
+  BX_REQUIRE(bias == nullptr || (reinterpret_cast<uintptr_t>(bias) & 15) == 0, "gemm: bias must be 16-byte aligned");
+  const bool wide = N > 128;
+#define BX_GEMM_CASE(ma, mb)                                                                                       \
+  if (a_major == ma && b_major == mb) {                                                                            \
+    if (wide) {                                                                                                    \
+      return d_is_f32 ? launch_gemm<ma, mb, 256, true>(A, lda, B, ldb, D, ldd, bias, aux, ld_aux, flags, splits, M, N, K, stream)  \
+                      : launch_gemm<ma, mb, 256, false>(A, lda, B, ldb, D, ldd, bias, aux, ld_aux, flags, splits, M, N, K, stream); \
+    } else {                                                                                                       \
+      return d_is_f32 ? launch_gemm<ma, mb, 128, true>(A, lda, B, ldb, D, ldd, bias, aux, ld_aux, flags, splits, M, N, K, stream)  \
+                      : launch_gemm<ma, mb, 128, false>(A, lda, B, ldb, D, ldd, bias, aux, ld_aux, flags, splits, M, N, K, stream); \
+    }                                                                                                              \
+  }
+  BX_GEMM_CASE(0, 1)
+  BX_GEMM_CASE(0, 0)
+  BX_GEMM_CASE(1, 1)
+  BX_GEMM_CASE(1, 0)
+#undef BX_GEMM_CASE
+  BX_REQUIRE(false, "gemm: bad majors %d/%d", a_major, b_major);
+}
+
+}  // namespace bx

@@ -1,0 +1,47 @@
+// Internal C++ declarations of the kernel launchers (definitions in gemm.cu / attention.cu / elementwise.cu).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace bx {
+
+int gemm_bf16(const void* A, long long lda, int a_major, const void* B, long long ldb, int b_major, void* D,
+              long long ldd, int d_is_f32, const float* bias, const void* aux, long long ld_aux, int flags,
+              int splits, long long M, long long N, long long K, cudaStream_t stream);
+
+int attn_fwd(const void* Q, long long ld_q, const void* K, long long ld_k, const void* V, long long ld_v, void* O,
+             long long ld_o, float* lse, const uint8_t* kpad, int causal, const float* maskf, long long mask_sb,
+             long long mask_sq, int B, int H, int Sq, int Sk, int dk, cudaStream_t st);
+int attn_bwd(const void* Q, long long ld_q, const void* K, long long ld_k, const void* V, long long ld_v, const void* dO,
+             long long ld_do, const float* lse, const float* delta, float* dq_acc, long long ld_dq, void* dK,
+             long long ld_dk, void* dV, long long ld_dv, const uint8_t* kpad, int causal, const float* maskf,
+             long long mask_sb, long long mask_sq, int B, int H, int Sq, int Sk, int dk, cudaStream_t st);
+int attn_probs(const void* Q, long long ld_q, const void* K, long long ld_k, const float* lse, float* P,
+               const uint8_t* kpad, int causal, const float* maskf, long long mask_sb, long long mask_sq, int B, int H,
+               int Sq, int Sk, int dk, cudaStream_t st);
+int attn_delta(const void* O, long long ld_o, const void* dO, long long ld_do, float* delta, int B, int S, int H, int dk,
+               cudaStream_t st);
+
+int embed_fwd(const long long* ids, const float* table, const float* pos, float* out_f32, void* out_bf16,
+              long long rows, int S, int d, long long V, float rate, unsigned long long seed, unsigned site,
+              cudaStream_t st);
+int embed_bwd(const long long* ids, const float* dx, float* dtable, long long rows, int d, long long V, float rate,
+              unsigned long long seed, unsigned site, cudaStream_t st);
+int residual_ln_fwd(float* y_z, const float* x, const float* gamma, const float* beta, float* out_f32, void* out_bf16,
+                    float* mean, float* rstd, long long rows, int d, float eps, float rate, unsigned long long seed,
+                    unsigned site, cudaStream_t st);
+int residual_ln_bwd(const float* dout, const float* z, const float* mean, const float* rstd, const float* gamma,
+                    float* dz, void* dy_sub, float* dgamma, float* dbeta, long long rows, int d, float rate,
+                    unsigned long long seed, unsigned site, cudaStream_t st);
+int xent(const void* logits, int logits_f32, long long ld, const long long* labels, int label_stride, int label_offset,
+         int T_len, void* dlogits, long long ld_d, float* row_loss, double* stats, long long rows, int V, float inv_batch,
+         cudaStream_t st);
+int colsum_bf16(const void* X, long long ld, float* out, long long rows, int N, cudaStream_t st);
+int adam_step(float* p, float* m, float* v, const float* g, void* shadow, long long n, float alpha, float b1, float b2,
+              float eps, cudaStream_t st);
+int cast_f32_bf16(const float* in, void* out, long long n, cudaStream_t st);
+int cast_bf16_f32(const void* in, float* out, long long n, cudaStream_t st);
+int cast_f32_bf16_strided(const float* in, void* out, long long rows, int d, long long ld_out, cudaStream_t st);
+int pad_mask(const long long* ids, uint8_t* mask, long long n, cudaStream_t st);
+
+}  // namespace bx
