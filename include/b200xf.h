@@ -59,12 +59,13 @@ int b200xf_attn_probs(const void* Q, int64_t ld_q, const void* K, int64_t ld_k, 
                       const uint8_t* kpad, int causal, const float* maskf, int64_t mask_sb, int64_t mask_sq, int B,
                       int H, int Sq, int Sk, int dk, b200xf_stream_t stream);
 
-/* ---- Embedding * sqrt(d) + pos_encoding[:, :S] + Dropout (Encoder.py:51-55, Decoder.py:65-69) and its gradient */
-int b200xf_embed_fwd(const int64_t* ids, const float* table, const float* pos, float* out_f32, void* out_bf16,
-                     int64_t rows, int S, int d, int64_t V, float rate, uint64_t seed, uint32_t site,
-                     b200xf_stream_t stream);
-int b200xf_embed_bwd(const int64_t* ids, const float* dx, float* dtable, int64_t rows, int d, int64_t V, float rate,
-                     uint64_t seed, uint32_t site, b200xf_stream_t stream);
+/* ---- Embedding * sqrt(d) + pos_encoding[:, :S] + Dropout (Encoder.py:51-55, Decoder.py:65-69) and its gradient.
+ *      row r = (b, s), rows = B*S; its token id is ids[b*id_stride + id_offset + s] (tar[:, :-1] without a copy). */
+int b200xf_embed_fwd(const int64_t* ids, int id_stride, int id_offset, const float* table, const float* pos,
+                     float* out_f32, void* out_bf16, int64_t rows, int S, int d, int64_t V, float rate, uint64_t seed,
+                     uint32_t site, b200xf_stream_t stream);
+int b200xf_embed_bwd(const int64_t* ids, int id_stride, int id_offset, const float* dx, float* dtable, int64_t rows,
+                     int S, int d, int64_t V, float rate, uint64_t seed, uint32_t site, b200xf_stream_t stream);
 
 /* ---- Dropout + residual add + LayerNormalization(eps) (Encoder.py:22-23,26-27; Decoder.py:30-31,35-36,39-40).
  *      y_z: in = sublayer output y, out = z = x + dropout(y) (kept for backward).                                 */
@@ -95,7 +96,9 @@ int b200xf_cast_f32_bf16(const float* in, void* out, int64_t n, b200xf_stream_t 
 int b200xf_cast_bf16_f32(const void* in, float* out, int64_t n, b200xf_stream_t stream);
 int b200xf_cast_f32_bf16_strided(const float* in, void* out, int64_t rows, int d, int64_t ld_out,
                                  b200xf_stream_t stream);
-int b200xf_pad_mask(const int64_t* ids, uint8_t* mask, int64_t n, b200xf_stream_t stream);
+/*      create_padding_mask (positionalencoding.py:25-30) in compact form: mask[b*S+s] = (ids[b*id_stride+id_offset+s] == 0) */
+int b200xf_pad_mask(const int64_t* ids, int id_stride, int id_offset, uint8_t* mask, int64_t rows, int S,
+                    b200xf_stream_t stream);
 
 /* ---- whole-model entry points (Transformer.call, Transformer.py:21-32; Train.train_step / test_step,
  *      train.py:124-156).  See transformer_b200/csrc/model.cu for the parameter-arena layout.                     */

@@ -294,14 +294,14 @@ def test_embed_fwd_bwd():
     ids = torch.randint(0, V, (B, S), generator=g).to(dev())
     table = rnd((V, d), 0.05, 1, torch.float32); pos = rnd((64, d), 1.0, 2, torch.float32)
     o32 = torch.empty(B * S, d, device=dev()); o16 = torch.empty(B * S, d, dtype=torch.bfloat16, device=dev())
-    L.call("b200xf_embed_fwd", L.ptr(ids), L.ptr(table), L.ptr(pos), L.ptr(o32), L.ptr(o16), B * S, S, d, V, 0.0, 0, 0, sp())
+    L.call("b200xf_embed_fwd", L.ptr(ids), S, 0, L.ptr(table), L.ptr(pos), L.ptr(o32), L.ptr(o16), B * S, S, d, V, 0.0, 0, 0, sp())
     torch.cuda.synchronize()
     ref = table[ids] * math.sqrt(d) + pos[:S][None]
     assert (o32.view(B, S, d) - ref).abs().max().item() < 1e-6
     assert (o16.float().view(B, S, d) - ref).abs().max().item() < 2e-2
     dx = rnd((B * S, d), 1.0, 3, torch.float32)
     dt = torch.zeros(V, d, device=dev())
-    L.call("b200xf_embed_bwd", L.ptr(ids), L.ptr(dx), L.ptr(dt), B * S, d, V, 0.0, 0, 0, sp())
+    L.call("b200xf_embed_bwd", L.ptr(ids), S, 0, L.ptr(dx), L.ptr(dt), B * S, S, d, V, 0.0, 0, 0, sp())
     torch.cuda.synchronize()
     dref = torch.zeros(V, d, device=dev()).index_add_(0, ids.view(-1), dx * math.sqrt(d))
     assert (dt - dref).abs().max().item() < 1e-3
@@ -353,7 +353,7 @@ def test_colsum_adam_casts_padmask():
     m1 = b1 * m0 + (1 - b1) * g; v1 = b2 * v0 + (1 - b2) * g * g; p1 = p0 - alpha * m1 / (v1.sqrt() + eps)
     assert (m - m1).abs().max().item() < 1e-6 and (v - v1).abs().max().item() < 1e-6 and (p - p1).abs().max().item() < 1e-6
     assert torch.equal(sh, p.bfloat16())
-    ids = torch.tensor([[3, 0, 5, 0]], device=dev()); mask = torch.empty(4, dtype=torch.uint8, device=dev())
-    L.call("b200xf_pad_mask", L.ptr(ids), L.ptr(mask), 4, sp())
+    ids = torch.tensor([[3, 0, 5, 0], [0, 7, 0, 0]], device=dev()); mask = torch.empty(6, dtype=torch.uint8, device=dev())
+    L.call("b200xf_pad_mask", L.ptr(ids), 4, 1, L.ptr(mask), 2, 3, sp())      # columns 1..3 of each row (tar[:, 1:])
     torch.cuda.synchronize()
-    assert mask.tolist() == [0, 1, 0, 1]
+    assert mask.tolist() == [1, 0, 1, 0, 1, 1]

@@ -41,8 +41,8 @@ _SIGS = {
                         _I64, _I, _I, _I, _I, _I, _P],
     "b200xf_attn_delta": [_P, _I64, _P, _I64, _P, _I, _I, _I, _I, _P],
     "b200xf_attn_probs": [_P, _I64, _P, _I64, _P, _P, _P, _I, _P, _I64, _I64, _I, _I, _I, _I, _I, _P],
-    "b200xf_embed_fwd": [_P, _P, _P, _P, _P, _I64, _I, _I, _I64, _F, _U64, _U32, _P],
-    "b200xf_embed_bwd": [_P, _P, _P, _I64, _I, _I64, _F, _U64, _U32, _P],
+    "b200xf_embed_fwd": [_P, _I, _I, _P, _P, _P, _P, _I64, _I, _I, _I64, _F, _U64, _U32, _P],
+    "b200xf_embed_bwd": [_P, _I, _I, _P, _P, _I64, _I, _I, _I64, _F, _U64, _U32, _P],
     "b200xf_residual_ln_fwd": [_P, _P, _P, _P, _P, _P, _P, _P, _I64, _I, _F, _F, _U64, _U32, _P],
     "b200xf_residual_ln_bwd": [_P, _P, _P, _P, _P, _P, _P, _P, _P, _I64, _I, _F, _U64, _U32, _P],
     "b200xf_xent": [_P, _I, _I64, _P, _I, _I, _I, _P, _I64, _P, _P, _I64, _I, _F, _P],
@@ -51,7 +51,7 @@ _SIGS = {
     "b200xf_cast_f32_bf16": [_P, _P, _I64, _P],
     "b200xf_cast_bf16_f32": [_P, _P, _I64, _P],
     "b200xf_cast_f32_bf16_strided": [_P, _P, _I64, _I, _I64, _P],
-    "b200xf_pad_mask": [_P, _P, _I64, _P],
+    "b200xf_pad_mask": [_P, _I, _I, _P, _I64, _I, _P],
     "b200xf_model_param_count": [C.POINTER(ModelConfig)],
     "b200xf_model_workspace_bytes": [C.POINTER(ModelConfig)],
     "b200xf_model_variable": [C.POINTER(ModelConfig), _I, C.c_char_p, _I, C.POINTER(_I64), C.POINTER(_I64),

@@ -41,15 +41,16 @@ int b200xf_attn_probs(const void* Q, int64_t ld_q, const void* K, int64_t ld_k, 
                       int H, int Sq, int Sk, int dk, b200xf_stream_t stream) {
   return bx::attn_probs(Q, ld_q, K, ld_k, lse, P, kpad, causal, maskf, mask_sb, mask_sq, B, H, Sq, Sk, dk, ST(stream));
 }
-int b200xf_embed_fwd(const int64_t* ids, const float* table, const float* pos, float* out_f32, void* out_bf16,
-                     int64_t rows, int S, int d, int64_t V, float rate, uint64_t seed, uint32_t site,
-                     b200xf_stream_t stream) {
-  return bx::embed_fwd(reinterpret_cast<const long long*>(ids), table, pos, out_f32, out_bf16, rows, S, d, V, rate, seed,
-                       site, ST(stream));
+int b200xf_embed_fwd(const int64_t* ids, int id_stride, int id_offset, const float* table, const float* pos,
+                     float* out_f32, void* out_bf16, int64_t rows, int S, int d, int64_t V, float rate, uint64_t seed,
+                     uint32_t site, b200xf_stream_t stream) {
+  return bx::embed_fwd(reinterpret_cast<const long long*>(ids), id_stride, id_offset, table, pos, out_f32, out_bf16, rows,
+                       S, d, V, rate, seed, site, ST(stream));
 }
-int b200xf_embed_bwd(const int64_t* ids, const float* dx, float* dtable, int64_t rows, int d, int64_t V, float rate,
-                     uint64_t seed, uint32_t site, b200xf_stream_t stream) {
-  return bx::embed_bwd(reinterpret_cast<const long long*>(ids), dx, dtable, rows, d, V, rate, seed, site, ST(stream));
+int b200xf_embed_bwd(const int64_t* ids, int id_stride, int id_offset, const float* dx, float* dtable, int64_t rows,
+                     int S, int d, int64_t V, float rate, uint64_t seed, uint32_t site, b200xf_stream_t stream) {
+  return bx::embed_bwd(reinterpret_cast<const long long*>(ids), id_stride, id_offset, dx, dtable, rows, S, d, V, rate,
+                       seed, site, ST(stream));
 }
 int b200xf_residual_ln_fwd(float* y_z, const float* x, const float* gamma, const float* beta, float* out_f32,
                            void* out_bf16, float* mean, float* rstd, int64_t rows, int d, float eps, float rate,
@@ -86,8 +87,9 @@ int b200xf_cast_f32_bf16_strided(const float* in, void* out, int64_t rows, int d
                                  b200xf_stream_t stream) {
   return bx::cast_f32_bf16_strided(in, out, rows, d, ld_out, ST(stream));
 }
-int b200xf_pad_mask(const int64_t* ids, uint8_t* mask, int64_t n, b200xf_stream_t stream) {
-  return bx::pad_mask(reinterpret_cast<const long long*>(ids), mask, n, ST(stream));
+int b200xf_pad_mask(const int64_t* ids, int id_stride, int id_offset, uint8_t* mask, int64_t rows, int S,
+                    b200xf_stream_t stream) {
+  return bx::pad_mask(reinterpret_cast<const long long*>(ids), id_stride, id_offset, mask, rows, S, ST(stream));
 }
 
 }  // extern "C"

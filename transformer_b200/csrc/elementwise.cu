@@ -49,14 +49,15 @@ __device__ __forceinline__ float warp_max(float v) {
 // ------------------------------------------------------------------------------------------------
 __global__ void embed_fwd_kernel(const long long* __restrict__ ids, const float* __restrict__ table,
                                  const float* __restrict__ pos, float* __restrict__ out_f32,
-                                 __nv_bfloat16* __restrict__ out_bf16, long long rows, int S, int d, long long V,
-                                 float scale, float rate, unsigned long long seed, uint32_t site) {
+                                 __nv_bfloat16* __restrict__ out_bf16, long long rows, int S, int id_stride,
+                                 int id_offset, int d, long long V, float scale, float rate, unsigned long long seed,
+                                 uint32_t site) {
   const int d4 = d >> 2;
   const long long total = rows * d4;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     const long long r = i / d4;
     const int c4 = (int)(i - r * d4);
-    long long id = ids[r];
+    long long id = ids[(r / S) * id_stride + id_offset + (r % S)];
     id = id < 0 ? 0 : (id >= V ? V - 1 : id);
     const float4 e = __ldg(reinterpret_cast<const float4*>(table + id * d) + c4);
     const float4 p = __ldg(reinterpret_cast<const float4*>(pos + (r % S) * (long long)d) + c4);
@@ -72,14 +73,14 @@ __global__ void embed_fwd_kernel(const long long* __restrict__ ids, const float*
 
 // backward: dTable[id] += dx * sqrt(d) * dropmask   (dense-equivalent IndexedSlices sum, Appendix A.8)
 __global__ void embed_bwd_kernel(const long long* __restrict__ ids, const float* __restrict__ dx,
-                                 float* __restrict__ dtable, long long rows, int d, long long V, float scale,
-                                 float rate, unsigned long long seed, uint32_t site) {
+                                 float* __restrict__ dtable, long long rows, int S, int id_stride, int id_offset, int d,
+                                 long long V, float scale, float rate, unsigned long long seed, uint32_t site) {
   const int d4 = d >> 2;
   const long long total = rows * d4;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     const long long r = i / d4;
     const int c4 = (int)(i - r * d4);
-    long long id = ids[r];
+    long long id = ids[(r / S) * id_stride + id_offset + (r % S)];
     id = id < 0 ? 0 : (id >= V ? V - 1 : id);
     float4 g = reinterpret_cast<const float4*>(dx)[i];
     if (rate > 0.f) {
@@ -256,9 +257,9 @@ __device__ __forceinline__ float ld_logit<__nv_bfloat16>(const __nv_bfloat16* p,
 
 template <typename T>
 __global__ void __launch_bounds__(256)
-xent_kernel(const T* __restrict__ logits, long long ld, const long long* __restrict__ labels, int label_stride,
-            int label_offset, int T_len, __nv_bfloat16* __restrict__ dlogits, long long ld_d, float* __restrict__ row_loss,
-            double* __restrict__ stats, int V, float inv_batch) {
+xent_kernel(const T* logits, long long ld, const long long* __restrict__ labels, int label_stride,
+            int label_offset, int T_len, __nv_bfloat16* dlogits, long long ld_d, float* __restrict__ row_loss,
+            double* __restrict__ stats, int V, float inv_batch) {   // dlogits may alias logits (no __restrict__)
   // labels for row r = (b, t) live at labels[b * label_stride + label_offset + t]  (tar[:, 1:] without a copy)
   const long long r = blockIdx.x;
   const T* row = logits + r * ld;
@@ -266,7 +267,7 @@ xent_kernel(const T* __restrict__ logits, long long ld, const long long* __restr
   long long label = labels[b * label_stride + label_offset + t];
   const bool nonpad = label != 0;
   if (label < 0 || label >= V) label = 0;
-  __shared__ float s_m[8], s_s[8];
+  __shared__ float s_m[8], s_s[8], s_lab;
   __shared__ int s_i[8];
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   // pass 1: online max / sum-exp / argmax (first index attaining the max, like tf.argmax)
@@ -274,6 +275,7 @@ xent_kernel(const T* __restrict__ logits, long long ld, const long long* __restr
   int am = 0x7fffffff;
   for (int c = threadIdx.x; c < V; c += blockDim.x) {
     const float x = ld_logit<T>(row, c);
+    if (c == (int)label) s_lab = x;      // captured now: pass 2 may overwrite the (aliased) row in place
     if (x > m) { s = s * __expf(m - x) + 1.f; m = x; am = c; }
     else s += __expf(x - m);
   }
@@ -299,7 +301,7 @@ xent_kernel(const T* __restrict__ logits, long long ld, const long long* __restr
   }
   const float lse = m + __logf(s);
   if (threadIdx.x == 0) {
-    const float loss = nonpad ? (lse - ld_logit<T>(row, label)) : 0.f;
+    const float loss = nonpad ? (lse - s_lab) : 0.f;
     if (row_loss) row_loss[r] = loss;
     atomicAdd(&stats[0], (double)loss);
     atomicAdd(&stats[1], (double)(am == (int)labels[b * label_stride + label_offset + t] ? 1.0 : 0.0));
@@ -389,9 +391,10 @@ cast_f32_bf16_strided_kernel(const float* __restrict__ in, __nv_bfloat16* __rest
 }
 
 // key-padding bytes: 1 where token id == 0   (positionalencoding.py:25-30, compact form)
-__global__ void pad_mask_kernel(const long long* __restrict__ ids, uint8_t* __restrict__ mask, long long n) {
+__global__ void pad_mask_kernel(const long long* __restrict__ ids, uint8_t* __restrict__ mask, long long n, int S,
+                                int id_stride, int id_offset) {
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
-    mask[i] = ids[i] == 0 ? 1 : 0;
+    mask[i] = ids[(i / S) * id_stride + id_offset + (i % S)] == 0 ? 1 : 0;
 }
 
 // attention backward pre-pass: delta[b,h,q] = sum_c dO[b,q,h*dk+c] * O[b,q,h*dk+c]
@@ -431,19 +434,20 @@ static inline int grid_for(long long work, int threads, int max_blocks_per_sm = 
   return (int)b;
 }
 
-int embed_fwd(const long long* ids, const float* table, const float* pos, float* out_f32, void* out_bf16,
-              long long rows, int S, int d, long long V, float rate, unsigned long long seed, unsigned site,
+int embed_fwd(const long long* ids, int id_stride, int id_offset, const float* table, const float* pos, float* out_f32,
+              void* out_bf16, long long rows, int S, int d, long long V, float rate, unsigned long long seed, unsigned site,
               cudaStream_t st) {
   BX_REQUIRE(d % 4 == 0, "embed: d_model %% 4 != 0");
-  embed_fwd_kernel<<<grid_for(rows * (d / 4), 256), 256, 0, st>>>(ids, table, pos, out_f32, (__nv_bfloat16*)out_bf16, rows, S, d,
-                                                                 V, sqrtf((float)d), rate, seed, site);
+  embed_fwd_kernel<<<grid_for(rows * (d / 4), 256), 256, 0, st>>>(ids, table, pos, out_f32, (__nv_bfloat16*)out_bf16, rows, S,
+                                                                 id_stride, id_offset, d, V, sqrtf((float)d), rate, seed, site);
   BX_POST_LAUNCH();
   return 0;
 }
-int embed_bwd(const long long* ids, const float* dx, float* dtable, long long rows, int d, long long V, float rate,
-              unsigned long long seed, unsigned site, cudaStream_t st) {
+int embed_bwd(const long long* ids, int id_stride, int id_offset, const float* dx, float* dtable, long long rows, int S,
+              int d, long long V, float rate, unsigned long long seed, unsigned site, cudaStream_t st) {
   BX_REQUIRE(d % 4 == 0, "embed: d_model %% 4 != 0");
-  embed_bwd_kernel<<<grid_for(rows * (d / 4), 256), 256, 0, st>>>(ids, dx, dtable, rows, d, V, sqrtf((float)d), rate, seed, site);
+  embed_bwd_kernel<<<grid_for(rows * (d / 4), 256), 256, 0, st>>>(ids, dx, dtable, rows, S, id_stride, id_offset, d, V,
+                                                                 sqrtf((float)d), rate, seed, site);
   BX_POST_LAUNCH();
   return 0;
 }
@@ -528,8 +532,8 @@ int cast_f32_bf16_strided(const float* in, void* out, long long rows, int d, lon
   BX_POST_LAUNCH();
   return 0;
 }
-int pad_mask(const long long* ids, uint8_t* mask, long long n, cudaStream_t st) {
-  pad_mask_kernel<<<grid_for(n, 256), 256, 0, st>>>(ids, mask, n);
+int pad_mask(const long long* ids, int id_stride, int id_offset, uint8_t* mask, long long rows, int S, cudaStream_t st) {
+  pad_mask_kernel<<<grid_for(rows * S, 256), 256, 0, st>>>(ids, mask, rows * S, S, id_stride, id_offset);
   BX_POST_LAUNCH();
   return 0;
 }

@@ -22,11 +22,12 @@ int attn_probs(const void* Q, long long ld_q, const void* K, long long ld_k, con
 int attn_delta(const void* O, long long ld_o, const void* dO, long long ld_do, float* delta, int B, int S, int H, int dk,
                cudaStream_t st);
 
-int embed_fwd(const long long* ids, const float* table, const float* pos, float* out_f32, void* out_bf16,
-              long long rows, int S, int d, long long V, float rate, unsigned long long seed, unsigned site,
+// ids of row r = (b, s) are read at ids[b * id_stride + id_offset + s]  (tar[:, :-1] without a copy)
+int embed_fwd(const long long* ids, int id_stride, int id_offset, const float* table, const float* pos, float* out_f32,
+              void* out_bf16, long long rows, int S, int d, long long V, float rate, unsigned long long seed, unsigned site,
               cudaStream_t st);
-int embed_bwd(const long long* ids, const float* dx, float* dtable, long long rows, int d, long long V, float rate,
-              unsigned long long seed, unsigned site, cudaStream_t st);
+int embed_bwd(const long long* ids, int id_stride, int id_offset, const float* dx, float* dtable, long long rows, int S,
+              int d, long long V, float rate, unsigned long long seed, unsigned site, cudaStream_t st);
 int residual_ln_fwd(float* y_z, const float* x, const float* gamma, const float* beta, float* out_f32, void* out_bf16,
                     float* mean, float* rstd, long long rows, int d, float eps, float rate, unsigned long long seed,
                     unsigned site, cudaStream_t st);
@@ -42,6 +43,6 @@ int adam_step(float* p, float* m, float* v, const float* g, void* shadow, long l
 int cast_f32_bf16(const float* in, void* out, long long n, cudaStream_t st);
 int cast_bf16_f32(const void* in, float* out, long long n, cudaStream_t st);
 int cast_f32_bf16_strided(const float* in, void* out, long long rows, int d, long long ld_out, cudaStream_t st);
-int pad_mask(const long long* ids, uint8_t* mask, long long n, cudaStream_t st);
+int pad_mask(const long long* ids, int id_stride, int id_offset, uint8_t* mask, long long rows, int S, cudaStream_t st);
 
 }  // namespace bx

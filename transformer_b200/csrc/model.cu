@@ -1,1 +1,600 @@
-// placeholder -- replaced by the model orchestration
+// Whole-model orchestration of the hot path: Transformer.call (Transformer.py:21-32) -> Encoder.call
+// (Encoder.py:48-60) / Decoder.call (Decoder.py:59-79) -> final_layer, the loss (train.py:83-88) and the
+// hand-written reverse pass that replaces tape.gradient (train.py:137).  One C call launches every kernel of a
+// phase on the caller's stream; nothing here allocates, synchronises or touches the host.
+//
+// PARAMETER ARENA (fp32; grads / Adam m / Adam v / bf16 shadow use the same offsets).  Order follows keras'
+// trainable_variables order at block granularity; Q/K/V kernels of one MultiHeadAttention are PACKED side by side
+// so the three Dense layers (Attention.py:62-64) run as one GEMM:
+//   enc_emb [Vin,d]
+//   per encoder layer: Wqkv [d,3d] bqkv [3d] Wo [d,d] bo [d] W1 [d,f] b1 [f] W2 [f,d] b2 [d] ln1g ln1b ln2g ln2b [d]
+//   dec_emb [Vtgt,d]
+//   per decoder layer: Wqkv bqkv Wo bo | Wq [d,d] bq [d] Wkv [d,2d] bkv [2d] Wo2 bo2 | W1 b1 W2 b2 | ln1g ln1b ln2g ln2b ln3g ln3b
+//   Wf [d,Vp] bf [Vp]                 (Vp = target vocab rounded up to 8 columns for 16-byte TMA row pitch)
+// b200xf_model_variable() exposes the keras-order per-variable (strided) views, e.g. wq.kernel = Wqkv[:, 0:d].
+#include <string.h>
+
+#include <string>
+#include <utility>
+#include <vector>
+
+#include "../../include/b200xf.h"
+#include "common.cuh"
+#include "kernels.h"
+
+namespace {
+
+using bf16 = __nv_bfloat16;
+
+inline int64_t align_up(int64_t x, int64_t a) { return (x + a - 1) / a * a; }
+
+struct MhaSelf { int64_t Wqkv, bqkv, Wo, bo; };
+struct MhaCross { int64_t Wq, bq, Wkv, bkv, Wo, bo; };
+struct Ffn { int64_t W1, b1, W2, b2; };
+struct EncLayerP { MhaSelf mha; Ffn ffn; int64_t ln1g, ln1b, ln2g, ln2b; };
+struct DecLayerP { MhaSelf mha1; MhaCross mha2; Ffn ffn; int64_t ln1g, ln1b, ln2g, ln2b, ln3g, ln3b; };
+
+struct VarView { std::string name; int64_t off, rows, cols, ld; };
+
+struct Layout {
+  int L, d, H, f, Vin, Vtgt, Vp;
+  int64_t enc_emb, dec_emb, Wf, bf, total;
+  int64_t stage_begin[3], stage_end[3];   // 0 final layer, 1 decoder (+emb), 2 encoder (+emb)
+  std::vector<EncLayerP> enc;
+  std::vector<DecLayerP> dec;
+  std::vector<VarView> vars;
+};
+
+struct Bump {
+  int64_t cur = 0;
+  int64_t take(int64_t n) { int64_t o = cur; cur = align_up(cur + n, 64); return o; }   // 256-byte aligned (fp32)
+};
+
+Layout make_layout(const b200xf_model_config& c) {
+  Layout lo;
+  lo.L = c.num_layers; lo.d = c.d_model; lo.H = c.num_heads; lo.f = c.dff;
+  lo.Vin = c.input_vocab_size; lo.Vtgt = c.target_vocab_size; lo.Vp = (int)align_up(c.target_vocab_size, 8);
+  const int64_t d = lo.d, f = lo.f;
+  Bump b;
+  auto self = [&](MhaSelf& m) { m.Wqkv = b.take(d * 3 * d); m.bqkv = b.take(3 * d); m.Wo = b.take(d * d); m.bo = b.take(d); };
+  auto ffn = [&](Ffn& m) { m.W1 = b.take(d * f); m.b1 = b.take(f); m.W2 = b.take(f * d); m.b2 = b.take(d); };
+  lo.stage_begin[2] = b.cur;
+  lo.enc_emb = b.take((int64_t)lo.Vin * d);
+  lo.enc.resize(lo.L);
+  for (auto& e : lo.enc) {
+    self(e.mha); ffn(e.ffn);
+    e.ln1g = b.take(d); e.ln1b = b.take(d); e.ln2g = b.take(d); e.ln2b = b.take(d);
+  }
+  lo.stage_end[2] = b.cur;
+  lo.stage_begin[1] = b.cur;
+  lo.dec_emb = b.take((int64_t)lo.Vtgt * d);
+  lo.dec.resize(lo.L);
+  for (auto& e : lo.dec) {
+    self(e.mha1);
+    e.mha2.Wq = b.take(d * d); e.mha2.bq = b.take(d); e.mha2.Wkv = b.take(d * 2 * d); e.mha2.bkv = b.take(2 * d);
+    e.mha2.Wo = b.take(d * d); e.mha2.bo = b.take(d);
+    ffn(e.ffn);
+    e.ln1g = b.take(d); e.ln1b = b.take(d); e.ln2g = b.take(d); e.ln2b = b.take(d); e.ln3g = b.take(d); e.ln3b = b.take(d);
+  }
+  lo.stage_end[1] = b.cur;
+  lo.stage_begin[0] = b.cur;
+  lo.Wf = b.take(d * (int64_t)lo.Vp);
+  lo.bf = b.take(lo.Vp);
+  lo.stage_end[0] = b.cur;
+  lo.total = b.cur;
+
+  // keras-order variable views
+  auto& v = lo.vars;
+  auto dense = [&](const std::string& p, int64_t k_off, int64_t rows, int64_t cols, int64_t ld, int64_t b_off) {
+    v.push_back({p + "/kernel", k_off, rows, cols, ld});
+    v.push_back({p + "/bias", b_off, cols, 0, 1});
+  };
+  auto self_vars = [&](const std::string& p, const MhaSelf& m) {
+    dense(p + "/wq", m.Wqkv, d, d, 3 * d, m.bqkv);
+    dense(p + "/wk", m.Wqkv + d, d, d, 3 * d, m.bqkv + d);
+    dense(p + "/wv", m.Wqkv + 2 * d, d, d, 3 * d, m.bqkv + 2 * d);
+    dense(p + "/dense", m.Wo, d, d, d, m.bo);
+  };
+  auto ffn_vars = [&](const std::string& p, const Ffn& m) {
+    dense(p + "/dense0", m.W1, d, f, f, m.b1);
+    dense(p + "/dense1", m.W2, f, d, d, m.b2);
+  };
+  auto ln_vars = [&](const std::string& p, int64_t g, int64_t be) {
+    v.push_back({p + "/gamma", g, d, 0, 1});
+    v.push_back({p + "/beta", be, d, 0, 1});
+  };
+  v.push_back({"encoder/embedding", lo.enc_emb, lo.Vin, d, d});
+  for (int i = 0; i < lo.L; ++i) {
+    const std::string p = "encoder/layer" + std::to_string(i);
+    self_vars(p + "/mha", lo.enc[i].mha);
+    ffn_vars(p + "/ffn", lo.enc[i].ffn);
+    ln_vars(p + "/layernorm1", lo.enc[i].ln1g, lo.enc[i].ln1b);
+    ln_vars(p + "/layernorm2", lo.enc[i].ln2g, lo.enc[i].ln2b);
+  }
+  v.push_back({"decoder/embedding", lo.dec_emb, lo.Vtgt, d, d});
+  for (int i = 0; i < lo.L; ++i) {
+    const std::string p = "decoder/layer" + std::to_string(i);
+    const DecLayerP& e = lo.dec[i];
+    self_vars(p + "/mha1", e.mha1);
+    dense(p + "/mha2/wq", e.mha2.Wq, d, d, d, e.mha2.bq);
+    dense(p + "/mha2/wk", e.mha2.Wkv, d, d, 2 * d, e.mha2.bkv);
+    dense(p + "/mha2/wv", e.mha2.Wkv + d, d, d, 2 * d, e.mha2.bkv + d);
+    dense(p + "/mha2/dense", e.mha2.Wo, d, d, d, e.mha2.bo);
+    ffn_vars(p + "/ffn", e.ffn);
+    ln_vars(p + "/layernorm1", e.ln1g, e.ln1b);
+    ln_vars(p + "/layernorm2", e.ln2g, e.ln2b);
+    ln_vars(p + "/layernorm3", e.ln3g, e.ln3b);
+  }
+  dense("final_layer", lo.Wf, d, lo.Vtgt, lo.Vp, lo.bf);
+  return lo;
+}
+
+// ---- workspace (activations kept for backward + gradient scratch), carved from one caller-owned buffer ----
+struct LnSave { float *z, *mean, *rstd; };
+struct EncAct { bf16* qkv; bf16* attn_o; float* lse; LnSave ln1; float* out1_32; bf16* out1_16; bf16* h; LnSave ln2; };
+struct DecAct {
+  bf16* qkv1; bf16* attn1_o; float* lse1; LnSave ln1; float* out1_32; bf16* out1_16;
+  bf16* q2; bf16* kv2; bf16* attn2_o; float* lse2; LnSave ln2; float* out2_32; bf16* out2_16;
+  bf16* h; LnSave ln3;
+};
+struct Work {
+  std::vector<float*> enc_x32, dec_x32;   // [L+1] layer inputs/outputs (index 0 = embedding output)
+  std::vector<bf16*> enc_x16, dec_x16;
+  std::vector<EncAct> enc;
+  std::vector<DecAct> dec;
+  bf16* logits;                           // [Mt, Vp] bf16, overwritten in place by dlogits
+  uint8_t *kpad_in, *kpad_tar;
+  // backward scratch
+  float *gA, *gB;                         // [Mmax, d] gradient stream (ping-pong)
+  float* d_enc_out;                       // [Ms, d] accumulates cross-attention K/V gradients of all decoder layers
+  bf16 *dy16, *dO16, *dqkv, *dh;          // [Mmax,d] [Mmax,d] [Mmax,3d] [Mmax,f]
+  float *dq_acc, *delta;                  // [Mmax,d] [B,H,Smax]
+  int64_t bytes;
+};
+
+struct ByteBump {
+  uint8_t* base; int64_t cur = 0;
+  template <typename T> T* take(int64_t n) {
+    T* p = base ? reinterpret_cast<T*>(base + cur) : nullptr;
+    cur = align_up(cur + n * (int64_t)sizeof(T), 1024);
+    return p;
+  }
+};
+
+Work make_work(const b200xf_model_config& c, const Layout& lo, void* base) {
+  Work w;
+  ByteBump b{reinterpret_cast<uint8_t*>(base)};
+  const int64_t d = lo.d, f = lo.f, H = lo.H, L = lo.L;
+  const int64_t Ms = (int64_t)c.max_batch * c.max_src_len, Mt = (int64_t)c.max_batch * c.max_tgt_len;
+  const int64_t Mx = Ms > Mt ? Ms : Mt;
+  const int64_t Smax = c.max_src_len > c.max_tgt_len ? c.max_src_len : c.max_tgt_len;
+  auto ln = [&](int64_t M) { LnSave s; s.z = b.take<float>(M * d); s.mean = b.take<float>(M); s.rstd = b.take<float>(M); return s; };
+  w.enc_x32.resize(L + 1); w.enc_x16.resize(L + 1); w.dec_x32.resize(L + 1); w.dec_x16.resize(L + 1);
+  for (int i = 0; i <= L; ++i) { w.enc_x32[i] = b.take<float>(Ms * d); w.enc_x16[i] = b.take<bf16>(Ms * d); }
+  for (int i = 0; i <= L; ++i) { w.dec_x32[i] = b.take<float>(Mt * d); w.dec_x16[i] = b.take<bf16>(Mt * d); }
+  w.enc.resize(L); w.dec.resize(L);
+  for (auto& a : w.enc) {
+    a.qkv = b.take<bf16>(Ms * 3 * d); a.attn_o = b.take<bf16>(Ms * d); a.lse = b.take<float>(c.max_batch * H * c.max_src_len);
+    a.ln1 = ln(Ms); a.out1_32 = b.take<float>(Ms * d); a.out1_16 = b.take<bf16>(Ms * d); a.h = b.take<bf16>(Ms * f); a.ln2 = ln(Ms);
+  }
+  for (auto& a : w.dec) {
+    a.qkv1 = b.take<bf16>(Mt * 3 * d); a.attn1_o = b.take<bf16>(Mt * d); a.lse1 = b.take<float>(c.max_batch * H * c.max_tgt_len);
+    a.ln1 = ln(Mt); a.out1_32 = b.take<float>(Mt * d); a.out1_16 = b.take<bf16>(Mt * d);
+    a.q2 = b.take<bf16>(Mt * d); a.kv2 = b.take<bf16>(Ms * 2 * d); a.attn2_o = b.take<bf16>(Mt * d);
+    a.lse2 = b.take<float>(c.max_batch * H * c.max_tgt_len);
+    a.ln2 = ln(Mt); a.out2_32 = b.take<float>(Mt * d); a.out2_16 = b.take<bf16>(Mt * d); a.h = b.take<bf16>(Mt * f); a.ln3 = ln(Mt);
+  }
+  w.logits = b.take<bf16>(Mt * lo.Vp);
+  w.kpad_in = b.take<uint8_t>(Ms); w.kpad_tar = b.take<uint8_t>(Mt);
+  w.gA = b.take<float>(Mx * d); w.gB = b.take<float>(Mx * d); w.d_enc_out = b.take<float>(Ms * d);
+  w.dy16 = b.take<bf16>(Mx * d); w.dO16 = b.take<bf16>(Mx * d); w.dqkv = b.take<bf16>(Mx * 3 * d); w.dh = b.take<bf16>(Mx * f);
+  w.dq_acc = b.take<float>(Mx * d); w.delta = b.take<float>(c.max_batch * H * Smax);
+  w.bytes = b.cur;
+  return w;
+}
+
+int validate(const b200xf_model_config& c) {
+  BX_REQUIRE(c.num_layers >= 1 && c.d_model >= 32 && c.num_heads >= 1 && c.dff >= 8, "model: bad sizes");
+  BX_REQUIRE(c.d_model % c.num_heads == 0, "model: d_model %% num_heads != 0 (Attention.py:42)");
+  const int dk = c.d_model / c.num_heads;
+  BX_REQUIRE(dk == 32 || dk == 64, "model: head depth %d unsupported (d_model/num_heads must be 32 or 64)", dk);
+  BX_REQUIRE(c.d_model % 8 == 0 && c.dff % 8 == 0 && c.d_model <= 1024, "model: d_model, dff must be multiples of 8; d_model <= 1024");
+  BX_REQUIRE(c.input_vocab_size >= 2 && c.target_vocab_size >= 2, "model: vocab too small");
+  BX_REQUIRE(c.max_batch >= 1 && c.max_src_len >= 1 && c.max_tgt_len >= 1, "model: bad workspace maxima");
+  BX_REQUIRE(c.pos_rows >= c.max_src_len && c.pos_rows >= c.max_tgt_len, "model: positional table shorter than max length");
+  BX_REQUIRE(c.dropout_rate >= 0.f && c.dropout_rate < 1.f, "model: dropout rate out of range");
+  return 0;
+}
+
+}  // namespace
+
+struct b200xf_model {
+  b200xf_model_config cfg;
+  Layout lo;
+  Work w;
+  float *P, *G, *Am, *Av;
+  bf16* Sh;
+  const float *pos_in, *pos_tgt;
+  // state of the last forward
+  int B = 0, S = 0, T = 0, training = 0;
+  uint64_t seed = 0;
+  const int64_t *inp = nullptr, *tar = nullptr;
+  int tar_stride = 0, tar_offset = 0;
+  const float *enc_mask = nullptr, *la_mask = nullptr, *dec_mask = nullptr;
+  int64_t la_bs = 0;
+  bool have_loss_grad = false;
+  bool logits_valid = false;   // w.logits holds the last forward's bf16 logits (not yet turned into dlogits)
+};
+
+namespace {
+
+using M = b200xf_model;
+
+#define RC(expr)                 \
+  do {                           \
+    int _rc = (expr);            \
+    if (_rc) return _rc;         \
+  } while (0)
+
+// dropout site ids (any distinct constants)
+inline uint32_t site_enc_embed() { return 1; }
+inline uint32_t site_dec_embed() { return 2; }
+inline uint32_t site_enc(int l, int k) { return 16 + l * 8 + k; }
+inline uint32_t site_dec(int l, int k) { return 4096 + l * 8 + k; }
+
+int pick_splits(int64_t Mo, int64_t No, int64_t Ktok) {
+  const int64_t bn = No > 128 ? 256 : 128;
+  const int64_t tiles = ((Mo + 127) / 128) * ((No + bn - 1) / bn);
+  const int64_t kblocks = (Ktok + 63) / 64;
+  int64_t s = (2 * bx::sm_count() + tiles - 1) / tiles;
+  if (s > kblocks / 4) s = kblocks / 4;
+  if (s < 1) s = 1;
+  return (int)s;
+}
+
+// y[M,N] = x[M,K] . W[K,N] + b        (keras Dense; W in keras [in,out] layout, row pitch ldw)
+int linear_fwd(const bf16* x, int64_t ldx, const bf16* W, int64_t ldw, const float* b, void* y, int64_t ldy, bool y_f32,
+               bool relu, int64_t Mr, int64_t N, int64_t K, cudaStream_t st) {
+  return bx::gemm_bf16(x, ldx, 0, W, ldw, 1, y, ldy, y_f32 ? 1 : 0, b, nullptr, 0, relu ? 1 : 0, 1, Mr, N, K, st);
+}
+// dx[M,K] (+)= dy[M,N] . W^T          (W [K,N] row-major is exactly the K-major B operand of this product)
+int linear_dgrad(const bf16* dy, int64_t ld_dy, const bf16* W, int64_t ldw, void* dx, int64_t ld_dx, bool dx_f32, bool accum,
+                 const bf16* relu_aux, int64_t ld_aux, int64_t Mr, int64_t N, int64_t K, cudaStream_t st) {
+  const int flags = (accum ? 2 : 0) | (relu_aux ? 4 : 0);
+  return bx::gemm_bf16(dy, ld_dy, 0, W, ldw, 0, dx, ld_dx, dx_f32 ? 1 : 0, nullptr, relu_aux, ld_aux, flags, 1, Mr, K, N, st);
+}
+// dW[K,N] += x[M,K]^T . dy[M,N] ; db[N] += colsum(dy)     (split-K over the token dimension, TMA reduce-add)
+int linear_wgrad(const bf16* x, int64_t ldx, const bf16* dy, int64_t ld_dy, float* dW, int64_t ldw, float* db, int64_t Mr,
+                 int64_t N, int64_t K, cudaStream_t st) {
+  RC(bx::gemm_bf16(x, ldx, 1, dy, ld_dy, 1, dW, ldw, 1, nullptr, nullptr, 0, 2, pick_splits(K, N, Mr), K, N, Mr, st));
+  if (db) RC(bx::colsum_bf16(dy, ld_dy, db, Mr, (int)N, st));
+  return 0;
+}
+
+struct MaskSpec { const uint8_t* kpad; int causal; const float* maskf; int64_t sb, sq; };
+
+MaskSpec enc_self_mask(const M* m) {
+  if (m->enc_mask) return {nullptr, 0, m->enc_mask, (int64_t)m->S, 0};
+  return {m->w.kpad_in, 0, nullptr, 0, 0};
+}
+MaskSpec dec_self_mask(const M* m) {
+  if (m->la_mask) return {nullptr, 0, m->la_mask, m->la_bs, (int64_t)m->T};
+  return {m->w.kpad_tar, 1, nullptr, 0, 0};
+}
+MaskSpec dec_cross_mask(const M* m) {
+  if (m->dec_mask) return {nullptr, 0, m->dec_mask, (int64_t)m->S, 0};
+  return {m->w.kpad_in, 0, nullptr, 0, 0};
+}
+
+int residual_ln(M* m, float* y_z, const float* x, int64_t g_off, int64_t b_off, float* out32, bf16* out16, const LnSave& s,
+                int64_t rows, uint32_t site, cudaStream_t st) {
+  const float rate = m->training ? m->cfg.dropout_rate : 0.f;
+  return bx::residual_ln_fwd(y_z, x, m->P + g_off, m->P + b_off, out32, out16, s.mean, s.rstd, rows, m->lo.d, m->cfg.ln_eps, rate,
+                             m->seed, site, st);
+}
+
+int forward_impl(M* m, float* logits_out, int64_t ld_logits, cudaStream_t st) {
+  const Layout& lo = m->lo;
+  Work& w = m->w;
+  const int d = lo.d, H = lo.H, f = lo.f, L = lo.L, dk = d / H;
+  const int B = m->B, S = m->S, T = m->T;
+  const int64_t Ms = (int64_t)B * S, Mt = (int64_t)B * T;
+  const float rate = m->training ? m->cfg.dropout_rate : 0.f;
+  const bf16* Sh = m->Sh;
+
+  RC(bx::pad_mask(reinterpret_cast<const long long*>(m->inp), S, 0, w.kpad_in, B, S, st));
+  RC(bx::pad_mask(reinterpret_cast<const long long*>(m->tar), m->tar_stride, m->tar_offset, w.kpad_tar, B, T, st));
+
+  // ---------------- encoder (Encoder.py:48-60) ----------------
+  RC(bx::embed_fwd(reinterpret_cast<const long long*>(m->inp), S, 0, m->P + lo.enc_emb, m->pos_in, w.enc_x32[0], w.enc_x16[0], Ms, S, d,
+                   lo.Vin, rate, m->seed, site_enc_embed(), st));
+  const MaskSpec em = enc_self_mask(m);
+  for (int l = 0; l < L; ++l) {
+    const EncLayerP& p = lo.enc[l];
+    EncAct& a = w.enc[l];
+    // MultiHeadAttention (Attention.py:59-78): packed QKV projection -> flash attention -> output projection
+    RC(linear_fwd(w.enc_x16[l], d, Sh + p.mha.Wqkv, 3 * d, m->P + p.mha.bqkv, a.qkv, 3 * d, false, false, Ms, 3 * d, d, st));
+    RC(bx::attn_fwd(a.qkv, 3 * d, a.qkv + d, 3 * d, a.qkv + 2 * d, 3 * d, a.attn_o, d, a.lse, em.kpad, em.causal, em.maskf, em.sb,
+                    em.sq, B, H, S, S, dk, st));
+    RC(linear_fwd(a.attn_o, d, Sh + p.mha.Wo, d, m->P + p.mha.bo, a.ln1.z, d, true, false, Ms, d, d, st));
+    RC(residual_ln(m, a.ln1.z, w.enc_x32[l], p.ln1g, p.ln1b, a.out1_32, a.out1_16, a.ln1, Ms, site_enc(l, 0), st));   // Encoder.py:22-23
+    // point_wise_feed_forward_network (point_ffn.py:3-7)
+    RC(linear_fwd(a.out1_16, d, Sh + p.ffn.W1, f, m->P + p.ffn.b1, a.h, f, false, true, Ms, f, d, st));
+    RC(linear_fwd(a.h, f, Sh + p.ffn.W2, d, m->P + p.ffn.b2, a.ln2.z, d, true, false, Ms, d, f, st));
+    RC(residual_ln(m, a.ln2.z, a.out1_32, p.ln2g, p.ln2b, w.enc_x32[l + 1], w.enc_x16[l + 1], a.ln2, Ms, site_enc(l, 1), st));   // Encoder.py:26-27
+  }
+  const bf16* enc_out16 = w.enc_x16[L];
+
+  // ---------------- decoder (Decoder.py:59-79) ----------------
+  RC(bx::embed_fwd(reinterpret_cast<const long long*>(m->tar), m->tar_stride, m->tar_offset, m->P + lo.dec_emb, m->pos_tgt, w.dec_x32[0],
+                   w.dec_x16[0], Mt, T, d, lo.Vtgt, rate, m->seed, site_dec_embed(), st));
+  const MaskSpec sm = dec_self_mask(m), cm = dec_cross_mask(m);
+  for (int l = 0; l < L; ++l) {
+    const DecLayerP& p = lo.dec[l];
+    DecAct& a = w.dec[l];
+    // mha1: look-ahead-masked self attention (Decoder.py:29-31)
+    RC(linear_fwd(w.dec_x16[l], d, Sh + p.mha1.Wqkv, 3 * d, m->P + p.mha1.bqkv, a.qkv1, 3 * d, false, false, Mt, 3 * d, d, st));
+    RC(bx::attn_fwd(a.qkv1, 3 * d, a.qkv1 + d, 3 * d, a.qkv1 + 2 * d, 3 * d, a.attn1_o, d, a.lse1, sm.kpad, sm.causal, sm.maskf, sm.sb,
+                    sm.sq, B, H, T, T, dk, st));
+    RC(linear_fwd(a.attn1_o, d, Sh + p.mha1.Wo, d, m->P + p.mha1.bo, a.ln1.z, d, true, false, Mt, d, d, st));
+    RC(residual_ln(m, a.ln1.z, w.dec_x32[l], p.ln1g, p.ln1b, a.out1_32, a.out1_16, a.ln1, Mt, site_dec(l, 0), st));
+    // mha2: q from the decoder stream, k = v = enc_output, encoder padding mask (Decoder.py:33-36)
+    RC(linear_fwd(a.out1_16, d, Sh + p.mha2.Wq, d, m->P + p.mha2.bq, a.q2, d, false, false, Mt, d, d, st));
+    RC(linear_fwd(enc_out16, d, Sh + p.mha2.Wkv, 2 * d, m->P + p.mha2.bkv, a.kv2, 2 * d, false, false, Ms, 2 * d, d, st));
+    RC(bx::attn_fwd(a.q2, d, a.kv2, 2 * d, a.kv2 + d, 2 * d, a.attn2_o, d, a.lse2, cm.kpad, cm.causal, cm.maskf, cm.sb, cm.sq, B, H, T, S,
+                    dk, st));
+    RC(linear_fwd(a.attn2_o, d, Sh + p.mha2.Wo, d, m->P + p.mha2.bo, a.ln2.z, d, true, false, Mt, d, d, st));
+    RC(residual_ln(m, a.ln2.z, a.out1_32, p.ln2g, p.ln2b, a.out2_32, a.out2_16, a.ln2, Mt, site_dec(l, 1), st));
+    // ffn (Decoder.py:38-40)
+    RC(linear_fwd(a.out2_16, d, Sh + p.ffn.W1, f, m->P + p.ffn.b1, a.h, f, false, true, Mt, f, d, st));
+    RC(linear_fwd(a.h, f, Sh + p.ffn.W2, d, m->P + p.ffn.b2, a.ln3.z, d, true, false, Mt, d, f, st));
+    RC(residual_ln(m, a.ln3.z, a.out2_32, p.ln3g, p.ln3b, w.dec_x32[l + 1], w.dec_x16[l + 1], a.ln3, Mt, site_dec(l, 2), st));
+  }
+  // ---------------- final_layer (Transformer.py:30) ----------------
+  if (logits_out != nullptr)
+    RC(linear_fwd(w.dec_x16[L], d, Sh + lo.Wf, lo.Vp, m->P + lo.bf, logits_out, ld_logits, true, false, Mt, lo.Vtgt, d, st));
+  else
+    RC(linear_fwd(w.dec_x16[L], d, Sh + lo.Wf, lo.Vp, m->P + lo.bf, w.logits, lo.Vp, false, false, Mt, lo.Vtgt, d, st));
+  return 0;
+}
+
+// LayerNorm + dropout + residual backward: g_in (gradient of the LN output) -> g_out (gradient of z, i.e. of the
+// residual input) and dy16 (gradient of the sublayer output, bf16)
+int residual_ln_back(M* m, const float* g_in, const LnSave& s, int64_t g_off, int64_t b_off, float* g_out, int64_t rows, uint32_t site,
+                     cudaStream_t st) {
+  const float rate = m->training ? m->cfg.dropout_rate : 0.f;
+  return bx::residual_ln_bwd(g_in, s.z, s.mean, s.rstd, m->P + g_off, g_out, m->w.dy16, m->G + g_off, m->G + b_off, rows, m->lo.d, rate,
+                             m->seed, site, st);
+}
+
+// FFN backward: dy16 = d(ffn output); x16 = ffn input; accumulates d(input) into g (fp32)
+int ffn_back(M* m, const Ffn& p, const bf16* x16, const bf16* h, float* g, int64_t rows, cudaStream_t st) {
+  const int d = m->lo.d, f = m->lo.f;
+  Work& w = m->w;
+  RC(linear_wgrad(h, f, w.dy16, d, m->G + p.W2, d, m->G + p.b2, rows, d, f, st));
+  RC(linear_dgrad(w.dy16, d, m->Sh + p.W2, d, w.dh, f, false, false, h, f, rows, d, f, st));     // dh = (dy . W2^T) o [h > 0]
+  RC(linear_wgrad(x16, d, w.dh, f, m->G + p.W1, f, m->G + p.b1, rows, f, d, st));
+  RC(linear_dgrad(w.dh, f, m->Sh + p.W1, f, g, d, true, true, nullptr, 0, rows, f, d, st));
+  return 0;
+}
+
+// self-attention block backward (packed QKV).  dy16 = d(out-projection output); accumulates d(x) into g.
+int self_attn_back(M* m, const MhaSelf& p, const bf16* x16, const bf16* qkv, const bf16* attn_o, const float* lse, const MaskSpec& mk,
+                   float* g, int S, cudaStream_t st) {
+  const int d = m->lo.d, H = m->lo.H, dk = d / H, B = m->B;
+  const int64_t rows = (int64_t)B * S;
+  Work& w = m->w;
+  RC(linear_wgrad(attn_o, d, w.dy16, d, m->G + p.Wo, d, m->G + p.bo, rows, d, d, st));
+  RC(linear_dgrad(w.dy16, d, m->Sh + p.Wo, d, w.dO16, d, false, false, nullptr, 0, rows, d, d, st));
+  RC(bx::attn_delta(attn_o, d, w.dO16, d, w.delta, B, S, H, dk, st));
+  BX_CHECK_CUDA(cudaMemsetAsync(w.dq_acc, 0, rows * d * sizeof(float), st));
+  RC(bx::attn_bwd(qkv, 3 * d, qkv + d, 3 * d, qkv + 2 * d, 3 * d, w.dO16, d, lse, w.delta, w.dq_acc, d, w.dqkv + d, 3 * d, w.dqkv + 2 * d,
+                  3 * d, mk.kpad, mk.causal, mk.maskf, mk.sb, mk.sq, B, H, S, S, dk, st));
+  RC(bx::cast_f32_bf16_strided(w.dq_acc, w.dqkv, rows, d, 3 * d, st));
+  RC(linear_wgrad(x16, d, w.dqkv, 3 * d, m->G + p.Wqkv, 3 * d, m->G + p.bqkv, rows, 3 * d, d, st));
+  RC(linear_dgrad(w.dqkv, 3 * d, m->Sh + p.Wqkv, 3 * d, g, d, true, true, nullptr, 0, rows, 3 * d, d, st));
+  return 0;
+}
+
+int backward_final(M* m, cudaStream_t st) {
+  const Layout& lo = m->lo;
+  Work& w = m->w;
+  const int d = lo.d, L = lo.L;
+  const int64_t Mt = (int64_t)m->B * m->T;
+  // dlogits (bf16, in w.logits) -> final_layer grads and d(dec_output) in gA
+  RC(linear_wgrad(w.dec_x16[L], d, w.logits, lo.Vp, m->G + lo.Wf, lo.Vp, m->G + lo.bf, Mt, lo.Vtgt, d, st));
+  RC(linear_dgrad(w.logits, lo.Vp, m->Sh + lo.Wf, lo.Vp, w.gA, d, true, false, nullptr, 0, Mt, lo.Vtgt, d, st));
+  return 0;
+}
+
+int backward_decoder(M* m, cudaStream_t st) {
+  const Layout& lo = m->lo;
+  Work& w = m->w;
+  const int d = lo.d, H = lo.H, L = lo.L, dk = d / H;
+  const int B = m->B, S = m->S, T = m->T;
+  const int64_t Ms = (int64_t)B * S, Mt = (int64_t)B * T;
+  const float rate = m->training ? m->cfg.dropout_rate : 0.f;
+  const MaskSpec sm = dec_self_mask(m), cm = dec_cross_mask(m);
+  BX_CHECK_CUDA(cudaMemsetAsync(w.d_enc_out, 0, Ms * d * sizeof(float), st));
+  float* g_in = w.gA;    // gradient of the current layer's output
+  float* g_out = w.gB;
+  for (int l = L - 1; l >= 0; --l) {
+    const DecLayerP& p = lo.dec[l];
+    DecAct& a = w.dec[l];
+    // out3 = LN3(out2 + drop(ffn(out2)))
+    RC(residual_ln_back(m, g_in, a.ln3, p.ln3g, p.ln3b, g_out, Mt, site_dec(l, 2), st));
+    RC(ffn_back(m, p.ffn, a.out2_16, a.h, g_out, Mt, st));
+    std::swap(g_in, g_out);
+    // out2 = LN2(out1 + drop(mha2(enc_out, enc_out, out1)))
+    RC(residual_ln_back(m, g_in, a.ln2, p.ln2g, p.ln2b, g_out, Mt, site_dec(l, 1), st));
+    RC(linear_wgrad(a.attn2_o, d, w.dy16, d, m->G + p.mha2.Wo, d, m->G + p.mha2.bo, Mt, d, d, st));
+    RC(linear_dgrad(w.dy16, d, m->Sh + p.mha2.Wo, d, w.dO16, d, false, false, nullptr, 0, Mt, d, d, st));
+    RC(bx::attn_delta(a.attn2_o, d, w.dO16, d, w.delta, B, T, H, dk, st));
+    BX_CHECK_CUDA(cudaMemsetAsync(w.dq_acc, 0, Mt * d * sizeof(float), st));
+    // dK/dV of the encoder memory go to dqkv[:, 0:2d) viewed as [Ms, 2d]
+    RC(bx::attn_bwd(a.q2, d, a.kv2, 2 * d, a.kv2 + d, 2 * d, w.dO16, d, a.lse2, w.delta, w.dq_acc, d, w.dqkv, 2 * d, w.dqkv + d, 2 * d,
+                    cm.kpad, cm.causal, cm.maskf, cm.sb, cm.sq, B, H, T, S, dk, st));
+    RC(linear_wgrad(w.enc_x16[L], d, w.dqkv, 2 * d, m->G + p.mha2.Wkv, 2 * d, m->G + p.mha2.bkv, Ms, 2 * d, d, st));
+    RC(linear_dgrad(w.dqkv, 2 * d, m->Sh + p.mha2.Wkv, 2 * d, w.d_enc_out, d, true, true, nullptr, 0, Ms, 2 * d, d, st));
+    RC(bx::cast_f32_bf16(w.dq_acc, w.dO16, Mt * d, st));   // dq2 (bf16) reuses dO16
+    RC(linear_wgrad(a.out1_16, d, w.dO16, d, m->G + p.mha2.Wq, d, m->G + p.mha2.bq, Mt, d, d, st));
+    RC(linear_dgrad(w.dO16, d, m->Sh + p.mha2.Wq, d, g_out, d, true, true, nullptr, 0, Mt, d, d, st));
+    std::swap(g_in, g_out);
+    // out1 = LN1(x + drop(mha1(x, x, x)))
+    RC(residual_ln_back(m, g_in, a.ln1, p.ln1g, p.ln1b, g_out, Mt, site_dec(l, 0), st));
+    RC(self_attn_back(m, p.mha1, w.dec_x16[l], a.qkv1, a.attn1_o, a.lse1, sm, g_out, T, st));
+    std::swap(g_in, g_out);
+  }
+  RC(bx::embed_bwd(reinterpret_cast<const long long*>(m->tar), m->tar_stride, m->tar_offset, g_in, m->G + lo.dec_emb, Mt, T, d, lo.Vtgt,
+                   rate, m->seed, site_dec_embed(), st));
+  return 0;
+}
+
+int backward_encoder(M* m, cudaStream_t st) {
+  const Layout& lo = m->lo;
+  Work& w = m->w;
+  const int d = lo.d, L = lo.L;
+  const int B = m->B, S = m->S;
+  const int64_t Ms = (int64_t)B * S;
+  const float rate = m->training ? m->cfg.dropout_rate : 0.f;
+  const MaskSpec em = enc_self_mask(m);
+  float* g_in = w.d_enc_out;
+  float* g_out = w.gA;
+  float* spare = w.gB;
+  for (int l = L - 1; l >= 0; --l) {
+    const EncLayerP& p = lo.enc[l];
+    EncAct& a = w.enc[l];
+    RC(residual_ln_back(m, g_in, a.ln2, p.ln2g, p.ln2b, g_out, Ms, site_enc(l, 1), st));
+    RC(ffn_back(m, p.ffn, a.out1_16, a.h, g_out, Ms, st));
+    { float* t = g_in; g_in = g_out; g_out = (t == w.d_enc_out) ? spare : t; }
+    RC(residual_ln_back(m, g_in, a.ln1, p.ln1g, p.ln1b, g_out, Ms, site_enc(l, 0), st));
+    RC(self_attn_back(m, p.mha, w.enc_x16[l], a.qkv, a.attn_o, a.lse, em, g_out, S, st));
+    std::swap(g_in, g_out);
+  }
+  RC(bx::embed_bwd(reinterpret_cast<const long long*>(m->inp), S, 0, g_in, m->G + lo.enc_emb, Ms, S, d, lo.Vin, rate, m->seed,
+                   site_enc_embed(), st));
+  return 0;
+}
+
+}  // namespace
+
+// ====================================================================================================
+// C ABI
+// ====================================================================================================
+extern "C" {
+
+int64_t b200xf_model_param_count(const b200xf_model_config* cfg) {
+  if (validate(*cfg)) return -1;
+  return make_layout(*cfg).total;
+}
+int64_t b200xf_model_workspace_bytes(const b200xf_model_config* cfg) {
+  if (validate(*cfg)) return -1;
+  Layout lo = make_layout(*cfg);
+  return make_work(*cfg, lo, nullptr).bytes;
+}
+int b200xf_model_variable(const b200xf_model_config* cfg, int index, char* name, int name_cap, int64_t* offset, int64_t* rows,
+                          int64_t* cols, int64_t* ld) {
+  RC(validate(*cfg));
+  Layout lo = make_layout(*cfg);
+  if (index < 0 || index >= (int)lo.vars.size()) return 1;
+  const VarView& v = lo.vars[index];
+  if (name && name_cap > 0) { strncpy(name, v.name.c_str(), name_cap - 1); name[name_cap - 1] = 0; }
+  *offset = v.off; *rows = v.rows; *cols = v.cols; *ld = v.ld;
+  return 0;
+}
+int b200xf_model_grad_range(const b200xf_model_config* cfg, int stage, int64_t* begin, int64_t* end) {
+  RC(validate(*cfg));
+  BX_REQUIRE(stage >= 0 && stage < 3, "grad_range: stage must be 0..2");
+  Layout lo = make_layout(*cfg);
+  *begin = lo.stage_begin[stage]; *end = lo.stage_end[stage];
+  return 0;
+}
+int b200xf_model_create(const b200xf_model_config* cfg, float* params, float* grads, float* adam_m, float* adam_v, void* shadow,
+                        const float* pos_in, const float* pos_tgt, void* workspace, b200xf_model** out) {
+  RC(validate(*cfg));
+  BX_REQUIRE(params && grads && shadow && pos_in && pos_tgt && workspace && out, "model_create: null buffer");
+  BX_REQUIRE((reinterpret_cast<uintptr_t>(params) & 255) == 0 && (reinterpret_cast<uintptr_t>(grads) & 255) == 0 &&
+                 (reinterpret_cast<uintptr_t>(shadow) & 255) == 0 && (reinterpret_cast<uintptr_t>(workspace) & 1023) == 0,
+             "model_create: arenas must be 256-byte aligned, workspace 1024-byte aligned");
+  b200xf_model* m = new b200xf_model();
+  m->cfg = *cfg;
+  m->lo = make_layout(*cfg);
+  m->w = make_work(*cfg, m->lo, workspace);
+  m->P = params; m->G = grads; m->Am = adam_m; m->Av = adam_v; m->Sh = reinterpret_cast<bf16*>(shadow);
+  m->pos_in = pos_in; m->pos_tgt = pos_tgt;
+  *out = m;
+  return 0;
+}
+void b200xf_model_destroy(b200xf_model* m) { delete m; }
+
+int b200xf_model_sync_shadow(b200xf_model* m, b200xf_stream_t stream) {
+  return bx::cast_f32_bf16(m->P, m->Sh, m->lo.total, reinterpret_cast<cudaStream_t>(stream));
+}
+
+int b200xf_model_forward(b200xf_model* m, const int64_t* inp, const int64_t* tar, int tar_stride, int tar_offset, int B, int S, int T,
+                         int training, uint64_t seed, const float* enc_mask, const float* look_ahead_mask, int64_t la_batch_stride,
+                         const float* dec_mask, float* logits_out, int64_t ld_logits, b200xf_stream_t stream) {
+  BX_REQUIRE(B >= 1 && B <= m->cfg.max_batch && S >= 1 && S <= m->cfg.max_src_len && T >= 1 && T <= m->cfg.max_tgt_len,
+             "forward: shape (B %d, S %d, T %d) exceeds the workspace (%d, %d, %d)", B, S, T, m->cfg.max_batch, m->cfg.max_src_len,
+             m->cfg.max_tgt_len);
+  BX_REQUIRE(tar_stride >= tar_offset + T, "forward: target stride/offset inconsistent");
+  BX_REQUIRE(logits_out == nullptr || ld_logits % 4 == 0, "forward: logits leading dimension must be a multiple of 4");
+  m->B = B; m->S = S; m->T = T; m->training = training; m->seed = seed;
+  m->inp = inp; m->tar = tar; m->tar_stride = tar_stride; m->tar_offset = tar_offset;
+  m->enc_mask = enc_mask; m->la_mask = look_ahead_mask; m->la_bs = la_batch_stride; m->dec_mask = dec_mask;
+  m->have_loss_grad = false;
+  m->logits_valid = logits_out == nullptr;
+  return forward_impl(m, logits_out, ld_logits, reinterpret_cast<cudaStream_t>(stream));
+}
+
+int b200xf_model_loss(b200xf_model* m, const int64_t* tar, int tar_stride, int label_offset, float inv_batch, double* stats, int with_grad,
+                      b200xf_stream_t stream) {
+  BX_REQUIRE(m->B > 0 && m->logits_valid, "loss: needs a preceding forward with logits_out == NULL (and no loss-with-grad since)");
+  const int64_t Mt = (int64_t)m->B * m->T;
+  RC(bx::xent(m->w.logits, 0, m->lo.Vp, reinterpret_cast<const long long*>(tar), tar_stride, label_offset, m->T,
+              with_grad ? m->w.logits : nullptr, m->lo.Vp, nullptr, stats, Mt, m->lo.Vtgt, inv_batch, reinterpret_cast<cudaStream_t>(stream)));
+  m->have_loss_grad = with_grad != 0;
+  if (with_grad) m->logits_valid = false;
+  return 0;
+}
+
+int b200xf_model_backward(b200xf_model* m, int stage, b200xf_stream_t stream) {
+  BX_REQUIRE(m->have_loss_grad, "backward: call b200xf_model_loss(with_grad=1) after a training forward first");
+  BX_REQUIRE(stage >= -1 && stage <= 2, "backward: stage must be -1..2");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (stage == -1 || stage == 0) RC(backward_final(m, st));
+  if (stage == -1 || stage == 1) RC(backward_decoder(m, st));
+  if (stage == -1 || stage == 2) RC(backward_encoder(m, st));
+  return 0;
+}
+
+int b200xf_model_attention_weights(b200xf_model* m, int layer, int block, float* P, b200xf_stream_t stream) {
+  BX_REQUIRE(m->B > 0, "attention_weights: no forward has run");
+  BX_REQUIRE(layer >= 0 && layer < m->lo.L && (block == 1 || block == 2), "attention_weights: bad layer/block");
+  const int d = m->lo.d, H = m->lo.H, dk = d / H;
+  const DecAct& a = m->w.dec[layer];
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (block == 1) {
+    const MaskSpec mk = dec_self_mask(m);
+    return bx::attn_probs(a.qkv1, 3 * d, a.qkv1 + d, 3 * d, a.lse1, P, mk.kpad, mk.causal, mk.maskf, mk.sb, mk.sq, m->B, H, m->T, m->T, dk, st);
+  }
+  const MaskSpec mk = dec_cross_mask(m);
+  return bx::attn_probs(a.q2, d, a.kv2, 2 * d, a.lse2, P, mk.kpad, mk.causal, mk.maskf, mk.sb, mk.sq, m->B, H, m->T, m->S, dk, st);
+}
+
+int b200xf_model_tap(b200xf_model* m, const char* name, float* out, b200xf_stream_t stream) {
+  BX_REQUIRE(m->B > 0, "tap: no forward has run");
+  const int d = m->lo.d, L = m->lo.L;
+  const float* src = nullptr;
+  int64_t rows = 0;
+  int idx = -1;
+  if (!strcmp(name, "enc_embed")) { src = m->w.enc_x32[0]; rows = (int64_t)m->B * m->S; }
+  else if (!strcmp(name, "dec_embed")) { src = m->w.dec_x32[0]; rows = (int64_t)m->B * m->T; }
+  else if (sscanf(name, "enc_layer%d", &idx) == 1 && idx >= 0 && idx < L) { src = m->w.enc_x32[idx + 1]; rows = (int64_t)m->B * m->S; }
+  else if (sscanf(name, "dec_layer%d", &idx) == 1 && idx >= 0 && idx < L) { src = m->w.dec_x32[idx + 1]; rows = (int64_t)m->B * m->T; }
+  BX_REQUIRE(src != nullptr, "tap: unknown activation '%s'", name);
+  BX_CHECK_CUDA(cudaMemcpyAsync(out, src, rows * d * sizeof(float), cudaMemcpyDeviceToDevice, reinterpret_cast<cudaStream_t>(stream)));
+  return 0;
+}
+
+}  // extern "C"
