@@ -1,0 +1,253 @@
+"""bench.py -- tokens/sec of one full training step (forward + loss + backward + gradient all-reduce + Adam) of
+transformer-base at seq_len 512 (BASELINE.json's metric; config C3), on N GPUs of one node.
+
+    python bench.py --gpus 1 --steps 20 --warmup 5
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P bench.py --gpus N ...
+    python bench.py --impl reference ...     # the reference's own CPU path (oracle restatement; TF2 is not installable)
+
+One JSON line on rank 0.  `value` = whole-job target tokens/s with inputs resident in HBM (CUDA events, max over
+ranks); `e2e` = the same step driven through the public API from pinned HOST batches with the loss read back every
+step; `roofline` = achieved/peak of the tcgen05 GEMM kernel measured live with CUDA events around every launch;
+`cpu_baseline` = the oracle on this box's host cores on a bounded sample.  Weak scaling: 64 sequences per GPU.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+CONFIGS = {
+    # name: (layers, d_model, heads, dff, vocab, seq_len, per-GPU batch)
+    "base_s512_b64": (6, 512, 8, 2048, 32768, 512, 64),     # BASELINE.json configs[2] -- the metric's "seq512"
+    "base_s128_b256": (6, 512, 8, 2048, 32768, 128, 256),   # configs[1]
+    "big_s256_b16": (6, 1024, 16, 4096, 32768, 256, 16),    # configs[3] per-GPU share of the global batch 128
+    "tiny_s40_b32": (2, 128, 4, 512, 8192, 40, 32),         # configs[0] shape (synthetic tokens)
+}
+
+
+def step_flops(L, d, f, V, B, S):
+    """3 * [L*(24BSd^2 + 12BS^2d + 8BSdf) + 2BSdV]  (S = T)."""
+    return 3.0 * (L * (24.0 * B * S * d * d + 12.0 * B * S * S * d + 8.0 * B * S * d * f) + 2.0 * B * S * d * V)
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        j = json.load(open(p))
+        return dict(src="measured", hbm=j["hbm_gbs"], tf_burst=j["bf16_tflops"], tf_sustained=j.get("bf16_tflops_sustained", j["bf16_tflops"]))
+    return dict(src="fallback", hbm=6650.0, tf_burst=1590.0, tf_sustained=1400.0)
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+
+    def __init__(self, index):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+            "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append((time.time(), line.strip()))
+
+    def stop(self, t0, t1):
+        if self.proc is None:
+            return None
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], 0, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for t, line in self.lines:
+            if t < t0 or t > t1 + 0.2:
+                continue
+            parts = [p.strip() for p in line.split(",")]
+            try:
+                sm.append(float(parts[0])); mx = max(mx, float(parts[1]))
+                for n, v in zip(names, parts[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(n)
+            except Exception:
+                pass
+        if not sm:
+            return None
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def cpu_reference_run(cfg_name, steps, warmup, sample_batch):
+    """The reference's CPU path: oracle restatement (torch-CPU fp32, eager, unfused, materialising P and logits like
+    Attention.py:20-32 / Transformer.py:30), all host threads, a bounded sample of the workload."""
+    import torch
+    from oracle import restatement as R
+    L_, d, H, f, V, S, _ = CONFIGS[cfg_name]
+    cores = len(os.sched_getaffinity(0))
+    torch.set_num_threads(cores)
+    cfg = R.make_cfg(L_, d, H, f, V, V, rate=0.0, max_position=S + 1)
+    P = R.init_params(L_, d, f, V, V, seed=42)
+    st = R.AdamState(P)
+    src, tar = R.synthetic_batch(sample_batch, S, S + 1, V, V, seed=1234)
+    for _ in range(warmup):
+        R.train_step(P, cfg, st, src, tar, sample_batch)
+    t0 = time.time()
+    for _ in range(steps):
+        R.train_step(P, cfg, st, src, tar, sample_batch)
+    dt = (time.time() - t0) / max(1, steps)
+    return dict(value=sample_batch * S / dt, unit="tokens/s", cores=cores, kind="port",
+                sample=f"{steps} full train steps (fwd+loss+bwd+Adam) of {cfg_name} at batch {sample_batch} (of {CONFIGS[cfg_name][6]}), torch-CPU fp32 oracle; TF2 not installable"), dt
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--config", default="base_s512_b64", choices=sorted(CONFIGS))
+    ap.add_argument("--dropout_rate", type=float, default=0.1)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    L_, d, H, f, V, S, Bper = CONFIGS[args.config]
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    N = max(args.gpus, 1)
+    config = {"workload": f"transformer-base train step {args.config}: {L_}L d{d} {H}h dff{f} V{V} seq_len {S}, {Bper} sequences per GPU"
+                          f" (global batch {Bper * N}), synthetic tokens, dropout {args.dropout_rate}",
+              "global_batch": Bper * N, "seq_len": S, "parallelism": f"dp{N}",
+              "l2": "per-step working set (activations+weights+grads >> 126 MB L2) is larger than L2; no explicit flush"}
+
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        steps = max(1, min(args.steps, 3)); warm = max(1, min(args.warmup, 1))
+        base, dt = cpu_reference_run(args.config, steps, warm, sample_batch=2)
+        line = {"impl": "reference", "metric": "tokens/sec (target positions) of one training step", "value": base["value"], "unit": "tokens/s",
+                "n_gpus": N, "steps": steps, "warmup": warm, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config, "cpu_baseline": base,
+                "e2e": {"value": base["value"], "unit": "tokens/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                "gpu_launches": 0}
+        print(json.dumps(line))
+        return
+
+    import torch
+    import torch.distributed as dist
+    from transformer_b200 import _lib as lib
+    from transformer_b200.Transformer import Transformer
+    from transformer_b200.distributed_train import DistributedTrain, init_process_group_from_env
+    from transformer_b200.utils import synthetic_batch
+
+    rank, local, world = init_process_group_from_env("nccl")
+    assert world == N or world == 1 and N == 1, f"--gpus {N} but WORLD_SIZE {world}"
+    dev = torch.device(f"cuda:{local}")
+    torch.cuda.set_device(dev)
+    model = Transformer(L_, d, H, f, V, V, rate=args.dropout_rate, device=dev, max_batch=Bper, max_src_len=S, max_tgt_len=S, pos_rows=S + 1)
+    trainer = DistributedTrain(1, True, model, None, None, Bper * N, Bper, None, None, 5, "ckpt", d)
+    # per-rank synthetic batches (pinned host memory); a few distinct ones are cycled
+    nb = 4
+    host = []
+    for i in range(nb):
+        s, t = synthetic_batch(Bper, S, S + 1, V, V, seed=1234 + 1000 * rank + i)
+        host.append((s.pin_memory(), t.pin_memory()))
+    resident = [(s.to(dev), t.to(dev)) for s, t in host]
+    h2d = host[0][0].numel() * 8 + host[0][1].numel() * 8
+    d2h = 4 * 8
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(steps):
+            fn(i)
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return ms.item()
+
+    def step_resident(i):
+        trainer.train_step(resident[i % nb])
+
+    stats_host = torch.zeros(4, dtype=torch.float64).pin_memory()
+
+    def step_e2e(i):
+        s, t = host[i % nb]
+        trainer.train_step((s.to(dev, non_blocking=True), t.to(dev, non_blocking=True)))
+        stats_host.copy_(trainer._stats, non_blocking=True)          # loss sum + accuracy counters of this step
+        torch.cuda.current_stream().synchronize()                    # the caller reads the loss every step
+
+    for i in range(max(3, args.warmup)):
+        step_resident(i)
+    barrier()
+    # ---- timed: resident inputs, live per-launch event timing of the tensor-core kernels ----
+    sampler = ClockSampler(local) if rank == 0 else None
+    launches0 = lib.launch_count()
+    lib.load().b200xf_prof_enable(1)
+    if sampler:
+        sampler.start()
+        time.sleep(0.3)
+    t0 = time.time()
+    ms_total = timed(step_resident, args.steps)
+    t1 = time.time()
+    clocks = sampler.stop(t0, t1) if sampler else None
+    lib.load().b200xf_prof_enable(0)
+    import ctypes as C
+    prof = (C.c_double * 9)()
+    lib.load().b200xf_prof_collect(prof, 3)
+    launches = lib.launch_count() - launches0
+    ms_step = ms_total / args.steps
+    tokens_step = Bper * N * S
+    value = tokens_step / (ms_step * 1e-3)
+    # ---- e2e: host batches in, loss out, every step ----
+    for i in range(2):
+        step_e2e(i)
+    ms_e2e = timed(step_e2e, args.steps) / args.steps
+    e2e_value = tokens_step / (ms_e2e * 1e-3)
+    loss_per_tok = float(stats_host[0]) / max(1.0, float(stats_host[3]))
+
+    if rank == 0:
+        peaks = measured_peaks()
+        gemm_ms, gemm_fl, gemm_n = prof[0], prof[1], prof[2]
+        ach = gemm_fl / (gemm_ms * 1e-3) / 1e12 if gemm_ms > 0 else 0.0
+        roof = {"bound": "tensor", "kernel": "bx::gemm_kernel (tcgen05 GEMM, all launches of the step: FFN, projections, vocab, dgrad, wgrad)",
+                "achieved": ach, "peak": peaks["tf_sustained"], "unit": "TFLOP/s", "frac": ach / peaks["tf_sustained"],
+                "peak_source": f"{peaks['src']} MEASURED_PEAKS.json bf16_tflops_sustained (kernel timed inside a long step)",
+                "traffic": None, "launches_per_step": gemm_n / args.steps, "share_of_step": gemm_ms / ms_total,
+                "attention_fwd": {"achieved": prof[4] / (prof[3] * 1e-3) / 1e12 if prof[3] > 0 else 0.0, "unit": "TFLOP/s (dense 4.B.H.Sq.Sk.dk)",
+                                  "share_of_step": prof[3] / ms_total},
+                "attention_bwd": {"achieved": prof[7] / (prof[6] * 1e-3) / 1e12 if prof[6] > 0 else 0.0, "unit": "TFLOP/s (dense)",
+                                  "share_of_step": prof[6] / ms_total},
+                "step_model_flops_tflops": step_flops(L_, d, f, V, Bper, S) / (ms_step * 1e-3) / 1e12}
+        line = {"metric": "tokens/sec (target positions) of one training step", "value": value, "unit": "tokens/s", "n_gpus": N, "steps": args.steps,
+                "warmup": max(3, args.warmup), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "bf16 operands / f32 accumulate, f32 master weights", "data": "synthetic", "config": config,
+                "e2e": {"value": e2e_value, "unit": "tokens/s", "ms_per_step": ms_e2e, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+                "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "loss_per_token": loss_per_tok}
+        if N == 1 and not args.no_cpu_baseline:
+            base, _ = cpu_reference_run(args.config, 2, 1, sample_batch=2)
+            line["cpu_baseline"] = base
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

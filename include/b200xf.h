@@ -26,6 +26,11 @@ const char* b200xf_last_error(void);
 int b200xf_version(void);
 /* number of kernels this library has launched on this process so far (bench.py's gpu_launches) */
 long long b200xf_launch_count(void);
+/* optional CUDA-event timing of every tensor-core kernel launch (used by bench.py for the live roofline numbers):
+ * categories 0 = GEMM, 1 = attention forward, 2 = attention backward; after synchronising the stream,
+ * b200xf_prof_collect fills out[cat*3 + {0,1,2}] = {total ms, total algorithmic flops, launches} and resets. */
+void b200xf_prof_enable(int on);
+int b200xf_prof_collect(double* out, int ncat);
 
 /* ---- dense contractions: keras Dense (Attention.py:62-64,77; point_ffn.py:5-6; Transformer.py:30) and their
  *      reverse-mode gradients (train.py:137).  D[M,N] (+)= epi(A[M,K] . B[K,N]).

@@ -1,0 +1,163 @@
+"""CPU-only checks of the host side: the C-ABI library loads and exports every declared symbol, the parameter-arena
+layout matches keras' trainable_variables order (oracle), schedule / flags / replica-split logic, and the N>1
+gradient-bucket all-reduce on world_size-2 gloo.  No compute entry point is called (no GPU here)."""
+import ctypes as C
+import os
+import re
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from oracle import restatement as R
+from transformer_b200 import _lib as L
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_loads_and_exports_every_declared_symbol():
+    lib = L.load()
+    header = open(os.path.join(ROOT, "include", "b200xf.h")).read()
+    declared = set(re.findall(r"\b(b200xf_[a-z0-9_]+)\s*\(", header))
+    declared -= {"b200xf_stream_t"}
+    assert len(declared) >= 30
+    for name in sorted(declared):
+        assert hasattr(lib, name), f"{name} declared in include/b200xf.h but not exported"
+    assert set(L.EXPORTED_SYMBOLS) == declared, set(L.EXPORTED_SYMBOLS) ^ declared
+    assert lib.b200xf_version() >= 100 and lib.b200xf_launch_count() == 0
+
+
+def _cfg(Lyr=2, d=128, H=2, f=256, Vin=1003, Vtgt=1009):
+    return L.ModelConfig(Lyr, d, H, f, Vin, Vtgt, 4, 64, 64, 128, 0.1, 1e-6)
+
+
+def _variables(cfg):
+    lib = L.load()
+    out = []
+    name = C.create_string_buffer(128)
+    off, rows, cols, ld = C.c_int64(), C.c_int64(), C.c_int64(), C.c_int64()
+    i = 0
+    while lib.b200xf_model_variable(C.byref(cfg), i, name, 128, C.byref(off), C.byref(rows), C.byref(cols), C.byref(ld)) == 0:
+        out.append((name.value.decode(), off.value, rows.value, cols.value, ld.value))
+        i += 1
+    return out
+
+
+def test_arena_layout_matches_keras_variable_order():
+    cfg = _cfg()
+    vs = _variables(cfg)
+    assert [v[0] for v in vs] == R.variable_names(2)
+    n = L.load().b200xf_model_param_count(C.byref(cfg))
+    used = np.zeros(n, dtype=np.int32)
+    for name, off, rows, cols, ld in vs:
+        shape = R.variable_shape(name, 128, 256, 1003, 1009)
+        assert shape == ((rows, cols) if cols else (rows,)), name
+        assert off % 4 == 0 and (cols == 0 or ld % 4 == 0)
+        for r in range(rows if cols else 1):
+            a = off + r * ld
+            used[a:a + (cols if cols else rows)] += 1
+    assert used.max() == 1                                   # views never overlap
+    # every logical parameter is inside exactly one of the three backward stages, and stages tile the arena
+    lib = L.load()
+    rng = []
+    for s in range(3):
+        b, e = C.c_int64(), C.c_int64()
+        assert lib.b200xf_model_grad_range(C.byref(cfg), s, C.byref(b), C.byref(e)) == 0
+        rng.append((b.value, e.value))
+    assert sorted(rng)[0][0] == 0 and sorted(rng)[-1][1] == n
+    assert sorted(rng)[0][1] == sorted(rng)[1][0] and sorted(rng)[1][1] == sorted(rng)[2][0]
+    fl = [v for v in vs if v[0].startswith("final_layer")]
+    assert all(rng[0][0] <= v[1] < rng[0][1] for v in fl)
+
+
+def test_param_count_base_and_errors():
+    cfg = L.ModelConfig(6, 512, 8, 2048, 32768, 32768, 64, 512, 512, 1024, 0.1, 1e-6)
+    n = L.load().b200xf_model_param_count(C.byref(cfg))
+    assert abs(n - 94.50e6) < 0.02e6                          # SURVEY Appendix B (+ alignment padding)
+    assert L.load().b200xf_model_workspace_bytes(C.byref(cfg)) > 1e9
+    bad = L.ModelConfig(2, 100, 3, 256, 10, 10, 1, 8, 8, 8, 0.1, 1e-6)      # d_model % num_heads != 0
+    assert L.load().b200xf_model_param_count(C.byref(bad)) < 0
+    assert b"num_heads" in L.load().b200xf_last_error()
+
+
+def test_schedule_matches_oracle_and_reference_values():
+    from transformer_b200.train import CustomSchedule
+    s = CustomSchedule(512)
+    for step in (0, 1, 2, 100, 59999, 60000, 60001, 10 ** 6):
+        assert s(step) == R.custom_schedule(step, 512)
+    assert s(0) == 0.0
+    np.testing.assert_allclose(s(60000), 1.8042195e-4, rtol=1e-6)
+
+
+def test_positional_encoding_and_masks_match_oracle(golden_dir):
+    from transformer_b200 import positionalencoding as pe
+    assert np.array_equal(pe.positional_encoding(64, 8).numpy(), np.load(os.path.join(golden_dir, "posenc_64x8.npy")))
+    inp = torch.tensor([[5, 3, 0], [0, 0, 1]]); tar = torch.tensor([[2, 0], [4, 4]])
+    for a, b in zip(pe.create_masks(inp, tar), R.create_masks(inp, tar)):
+        assert torch.equal(a, b)
+
+
+def test_replica_split_and_flags():
+    from transformer_b200.distributed_train import split_replica_batch, MirroredStrategy
+    assert split_replica_batch(128, 8) == 16
+    with pytest.raises(ValueError, match="divisible"):
+        split_replica_batch(130, 8)
+    st = MirroredStrategy()
+    assert st.num_replicas_in_sync == 1
+    src = torch.arange(12).view(4, 3); tar = torch.arange(16).view(4, 4)
+    s, t = st.shard(src, tar)
+    assert torch.equal(s, src) and torch.equal(t, tar)
+    from absl import flags
+    from transformer_b200 import utils
+    if "num_layers" not in flags.FLAGS:
+        utils.transformer_flags()
+    flags.FLAGS(["prog"])
+    d = utils.flags_dict()
+    assert d["num_layers"] == 4 and d["d_model"] == 512 and d["dff"] == 1024 and d["num_heads"] == 4 and d["batch_size"] == 64
+    assert d["dropout_rate"] == 0.1 and d["sequence_length"] == 50 and d["per_replica_batch_size"] == 16
+
+
+def _free_port():
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); p = s.getsockname()[1]; s.close(); return p
+
+
+def _dp_worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from transformer_b200.distributed_train import GradientBuckets, MirroredStrategy
+    # DP-equivalence with the ORACLE's gradients pushed through the product's bucket logic (Appendix A.10):
+    cfg = R.make_cfg(1, 32, 1, 64, 37, 37, rate=0.0, max_position=16)
+    P = R.init_params(1, 32, 64, 37, 37, seed=3, perturb=True, dtype=torch.float64)
+    src, tar = R.synthetic_batch(4, 5, 7, 37, 37, pad_tail=True)
+    st = MirroredStrategy()
+    s, t = st.shard(src, tar)
+    _, g, _, _ = R.loss_and_grads(P, cfg, s, t, 4)            # per-replica loss = sum_local / B_global
+    flat = torch.cat([v.reshape(-1) for v in g.values()])
+    n = flat.numel()
+    buckets = GradientBuckets([(2 * n // 3, n), (n // 3, 2 * n // 3), (0, n // 3)])
+    for stage in range(3):
+        buckets.reduce_stage(flat, stage)
+    buckets.wait()
+    if rank == 0:
+        _, g_full, _, _ = R.loss_and_grads(P, cfg, src, tar, 4)
+        full = torch.cat([v.reshape(-1) for v in g_full.values()])
+        q.put(float((flat - full).abs().max()))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_gradient_buckets_allreduce_gloo_world2():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_dp_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    err = q.get(timeout=120)
+    for p in procs:
+        p.join(60)
+        assert p.exitcode == 0
+    assert err < 1e-10, err

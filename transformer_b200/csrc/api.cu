@@ -11,6 +11,8 @@ extern "C" {
 const char* b200xf_last_error(void) { return bx::last_error(); }
 int b200xf_version(void) { return 100; }
 long long b200xf_launch_count(void) { return bx::launch_count(); }
+void b200xf_prof_enable(int on) { bx::prof_enable(on); }
+int b200xf_prof_collect(double* out, int ncat) { return bx::prof_collect(out, ncat); }
 
 int b200xf_gemm_bf16(const void* A, int64_t lda, int a_major, const void* B, int64_t ldb, int b_major, void* D,
                      int64_t ldd, int d_is_f32, const float* bias, const void* aux, int64_t ld_aux, int flags,

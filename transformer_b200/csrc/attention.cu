@@ -641,7 +641,9 @@ static int attn_fwd_launch(const void* Q, long long ld_q, const void* K, long lo
     attr_done = true;
   }
   dim3 grid((Sq + 255) / 256, H, B);
+  void* pb = prof_on() ? prof_begin(st) : nullptr;
   kern<<<grid, ATTN_FWD_THREADS, L::BYTES, st>>>(tmQ, tmK, tmV, tmO, lse, mask, H, Sq, Sk, 1.f / sqrtf((float)DK));
+  if (pb) prof_end(pb, 1, 4.0 * B * H * (double)Sq * Sk * DK, st);     // dense count, as the reference computes it
   BX_POST_LAUNCH();
   return 0;
 }
@@ -668,8 +670,10 @@ static int attn_bwd_launch(const void* Q, long long ld_q, const void* K, long lo
     attr_done = true;
   }
   dim3 grid((Sk + 127) / 128, H, B);
+  void* pb = prof_on() ? prof_begin(st) : nullptr;
   kern<<<grid, ATTN_BWD_THREADS, L::BYTES, st>>>(tmQ, tmK, tmV, tmdO, tmdK, tmdV, lse, delta, dq_acc, ld_dq, mask, H, Sq,
                                                  Sk, 1.f / sqrtf((float)DK));
+  if (pb) prof_end(pb, 2, 8.0 * B * H * (double)Sq * Sk * DK, st);     // 2x the forward's 4.B.H.Sq.Sk.dk
   BX_POST_LAUNCH();
   return 0;
 }

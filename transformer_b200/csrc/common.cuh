@@ -34,6 +34,13 @@ long long launch_count();
     BX_CHECK_CUDA(cudaGetLastError());         \
   } while (0)
 
+// per-launch event timing (off by default); cat: 0 = GEMM, 1 = attention fwd, 2 = attention bwd; work = flops
+bool prof_on();
+void prof_enable(int on);
+void* prof_begin(cudaStream_t st);
+void prof_end(void* begin, int cat, double work, cudaStream_t st);
+int prof_collect(double* out, int ncat);
+
 #define BX_REQUIRE(cond, ...)                                                                    \
   do {                                                                                           \
     if (!(cond)) {                                                                               \

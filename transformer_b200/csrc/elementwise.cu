@@ -474,6 +474,13 @@ int residual_ln_bwd(const float* dout, const float* z, const float* mean, const 
   BX_REQUIRE(d % 4 == 0 && d <= 1024, "layernorm: need d %% 4 == 0 and d <= 1024 (got %d)", d);
   const int grid = grid_for(rows * 32, 256, 2);
   const size_t smem = (size_t)2 * 8 * d * sizeof(float);
+  if (smem > 48 * 1024) {   // only the d > 768 instantiation can exceed the default dynamic-smem limit
+    static bool attr_done = false;
+    if (!attr_done) {
+      BX_CHECK_CUDA(cudaFuncSetAttribute(residual_ln_bwd_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 8 * 1024 * 4));
+      attr_done = true;
+    }
+  }
   BX_LN_DISPATCH(residual_ln_bwd_kernel, <<<grid, 256, smem, st>>>(dout, z, mean, rstd, gamma, dz, (__nv_bfloat16*)dy_sub, dgamma,
                                                                   dbeta, rows, d, rate, seed, site))
   BX_POST_LAUNCH();

@@ -274,8 +274,10 @@ static int launch_gemm(const void* A, long long lda, const void* B, long long ld
   const long long m_tiles = (M + GEMM_BM - 1) / GEMM_BM, n_tiles = (N + BN - 1) / BN;
   const long long total = m_tiles * n_tiles * splits;
   const int grid = (int)(total < sm_count() ? total : sm_count());
+  void* pb = prof_on() ? prof_begin(stream) : nullptr;
   kern<<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, tmD, (int)M, (int)N, (int)K, splits, bias,
                                                         reinterpret_cast<const __nv_bfloat16*>(aux), ld_aux, flags);
+  if (pb) prof_end(pb, 0, 2.0 * (double)M * (double)N * (double)K, stream);
   BX_POST_LAUNCH();
   return 0;
 }

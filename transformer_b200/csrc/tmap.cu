@@ -5,6 +5,7 @@
 
 #include <atomic>
 #include <mutex>
+#include <vector>
 
 #include "common.cuh"
 
@@ -23,6 +24,47 @@ const char* last_error() { return g_err; }
 static std::atomic<long long> g_launches{0};
 void note_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 long long launch_count() { return g_launches.load(std::memory_order_relaxed); }
+
+// ---- optional per-launch CUDA-event timing of the tensor-core kernels (bench.py's live roofline numbers) ----
+struct ProfRec { cudaEvent_t e0, e1; int cat; double work; };
+static bool g_prof_on = false;
+static std::vector<ProfRec> g_prof;
+static std::vector<cudaEvent_t> g_event_pool;
+static std::mutex g_prof_mu;
+bool prof_on() { return g_prof_on; }
+void prof_enable(int on) { g_prof_on = on != 0; }
+static cudaEvent_t prof_event() {
+  if (!g_event_pool.empty()) { cudaEvent_t e = g_event_pool.back(); g_event_pool.pop_back(); return e; }
+  cudaEvent_t e = nullptr;
+  cudaEventCreate(&e);
+  return e;
+}
+void* prof_begin(cudaStream_t st) {
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  cudaEvent_t e = prof_event();
+  cudaEventRecord(e, st);
+  return e;
+}
+void prof_end(void* begin, int cat, double work, cudaStream_t st) {
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  cudaEvent_t e1 = prof_event();
+  cudaEventRecord(e1, st);
+  g_prof.push_back({reinterpret_cast<cudaEvent_t>(begin), e1, cat, work});
+}
+// out[cat*3 + {0,1,2}] = {total ms, total work (flops), launches}; call after the stream is synchronised.
+int prof_collect(double* out, int ncat) {
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  for (int i = 0; i < ncat * 3; ++i) out[i] = 0.0;
+  for (auto& r : g_prof) {
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, r.e0, r.e1) == cudaSuccess && r.cat >= 0 && r.cat < ncat) {
+      out[r.cat * 3 + 0] += ms; out[r.cat * 3 + 1] += r.work; out[r.cat * 3 + 2] += 1.0;
+    }
+    g_event_pool.push_back(r.e0); g_event_pool.push_back(r.e1);
+  }
+  g_prof.clear();
+  return 0;
+}
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,

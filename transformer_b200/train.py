@@ -1,0 +1,186 @@
+"""Mirror of the reference's train.py hot path: CustomSchedule (train.py:21-34) and Train (train.py:37-213) with the
+same constructor, method names and metric attributes -- but ``train_step`` is one fused device step:
+
+    zero grads -> forward (training=True) -> masked sparse-softmax-xent (+ accuracy counters, + dlogits)
+    -> hand-written backward -> [data-parallel: SUM all-reduce of the gradient arena] -> fused TF-form Adam
+
+Logits and attention weights are never materialised inside ``train_step`` (the reference discards the latter,
+train.py:134).  No host synchronisation happens inside a step; metrics are read back only by ``.result()``.
+"""
+from __future__ import annotations
+
+import math
+import time
+
+import numpy as np
+import torch
+
+from . import _lib as L
+
+
+class CustomSchedule:
+    """train.py:21-34: ``rsqrt(d_model) * min(rsqrt(step), step * warmup_steps**-1.5)`` evaluated in float32."""
+
+    def __init__(self, d_model, warmup_steps=60000):
+        self.d_model = np.float32(d_model)
+        self.warmup_steps = warmup_steps
+
+    def __call__(self, step):
+        step = np.float32(step)
+        with np.errstate(divide="ignore"):
+            arg1 = np.float32(1.0) / np.sqrt(step, dtype=np.float32)
+        arg2 = step * np.float32(float(self.warmup_steps) ** -1.5)
+        return np.float32(np.float32(1.0) / np.sqrt(self.d_model)) * np.minimum(arg1, arg2)
+
+
+class Mean:
+    """keras.metrics.Mean stand-in: running mean of the values passed to ``__call__`` (kept on the device)."""
+
+    def __init__(self, name, device):
+        self.name = name
+        self._acc = torch.zeros(2, dtype=torch.float64, device=device)      # [sum, count]
+
+    def __call__(self, value):
+        self._acc[0] += value
+        self._acc[1] += 1
+
+    def add_(self, total, count):
+        self._acc[0] += total
+        self._acc[1] += count
+
+    def result(self):
+        s, c = self._acc.tolist()
+        return s / c if c else 0.0
+
+    def reset_states(self):
+        self._acc.zero_()
+
+
+class SparseCategoricalAccuracy(Mean):
+    """keras.metrics.SparseCategoricalAccuracy stand-in: mean of argmax==label over ALL positions (train.py:141)."""
+
+
+class Adam:
+    """keras Adam(lr=schedule, beta_1, beta_2, epsilon) in TF form, fused over the flat arena."""
+
+    def __init__(self, learning_rate, beta_1=0.9, beta_2=0.98, epsilon=1e-9):
+        self.learning_rate, self.beta_1, self.beta_2, self.epsilon = learning_rate, beta_1, beta_2, epsilon
+        self.iterations = 0
+
+    def current_lr(self):
+        lr = self.learning_rate
+        return float(lr(self.iterations)) if callable(lr) else float(lr)
+
+    def apply_gradients(self, transformer):
+        t = self.iterations + 1
+        lr_t = self.current_lr()                                              # evaluated at the 0-based iteration count
+        alpha = lr_t * math.sqrt(1.0 - self.beta_2 ** t) / (1.0 - self.beta_1 ** t)
+        L.call("b200xf_adam_step", L.ptr(transformer.params), L.ptr(transformer.adam_m), L.ptr(transformer.adam_v),
+               L.ptr(transformer.grads), L.ptr(transformer.shadow), transformer._n, alpha, self.beta_1, self.beta_2, self.epsilon,
+               L.stream_ptr())
+        self.iterations += 1
+        return lr_t
+
+
+class Train(object):
+    """Train class (train.py:37-80).
+
+    Args:
+        epochs, enable_function, transformer, src_tokenizer, tgt_tokenizer, batch_size, train_log_dir, test_log_dir,
+        max_ckpt_keep, ckpt_path, d_model: as in the reference.  ``enable_function`` is accepted and ignored (there is
+        no graph tracing; every step is already a fixed kernel sequence).
+    """
+
+    def __init__(self, epochs, enable_function, transformer, src_tokenizer, tgt_tokenizer, batch_size, train_log_dir,
+                 test_log_dir, max_ckpt_keep, ckpt_path, d_model, warmup_steps=60000, seed=0):
+        self.epochs = epochs
+        self.enable_function = enable_function
+        self.transformer = transformer
+        self.src_tokenizer = src_tokenizer
+        self.tgt_tokenizer = tgt_tokenizer
+        self.batch_size = batch_size                                           # GLOBAL batch size (train.py:88)
+        self.learning_rate = CustomSchedule(d_model, warmup_steps)
+        self.optimizer = Adam(self.learning_rate, beta_1=0.9, beta_2=0.98, epsilon=1e-9)      # train.py:65-66
+        dev = transformer.device
+        self.train_loss = Mean("train_loss", dev)
+        self.test_loss = Mean("test_loss", dev)
+        self.train_accuracy = SparseCategoricalAccuracy("train_accuracy", dev)
+        self.test_accuracy = SparseCategoricalAccuracy("test_accuracy", dev)
+        self.train_log_dir, self.test_log_dir = train_log_dir, test_log_dir
+        self.max_ckpt_keep, self.ckpt_path = max_ckpt_keep, ckpt_path
+        self._stats = torch.zeros(4, dtype=torch.float64, device=dev)          # per-step {loss_sum, correct, positions, nonpad}
+        self._seed = int(seed)
+        self.last_lr = 0.0
+
+    # -- train.py:83-88 on materialised predictions (API parity; train_step uses the fused path) ---------------------
+    def loss_function(self, real, pred):
+        real = real.to(self.transformer.device, torch.int64).contiguous()
+        B, T = real.shape
+        V = pred.shape[-1]
+        ld = (V + 3) // 4 * 4
+        buf = torch.zeros((B * T, ld), dtype=torch.float32, device=real.device)
+        buf[:, :V] = pred.reshape(B * T, V)
+        stats = torch.zeros(4, dtype=torch.float64, device=real.device)
+        L.call("b200xf_xent", L.ptr(buf), 1, ld, L.ptr(real), T, 0, T, None, 0, None, L.ptr(stats), B * T, V,
+               1.0 / self.batch_size, L.stream_ptr())
+        return stats[0] * (1.0 / self.batch_size)
+
+    # -- hooks for DistributedTrain -----------------------------------------------------------------------------------
+    def _reduce_gradients(self, stage):      # called after each backward stage; single device: nothing to do
+        pass
+
+    def _finish_gradients(self):
+        pass
+
+    def _step_core(self, src, tar, training):
+        tr = self.transformer
+        src = src.to(tr.device, torch.int64).contiguous()
+        tar = tar.to(tr.device, torch.int64).contiguous()
+        T = tar.shape[1] - 1                                                   # tar_inp = tar[:, :-1]; tar_real = tar[:, 1:]
+        self._stats.zero_()
+        seed = self._seed + self.optimizer.iterations
+        tr._forward(src, tar, 0, T, training, seed=seed, want_logits=False)
+        L.call("b200xf_model_loss", tr._handle, L.ptr(tar), tar.shape[1], 1, 1.0 / self.batch_size, L.ptr(self._stats),
+               int(training), L.stream_ptr())
+
+    def train_step(self, inputs):
+        """One training step (train.py:124-141).  inputs: (src (B,S) int64, tar (B,T+1) int64)."""
+        src, tar = inputs
+        tr = self.transformer
+        tr.zero_grads()
+        self._step_core(src, tar, True)
+        for stage in (0, 1, 2):                                                # final layer | decoder | encoder
+            L.call("b200xf_model_backward", tr._handle, stage, L.stream_ptr())
+            self._reduce_gradients(stage)
+        self._finish_gradients()
+        self.last_lr = self.optimizer.apply_gradients(tr)
+        self.train_loss(self._stats[0] * (1.0 / self.batch_size))
+        self.train_accuracy.add_(self._stats[1], self._stats[2])
+
+    def test_step(self, inputs):
+        """One test step (train.py:144-156)."""
+        src, tar = inputs
+        self._step_core(src, tar, False)
+        self.test_loss(self._stats[0] * (1.0 / self.batch_size))
+        self.test_accuracy.add_(self._stats[1], self._stats[2])
+
+    def training_loop(self, train_dataset, test_dataset):
+        """Custom training and testing loop (train.py:167-213): same cadence and print template."""
+        template = 'Epoch {}  Loss {:.4f} Accuracy {:.4f}, Test Loss {:.4f}, Test Accuracy {:.4f}'
+        for epoch in range(self.epochs):
+            self.train_loss.reset_states()
+            self.test_loss.reset_states()
+            self.train_accuracy.reset_states()
+            self.test_accuracy.reset_states()
+            start = time.time()
+            counter = 0
+            for src, tgt in train_dataset:
+                self.train_step((src, tgt))
+                counter += 1
+                if (counter + 1) % 100 == 0:
+                    for t_src, t_tgt in test_dataset:
+                        self.test_step((t_src, t_tgt))
+                    print(template.format(epoch + 1, self.train_loss.result(), self.train_accuracy.result() * 100,
+                                          self.test_loss.result(), self.test_accuracy.result() * 100))
+            torch.cuda.synchronize()
+            print('Time taken for {} epoch: {} secs\n'.format(epoch + 1, (time.time() - start)))
