@@ -78,8 +78,9 @@ int b200xf_residual_ln_fwd(float* y_z, const float* x, const float* gamma, const
                            void* out_bf16, float* mean, float* rstd, int64_t rows, int d, float eps, float rate,
                            uint64_t seed, uint32_t site, b200xf_stream_t stream);
 int b200xf_residual_ln_bwd(const float* dout, const float* z, const float* mean, const float* rstd, const float* gamma,
-                           float* dz, void* dy_sub_bf16, float* dgamma, float* dbeta, int64_t rows, int d, float rate,
-                           uint64_t seed, uint32_t site, b200xf_stream_t stream);
+                           float* dz, void* dy_sub_bf16, float* dgamma, float* dbeta, float* dbias, int64_t rows, int d,
+                           float rate, uint64_t seed, uint32_t site, b200xf_stream_t stream);
+/*      dbias (may be NULL) += column sums of dy_sub: the bias gradient of the sublayer's last Dense, for free */
 
 /* ---- Train.loss_function + SparseCategoricalAccuracy (train.py:83-88, 141) and d(loss)/d(logits).
  *      row r = (b, t) reads label labels[b*label_stride + label_offset + t] (tar[:, 1:] without a copy).

@@ -247,10 +247,11 @@ def test_residual_layernorm_fwd_bwd(d):
     dout = rnd((rows, d), 1.0, 5, torch.float32)
     out_ref.backward(dout)
     dz = torch.empty_like(y); dy16 = torch.empty(rows, d, dtype=torch.bfloat16, device=dev())
-    dg = torch.zeros(d, device=dev()); db = torch.zeros(d, device=dev())
-    L.call("b200xf_residual_ln_bwd", L.ptr(dout), L.ptr(yz), L.ptr(mean), L.ptr(rstd), L.ptr(gamma), L.ptr(dz), L.ptr(dy16), L.ptr(dg), L.ptr(db),
+    dg = torch.zeros(d, device=dev()); db = torch.zeros(d, device=dev()); dbias = torch.zeros(d, device=dev())
+    L.call("b200xf_residual_ln_bwd", L.ptr(dout), L.ptr(yz), L.ptr(mean), L.ptr(rstd), L.ptr(gamma), L.ptr(dz), L.ptr(dy16), L.ptr(dg), L.ptr(db), L.ptr(dbias),
            rows, d, 0.0, 0, 0, sp())
     torch.cuda.synchronize()
+    assert (dbias - z_ref.grad.sum(0)).abs().max().item() < 2e-3 * max(1.0, z_ref.grad.sum(0).abs().max().item())
     assert (dz - z_ref.grad).abs().max().item() < 2e-4
     assert (dy16.float() - z_ref.grad).abs().max().item() < 3e-2
     g_ref = (dout * (out_ref.detach() - beta) / gamma).sum(0)
@@ -275,7 +276,7 @@ def test_dropout_fwd_bwd_consistent():
     dout = torch.ones(rows, d, device=dev()) * torch.arange(d, device=dev())
     dz = torch.empty_like(y); dy16 = torch.empty(rows, d, dtype=torch.bfloat16, device=dev())
     dg = torch.zeros(d, device=dev()); db = torch.zeros(d, device=dev())
-    L.call("b200xf_residual_ln_bwd", L.ptr(dout), L.ptr(yz), L.ptr(mean), L.ptr(rstd), L.ptr(gamma), L.ptr(dz), L.ptr(dy16), L.ptr(dg), L.ptr(db),
+    L.call("b200xf_residual_ln_bwd", L.ptr(dout), L.ptr(yz), L.ptr(mean), L.ptr(rstd), L.ptr(gamma), L.ptr(dz), L.ptr(dy16), L.ptr(dg), L.ptr(db), None,
            rows, d, rate, 1234, 7, sp())
     torch.cuda.synchronize()
     want = dz * keep / (1 - rate)

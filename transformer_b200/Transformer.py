@@ -217,12 +217,10 @@ class Transformer:
             if la_m.dim() == 2:
                 la_m = la_m[None, None]
             assert la_m.shape[-2:] == (T, T), "look_ahead_mask must be (.., T, T)"
-            la_m = la_m.contiguous()
-            la_bs = T * T if la_m.shape[0] == B and B > 1 else (T * T if la_m.shape[0] == B else 0)
             if la_m.shape[0] not in (1, B):
                 raise ValueError("look_ahead_mask batch dimension must be 1 or batch_size")
-            if la_m.shape[0] == 1:
-                la_bs = 0
+            la_m = la_m.reshape(la_m.shape[0], T, T).contiguous()
+            la_bs = T * T if la_m.shape[0] == B and B > 1 else 0      # batch stride (0 = broadcast over the batch)
         logits = None
         ld = 0
         if want_logits:

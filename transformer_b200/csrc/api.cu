@@ -61,9 +61,9 @@ int b200xf_residual_ln_fwd(float* y_z, const float* x, const float* gamma, const
                              ST(stream));
 }
 int b200xf_residual_ln_bwd(const float* dout, const float* z, const float* mean, const float* rstd, const float* gamma,
-                           float* dz, void* dy_sub_bf16, float* dgamma, float* dbeta, int64_t rows, int d, float rate,
-                           uint64_t seed, uint32_t site, b200xf_stream_t stream) {
-  return bx::residual_ln_bwd(dout, z, mean, rstd, gamma, dz, dy_sub_bf16, dgamma, dbeta, rows, d, rate, seed, site,
+                           float* dz, void* dy_sub_bf16, float* dgamma, float* dbeta, float* dbias, int64_t rows, int d,
+                           float rate, uint64_t seed, uint32_t site, b200xf_stream_t stream) {
+  return bx::residual_ln_bwd(dout, z, mean, rstd, gamma, dz, dy_sub_bf16, dgamma, dbeta, dbias, rows, d, rate, seed, site,
                              ST(stream));
 }
 int b200xf_xent(const void* logits, int logits_f32, int64_t ld, const int64_t* labels, int label_stride,

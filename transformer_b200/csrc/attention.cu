@@ -227,16 +227,34 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         auto sel4 = [](const uint32_t (&a)[4], int c) -> uint32_t {
           return c == 0 ? a[0] : (c == 1 ? a[1] : (c == 2 ? a[2] : a[3]));
         };
+        // a tile with no padded / out-of-range key, off the causal boundary and without a float mask needs no
+        // per-element mask logic: the common case for every tile but the diagonal / tail ones
+        const bool plain = !diag && mrow == nullptr &&
+                           ((padbits[0] | padbits[1] | padbits[2] | padbits[3] | oobbits[0] | oobbits[1] | oobbits[2] | oobbits[3]) == 0u);
+        const float sl2 = scale * kLog2e;
         // pass 1: row max
         float m_new = m_run;
+        if (plain) {
+          float mx = -INFINITY;
 #pragma unroll 1
-        for (int c = 0; c < 4; ++c) {
-          uint32_t r[32];
-          tmem_ld_x32(tS[s] + lane_sel + c * 32, r);
-          tmem_ld_wait();
-          const uint32_t pb = sel4(padbits, c), ob = sel4(oobbits, c);
+          for (int c = 0; c < 4; ++c) {
+            uint32_t r[32];
+            tmem_ld_x32(tS[s] + lane_sel + c * 32, r);
+            tmem_ld_wait();
 #pragma unroll
-          for (int e = 0; e < 32; ++e) m_new = fmaxf(m_new, logit(__uint_as_float(r[e]), pb, ob, c, e));
+            for (int e = 0; e < 32; ++e) mx = fmaxf(mx, __uint_as_float(r[e]));
+          }
+          m_new = fmaxf(m_run, mx * scale);
+        } else {
+#pragma unroll 1
+          for (int c = 0; c < 4; ++c) {
+            uint32_t r[32];
+            tmem_ld_x32(tS[s] + lane_sel + c * 32, r);
+            tmem_ld_wait();
+            const uint32_t pb = sel4(padbits, c), ob = sel4(oobbits, c);
+#pragma unroll
+            for (int e = 0; e < 32; ++e) m_new = fmaxf(m_new, logit(__uint_as_float(r[e]), pb, ob, c, e));
+          }
         }
         const float alpha = fast_exp2((m_run - m_new) * kLog2e);   // first tile: exp2(-inf) = 0
         const float mb = m_new * kLog2e;
@@ -248,11 +266,19 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
           tmem_ld_x32(tS[s] + lane_sel + c * 32, r);
           tmem_ld_wait();
           float p[32];
-          const uint32_t pb = sel4(padbits, c), ob = sel4(oobbits, c);
+          if (plain) {
 #pragma unroll
-          for (int e = 0; e < 32; ++e) {
-            p[e] = fast_exp2(logit(__uint_as_float(r[e]), pb, ob, c, e) * kLog2e - mb);
-            rsum += p[e];
+            for (int e = 0; e < 32; ++e) {
+              p[e] = fast_exp2(__uint_as_float(r[e]) * sl2 - mb);
+              rsum += p[e];
+            }
+          } else {
+            const uint32_t pb = sel4(padbits, c), ob = sel4(oobbits, c);
+#pragma unroll
+            for (int e = 0; e < 32; ++e) {
+              p[e] = fast_exp2(logit(__uint_as_float(r[e]), pb, ob, c, e) * kLog2e - mb);
+              rsum += p[e];
+            }
           }
           const uint32_t panel = sPs + (c >> 1) * 16384;
 #pragma unroll
@@ -317,24 +343,21 @@ struct BwdSmem {
   static constexpr uint32_t OFF_DO = OFF_Q + 2 * C::TILE_BYTES;     // 2 stages
   static constexpr uint32_t OFF_PT = OFF_DO + 2 * C::TILE_BYTES;    // P^T   [kv 128][q 128] bf16, two panels
   static constexpr uint32_t OFF_DST = OFF_PT + C::P_BYTES;          // dS^T
-  static constexpr uint32_t OFF_ROW = OFF_DST + C::P_BYTES;         // lse/delta: 2 buffers x (128 + 128) floats
+  static constexpr uint32_t OFF_DQ = OFF_DST + C::P_BYTES;          // dQ tile fp32 [128 x DK] as two [128 x DK/2] boxes (TMA reduce-add staging)
+  static constexpr uint32_t OFF_ROW = OFF_DQ + 2 * C::TILE_BYTES;   // lse/delta: 2 buffers x (128 + 128) floats
   static constexpr uint32_t OFF_BAR = OFF_ROW + 2 * 256 * 4;
   static constexpr uint32_t BYTES = OFF_BAR + 256 + 1024;
 };
 
 constexpr int ATTN_BWD_THREADS = 320;  // w0 TMA, w1 MMA(+TMEM alloc), w2-9 compute (rows x 2 column halves)
 
-__device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float c, float d) {
-  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
-}
-
 template <int DK>
 __global__ void __launch_bounds__(ATTN_BWD_THREADS, 1)
 attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                 const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmdO,
                 const __grid_constant__ CUtensorMap tmdK, const __grid_constant__ CUtensorMap tmdV,
-                const float* __restrict__ lse, const float* __restrict__ delta, float* __restrict__ dq_acc,
-                long long ld_dq, AttnMask mask, int H, int Sq, int Sk, float scale) {
+                const __grid_constant__ CUtensorMap tmdQ, const float* __restrict__ lse, const float* __restrict__ delta,
+                AttnMask mask, int H, int Sq, int Sk, float scale) {
   using C = AttnCfg<DK>;
   using L = BwdSmem<DK>;
   extern __shared__ uint8_t smem_raw[];
@@ -358,7 +381,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
 
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&tmQ); prefetch_tmap(&tmK); prefetch_tmap(&tmV); prefetch_tmap(&tmdO);
-    prefetch_tmap(&tmdK); prefetch_tmap(&tmdV);
+    prefetch_tmap(&tmdK); prefetch_tmap(&tmdV); prefetch_tmap(&tmdQ);
     mbar_init(kv_full, 1);
     for (int i = 0; i < 2; ++i) { mbar_init(&qdo_full[i], 1); mbar_init(&qdo_empty[i], 1); }
     mbar_init(sdp_full, 1); mbar_init(pds_full, 256); mbar_init(dq_full, 1);
@@ -461,6 +484,9 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     const uint32_t sPt = smem_u32(smem + L::OFF_PT), sdSt = smem_u32(smem + L::OFF_DST);
     const float sl2 = scale * kLog2e;
     const float inv_sk = 1.f / (float)Sk;
+    const uint32_t sDQ = smem_u32(smem + L::OFF_DQ);
+    // no padded / out-of-range key among this warp's rows (fixed for the whole CTA)
+    const bool rows_clean = !__any_sync(0xffffffffu, kv_pad || !kv_valid);
     int n = 0;
     for (int i = i_start; i < nq; ++i, ++n) {
       const int qt0 = i * 128;
@@ -471,8 +497,10 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         if (ctid < 128) rb[ctid] = qq < Sq ? lse[off] * kLog2e : INFINITY;
         else rb[ctid] = qq < Sq ? delta[off] : 0.f;
       }
+      if (ctid == 0) tma_store_wait_read<0>();      // previous tile's dQ reduce has finished reading its staging
       named_bar_sync(1, 256);
       const bool diag = mask.causal && (qt0 < kv0 + 128);   // tile touches the causal boundary (some q < kv)
+      const bool plain = rows_clean && !diag && mask.maskf == nullptr;   // no mask logic needed in this tile
       mbar_wait(sdp_full, n & 1);
       tcgen05_after_thread_sync();
 #pragma unroll 1
@@ -483,6 +511,13 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         tmem_ld_x32(tdPt + lane_sel + col0, rp);
         tmem_ld_wait();
         float p[32], ds[32];
+        if (plain) {
+#pragma unroll
+          for (int e = 0; e < 32; ++e) {
+            p[e] = fast_exp2(__uint_as_float(rs[e]) * sl2 - rb[col0 + e]);
+            ds[e] = p[e] * (__uint_as_float(rp[e]) - rb[128 + col0 + e]) * scale;
+          }
+        } else
 #pragma unroll
         for (int e = 0; e < 32; ++e) {
           const int qi = qt0 + col0 + e;
@@ -511,36 +546,35 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       fence_proxy_async_smem();
       tcgen05_before_thread_sync();
       mbar_arrive(pds_full);
-      // dQ tile: row = query, this warp's half of the dk columns -> fp32 red.add into the accumulator
+      // dQ tile: row = query, this warp's half of the dk columns -> fp32 smem staging -> ONE TMA reduce-add per half
+      // (cp.reduce.async.bulk.tensor .add.f32 into the caller-zeroed accumulator; rows >= Sq are clipped by TMA)
       mbar_wait(dq_full, n & 1);
       tcgen05_after_thread_sync();
       {
         constexpr int HC = DK / 2;
-        const int qi = qt0 + (int)row;
-        float* dst = dq_acc + ((long long)b * Sq + qi) * ld_dq + h * DK + half * HC;
+        const uint32_t stg = sDQ + half * C::TILE_BYTES;
         if (HC == 32) {
           uint32_t r[32];
           tmem_ld_x32(tdQ + lane_sel + half * HC, r);
           tmem_ld_wait();
-          if (qi < Sq) {
 #pragma unroll
-            for (int g = 0; g < 8; ++g)
-              red_add_v4(dst + 4 * g, __uint_as_float(r[4 * g]), __uint_as_float(r[4 * g + 1]),
-                         __uint_as_float(r[4 * g + 2]), __uint_as_float(r[4 * g + 3]));
-          }
+          for (int g = 0; g < 8; ++g) st_shared_v4(stg + swz_off<DK>(row, g), r[4 * g], r[4 * g + 1], r[4 * g + 2], r[4 * g + 3]);
         } else {
           uint32_t r[16];
           tmem_ld_x16(tdQ + lane_sel + half * HC, r);
           tmem_ld_wait();
-          if (qi < Sq) {
 #pragma unroll
-            for (int g = 0; g < 4; ++g)
-              red_add_v4(dst + 4 * g, __uint_as_float(r[4 * g]), __uint_as_float(r[4 * g + 1]),
-                         __uint_as_float(r[4 * g + 2]), __uint_as_float(r[4 * g + 3]));
-          }
+          for (int g = 0; g < 4; ++g) st_shared_v4(stg + swz_off<DK>(row, g), r[4 * g], r[4 * g + 1], r[4 * g + 2], r[4 * g + 3]);
+        }
+        tcgen05_before_thread_sync();
+        fence_proxy_async_smem();
+        named_bar_sync(2, 256);
+        if (ctid == 0) {
+          tma_reduce_add_3d(&tmdQ, smem + L::OFF_DQ, h * DK, qt0, b);
+          tma_reduce_add_3d(&tmdQ, smem + L::OFF_DQ + C::TILE_BYTES, h * DK + HC, qt0, b);
+          tma_store_commit();
         }
       }
-      tcgen05_before_thread_sync();
     }
     // epilogue: dV, dK (TMEM) -> bf16 -> smem (reuse P^T / dS^T buffers) -> TMA store
     {
@@ -655,7 +689,7 @@ static int attn_bwd_launch(const void* Q, long long ld_q, const void* K, long lo
                            int B, int H, int Sq, int Sk, cudaStream_t st) {
   using L = BwdSmem<DK>;
   const int swz = DK * 2;
-  CUtensorMap tmQ, tmK, tmV, tmdO, tmdK, tmdV;
+  CUtensorMap tmQ, tmK, tmV, tmdO, tmdK, tmdV, tmdQ;
   int rc;
   if ((rc = encode_tmap_3d(&tmQ, 0, Q, (uint64_t)H * DK, Sq, B, ld_q, (uint64_t)Sq * ld_q, DK, 128, 1, swz))) return rc;
   if ((rc = encode_tmap_3d(&tmK, 0, K, (uint64_t)H * DK, Sk, B, ld_k, (uint64_t)Sk * ld_k, DK, 128, 1, swz))) return rc;
@@ -663,6 +697,7 @@ static int attn_bwd_launch(const void* Q, long long ld_q, const void* K, long lo
   if ((rc = encode_tmap_3d(&tmdO, 0, dO, (uint64_t)H * DK, Sq, B, ld_do, (uint64_t)Sq * ld_do, DK, 128, 1, swz))) return rc;
   if ((rc = encode_tmap_3d(&tmdK, 0, dK, (uint64_t)H * DK, Sk, B, ld_dk, (uint64_t)Sk * ld_dk, DK, 128, 1, swz))) return rc;
   if ((rc = encode_tmap_3d(&tmdV, 0, dV, (uint64_t)H * DK, Sk, B, ld_dv, (uint64_t)Sk * ld_dv, DK, 128, 1, swz))) return rc;
+  if ((rc = encode_tmap_3d(&tmdQ, 1, dq_acc, (uint64_t)H * DK, Sq, B, ld_dq, (uint64_t)Sq * ld_dq, DK / 2, 128, 1, swz))) return rc;
   auto kern = attn_bwd_kernel<DK>;
   static bool attr_done = false;
   if (!attr_done) {
@@ -671,8 +706,8 @@ static int attn_bwd_launch(const void* Q, long long ld_q, const void* K, long lo
   }
   dim3 grid((Sk + 127) / 128, H, B);
   void* pb = prof_on() ? prof_begin(st) : nullptr;
-  kern<<<grid, ATTN_BWD_THREADS, L::BYTES, st>>>(tmQ, tmK, tmV, tmdO, tmdK, tmdV, lse, delta, dq_acc, ld_dq, mask, H, Sq,
-                                                 Sk, 1.f / sqrtf((float)DK));
+  kern<<<grid, ATTN_BWD_THREADS, L::BYTES, st>>>(tmQ, tmK, tmV, tmdO, tmdK, tmdV, tmdQ, lse, delta, mask, H, Sq, Sk,
+                                                 1.f / sqrtf((float)DK));
   if (pb) prof_end(pb, 2, 8.0 * B * H * (double)Sq * Sk * DK, st);     // 2x the forward's 4.B.H.Sq.Sk.dk
   BX_POST_LAUNCH();
   return 0;

@@ -167,19 +167,22 @@ residual_ln_fwd_kernel(float* __restrict__ y_z, const float* __restrict__ x, con
 //   dy_sub = dz * dropmask/(1-rate)                                      (bf16, gradient to the sublayer output)
 //   dgamma += sum_rows dy*xhat ; dbeta += sum_rows dy                    (block partials -> atomicAdd)
 template <int NV>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, NV >= 8 ? 1 : 2)
 residual_ln_bwd_kernel(const float* __restrict__ dout, const float* __restrict__ z, const float* __restrict__ mean_in,
                        const float* __restrict__ rstd_in, const float* __restrict__ gamma, float* __restrict__ dz,
                        __nv_bfloat16* __restrict__ dy_sub, float* __restrict__ dgamma, float* __restrict__ dbeta,
-                       long long rows, int d, float rate, unsigned long long seed, uint32_t site) {
-  extern __shared__ float red[];  // [2][warps][d]   (dgamma partials, dbeta partials)
+                       float* __restrict__ dbias, long long rows, int d, float rate, unsigned long long seed,
+                       uint32_t site) {
+  extern __shared__ float red[];  // [3][d]: dgamma, dbeta, dbias partials of this block (shared-memory atomics)
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, nw = blockDim.x >> 5;
   const long long warp_global = (long long)blockIdx.x * nw + wib;
   const long long nwarps = (long long)gridDim.x * nw;
   const int d4 = d >> 2;
-  float4 ag[NV], ab[NV];
+  for (int c = threadIdx.x; c < 3 * d; c += blockDim.x) red[c] = 0.f;
+  __syncthreads();
+  float4 ag[NV], ab[NV], ac[NV];
 #pragma unroll
-  for (int i = 0; i < NV; ++i) { ag[i] = make_float4(0, 0, 0, 0); ab[i] = make_float4(0, 0, 0, 0); }
+  for (int i = 0; i < NV; ++i) { ag[i] = make_float4(0, 0, 0, 0); ab[i] = make_float4(0, 0, 0, 0); ac[i] = make_float4(0, 0, 0, 0); }
   for (long long r = warp_global; r < rows; r += nwarps) {
     const float mean = mean_in[r], rstd = rstd_in[r];
     float4 xh[NV], gd[NV];
@@ -217,27 +220,28 @@ residual_ln_bwd_kernel(const float* __restrict__ dout, const float* __restrict__
           const float4 k = dropout_scale4(seed, site, (unsigned long long)idx, rate);
           o.x *= k.x; o.y *= k.y; o.z *= k.z; o.w *= k.w;
         }
+        ac[i].x += o.x; ac[i].y += o.y; ac[i].z += o.z; ac[i].w += o.w;     // bias grad of the sublayer's last Dense
         reinterpret_cast<uint2*>(dy_sub)[idx] = make_uint2(pack_bf16x2(o.x, o.y), pack_bf16x2(o.z, o.w));
       }
     }
   }
-  // block reduction of dgamma / dbeta partials
-  float* rg = red;
-  float* rb = red + (size_t)nw * d;
 #pragma unroll
   for (int i = 0; i < NV; ++i) {
-    const int c4 = lane + 32 * i;
-    if (c4 < d4) {
-      reinterpret_cast<float4*>(rg + (size_t)wib * d)[c4] = ag[i];
-      reinterpret_cast<float4*>(rb + (size_t)wib * d)[c4] = ab[i];
+    const int c = (lane + 32 * i) * 4;
+    if (c < d) {
+      atomicAdd(red + c + 0, ag[i].x); atomicAdd(red + c + 1, ag[i].y); atomicAdd(red + c + 2, ag[i].z); atomicAdd(red + c + 3, ag[i].w);
+      atomicAdd(red + d + c + 0, ab[i].x); atomicAdd(red + d + c + 1, ab[i].y); atomicAdd(red + d + c + 2, ab[i].z); atomicAdd(red + d + c + 3, ab[i].w);
+      if (dbias != nullptr) {
+        atomicAdd(red + 2 * d + c + 0, ac[i].x); atomicAdd(red + 2 * d + c + 1, ac[i].y);
+        atomicAdd(red + 2 * d + c + 2, ac[i].z); atomicAdd(red + 2 * d + c + 3, ac[i].w);
+      }
     }
   }
   __syncthreads();
   for (int c = threadIdx.x; c < d; c += blockDim.x) {
-    float sg = 0.f, sb = 0.f;
-    for (int w = 0; w < nw; ++w) { sg += rg[(size_t)w * d + c]; sb += rb[(size_t)w * d + c]; }
-    atomicAdd(dgamma + c, sg);
-    atomicAdd(dbeta + c, sb);
+    atomicAdd(dgamma + c, red[c]);
+    atomicAdd(dbeta + c, red[d + c]);
+    if (dbias != nullptr) atomicAdd(dbias + c, red[2 * d + c]);
   }
 }
 
@@ -248,43 +252,73 @@ residual_ln_bwd_kernel(const float* __restrict__ dout, const float* __restrict__
 //   one CTA per row; logits bf16 or fp32 [rows, ld], V valid columns; dlogits bf16 [rows, ld_d] (may alias
 //   a bf16 logits buffer).  stats: double[0] loss_sum, [1] correct, [2] positions, [3] nonpad
 // ------------------------------------------------------------------------------------------------
-template <typename T>
-__device__ __forceinline__ float ld_logit(const T* p, long long i);
-template <>
-__device__ __forceinline__ float ld_logit<float>(const float* p, long long i) { return p[i]; }
-template <>
-__device__ __forceinline__ float ld_logit<__nv_bfloat16>(const __nv_bfloat16* p, long long i) { return __bfloat162float(p[i]); }
+template <typename T> struct LogitVec;
+template <> struct LogitVec<float> {
+  static constexpr int N = 4;
+  static __device__ __forceinline__ void load(const float* p, float (&x)[8]) {
+    const float4 v = *reinterpret_cast<const float4*>(p);
+    x[0] = v.x; x[1] = v.y; x[2] = v.z; x[3] = v.w;
+  }
+};
+template <> struct LogitVec<__nv_bfloat16> {
+  static constexpr int N = 8;
+  static __device__ __forceinline__ void load(const __nv_bfloat16* p, float (&x)[8]) {
+    const uint4 v = *reinterpret_cast<const uint4*>(p);
+    const float2 a = unpack_bf16x2(v.x), b = unpack_bf16x2(v.y), c = unpack_bf16x2(v.z), d = unpack_bf16x2(v.w);
+    x[0] = a.x; x[1] = a.y; x[2] = b.x; x[3] = b.y; x[4] = c.x; x[5] = c.y; x[6] = d.x; x[7] = d.y;
+  }
+};
 
 template <typename T>
 __global__ void __launch_bounds__(256)
 xent_kernel(const T* logits, long long ld, const long long* __restrict__ labels, int label_stride,
             int label_offset, int T_len, __nv_bfloat16* dlogits, long long ld_d, float* __restrict__ row_loss,
             double* __restrict__ stats, int V, float inv_batch) {   // dlogits may alias logits (no __restrict__)
-  // labels for row r = (b, t) live at labels[b * label_stride + label_offset + t]  (tar[:, 1:] without a copy)
+  // one CTA per row, 16-byte vector loads.  labels for row r = (b, t) live at labels[b*label_stride + label_offset + t]
+  constexpr int VEC = LogitVec<T>::N;
+  constexpr float L2E = 1.4426950408889634f, LN2 = 0.6931471805599453f;
   const long long r = blockIdx.x;
   const T* row = logits + r * ld;
   const long long b = r / T_len, t = r % T_len;
-  long long label = labels[b * label_stride + label_offset + t];
-  const bool nonpad = label != 0;
-  if (label < 0 || label >= V) label = 0;
+  const long long raw_label = labels[b * label_stride + label_offset + t];
+  const bool nonpad = raw_label != 0;
+  const int label = (raw_label < 0 || raw_label >= V) ? 0 : (int)raw_label;
   __shared__ float s_m[8], s_s[8], s_lab;
   __shared__ int s_i[8];
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const int nvec = (V + VEC - 1) / VEC;          // ld is a multiple of VEC, so every vector lies inside the row
   // pass 1: online max / sum-exp / argmax (first index attaining the max, like tf.argmax)
   float m = -INFINITY, s = 0.f;
   int am = 0x7fffffff;
-  for (int c = threadIdx.x; c < V; c += blockDim.x) {
-    const float x = ld_logit<T>(row, c);
-    if (c == (int)label) s_lab = x;      // captured now: pass 2 may overwrite the (aliased) row in place
-    if (x > m) { s = s * __expf(m - x) + 1.f; m = x; am = c; }
-    else s += __expf(x - m);
+  for (int i = threadIdx.x; i < nvec; i += blockDim.x) {
+    float x[8];
+    LogitVec<T>::load(row + (long long)i * VEC, x);
+    const int c0 = i * VEC;
+    float vmax = -INFINITY;
+#pragma unroll
+    for (int e = 0; e < VEC; ++e) {
+      if (c0 + e >= V) x[e] = -INFINITY;
+      if (c0 + e == label) s_lab = x[e];     // captured now: pass 2 may overwrite the (aliased) row in place
+      if (x[e] > vmax) vmax = x[e];
+    }
+    if (vmax > m) {
+      int first = 0;
+#pragma unroll
+      for (int e = VEC - 1; e >= 0; --e) if (x[e] == vmax) first = e;
+      am = c0 + first;
+      s *= fast_exp2((m - vmax) * L2E);
+      m = vmax;
+    }
+    const float mb = m * L2E;
+#pragma unroll
+    for (int e = 0; e < VEC; ++e) s += fast_exp2(x[e] * L2E - mb);
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
     const float m2 = __shfl_xor_sync(0xffffffffu, m, o), s2 = __shfl_xor_sync(0xffffffffu, s, o);
     const int a2 = __shfl_xor_sync(0xffffffffu, am, o);
     const float mn = fmaxf(m, m2);
-    s = (m == -INFINITY ? 0.f : s * __expf(m - mn)) + (m2 == -INFINITY ? 0.f : s2 * __expf(m2 - mn));
+    s = (m == -INFINITY ? 0.f : s * fast_exp2((m - mn) * L2E)) + (m2 == -INFINITY ? 0.f : s2 * fast_exp2((m2 - mn) * L2E));
     am = (m2 > m || (m2 == m && a2 < am)) ? a2 : am;
     m = mn;
   }
@@ -295,50 +329,80 @@ xent_kernel(const T* logits, long long ld, const long long* __restrict__ labels,
     const float m2 = s_m[w], s2 = s_s[w];
     const int a2 = s_i[w];
     const float mn = fmaxf(m, m2);
-    s = (m == -INFINITY ? 0.f : s * __expf(m - mn)) + (m2 == -INFINITY ? 0.f : s2 * __expf(m2 - mn));
+    s = (m == -INFINITY ? 0.f : s * fast_exp2((m - mn) * L2E)) + (m2 == -INFINITY ? 0.f : s2 * fast_exp2((m2 - mn) * L2E));
     am = (m2 > m || (m2 == m && a2 < am)) ? a2 : am;
     m = mn;
   }
-  const float lse = m + __logf(s);
+  const float lse = m + __log2f(s) * LN2;
   if (threadIdx.x == 0) {
     const float loss = nonpad ? (lse - s_lab) : 0.f;
     if (row_loss) row_loss[r] = loss;
     atomicAdd(&stats[0], (double)loss);
-    atomicAdd(&stats[1], (double)(am == (int)labels[b * label_stride + label_offset + t] ? 1.0 : 0.0));
+    atomicAdd(&stats[1], (double)((long long)am == raw_label ? 1.0 : 0.0));
     atomicAdd(&stats[2], 1.0);
     atomicAdd(&stats[3], nonpad ? 1.0 : 0.0);
   }
   if (dlogits == nullptr) return;
-  // pass 2: gradient (row re-read hits L1/L2)
+  // pass 2: gradient (row re-read hits L1/L2); padded columns [V, ld_d) are zeroed
   const float gscale = nonpad ? inv_batch : 0.f;
+  const float lb = lse * L2E;
   __nv_bfloat16* drow = dlogits + r * ld_d;
-  for (int c = threadIdx.x; c < V; c += blockDim.x) {
-    const float x = ld_logit<T>(row, c);
-    float g = __expf(x - lse);
-    if (c == (int)label) g -= 1.f;
-    drow[c] = __float2bfloat16(g * gscale);
+  for (int i = threadIdx.x; i < nvec; i += blockDim.x) {
+    float x[8];
+    LogitVec<T>::load(row + (long long)i * VEC, x);
+    const int c0 = i * VEC;
+    float g[8];
+#pragma unroll
+    for (int e = 0; e < VEC; ++e) {
+      float v = fast_exp2(x[e] * L2E - lb);
+      if (c0 + e == label) v -= 1.f;
+      g[e] = (c0 + e < V) ? v * gscale : 0.f;
+    }
+    if (VEC == 8) {
+      *reinterpret_cast<uint4*>(drow + c0) = make_uint4(pack_bf16x2(g[0], g[1]), pack_bf16x2(g[2], g[3]), pack_bf16x2(g[4], g[5]),
+                                                        pack_bf16x2(g[6], g[7]));
+    } else {
+      *reinterpret_cast<uint2*>(drow + c0) = make_uint2(pack_bf16x2(g[0], g[1]), pack_bf16x2(g[2], g[3]));
+    }
   }
-  for (long long c = V + threadIdx.x; c < ld_d; c += blockDim.x) drow[c] = __float2bfloat16(0.f);  // padded columns
+  for (long long c = (long long)nvec * VEC + threadIdx.x; c < ld_d; c += blockDim.x) drow[c] = __float2bfloat16(0.f);
 }
 
 // ------------------------------------------------------------------------------------------------
 // column sums: out[n] += sum_m X[m, n]   (bias gradients = reduce of dY over tokens)
+//   block = 16 column groups (8 bf16 = 16 bytes each) x 16 row lanes; grid.y splits the rows.
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
 colsum_bf16_kernel(const __nv_bfloat16* __restrict__ X, long long ld, float* __restrict__ out, long long rows, int N,
                    int rows_per_block) {
-  // block (bx, by): columns [bx*512, +512) (2 per thread), rows [by*rows_per_block, ...)
-  const int c = (blockIdx.x * blockDim.x + threadIdx.x) * 2;
-  if (c >= N) return;
+  __shared__ float sm[16][132];
+  const int cg = threadIdx.x & 15, rl = threadIdx.x >> 4;
+  const int c0 = blockIdx.x * 128 + cg * 8;
   const long long r0 = (long long)blockIdx.y * rows_per_block;
   const long long r1 = r0 + rows_per_block < rows ? r0 + rows_per_block : rows;
-  float a0 = 0.f, a1 = 0.f;
-  for (long long r = r0; r < r1; ++r) {
-    const float2 f = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(X + r * ld + c));
-    a0 += f.x; a1 += f.y;
+  float acc[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) acc[e] = 0.f;
+  if (c0 < N) {
+#pragma unroll 4
+    for (long long r = r0 + rl; r < r1; r += 16) {
+      const uint4 v = __ldg(reinterpret_cast<const uint4*>(X + r * ld + c0));
+      const float2 a = unpack_bf16x2(v.x), b = unpack_bf16x2(v.y), c = unpack_bf16x2(v.z), d = unpack_bf16x2(v.w);
+      acc[0] += a.x; acc[1] += a.y; acc[2] += b.x; acc[3] += b.y; acc[4] += c.x; acc[5] += c.y; acc[6] += d.x; acc[7] += d.y;
+    }
   }
-  atomicAdd(out + c, a0);
-  if (c + 1 < N) atomicAdd(out + c + 1, a1);
+#pragma unroll
+  for (int e = 0; e < 8; ++e) sm[rl][cg * 8 + e] = acc[e];
+  __syncthreads();
+  if (threadIdx.x < 128) {
+    const int c = blockIdx.x * 128 + threadIdx.x;
+    if (c < N) {
+      float t = 0.f;
+#pragma unroll
+      for (int k = 0; k < 16; ++k) t += sm[k][threadIdx.x];
+      atomicAdd(out + c, t);
+    }
+  }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -398,29 +462,28 @@ __global__ void pad_mask_kernel(const long long* __restrict__ ids, uint8_t* __re
 }
 
 // attention backward pre-pass: delta[b,h,q] = sum_c dO[b,q,h*dk+c] * O[b,q,h*dk+c]
+//   one thread per (b, h, q), q fastest: coalesced stores; each thread streams its own 2*dk-byte rows (16-byte loads)
 __global__ void __launch_bounds__(256)
 attn_delta_kernel(const __nv_bfloat16* __restrict__ O, long long ld_o, const __nv_bfloat16* __restrict__ dO,
                   long long ld_do, float* __restrict__ delta, int B, int S, int H, int dk) {
-  // one warp per (b, q, h)
-  const int lane = threadIdx.x & 31;
-  const long long w = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
-  const long long total = (long long)B * S * H;
-  if (w >= total) return;
-  const int h = (int)(w % H);
-  const long long bq = w / H;
-  const __nv_bfloat16* o = O + bq * ld_o + h * dk;
-  const __nv_bfloat16* g = dO + bq * ld_do + h * dk;
+  const long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  const long long total = (long long)B * H * S;
+  if (idx >= total) return;
+  const int q = (int)(idx % S);
+  const long long bh = idx / S;
+  const int h = (int)(bh % H);
+  const long long b = bh / H;
+  const __nv_bfloat16* o = O + (b * S + q) * ld_o + h * dk;
+  const __nv_bfloat16* g = dO + (b * S + q) * ld_do + h * dk;
   float s = 0.f;
-  for (int c = lane * 2; c < dk; c += 64) {
-    const float2 a = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(o + c));
-    const float2 b = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(g + c));
-    s += a.x * b.x + a.y * b.y;
+  for (int c = 0; c < dk; c += 8) {
+    const uint4 a = __ldg(reinterpret_cast<const uint4*>(o + c));
+    const uint4 d = __ldg(reinterpret_cast<const uint4*>(g + c));
+    const float2 a0 = unpack_bf16x2(a.x), a1 = unpack_bf16x2(a.y), a2 = unpack_bf16x2(a.z), a3 = unpack_bf16x2(a.w);
+    const float2 d0 = unpack_bf16x2(d.x), d1 = unpack_bf16x2(d.y), d2 = unpack_bf16x2(d.z), d3 = unpack_bf16x2(d.w);
+    s += a0.x * d0.x + a0.y * d0.y + a1.x * d1.x + a1.y * d1.y + a2.x * d2.x + a2.y * d2.y + a3.x * d3.x + a3.y * d3.y;
   }
-  s = warp_sum(s);
-  if (lane == 0) {
-    const long long b = bq / S, q = bq % S;
-    delta[(b * H + h) * S + q] = s;
-  }
+  delta[idx] = s;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -469,20 +532,13 @@ int residual_ln_fwd(float* y_z, const float* x, const float* gamma, const float*
   return 0;
 }
 int residual_ln_bwd(const float* dout, const float* z, const float* mean, const float* rstd, const float* gamma,
-                    float* dz, void* dy_sub, float* dgamma, float* dbeta, long long rows, int d, float rate,
+                    float* dz, void* dy_sub, float* dgamma, float* dbeta, float* dbias, long long rows, int d, float rate,
                     unsigned long long seed, unsigned site, cudaStream_t st) {
   BX_REQUIRE(d % 4 == 0 && d <= 1024, "layernorm: need d %% 4 == 0 and d <= 1024 (got %d)", d);
   const int grid = grid_for(rows * 32, 256, 2);
-  const size_t smem = (size_t)2 * 8 * d * sizeof(float);
-  if (smem > 48 * 1024) {   // only the d > 768 instantiation can exceed the default dynamic-smem limit
-    static bool attr_done = false;
-    if (!attr_done) {
-      BX_CHECK_CUDA(cudaFuncSetAttribute(residual_ln_bwd_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 8 * 1024 * 4));
-      attr_done = true;
-    }
-  }
+  const size_t smem = (size_t)3 * d * sizeof(float);
   BX_LN_DISPATCH(residual_ln_bwd_kernel, <<<grid, 256, smem, st>>>(dout, z, mean, rstd, gamma, dz, (__nv_bfloat16*)dy_sub, dgamma,
-                                                                  dbeta, rows, d, rate, seed, site))
+                                                                  dbeta, dbias, rows, d, rate, seed, site))
   BX_POST_LAUNCH();
   return 0;
 }
@@ -503,14 +559,14 @@ int xent(const void* logits, int logits_f32, long long ld, const long long* labe
 }
 
 int colsum_bf16(const void* X, long long ld, float* out, long long rows, int N, cudaStream_t st) {
-  BX_REQUIRE(ld % 2 == 0, "colsum: ld must be even");
-  const int bx_ = (N + 511) / 512;
-  long long by = (long long)sm_count() * 4 / bx_;
+  BX_REQUIRE(ld % 8 == 0 && (reinterpret_cast<uintptr_t>(X) & 15) == 0, "colsum: X must be 16-byte aligned with ld %% 8 == 0");
+  const int bx_ = (N + 127) / 128;
+  long long by = (long long)sm_count() * 6 / bx_;
   if (by < 1) by = 1;
-  int rpb = (int)((rows + by - 1) / by);
-  if (rpb < 32) rpb = 32;
+  long long rpb = (rows + by - 1) / by;
+  rpb = (rpb + 63) / 64 * 64;
   by = (rows + rpb - 1) / rpb;
-  colsum_bf16_kernel<<<dim3(bx_, (unsigned)by), 256, 0, st>>>((const __nv_bfloat16*)X, ld, out, rows, N, rpb);
+  colsum_bf16_kernel<<<dim3(bx_, (unsigned)by), 256, 0, st>>>((const __nv_bfloat16*)X, ld, out, rows, N, (int)rpb);
   BX_POST_LAUNCH();
   return 0;
 }
@@ -546,9 +602,10 @@ int pad_mask(const long long* ids, int id_stride, int id_offset, uint8_t* mask, 
 }
 int attn_delta(const void* O, long long ld_o, const void* dO, long long ld_do, float* delta, int B, int S, int H, int dk,
                cudaStream_t st) {
-  const long long warps = (long long)B * S * H;
-  attn_delta_kernel<<<(unsigned)((warps * 32 + 255) / 256), 256, 0, st>>>((const __nv_bfloat16*)O, ld_o, (const __nv_bfloat16*)dO,
-                                                                          ld_do, delta, B, S, H, dk);
+  BX_REQUIRE(dk % 8 == 0 && ld_o % 8 == 0 && ld_do % 8 == 0, "attn_delta: dk and leading dimensions must be multiples of 8");
+  const long long n = (long long)B * S * H;
+  attn_delta_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>((const __nv_bfloat16*)O, ld_o, (const __nv_bfloat16*)dO, ld_do, delta, B,
+                                                                 S, H, dk);
   BX_POST_LAUNCH();
   return 0;
 }

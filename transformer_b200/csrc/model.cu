@@ -360,18 +360,19 @@ int forward_impl(M* m, float* logits_out, int64_t ld_logits, cudaStream_t st) {
 
 // LayerNorm + dropout + residual backward: g_in (gradient of the LN output) -> g_out (gradient of z, i.e. of the
 // residual input) and dy16 (gradient of the sublayer output, bf16)
-int residual_ln_back(M* m, const float* g_in, const LnSave& s, int64_t g_off, int64_t b_off, float* g_out, int64_t rows, uint32_t site,
-                     cudaStream_t st) {
+// `bias_off`: bias of the sublayer's last Dense -- its gradient (column sums of dy16) falls out of this kernel for free
+int residual_ln_back(M* m, const float* g_in, const LnSave& s, int64_t g_off, int64_t b_off, int64_t bias_off, float* g_out, int64_t rows,
+                     uint32_t site, cudaStream_t st) {
   const float rate = m->training ? m->cfg.dropout_rate : 0.f;
-  return bx::residual_ln_bwd(g_in, s.z, s.mean, s.rstd, m->P + g_off, g_out, m->w.dy16, m->G + g_off, m->G + b_off, rows, m->lo.d, rate,
-                             m->seed, site, st);
+  return bx::residual_ln_bwd(g_in, s.z, s.mean, s.rstd, m->P + g_off, g_out, m->w.dy16, m->G + g_off, m->G + b_off, m->G + bias_off, rows,
+                             m->lo.d, rate, m->seed, site, st);
 }
 
 // FFN backward: dy16 = d(ffn output); x16 = ffn input; accumulates d(input) into g (fp32)
 int ffn_back(M* m, const Ffn& p, const bf16* x16, const bf16* h, float* g, int64_t rows, cudaStream_t st) {
   const int d = m->lo.d, f = m->lo.f;
   Work& w = m->w;
-  RC(linear_wgrad(h, f, w.dy16, d, m->G + p.W2, d, m->G + p.b2, rows, d, f, st));
+  RC(linear_wgrad(h, f, w.dy16, d, m->G + p.W2, d, nullptr, rows, d, f, st));                 // db2: from the LN backward
   RC(linear_dgrad(w.dy16, d, m->Sh + p.W2, d, w.dh, f, false, false, h, f, rows, d, f, st));     // dh = (dy . W2^T) o [h > 0]
   RC(linear_wgrad(x16, d, w.dh, f, m->G + p.W1, f, m->G + p.b1, rows, f, d, st));
   RC(linear_dgrad(w.dh, f, m->Sh + p.W1, f, g, d, true, true, nullptr, 0, rows, f, d, st));
@@ -384,7 +385,7 @@ int self_attn_back(M* m, const MhaSelf& p, const bf16* x16, const bf16* qkv, con
   const int d = m->lo.d, H = m->lo.H, dk = d / H, B = m->B;
   const int64_t rows = (int64_t)B * S;
   Work& w = m->w;
-  RC(linear_wgrad(attn_o, d, w.dy16, d, m->G + p.Wo, d, m->G + p.bo, rows, d, d, st));
+  RC(linear_wgrad(attn_o, d, w.dy16, d, m->G + p.Wo, d, nullptr, rows, d, d, st));             // dbo: from the LN backward
   RC(linear_dgrad(w.dy16, d, m->Sh + p.Wo, d, w.dO16, d, false, false, nullptr, 0, rows, d, d, st));
   RC(bx::attn_delta(attn_o, d, w.dO16, d, w.delta, B, S, H, dk, st));
   BX_CHECK_CUDA(cudaMemsetAsync(w.dq_acc, 0, rows * d * sizeof(float), st));
@@ -422,12 +423,12 @@ int backward_decoder(M* m, cudaStream_t st) {
     const DecLayerP& p = lo.dec[l];
     DecAct& a = w.dec[l];
     // out3 = LN3(out2 + drop(ffn(out2)))
-    RC(residual_ln_back(m, g_in, a.ln3, p.ln3g, p.ln3b, g_out, Mt, site_dec(l, 2), st));
+    RC(residual_ln_back(m, g_in, a.ln3, p.ln3g, p.ln3b, p.ffn.b2, g_out, Mt, site_dec(l, 2), st));
     RC(ffn_back(m, p.ffn, a.out2_16, a.h, g_out, Mt, st));
     std::swap(g_in, g_out);
     // out2 = LN2(out1 + drop(mha2(enc_out, enc_out, out1)))
-    RC(residual_ln_back(m, g_in, a.ln2, p.ln2g, p.ln2b, g_out, Mt, site_dec(l, 1), st));
-    RC(linear_wgrad(a.attn2_o, d, w.dy16, d, m->G + p.mha2.Wo, d, m->G + p.mha2.bo, Mt, d, d, st));
+    RC(residual_ln_back(m, g_in, a.ln2, p.ln2g, p.ln2b, p.mha2.bo, g_out, Mt, site_dec(l, 1), st));
+    RC(linear_wgrad(a.attn2_o, d, w.dy16, d, m->G + p.mha2.Wo, d, nullptr, Mt, d, d, st));
     RC(linear_dgrad(w.dy16, d, m->Sh + p.mha2.Wo, d, w.dO16, d, false, false, nullptr, 0, Mt, d, d, st));
     RC(bx::attn_delta(a.attn2_o, d, w.dO16, d, w.delta, B, T, H, dk, st));
     BX_CHECK_CUDA(cudaMemsetAsync(w.dq_acc, 0, Mt * d * sizeof(float), st));
@@ -441,7 +442,7 @@ int backward_decoder(M* m, cudaStream_t st) {
     RC(linear_dgrad(w.dO16, d, m->Sh + p.mha2.Wq, d, g_out, d, true, true, nullptr, 0, Mt, d, d, st));
     std::swap(g_in, g_out);
     // out1 = LN1(x + drop(mha1(x, x, x)))
-    RC(residual_ln_back(m, g_in, a.ln1, p.ln1g, p.ln1b, g_out, Mt, site_dec(l, 0), st));
+    RC(residual_ln_back(m, g_in, a.ln1, p.ln1g, p.ln1b, p.mha1.bo, g_out, Mt, site_dec(l, 0), st));
     RC(self_attn_back(m, p.mha1, w.dec_x16[l], a.qkv1, a.attn1_o, a.lse1, sm, g_out, T, st));
     std::swap(g_in, g_out);
   }
@@ -464,10 +465,10 @@ int backward_encoder(M* m, cudaStream_t st) {
   for (int l = L - 1; l >= 0; --l) {
     const EncLayerP& p = lo.enc[l];
     EncAct& a = w.enc[l];
-    RC(residual_ln_back(m, g_in, a.ln2, p.ln2g, p.ln2b, g_out, Ms, site_enc(l, 1), st));
+    RC(residual_ln_back(m, g_in, a.ln2, p.ln2g, p.ln2b, p.ffn.b2, g_out, Ms, site_enc(l, 1), st));
     RC(ffn_back(m, p.ffn, a.out1_16, a.h, g_out, Ms, st));
     { float* t = g_in; g_in = g_out; g_out = (t == w.d_enc_out) ? spare : t; }
-    RC(residual_ln_back(m, g_in, a.ln1, p.ln1g, p.ln1b, g_out, Ms, site_enc(l, 0), st));
+    RC(residual_ln_back(m, g_in, a.ln1, p.ln1g, p.ln1b, p.mha.bo, g_out, Ms, site_enc(l, 0), st));
     RC(self_attn_back(m, p.mha, w.enc_x16[l], a.qkv, a.attn_o, a.lse, em, g_out, S, st));
     std::swap(g_in, g_out);
   }
