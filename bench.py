@@ -93,7 +93,8 @@ def cpu_reference_run(cfg_name, steps, warmup, sample_batch):
     import torch
     from oracle import restatement as R
     L_, d, H, f, V, S, _ = CONFIGS[cfg_name]
-    cores = len(os.sched_getaffinity(0))
+    avail = len(os.sched_getaffinity(0))
+    cores = min(avail, 32)       # eager fp32 ops of this size stop scaling (and regress badly) beyond ~32 threads
     torch.set_num_threads(cores)
     cfg = R.make_cfg(L_, d, H, f, V, V, rate=0.0, max_position=S + 1)
     P = R.init_params(L_, d, f, V, V, seed=42)
@@ -106,7 +107,7 @@ def cpu_reference_run(cfg_name, steps, warmup, sample_batch):
         R.train_step(P, cfg, st, src, tar, sample_batch)
     dt = (time.time() - t0) / max(1, steps)
     return dict(value=sample_batch * S / dt, unit="tokens/s", cores=cores, kind="port",
-                sample=f"{steps} full train steps (fwd+loss+bwd+Adam) of {cfg_name} at batch {sample_batch} (of {CONFIGS[cfg_name][6]}), torch-CPU fp32 oracle; TF2 not installable"), dt
+                sample=f"{steps} full train steps (fwd+loss+bwd+Adam) of {cfg_name} at batch {sample_batch} (of {CONFIGS[cfg_name][6]}), torch-CPU fp32 oracle, {cores} of {avail} host threads; TF2 not installable"), dt
 
 
 def main():

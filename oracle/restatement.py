@@ -145,9 +145,19 @@ def init_params(num_layers, d_model, dff, input_vocab_size, target_vocab_size, s
 # --------------------------------------------------------------------------------------------------
 
 
+# Test-only switch: round every matmul OPERAND to bfloat16 (products/accumulation stay fp32), i.e. what a bf16
+# tensor-core implementation of the same graph computes.  Used by tests to calibrate tolerances ("how far does bf16
+# operand rounding alone move this quantity?"); the reference semantics are EMULATE_BF16 = False.
+EMULATE_BF16 = False
+
+
+def _op(x):
+    return x.bfloat16().to(x.dtype) if EMULATE_BF16 else x
+
+
 def dense(x, kernel, bias):
     """keras Dense: ``x . kernel + bias`` over the last axis (Appendix A.1)."""
-    return x @ kernel + bias
+    return _op(x) @ _op(kernel) + bias
 
 
 def layer_norm(x, gamma, beta, eps=1e-6):
@@ -167,13 +177,13 @@ def dropout(x, rate, training, generator=None):
 
 def scaled_dot_product_attention(q, k, v, mask):
     """Attention.py:3-34."""
-    matmul_qk = q @ k.transpose(-1, -2)                                   # Attention.py:20
+    matmul_qk = _op(q) @ _op(k).transpose(-1, -2)                         # Attention.py:20
     dk = torch.tensor(float(k.shape[-1]), dtype=q.dtype)                  # Attention.py:21
     scaled_attention_logits = matmul_qk / torch.sqrt(dk)                  # Attention.py:22
     if mask is not None:
         scaled_attention_logits = scaled_attention_logits + (mask.to(q.dtype) * -1e9)   # Attention.py:25-26
     attention_weights = torch.softmax(scaled_attention_logits, dim=-1)    # Attention.py:30
-    output = attention_weights @ v                                        # Attention.py:32
+    output = _op(attention_weights) @ _op(v)                              # Attention.py:32
     return output, attention_weights
 
 

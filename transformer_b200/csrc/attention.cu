@@ -232,28 +232,27 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         const bool plain = !diag && mrow == nullptr &&
                            ((padbits[0] | padbits[1] | padbits[2] | padbits[3] | oobbits[0] | oobbits[1] | oobbits[2] | oobbits[3]) == 0u);
         const float sl2 = scale * kLog2e;
-        // pass 1: row max
+        // pass 1: row max   (TMEM loads are issued two 32-column chunks at a time, one wait per pair)
         float m_new = m_run;
-        if (plain) {
-          float mx = -INFINITY;
 #pragma unroll 1
-          for (int c = 0; c < 4; ++c) {
-            uint32_t r[32];
-            tmem_ld_x32(tS[s] + lane_sel + c * 32, r);
-            tmem_ld_wait();
+        for (int c2 = 0; c2 < 2; ++c2) {
+          uint32_t ra[32], rb2[32];
+          tmem_ld_x32(tS[s] + lane_sel + c2 * 64, ra);
+          tmem_ld_x32(tS[s] + lane_sel + c2 * 64 + 32, rb2);
+          tmem_ld_wait();
+          if (plain) {
+            float mx = -INFINITY;
 #pragma unroll
-            for (int e = 0; e < 32; ++e) mx = fmaxf(mx, __uint_as_float(r[e]));
-          }
-          m_new = fmaxf(m_run, mx * scale);
-        } else {
-#pragma unroll 1
-          for (int c = 0; c < 4; ++c) {
-            uint32_t r[32];
-            tmem_ld_x32(tS[s] + lane_sel + c * 32, r);
-            tmem_ld_wait();
-            const uint32_t pb = sel4(padbits, c), ob = sel4(oobbits, c);
+            for (int e = 0; e < 32; ++e) mx = fmaxf(mx, fmaxf(__uint_as_float(ra[e]), __uint_as_float(rb2[e])));
+            m_new = fmaxf(m_new, mx * scale);
+          } else {
+            const uint32_t pa = sel4(padbits, 2 * c2), oa = sel4(oobbits, 2 * c2);
+            const uint32_t pb = sel4(padbits, 2 * c2 + 1), ob = sel4(oobbits, 2 * c2 + 1);
 #pragma unroll
-            for (int e = 0; e < 32; ++e) m_new = fmaxf(m_new, logit(__uint_as_float(r[e]), pb, ob, c, e));
+            for (int e = 0; e < 32; ++e) {
+              m_new = fmaxf(m_new, logit(__uint_as_float(ra[e]), pa, oa, 2 * c2, e));
+              m_new = fmaxf(m_new, logit(__uint_as_float(rb2[e]), pb, ob, 2 * c2 + 1, e));
+            }
           }
         }
         const float alpha = fast_exp2((m_run - m_new) * kLog2e);   // first tile: exp2(-inf) = 0
@@ -261,31 +260,36 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         // pass 2: p = exp(t - m), row sum (fp32), P -> bf16 -> smem (K-major SWIZZLE_128B, two 64-key panels)
         float rsum = 0.f;
 #pragma unroll 1
-        for (int c = 0; c < 4; ++c) {
-          uint32_t r[32];
-          tmem_ld_x32(tS[s] + lane_sel + c * 32, r);
+        for (int c2 = 0; c2 < 2; ++c2) {
+          uint32_t rr[2][32];
+          tmem_ld_x32(tS[s] + lane_sel + c2 * 64, rr[0]);
+          tmem_ld_x32(tS[s] + lane_sel + c2 * 64 + 32, rr[1]);
           tmem_ld_wait();
-          float p[32];
-          if (plain) {
+          const uint32_t panel = sPs + c2 * 16384;
 #pragma unroll
-            for (int e = 0; e < 32; ++e) {
-              p[e] = fast_exp2(__uint_as_float(r[e]) * sl2 - mb);
-              rsum += p[e];
-            }
-          } else {
-            const uint32_t pb = sel4(padbits, c), ob = sel4(oobbits, c);
+          for (int hc = 0; hc < 2; ++hc) {
+            const int c = 2 * c2 + hc;
+            float p[32];
+            if (plain) {
 #pragma unroll
-            for (int e = 0; e < 32; ++e) {
-              p[e] = fast_exp2(logit(__uint_as_float(r[e]), pb, ob, c, e) * kLog2e - mb);
-              rsum += p[e];
+              for (int e = 0; e < 32; ++e) {
+                p[e] = fast_exp2(__uint_as_float(rr[hc][e]) * sl2 - mb);
+                rsum += p[e];
+              }
+            } else {
+              const uint32_t pb = sel4(padbits, c), ob = sel4(oobbits, c);
+#pragma unroll
+              for (int e = 0; e < 32; ++e) {
+                p[e] = fast_exp2(logit(__uint_as_float(rr[hc][e]), pb, ob, c, e) * kLog2e - mb);
+                rsum += p[e];
+              }
             }
+#pragma unroll
+            for (int g = 0; g < 4; ++g)
+              st_shared_v4(panel + swz128_off(row, hc * 4 + g), pack_bf16x2(p[8 * g], p[8 * g + 1]),
+                           pack_bf16x2(p[8 * g + 2], p[8 * g + 3]), pack_bf16x2(p[8 * g + 4], p[8 * g + 5]),
+                           pack_bf16x2(p[8 * g + 6], p[8 * g + 7]));
           }
-          const uint32_t panel = sPs + (c >> 1) * 16384;
-#pragma unroll
-          for (int g = 0; g < 4; ++g)
-            st_shared_v4(panel + swz128_off(row, (c & 1) * 4 + g), pack_bf16x2(p[8 * g], p[8 * g + 1]),
-                         pack_bf16x2(p[8 * g + 2], p[8 * g + 3]), pack_bf16x2(p[8 * g + 4], p[8 * g + 5]),
-                         pack_bf16x2(p[8 * g + 6], p[8 * g + 7]));
         }
         fence_proxy_async_smem();
         tcgen05_before_thread_sync();
@@ -295,13 +299,15 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         // accumulate this tile's P.V
         mbar_wait(&o_full[s], j & 1);
         tcgen05_after_thread_sync();
+        {
+          uint32_t ro[DK / 32][32];
 #pragma unroll
-        for (int c = 0; c < DK / 32; ++c) {
-          uint32_t r[32];
-          tmem_ld_x32(tO[s] + lane_sel + c * 32, r);
+          for (int c = 0; c < DK / 32; ++c) tmem_ld_x32(tO[s] + lane_sel + c * 32, ro[c]);
           tmem_ld_wait();
 #pragma unroll
-          for (int e = 0; e < 32; ++e) acc[c * 32 + e] = acc[c * 32 + e] * alpha + __uint_as_float(r[e]);
+          for (int c = 0; c < DK / 32; ++c)
+#pragma unroll
+            for (int e = 0; e < 32; ++e) acc[c * 32 + e] = acc[c * 32 + e] * alpha + __uint_as_float(ro[c][e]);
         }
         tcgen05_before_thread_sync();
       }

@@ -167,7 +167,7 @@ residual_ln_fwd_kernel(float* __restrict__ y_z, const float* __restrict__ x, con
 //   dy_sub = dz * dropmask/(1-rate)                                      (bf16, gradient to the sublayer output)
 //   dgamma += sum_rows dy*xhat ; dbeta += sum_rows dy                    (block partials -> atomicAdd)
 template <int NV>
-__global__ void __launch_bounds__(256, NV >= 8 ? 1 : 2)
+__global__ void __launch_bounds__(256, NV >= 8 ? 1 : 3)
 residual_ln_bwd_kernel(const float* __restrict__ dout, const float* __restrict__ z, const float* __restrict__ mean_in,
                        const float* __restrict__ rstd_in, const float* __restrict__ gamma, float* __restrict__ dz,
                        __nv_bfloat16* __restrict__ dy_sub, float* __restrict__ dgamma, float* __restrict__ dbeta,
@@ -185,22 +185,22 @@ residual_ln_bwd_kernel(const float* __restrict__ dout, const float* __restrict__
   for (int i = 0; i < NV; ++i) { ag[i] = make_float4(0, 0, 0, 0); ab[i] = make_float4(0, 0, 0, 0); ac[i] = make_float4(0, 0, 0, 0); }
   for (long long r = warp_global; r < rows; r += nwarps) {
     const float mean = mean_in[r], rstd = rstd_in[r];
-    float4 xh[NV], gd[NV];
     float s1 = 0.f, s2 = 0.f;
+    // phase 1: row statistics + dgamma/dbeta partials.  xhat / gamma*dy are NOT kept in registers (3 CTAs per SM);
+    // phase 2 re-reads the row, which is still in L1.
 #pragma unroll
     for (int i = 0; i < NV; ++i) {
       const int c4 = lane + 32 * i;
-      xh[i] = make_float4(0, 0, 0, 0); gd[i] = make_float4(0, 0, 0, 0);
       if (c4 < d4) {
         const long long idx = r * d4 + c4;
         const float4 dyv = reinterpret_cast<const float4*>(dout)[idx];
         const float4 zv = reinterpret_cast<const float4*>(z)[idx];
         const float4 g = __ldg(reinterpret_cast<const float4*>(gamma) + c4);
-        xh[i] = make_float4((zv.x - mean) * rstd, (zv.y - mean) * rstd, (zv.z - mean) * rstd, (zv.w - mean) * rstd);
-        gd[i] = make_float4(g.x * dyv.x, g.y * dyv.y, g.z * dyv.z, g.w * dyv.w);
-        s1 += gd[i].x + gd[i].y + gd[i].z + gd[i].w;
-        s2 += gd[i].x * xh[i].x + gd[i].y * xh[i].y + gd[i].z * xh[i].z + gd[i].w * xh[i].w;
-        ag[i].x += dyv.x * xh[i].x; ag[i].y += dyv.y * xh[i].y; ag[i].z += dyv.z * xh[i].z; ag[i].w += dyv.w * xh[i].w;
+        const float4 xh = make_float4((zv.x - mean) * rstd, (zv.y - mean) * rstd, (zv.z - mean) * rstd, (zv.w - mean) * rstd);
+        const float4 gd = make_float4(g.x * dyv.x, g.y * dyv.y, g.z * dyv.z, g.w * dyv.w);
+        s1 += gd.x + gd.y + gd.z + gd.w;
+        s2 += gd.x * xh.x + gd.y * xh.y + gd.z * xh.z + gd.w * xh.w;
+        ag[i].x += dyv.x * xh.x; ag[i].y += dyv.y * xh.y; ag[i].z += dyv.z * xh.z; ag[i].w += dyv.w * xh.w;
         ab[i].x += dyv.x; ab[i].y += dyv.y; ab[i].z += dyv.z; ab[i].w += dyv.w;
       }
     }
@@ -210,11 +210,14 @@ residual_ln_bwd_kernel(const float* __restrict__ dout, const float* __restrict__
       const int c4 = lane + 32 * i;
       if (c4 < d4) {
         const long long idx = r * d4 + c4;
+        const float4 dyv = reinterpret_cast<const float4*>(dout)[idx];
+        const float4 zv = reinterpret_cast<const float4*>(z)[idx];
+        const float4 g = __ldg(reinterpret_cast<const float4*>(gamma) + c4);
         float4 o;
-        o.x = rstd * (gd[i].x - m1 - xh[i].x * m2);
-        o.y = rstd * (gd[i].y - m1 - xh[i].y * m2);
-        o.z = rstd * (gd[i].z - m1 - xh[i].z * m2);
-        o.w = rstd * (gd[i].w - m1 - xh[i].w * m2);
+        o.x = rstd * (g.x * dyv.x - m1 - (zv.x - mean) * rstd * m2);
+        o.y = rstd * (g.y * dyv.y - m1 - (zv.y - mean) * rstd * m2);
+        o.z = rstd * (g.z * dyv.z - m1 - (zv.z - mean) * rstd * m2);
+        o.w = rstd * (g.w * dyv.w - m1 - (zv.w - mean) * rstd * m2);
         reinterpret_cast<float4*>(dz)[idx] = o;
         if (rate > 0.f) {
           const float4 k = dropout_scale4(seed, site, (unsigned long long)idx, rate);
@@ -535,7 +538,7 @@ int residual_ln_bwd(const float* dout, const float* z, const float* mean, const 
                     float* dz, void* dy_sub, float* dgamma, float* dbeta, float* dbias, long long rows, int d, float rate,
                     unsigned long long seed, unsigned site, cudaStream_t st) {
   BX_REQUIRE(d % 4 == 0 && d <= 1024, "layernorm: need d %% 4 == 0 and d <= 1024 (got %d)", d);
-  const int grid = grid_for(rows * 32, 256, 2);
+  const int grid = grid_for(rows * 32, 256, 3);
   const size_t smem = (size_t)3 * d * sizeof(float);
   BX_LN_DISPATCH(residual_ln_bwd_kernel, <<<grid, 256, smem, st>>>(dout, z, mean, rstd, gamma, dz, (__nv_bfloat16*)dy_sub, dgamma,
                                                                   dbeta, dbias, rows, d, rate, seed, site))

@@ -162,18 +162,16 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       for (int c = 0; c < BN / OUT_COLS; ++c) {
         const int nc = n0 + c * OUT_COLS;
         if (nc >= N) break;
-        if (epi_tid == 0) tma_store_wait_read<1>();   // staging buffer `buf` no longer being read
-        named_bar_sync(1, 128);
         float v[OUT_COLS];
         {
-          uint32_t r[32];
+          uint32_t r[OUT_COLS / 32][32];
 #pragma unroll
-          for (int h = 0; h < OUT_COLS / 32; ++h) {
-            tmem_ld_x32(t_row + c * OUT_COLS + h * 32, r);
-            tmem_ld_wait();
+          for (int h = 0; h < OUT_COLS / 32; ++h) tmem_ld_x32(t_row + c * OUT_COLS + h * 32, r[h]);
+          tmem_ld_wait();
 #pragma unroll
-            for (int j = 0; j < 32; ++j) v[h * 32 + j] = __uint_as_float(r[j]);
-          }
+          for (int h = 0; h < OUT_COLS / 32; ++h)
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[h * 32 + j] = __uint_as_float(r[h][j]);
         }
         if (bias != nullptr) {
           if (nc + OUT_COLS <= N) {
@@ -213,6 +211,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
               if (nc + j < N && !(__bfloat162float(ap[j]) > 0.f)) v[j] = 0.f;
           }
         }
+        // staging buffer `buf` is free: the barrier of the previous chunk was passed only after thread 0 had seen
+        // the TMA store that last read it complete (two buffers, ONE named barrier per chunk).
         const uint32_t stg = stg_base + buf * Cfg::D_BYTES;
         if (kOutF32) {
 #pragma unroll
@@ -227,6 +227,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                          pack_bf16x2(v[8 * j + 6], v[8 * j + 7]));
         }
         fence_proxy_async_smem();
+        if (epi_tid == 0) tma_store_wait_read<0>();   // the previous chunk's store has drained the OTHER buffer
         named_bar_sync(1, 128);
         if (epi_tid == 0) {
           if (flags & GEMM_FLAG_ACCUM) tma_reduce_add_2d(&tmD, smem + Cfg::OFF_D + buf * Cfg::D_BYTES, nc, m0);
