@@ -177,8 +177,11 @@ def test_loss_curve_with_moving_weights():
     the north-star 1e-3 bound applies to the reference schedule above."""
     worst, P, model = _lockstep(200, 40, tol=1e-2)
     print("worst rel loss err (warmup 200):", worst)
-    drift = max(rel(v.value.cpu(), P[v.name]) for v in model.trainable_variables)
-    assert drift <= 5e-2, f"weights drifted from the oracle's: {drift}"
+    ours = torch.cat([v.value.cpu().reshape(-1) for v in model.trainable_variables])
+    theirs = torch.cat([P[v.name].reshape(-1) for v in model.trainable_variables])
+    drift = rel(ours, theirs)                      # global relative L2 distance between the two trained weight sets
+    print("weight drift after 40 moving steps:", drift)
+    assert drift <= 2e-2, f"weights drifted from the oracle's: {drift}"
 
 
 def test_dropout_training_runs_and_is_seeded():
