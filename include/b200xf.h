@@ -38,6 +38,10 @@ int b200xf_prof_collect(double* out, int ncat);
  *                         1 = M resp. N contiguous   (A stored [K,M], B stored [K,N] -- the keras kernel layout).
  *      flags: 1 = ReLU, 2 = accumulate into fp32 D (TMA reduce-add; required for splits > 1),
  *             4 = multiply by (aux > 0) (ReLU backward, aux bf16 [M, ld_aux]).                                   */
+/*      splits: K-split count for ACCUM GEMMs (<= 0: chosen by the library).  Tiles are 128 x BN per CTA or, for
+ *      M > 128 and N > 128, 256 x 256 per CTA PAIR (tcgen05 cta_group::2); b200xf_gemm_force_cta_group(1|2)
+ *      overrides the choice (0 restores it) -- used by tests and benchmarks.                                   */
+void b200xf_gemm_force_cta_group(int cg);
 int b200xf_gemm_bf16(const void* A, int64_t lda, int a_major, const void* B, int64_t ldb, int b_major, void* D,
                      int64_t ldd, int d_is_f32, const float* bias, const void* aux, int64_t ld_aux, int flags,
                      int splits, int64_t M, int64_t N, int64_t K, b200xf_stream_t stream);

@@ -86,21 +86,29 @@ def run_gemm(M, N, K, a_major, b_major, out_f32, bias=False, relu=False, aux=Fal
     return err
 
 
+@pytest.fixture(params=[1, 2], ids=["cta1", "ctapair"])
+def cta_group(request):
+    """run every GEMM test on both tile engines: single-CTA 128xBN tiles and cta_group::2 pair tiles (256x256)"""
+    L.load().b200xf_gemm_force_cta_group(request.param)
+    yield request.param
+    L.load().b200xf_gemm_force_cta_group(0)
+
+
 @pytest.mark.parametrize("a_major,b_major", [(0, 1), (0, 0), (1, 1), (1, 0)])
 @pytest.mark.parametrize("out_f32", [False, True])
-def test_gemm_majors_basic(a_major, b_major, out_f32):
+def test_gemm_majors_basic(a_major, b_major, out_f32, cta_group):
     run_gemm(256, 256, 128, a_major, b_major, out_f32)
     run_gemm(128, 64, 64, a_major, b_major, out_f32)          # BN=128 path, single k-block
 
 
 @pytest.mark.parametrize("a_major,b_major", [(0, 1), (0, 0), (1, 1)])
-def test_gemm_ragged_shapes(a_major, b_major):
+def test_gemm_ragged_shapes(a_major, b_major, cta_group):
     run_gemm(300, 200, 136, a_major, b_major, True)           # ragged M, N, K
     run_gemm(643, 520, 200, a_major, b_major, False)
     run_gemm(77, 40, 72, a_major, b_major, True)
 
 
-def test_gemm_epilogues():
+def test_gemm_epilogues(cta_group):
     run_gemm(384, 512, 256, 0, 1, False, bias=True, relu=True)            # FFN dense0 (point_ffn.py:5)
     run_gemm(384, 512, 256, 0, 1, True, bias=True)                        # dense (Attention.py:77)
     run_gemm(384, 512, 256, 0, 0, False, aux=True)                        # ReLU-backward dgrad
@@ -110,9 +118,11 @@ def test_gemm_epilogues():
     run_gemm(512, 2048, 3000, 1, 1, True, accum=True, splits=5)
 
 
-def test_gemm_multi_wave_persistent():
+def test_gemm_multi_wave_persistent(cta_group):
     run_gemm(4096, 2048, 512, 0, 1, False, bias=True, relu=True)          # 512 tiles > 148 SMs: ring + TMEM double buffer
     run_gemm(4096, 512, 2048, 0, 1, True, bias=True)
+    run_gemm(9000, 1000, 520, 0, 0, True, accum=True)                      # odd pair count, ragged everything
+    run_gemm(512, 2048, 8192, 1, 1, True, accum=True, splits=0)            # wgrad, library-chosen split-K
 
 
 # ------------------------------------------------------------------------------------------------

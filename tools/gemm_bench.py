@@ -44,6 +44,8 @@ def bench(M, N, K, a_major, b_major, out_f32, flags=0, splits=1, bias=True, iter
 
 
 if __name__ == "__main__":
+    if len(sys.argv) > 1:
+        L.load().b200xf_gemm_force_cta_group(int(sys.argv[1]))
     M = 32768
     rows = [
         bench(M, 2048, 512, 0, 1, False, flags=1),            # FFN dense0 fwd (bias+relu)

@@ -69,11 +69,12 @@ _SIGS = {
     "b200xf_version": [],
     "b200xf_launch_count": [],
     "b200xf_prof_enable": [_I],
+    "b200xf_gemm_force_cta_group": [_I],
     "b200xf_prof_collect": [C.POINTER(C.c_double), _I],
 }
 _RESTYPES = {"b200xf_last_error": C.c_char_p, "b200xf_launch_count": C.c_longlong,
              "b200xf_model_param_count": _I64, "b200xf_model_workspace_bytes": _I64,
-             "b200xf_model_destroy": None, "b200xf_prof_enable": None}
+             "b200xf_model_destroy": None, "b200xf_prof_enable": None, "b200xf_gemm_force_cta_group": None}
 
 EXPORTED_SYMBOLS = tuple(_SIGS)
 

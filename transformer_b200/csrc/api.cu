@@ -12,6 +12,7 @@ const char* b200xf_last_error(void) { return bx::last_error(); }
 int b200xf_version(void) { return 100; }
 long long b200xf_launch_count(void) { return bx::launch_count(); }
 void b200xf_prof_enable(int on) { bx::prof_enable(on); }
+void b200xf_gemm_force_cta_group(int cg) { bx::gemm_force_cta_group(cg); }
 int b200xf_prof_collect(double* out, int ncat) { return bx::prof_collect(out, ncat); }
 
 int b200xf_gemm_bf16(const void* A, int64_t lda, int a_major, const void* B, int64_t ldb, int b_major, void* D,

@@ -22,11 +22,13 @@ constexpr int GEMM_FLAG_RELU = 1;       // out = max(out, 0)
 constexpr int GEMM_FLAG_ACCUM = 2;      // D += out (TMA reduce-add; fp32 D only)
 constexpr int GEMM_FLAG_AUX_MASK = 4;   // out *= (aux[m,n] > 0)   (ReLU backward; aux bf16)
 
-template <int BN>
+// CG = CTAs cooperating on one tile: 1 (128 x BN tile) or 2 (a CTA pair, cta_group::2: 256 x BN tile; each CTA stages
+// its own 128 rows of A and its own BN/2 columns of B, so L2->smem traffic per flop drops by a third)
+template <int BN, int CG>
 struct GemmCfg {
-  static constexpr int kStages = BN == 256 ? 4 : 6;
   static constexpr uint32_t A_BYTES = GEMM_BM * GEMM_BK * 2;
-  static constexpr uint32_t B_BYTES = BN * GEMM_BK * 2;
+  static constexpr uint32_t B_BYTES = (BN / CG) * GEMM_BK * 2;
+  static constexpr int kStages = (A_BYTES + B_BYTES) == 49152 ? 4 : ((A_BYTES + B_BYTES) == 32768 ? 6 : 8);
   static constexpr uint32_t STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr uint32_t D_BYTES = GEMM_BM * 128;  // one 128-byte-wide staging box
   static constexpr uint32_t OFF_D = kStages * STAGE_BYTES;
@@ -35,14 +37,15 @@ struct GemmCfg {
   static constexpr uint32_t TMEM_COLS = 2 * BN;
 };
 
-template <int MA, int MB, int BN, bool kOutF32>
+template <int MA, int MB, int BN, bool kOutF32, int CG>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
             const __grid_constant__ CUtensorMap tmD, int M, int N, int K, int splits,
             const float* __restrict__ bias, const __nv_bfloat16* __restrict__ aux, long long ld_aux, int flags) {
-  using Cfg = GemmCfg<BN>;
+  using Cfg = GemmCfg<BN, CG>;
   constexpr int kStages = Cfg::kStages;
   constexpr int OUT_COLS = kOutF32 ? 32 : 64;  // columns per 128-byte staging row
+  constexpr int BNC = BN / CG;                 // B columns staged by this CTA
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -54,6 +57,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
 
   const uint32_t warp = warp_idx();
   const uint32_t lane = lane_idx();
+  const uint32_t rank = CG == 2 ? cluster_ctarank() : 0u;   // rank 0 of a pair issues the MMAs
+  const bool leader = rank == 0u;
 
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&tmA);
@@ -62,22 +67,26 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   }
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < kStages; ++i) {
-      mbar_init(&full_bar[i], 1);
+      mbar_init(&full_bar[i], CG);       // pair: the leader's barrier collects one arrive per CTA (+ both CTAs' bytes)
       mbar_init(&empty_bar[i], 1);
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tmem_full[i], 1);
-      mbar_init(&tmem_empty[i], 128);
+      mbar_init(&tmem_empty[i], 128 * CG);   // pair: the leader's barrier collects both CTAs' epilogue threads
     }
     fence_barrier_init();
   }
-  if (warp == 2) tmem_alloc<Cfg::TMEM_COLS>(tmem_ptr);
+  if (warp == 2) {
+    if (CG == 2) tmem_alloc_2sm<Cfg::TMEM_COLS>(tmem_ptr);
+    else tmem_alloc<Cfg::TMEM_COLS>(tmem_ptr);
+  }
   tcgen05_before_thread_sync();
-  __syncthreads();
+  if (CG == 2) cluster_sync_all(); else __syncthreads();
   tcgen05_after_thread_sync();
   const uint32_t tmem_base = *tmem_ptr;
+  const int cta = blockIdx.x / CG, ncta = gridDim.x / CG;    // tile-scheduling unit: a CTA or a CTA pair
 
-  const int m_tiles = (M + GEMM_BM - 1) / GEMM_BM;
+  const int m_tiles = (M + GEMM_BM * CG - 1) / (GEMM_BM * CG);
   const int n_tiles = (N + BN - 1) / BN;
   const int kblocks = (K + GEMM_BK - 1) / GEMM_BK;
   const int tiles_mn = m_tiles * n_tiles;
@@ -86,36 +95,56 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   if (warp == 0 && lane == 0) {
     // ===================================== TMA producer =====================================
     uint32_t stage = 0, phase = 0;
-    for (int t = blockIdx.x; t < total; t += gridDim.x) {
+    for (int t = cta; t < total; t += ncta) {
       const int split = t / tiles_mn, rem = t % tiles_mn;
-      const int m0 = (rem / n_tiles) * GEMM_BM, n0 = (rem % n_tiles) * BN;
+      const int m0 = (rem / n_tiles) * (GEMM_BM * CG) + (int)rank * GEMM_BM;   // this CTA's 128 rows of A
+      const int n0 = (rem % n_tiles) * BN + (int)rank * BNC;                     // this CTA's BN/CG columns of B
       const int kb0 = (int)((long long)split * kblocks / splits), kb1 = (int)((long long)(split + 1) * kblocks / splits);
       for (int kb = kb0; kb < kb1; ++kb) {
         mbar_wait(&empty_bar[stage], phase ^ 1);
         uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
         uint8_t* sb = sa + Cfg::A_BYTES;
-        mbar_arrive_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
         const int k0 = kb * GEMM_BK;
-        if (MA == 0) {
-          tma_load_2d(sa, &tmA, &full_bar[stage], k0, m0);
-        } else {
+        if (CG == 1) {
+          mbar_arrive_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
+          if (MA == 0) {
+            tma_load_2d(sa, &tmA, &full_bar[stage], k0, m0);
+          } else {
 #pragma unroll
-          for (int p = 0; p < GEMM_BM / 64; ++p) tma_load_2d(sa + p * 8192, &tmA, &full_bar[stage], m0 + p * 64, k0);
-        }
-        if (MB == 0) {
-          tma_load_2d(sb, &tmB, &full_bar[stage], k0, n0);
-        } else {
+            for (int p = 0; p < GEMM_BM / 64; ++p) tma_load_2d(sa + p * 8192, &tmA, &full_bar[stage], m0 + p * 64, k0);
+          }
+          if (MB == 0) {
+            tma_load_2d(sb, &tmB, &full_bar[stage], k0, n0);
+          } else {
 #pragma unroll
-          for (int p = 0; p < BN / 64; ++p) tma_load_2d(sb + p * 8192, &tmB, &full_bar[stage], n0 + p * 64, k0);
+            for (int p = 0; p < BNC / 64; ++p) tma_load_2d(sb + p * 8192, &tmB, &full_bar[stage], n0 + p * 64, k0);
+          }
+        } else {
+          // both CTAs load into their OWN smem; all bytes are credited to the LEADER's full barrier
+          const uint32_t lbar = mapa_u32(smem_u32(&full_bar[stage]), 0);
+          if (leader) mbar_arrive_expect_tx(&full_bar[stage], 2 * Cfg::STAGE_BYTES);
+          else mbar_arrive_cluster(lbar);
+          if (MA == 0) {
+            tma_load_2d_2sm(sa, &tmA, lbar, k0, m0);
+          } else {
+#pragma unroll
+            for (int p = 0; p < GEMM_BM / 64; ++p) tma_load_2d_2sm(sa + p * 8192, &tmA, lbar, m0 + p * 64, k0);
+          }
+          if (MB == 0) {
+            tma_load_2d_2sm(sb, &tmB, lbar, k0, n0);
+          } else {
+#pragma unroll
+            for (int p = 0; p < BNC / 64; ++p) tma_load_2d_2sm(sb + p * 8192, &tmB, lbar, n0 + p * 64, k0);
+          }
         }
         if (++stage == kStages) { stage = 0; phase ^= 1; }
       }
     }
-  } else if (warp == 1) {
-    // ===================================== MMA issuer =====================================
-    constexpr uint32_t idesc = make_idesc_bf16(GEMM_BM, BN, MA, MB);
+  } else if (warp == 1 && leader) {
+    // ===================================== MMA issuer (pair: leader CTA only) =====================================
+    constexpr uint32_t idesc = make_idesc_bf16(GEMM_BM * CG, BN, MA, MB);
     uint32_t stage = 0, phase = 0, it = 0;
-    for (int t = blockIdx.x; t < total; t += gridDim.x, ++it) {
+    for (int t = cta; t < total; t += ncta, ++it) {
       const int split = t / tiles_mn;
       const int kb0 = (int)((long long)split * kblocks / splits), kb1 = (int)((long long)(split + 1) * kblocks / splits);
       const uint32_t acc = it & 1u, acc_phase = (it >> 1) & 1u;
@@ -134,10 +163,17 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                                            : make_smem_desc(sa + k * 2048, GEMM_BK * 128, 1024, kSwz128);
             const uint64_t bdesc = MB == 0 ? make_smem_desc(sb + k * 32, 0, 1024, kSwz128)
                                            : make_smem_desc(sb + k * 2048, GEMM_BK * 128, 1024, kSwz128);
-            umma_f16(d_tmem, adesc, bdesc, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+            if (CG == 2) umma_f16_2sm(d_tmem, adesc, bdesc, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+            else umma_f16(d_tmem, adesc, bdesc, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
           }
-          umma_commit(&empty_bar[stage]);                    // frees the smem slot once these MMAs retire
-          if (kb == kb1 - 1) umma_commit(&tmem_full[acc]);   // accumulator ready for the epilogue
+          // frees the smem slot once these MMAs retire; on the last k-block the accumulator is ready for the epilogue
+          if (CG == 2) {
+            umma_commit_2sm(&empty_bar[stage]);              // multicast: same barrier offset in both CTAs
+            if (kb == kb1 - 1) umma_commit_2sm(&tmem_full[acc]);
+          } else {
+            umma_commit(&empty_bar[stage]);
+            if (kb == kb1 - 1) umma_commit(&tmem_full[acc]);
+          }
         }
         __syncwarp();
         if (++stage == kStages) { stage = 0; phase ^= 1; }
@@ -150,9 +186,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     const uint32_t epi_tid = threadIdx.x - 128u;
     const uint32_t stg_base = smem_u32(smem + Cfg::OFF_D);
     uint32_t it = 0, buf = 0;
-    for (int t = blockIdx.x; t < total; t += gridDim.x, ++it) {
+    for (int t = cta; t < total; t += ncta, ++it) {
       const int rem = t % tiles_mn;
-      const int m0 = (rem / n_tiles) * GEMM_BM, n0 = (rem % n_tiles) * BN;
+      const int m0 = (rem / n_tiles) * (GEMM_BM * CG) + (int)rank * GEMM_BM, n0 = (rem % n_tiles) * BN;
       const uint32_t acc = it & 1u, acc_phase = (it >> 1) & 1u;
       mbar_wait(&tmem_full[acc], acc_phase);
       tcgen05_after_thread_sync();
@@ -237,83 +273,110 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         buf ^= 1u;
       }
       tcgen05_before_thread_sync();
-      mbar_arrive(&tmem_empty[acc]);
+      if (CG == 2) mbar_arrive_cluster(mapa_u32(smem_u32(&tmem_empty[acc]), 0));   // the leader's barrier
+      else mbar_arrive(&tmem_empty[acc]);
     }
     if (epi_tid == 0) tma_store_wait_all<0>();
   }
 
   tcgen05_before_thread_sync();
-  __syncthreads();
+  if (CG == 2) cluster_sync_all(); else __syncthreads();   // pair: the peer's smem/TMEM stay alive until both are done
   tcgen05_after_thread_sync();
-  if (warp == 2) tmem_dealloc<Cfg::TMEM_COLS>(tmem_base);
+  if (warp == 2) {
+    if (CG == 2) tmem_dealloc_2sm<Cfg::TMEM_COLS>(tmem_base);
+    else tmem_dealloc<Cfg::TMEM_COLS>(tmem_base);
+  }
 }
 
 // ------------------------------------------------------------------------------------------------
 // host launcher
 // ------------------------------------------------------------------------------------------------
-template <int MA, int MB, int BN, bool kOutF32>
+// split-K factor for a reduce-add GEMM: aim at ~2 full waves of tile units
+static int auto_splits(long long tiles, long long kblocks, int groups) {
+  if (tiles >= 2 * groups) return 1;
+  long long s = (2 * groups + tiles / 2) / tiles;
+  if (s > kblocks / 4) s = kblocks / 4;
+  return (int)(s < 1 ? 1 : s);
+}
+
+template <int MA, int MB, int BN, bool kOutF32, int CG>
 static int launch_gemm(const void* A, long long lda, const void* B, long long ldb, void* D, long long ldd,
                        const float* bias, const void* aux, long long ld_aux, int flags, int splits, long long M,
                        long long N, long long K, cudaStream_t stream) {
-  using Cfg = GemmCfg<BN>;
+  using Cfg = GemmCfg<BN, CG>;
   CUtensorMap tmA, tmB, tmD;
   int rc;
   if (MA == 0) rc = encode_tmap_2d(&tmA, 0, A, K, M, lda, 64, GEMM_BM, 128);
   else rc = encode_tmap_2d(&tmA, 0, A, M, K, lda, 64, 64, 128);
   if (rc) return rc;
-  if (MB == 0) rc = encode_tmap_2d(&tmB, 0, B, K, N, ldb, 64, BN, 128);
+  if (MB == 0) rc = encode_tmap_2d(&tmB, 0, B, K, N, ldb, 64, BN / CG, 128);
   else rc = encode_tmap_2d(&tmB, 0, B, N, K, ldb, 64, 64, 128);
   if (rc) return rc;
   rc = encode_tmap_2d(&tmD, kOutF32 ? 1 : 0, D, N, M, ldd, kOutF32 ? 32 : 64, GEMM_BM, 128);
   if (rc) return rc;
-  auto kern = gemm_kernel<MA, MB, BN, kOutF32>;
+  auto kern = gemm_kernel<MA, MB, BN, kOutF32, CG>;
   static bool attr_done = false;
   if (!attr_done) {
     BX_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
     attr_done = true;
   }
-  const long long m_tiles = (M + GEMM_BM - 1) / GEMM_BM, n_tiles = (N + BN - 1) / BN;
+  const long long m_tiles = (M + GEMM_BM * CG - 1) / (GEMM_BM * CG), n_tiles = (N + BN - 1) / BN;
+  const long long kblocks = (K + GEMM_BK - 1) / GEMM_BK;
+  const int groups = sm_count() / CG;
+  if (splits <= 0) splits = (flags & GEMM_FLAG_ACCUM) ? auto_splits(m_tiles * n_tiles, kblocks, groups) : 1;
+  if (splits > kblocks) splits = (int)kblocks;
   const long long total = m_tiles * n_tiles * splits;
-  const int grid = (int)(total < sm_count() ? total : sm_count());
+  const int grid = (int)(total < groups ? total : groups) * CG;
   void* pb = prof_on() ? prof_begin(stream) : nullptr;
-  kern<<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, tmD, (int)M, (int)N, (int)K, splits, bias,
-                                                        reinterpret_cast<const __nv_bfloat16*>(aux), ld_aux, flags);
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(GEMM_THREADS);
+  cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CG; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  BX_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, tmA, tmB, tmD, (int)M, (int)N, (int)K, splits, bias,
+                                   reinterpret_cast<const __nv_bfloat16*>(aux), ld_aux, flags));
   if (pb) prof_end(pb, 0, 2.0 * (double)M * (double)N * (double)K, stream);
   BX_POST_LAUNCH();
   return 0;
 }
+
+static int g_force_cg = 0;   // 0 = heuristic, 1 / 2 = force (tests and benchmarks)
+void gemm_force_cta_group(int cg) { g_force_cg = cg; }
 
 int gemm_bf16(const void* A, long long lda, int a_major, const void* B, long long ldb, int b_major, void* D,
               long long ldd, int d_is_f32, const float* bias, const void* aux, long long ld_aux, int flags,
               int splits, long long M, long long N, long long K, cudaStream_t stream) {
   BX_REQUIRE(M > 0 && N > 0 && K > 0, "gemm: empty problem %lld x %lld x %lld", M, N, K);
   BX_REQUIRE(M < (1ll << 31) && N < (1ll << 31) && K < (1ll << 31), "gemm: dimension too large");
-  const long long kblocks = (K + GEMM_BK - 1) / GEMM_BK;
-  if (splits < 1) splits = 1;
-  if (splits > kblocks) splits = (int)kblocks;
-  BX_REQUIRE(splits == 1 || ((flags & GEMM_FLAG_ACCUM) && d_is_f32), "gemm: split-K needs fp32 D with ACCUM");
+  BX_REQUIRE(splits <= 1 || ((flags & GEMM_FLAG_ACCUM) && d_is_f32), "gemm: split-K needs fp32 D with ACCUM");
   BX_REQUIRE(!(flags & GEMM_FLAG_ACCUM) || d_is_f32, "gemm: ACCUM needs fp32 D");
   BX_REQUIRE(!(flags & GEMM_FLAG_AUX_MASK) || aux != nullptr, "gemm: AUX_MASK without aux");
   BX_REQUIRE(!(flags & GEMM_FLAG_AUX_MASK) || (ld_aux % 8 == 0 && (reinterpret_cast<uintptr_t>(aux) & 15) == 0),
              "gemm: aux must be 16-byte aligned with ld %% 8 == 0");
   BX_REQUIRE(bias == nullptr || (reinterpret_cast<uintptr_t>(bias) & 15) == 0, "gemm: bias must be 16-byte aligned");
+  BX_REQUIRE(a_major >= 0 && a_major <= 1 && b_major >= 0 && b_major <= 1, "gemm: bad majors %d/%d", a_major, b_major);
   const bool wide = N > 128;
-#define BX_GEMM_CASE(ma, mb)                                                                                       \
-  if (a_major == ma && b_major == mb) {                                                                            \
-    if (wide) {                                                                                                    \
-      return d_is_f32 ? launch_gemm<ma, mb, 256, true>(A, lda, B, ldb, D, ldd, bias, aux, ld_aux, flags, splits, M, N, K, stream)  \
-                      : launch_gemm<ma, mb, 256, false>(A, lda, B, ldb, D, ldd, bias, aux, ld_aux, flags, splits, M, N, K, stream); \
-    } else {                                                                                                       \
-      return d_is_f32 ? launch_gemm<ma, mb, 128, true>(A, lda, B, ldb, D, ldd, bias, aux, ld_aux, flags, splits, M, N, K, stream)  \
-                      : launch_gemm<ma, mb, 128, false>(A, lda, B, ldb, D, ldd, bias, aux, ld_aux, flags, splits, M, N, K, stream); \
-    }                                                                                                              \
+  const bool pair = g_force_cg ? g_force_cg == 2 : (M > 128 && wide);   // CTA pairs need >= 2 row tiles; 256-wide N tile only
+#define BX_GEMM_GO(ma, mb, bn, f32, cg) \
+  return launch_gemm<ma, mb, bn, f32, cg>(A, lda, B, ldb, D, ldd, bias, aux, ld_aux, flags, splits, M, N, K, stream)
+#define BX_GEMM_CASE(ma, mb)                                              \
+  if (a_major == ma && b_major == mb) {                                   \
+    if (wide && pair) { if (d_is_f32) BX_GEMM_GO(ma, mb, 256, true, 2); else BX_GEMM_GO(ma, mb, 256, false, 2); } \
+    if (wide) { if (d_is_f32) BX_GEMM_GO(ma, mb, 256, true, 1); else BX_GEMM_GO(ma, mb, 256, false, 1); }         \
+    if (d_is_f32) BX_GEMM_GO(ma, mb, 128, true, 1); else BX_GEMM_GO(ma, mb, 128, false, 1);                       \
   }
   BX_GEMM_CASE(0, 1)
   BX_GEMM_CASE(0, 0)
   BX_GEMM_CASE(1, 1)
   BX_GEMM_CASE(1, 0)
 #undef BX_GEMM_CASE
-  BX_REQUIRE(false, "gemm: bad majors %d/%d", a_major, b_major);
+#undef BX_GEMM_GO
+  return 1;
 }
 
 }  // namespace bx

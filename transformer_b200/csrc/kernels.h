@@ -9,6 +9,8 @@ int gemm_bf16(const void* A, long long lda, int a_major, const void* B, long lon
               long long ldd, int d_is_f32, const float* bias, const void* aux, long long ld_aux, int flags,
               int splits, long long M, long long N, long long K, cudaStream_t stream);
 
+void gemm_force_cta_group(int cg);   // 0 = heuristic, 1 / 2 = force single-CTA / CTA-pair tiles (tests, benchmarks)
+
 int attn_fwd(const void* Q, long long ld_q, const void* K, long long ld_k, const void* V, long long ld_v, void* O,
              long long ld_o, float* lse, const uint8_t* kpad, int causal, const float* maskf, long long mask_sb,
              long long mask_sq, int B, int H, int Sq, int Sk, int dk, cudaStream_t st);

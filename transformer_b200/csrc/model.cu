@@ -242,16 +242,6 @@ inline uint32_t site_dec_embed() { return 2; }
 inline uint32_t site_enc(int l, int k) { return 16 + l * 8 + k; }
 inline uint32_t site_dec(int l, int k) { return 4096 + l * 8 + k; }
 
-int pick_splits(int64_t Mo, int64_t No, int64_t Ktok) {
-  const int64_t bn = No > 128 ? 256 : 128;
-  const int64_t tiles = ((Mo + 127) / 128) * ((No + bn - 1) / bn);
-  const int64_t kblocks = (Ktok + 63) / 64;
-  int64_t s = (2 * bx::sm_count() + tiles - 1) / tiles;
-  if (s > kblocks / 4) s = kblocks / 4;
-  if (s < 1) s = 1;
-  return (int)s;
-}
-
 // y[M,N] = x[M,K] . W[K,N] + b        (keras Dense; W in keras [in,out] layout, row pitch ldw)
 int linear_fwd(const bf16* x, int64_t ldx, const bf16* W, int64_t ldw, const float* b, void* y, int64_t ldy, bool y_f32,
                bool relu, int64_t Mr, int64_t N, int64_t K, cudaStream_t st) {
@@ -266,7 +256,7 @@ int linear_dgrad(const bf16* dy, int64_t ld_dy, const bf16* W, int64_t ldw, void
 // dW[K,N] += x[M,K]^T . dy[M,N] ; db[N] += colsum(dy)     (split-K over the token dimension, TMA reduce-add)
 int linear_wgrad(const bf16* x, int64_t ldx, const bf16* dy, int64_t ld_dy, float* dW, int64_t ldw, float* db, int64_t Mr,
                  int64_t N, int64_t K, cudaStream_t st) {
-  RC(bx::gemm_bf16(x, ldx, 1, dy, ld_dy, 1, dW, ldw, 1, nullptr, nullptr, 0, 2, pick_splits(K, N, Mr), K, N, Mr, st));
+  RC(bx::gemm_bf16(x, ldx, 1, dy, ld_dy, 1, dW, ldw, 1, nullptr, nullptr, 0, 2, /*splits: auto*/ 0, K, N, Mr, st));
   if (db) RC(bx::colsum_bf16(dy, ld_dy, db, Mr, (int)N, st));
   return 0;
 }
