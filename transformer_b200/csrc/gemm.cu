@@ -323,13 +323,10 @@ static int launch_gemm(const void* A, long long lda, const void* B, long long ld
   const long long m_tiles = (M + GEMM_BM * CG - 1) / (GEMM_BM * CG), n_tiles = (N + BN - 1) / BN;
   const long long kblocks = (K + GEMM_BK - 1) / GEMM_BK;
   const int groups = sm_count() / CG;
+  const int splits0 = splits;
   if (splits <= 0) splits = (flags & GEMM_FLAG_ACCUM) ? auto_splits(m_tiles * n_tiles, kblocks, groups) : 1;
   if (splits > kblocks) splits = (int)kblocks;
-  const long long total = m_tiles * n_tiles * splits;
-  const int grid = (int)(total < groups ? total : groups) * CG;
-  void* pb = prof_on() ? prof_begin(stream) : nullptr;
   cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3(grid);
   cfg.blockDim = dim3(GEMM_THREADS);
   cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
   cfg.stream = stream;
@@ -338,6 +335,26 @@ static int launch_gemm(const void* A, long long lda, const void* B, long long ld
   attr[0].val.clusterDim.x = CG; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
+  // The tile schedule is static (tile = unit + i * units), so every unit must be co-resident.  Not every TPC can
+  // host a 2-CTA cluster (SMs are yield-harvested individually): ask the runtime how many clusters fit at once.
+  static int max_units = 0;
+  if (max_units == 0) {
+    max_units = groups;
+    if (CG == 2) {
+      cfg.gridDim = dim3(groups * CG);
+      int n = 0;
+      if (cudaOccupancyMaxActiveClusters(&n, kern, &cfg) == cudaSuccess && n > 0 && n < max_units) max_units = n;
+      (void)cudaGetLastError();
+    }
+  }
+  if (splits0 <= 0 && (flags & GEMM_FLAG_ACCUM)) {   // re-balance split-K against the real number of co-resident units
+    splits = auto_splits(m_tiles * n_tiles, kblocks, max_units);
+    if (splits > kblocks) splits = (int)kblocks;
+  }
+  const long long total2 = m_tiles * n_tiles * splits;
+  const int grid = (int)(total2 < max_units ? total2 : max_units) * CG;
+  cfg.gridDim = dim3(grid);
+  void* pb = prof_on() ? prof_begin(stream) : nullptr;
   BX_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, tmA, tmB, tmD, (int)M, (int)N, (int)K, splits, bias,
                                    reinterpret_cast<const __nv_bfloat16*>(aux), ld_aux, flags));
   if (pb) prof_end(pb, 0, 2.0 * (double)M * (double)N * (double)K, stream);
