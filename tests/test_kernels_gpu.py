@@ -118,6 +118,29 @@ def test_gemm_epilogues(cta_group):
     run_gemm(512, 2048, 3000, 1, 1, True, accum=True, splits=5)
 
 
+def test_gemm_relu_bitmask_roundtrip(cta_group):
+    """forward FFN epilogue stores a 1-bit (relu(x.W+b) > 0) gate per element; the dgrad epilogue applies it"""
+    M, N, K = 700, 512, 192
+    A = rnd((M, K), 1.0, 1); W = rnd((K, N), 1.0, 2); bias = rnd((N,), 1.0, 3, torch.float32)
+    H = torch.full((M, N), float("nan"), dtype=torch.bfloat16, device=dev())
+    bits = torch.zeros((M, N // 64), dtype=torch.int64, device=dev())
+    L.call("b200xf_gemm_bf16", L.ptr(A), K, 0, L.ptr(W), N, 1, L.ptr(H), N, 0, L.ptr(bias), L.ptr(bits), N // 64, 1 | 8, 1, M, N, K, sp())
+    torch.cuda.synchronize()
+    pre = A.float() @ W.float() + bias
+    assert (H.float() - torch.relu(pre)).abs().max().item() < 0.3
+    got = ((bits[:, :, None] >> torch.arange(64, device=dev())) & 1).reshape(M, N).bool()
+    sure = pre.abs() > 1e-3
+    assert torch.equal(got[sure], (pre > 0)[sure])
+    # backward: dh = (dy . W2^T) o gate, with W2 [N, K2] keras layout
+    K2 = 256
+    dy = rnd((M, K2), 1.0, 4); W2 = rnd((N, K2), 1.0, 5)
+    dh = torch.full((M, N), float("nan"), dtype=torch.bfloat16, device=dev())
+    L.call("b200xf_gemm_bf16", L.ptr(dy), K2, 0, L.ptr(W2), K2, 0, L.ptr(dh), N, 0, None, L.ptr(bits), N // 64, 16, 1, M, N, K2, sp())
+    torch.cuda.synchronize()
+    ref = (dy.float() @ W2.float().t()) * got
+    assert (dh.float() - ref).abs().max().item() < 0.02 * max(1.0, ref.abs().max().item())
+
+
 def test_gemm_multi_wave_persistent(cta_group):
     run_gemm(4096, 2048, 512, 0, 1, False, bias=True, relu=True)          # 512 tiles > 148 SMs: ring + TMEM double buffer
     run_gemm(4096, 512, 2048, 0, 1, True, bias=True)

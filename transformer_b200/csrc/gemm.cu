@@ -21,6 +21,8 @@ constexpr int GEMM_THREADS = 256;  // w0 TMA, w1 MMA, w2 TMEM alloc, w3 idle, w4
 constexpr int GEMM_FLAG_RELU = 1;       // out = max(out, 0)
 constexpr int GEMM_FLAG_ACCUM = 2;      // D += out (TMA reduce-add; fp32 D only)
 constexpr int GEMM_FLAG_AUX_MASK = 4;   // out *= (aux[m,n] > 0)   (ReLU backward; aux bf16)
+constexpr int GEMM_FLAG_BITS_OUT = 8;   // with RELU, bf16 out: also store a 1-bit-per-element (out > 0) mask, 64 columns per uint64
+constexpr int GEMM_FLAG_BITS_MASK = 16; // out *= mask bit (ReLU backward from the compact mask; aux = uint64 words, ld_aux in words)
 
 // CG = CTAs cooperating on one tile: 1 (128 x BN tile) or 2 (a CTA pair, cta_group::2: 256 x BN tile; each CTA stages
 // its own 128 rows of A and its own BN/2 columns of B, so L2->smem traffic per flop drops by a third)
@@ -41,7 +43,8 @@ template <int MA, int MB, int BN, bool kOutF32, int CG>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
             const __grid_constant__ CUtensorMap tmD, int M, int N, int K, int splits,
-            const float* __restrict__ bias, const __nv_bfloat16* __restrict__ aux, long long ld_aux, int flags) {
+            const float* __restrict__ bias, void* aux_v, long long ld_aux, int flags) {
+  const __nv_bfloat16* aux = reinterpret_cast<const __nv_bfloat16*>(aux_v);
   using Cfg = GemmCfg<BN, CG>;
   constexpr int kStages = Cfg::kStages;
   constexpr int OUT_COLS = kOutF32 ? 32 : 64;  // columns per 128-byte staging row
@@ -226,6 +229,18 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         if (flags & GEMM_FLAG_RELU) {
 #pragma unroll
           for (int j = 0; j < OUT_COLS; ++j) v[j] = fmaxf(v[j], 0.f);
+          if (!kOutF32 && (flags & GEMM_FLAG_BITS_OUT) && grow < M) {   // compact ReLU gate for the backward pass
+            unsigned long long bits = 0ull;
+#pragma unroll
+            for (int j = 0; j < OUT_COLS; ++j) bits |= (unsigned long long)(v[j] > 0.f) << j;
+            reinterpret_cast<unsigned long long*>(aux_v)[grow * ld_aux + (nc >> 6)] = bits;
+          }
+        }
+        if (!kOutF32 && (flags & GEMM_FLAG_BITS_MASK)) {
+          const unsigned long long bits = grow < M ? __ldg(reinterpret_cast<const unsigned long long*>(aux_v) + grow * ld_aux + (nc >> 6)) : 0ull;
+#pragma unroll
+          for (int j = 0; j < OUT_COLS; ++j)
+            if (!((bits >> j) & 1ull)) v[j] = 0.f;
         }
         if ((flags & GEMM_FLAG_AUX_MASK) && grow < M) {
           const __nv_bfloat16* ap = aux + grow * ld_aux + nc;
@@ -355,8 +370,8 @@ static int launch_gemm(const void* A, long long lda, const void* B, long long ld
   const int grid = (int)(total2 < max_units ? total2 : max_units) * CG;
   cfg.gridDim = dim3(grid);
   void* pb = prof_on() ? prof_begin(stream) : nullptr;
-  BX_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, tmA, tmB, tmD, (int)M, (int)N, (int)K, splits, bias,
-                                   reinterpret_cast<const __nv_bfloat16*>(aux), ld_aux, flags));
+  BX_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, tmA, tmB, tmD, (int)M, (int)N, (int)K, splits, bias, const_cast<void*>(aux), ld_aux,
+                                   flags));
   if (pb) prof_end(pb, 0, 2.0 * (double)M * (double)N * (double)K, stream);
   BX_POST_LAUNCH();
   return 0;
@@ -376,6 +391,9 @@ int gemm_bf16(const void* A, long long lda, int a_major, const void* B, long lon
   BX_REQUIRE(!(flags & GEMM_FLAG_AUX_MASK) || (ld_aux % 8 == 0 && (reinterpret_cast<uintptr_t>(aux) & 15) == 0),
              "gemm: aux must be 16-byte aligned with ld %% 8 == 0");
   BX_REQUIRE(bias == nullptr || (reinterpret_cast<uintptr_t>(bias) & 15) == 0, "gemm: bias must be 16-byte aligned");
+  BX_REQUIRE(!(flags & (GEMM_FLAG_BITS_OUT | GEMM_FLAG_BITS_MASK)) ||
+                 (aux != nullptr && !d_is_f32 && N % 64 == 0 && (reinterpret_cast<uintptr_t>(aux) & 7) == 0),
+             "gemm: bit-mask epilogues need bf16 D, N %% 64 == 0 and an 8-byte aligned mask buffer");
   BX_REQUIRE(a_major >= 0 && a_major <= 1 && b_major >= 0 && b_major <= 1, "gemm: bad majors %d/%d", a_major, b_major);
   const bool wide = N > 128;
   const bool pair = g_force_cg ? g_force_cg == 2 : (M > 128 && wide);   // CTA pairs need >= 2 row tiles; 256-wide N tile only

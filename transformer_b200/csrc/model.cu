@@ -131,11 +131,11 @@ Layout make_layout(const b200xf_model_config& c) {
 
 // ---- workspace (activations kept for backward + gradient scratch), carved from one caller-owned buffer ----
 struct LnSave { float *z, *mean, *rstd; };
-struct EncAct { bf16* qkv; bf16* attn_o; float* lse; LnSave ln1; float* out1_32; bf16* out1_16; bf16* h; LnSave ln2; };
+struct EncAct { bf16* qkv; bf16* attn_o; float* lse; LnSave ln1; float* out1_32; bf16* out1_16; bf16* h; uint64_t* hbits; LnSave ln2; };
 struct DecAct {
   bf16* qkv1; bf16* attn1_o; float* lse1; LnSave ln1; float* out1_32; bf16* out1_16;
   bf16* q2; bf16* kv2; bf16* attn2_o; float* lse2; LnSave ln2; float* out2_32; bf16* out2_16;
-  bf16* h; LnSave ln3;
+  bf16* h; uint64_t* hbits; LnSave ln3;
 };
 struct Work {
   std::vector<float*> enc_x32, dec_x32;   // [L+1] layer inputs/outputs (index 0 = embedding output)
@@ -175,14 +175,14 @@ Work make_work(const b200xf_model_config& c, const Layout& lo, void* base) {
   w.enc.resize(L); w.dec.resize(L);
   for (auto& a : w.enc) {
     a.qkv = b.take<bf16>(Ms * 3 * d); a.attn_o = b.take<bf16>(Ms * d); a.lse = b.take<float>(c.max_batch * H * c.max_src_len);
-    a.ln1 = ln(Ms); a.out1_32 = b.take<float>(Ms * d); a.out1_16 = b.take<bf16>(Ms * d); a.h = b.take<bf16>(Ms * f); a.ln2 = ln(Ms);
+    a.ln1 = ln(Ms); a.out1_32 = b.take<float>(Ms * d); a.out1_16 = b.take<bf16>(Ms * d); a.h = b.take<bf16>(Ms * f); a.hbits = b.take<uint64_t>(Ms * ((f + 63) / 64)); a.ln2 = ln(Ms);
   }
   for (auto& a : w.dec) {
     a.qkv1 = b.take<bf16>(Mt * 3 * d); a.attn1_o = b.take<bf16>(Mt * d); a.lse1 = b.take<float>(c.max_batch * H * c.max_tgt_len);
     a.ln1 = ln(Mt); a.out1_32 = b.take<float>(Mt * d); a.out1_16 = b.take<bf16>(Mt * d);
     a.q2 = b.take<bf16>(Mt * d); a.kv2 = b.take<bf16>(Ms * 2 * d); a.attn2_o = b.take<bf16>(Mt * d);
     a.lse2 = b.take<float>(c.max_batch * H * c.max_tgt_len);
-    a.ln2 = ln(Mt); a.out2_32 = b.take<float>(Mt * d); a.out2_16 = b.take<bf16>(Mt * d); a.h = b.take<bf16>(Mt * f); a.ln3 = ln(Mt);
+    a.ln2 = ln(Mt); a.out2_32 = b.take<float>(Mt * d); a.out2_16 = b.take<bf16>(Mt * d); a.h = b.take<bf16>(Mt * f); a.hbits = b.take<uint64_t>(Mt * ((f + 63) / 64)); a.ln3 = ln(Mt);
   }
   w.logits = b.take<bf16>(Mt * lo.Vp);
   w.kpad_in = b.take<uint8_t>(Ms); w.kpad_tar = b.take<uint8_t>(Mt);
@@ -244,12 +244,17 @@ inline uint32_t site_dec(int l, int k) { return 4096 + l * 8 + k; }
 
 // y[M,N] = x[M,K] . W[K,N] + b        (keras Dense; W in keras [in,out] layout, row pitch ldw)
 int linear_fwd(const bf16* x, int64_t ldx, const bf16* W, int64_t ldw, const float* b, void* y, int64_t ldy, bool y_f32,
-               bool relu, int64_t Mr, int64_t N, int64_t K, cudaStream_t st) {
-  return bx::gemm_bf16(x, ldx, 0, W, ldw, 1, y, ldy, y_f32 ? 1 : 0, b, nullptr, 0, relu ? 1 : 0, 1, Mr, N, K, st);
+               bool relu, int64_t Mr, int64_t N, int64_t K, cudaStream_t st, uint64_t* relu_bits = nullptr) {
+  const bool bits = relu && relu_bits != nullptr && !y_f32 && N % 64 == 0;    // compact (y > 0) gate, 1 bit per element
+  return bx::gemm_bf16(x, ldx, 0, W, ldw, 1, y, ldy, y_f32 ? 1 : 0, b, bits ? relu_bits : nullptr, bits ? N / 64 : 0,
+                       (relu ? 1 : 0) | (bits ? 8 : 0), 1, Mr, N, K, st);
 }
 // dx[M,K] (+)= dy[M,N] . W^T          (W [K,N] row-major is exactly the K-major B operand of this product)
 int linear_dgrad(const bf16* dy, int64_t ld_dy, const bf16* W, int64_t ldw, void* dx, int64_t ld_dx, bool dx_f32, bool accum,
-                 const bf16* relu_aux, int64_t ld_aux, int64_t Mr, int64_t N, int64_t K, cudaStream_t st) {
+                 const bf16* relu_aux, int64_t ld_aux, int64_t Mr, int64_t N, int64_t K, cudaStream_t st,
+                 const uint64_t* relu_bits = nullptr) {
+  if (relu_bits != nullptr && !dx_f32 && K % 64 == 0)     // ReLU gate from the compact mask the forward epilogue stored
+    return bx::gemm_bf16(dy, ld_dy, 0, W, ldw, 0, dx, ld_dx, 0, nullptr, relu_bits, K / 64, (accum ? 2 : 0) | 16, 1, Mr, K, N, st);
   const int flags = (accum ? 2 : 0) | (relu_aux ? 4 : 0);
   return bx::gemm_bf16(dy, ld_dy, 0, W, ldw, 0, dx, ld_dx, dx_f32 ? 1 : 0, nullptr, relu_aux, ld_aux, flags, 1, Mr, K, N, st);
 }
@@ -309,7 +314,7 @@ int forward_impl(M* m, float* logits_out, int64_t ld_logits, cudaStream_t st) {
     RC(linear_fwd(a.attn_o, d, Sh + p.mha.Wo, d, m->P + p.mha.bo, a.ln1.z, d, true, false, Ms, d, d, st));
     RC(residual_ln(m, a.ln1.z, w.enc_x32[l], p.ln1g, p.ln1b, a.out1_32, a.out1_16, a.ln1, Ms, site_enc(l, 0), st));   // Encoder.py:22-23
     // point_wise_feed_forward_network (point_ffn.py:3-7)
-    RC(linear_fwd(a.out1_16, d, Sh + p.ffn.W1, f, m->P + p.ffn.b1, a.h, f, false, true, Ms, f, d, st));
+    RC(linear_fwd(a.out1_16, d, Sh + p.ffn.W1, f, m->P + p.ffn.b1, a.h, f, false, true, Ms, f, d, st, a.hbits));
     RC(linear_fwd(a.h, f, Sh + p.ffn.W2, d, m->P + p.ffn.b2, a.ln2.z, d, true, false, Ms, d, f, st));
     RC(residual_ln(m, a.ln2.z, a.out1_32, p.ln2g, p.ln2b, w.enc_x32[l + 1], w.enc_x16[l + 1], a.ln2, Ms, site_enc(l, 1), st));   // Encoder.py:26-27
   }
@@ -336,7 +341,7 @@ int forward_impl(M* m, float* logits_out, int64_t ld_logits, cudaStream_t st) {
     RC(linear_fwd(a.attn2_o, d, Sh + p.mha2.Wo, d, m->P + p.mha2.bo, a.ln2.z, d, true, false, Mt, d, d, st));
     RC(residual_ln(m, a.ln2.z, a.out1_32, p.ln2g, p.ln2b, a.out2_32, a.out2_16, a.ln2, Mt, site_dec(l, 1), st));
     // ffn (Decoder.py:38-40)
-    RC(linear_fwd(a.out2_16, d, Sh + p.ffn.W1, f, m->P + p.ffn.b1, a.h, f, false, true, Mt, f, d, st));
+    RC(linear_fwd(a.out2_16, d, Sh + p.ffn.W1, f, m->P + p.ffn.b1, a.h, f, false, true, Mt, f, d, st, a.hbits));
     RC(linear_fwd(a.h, f, Sh + p.ffn.W2, d, m->P + p.ffn.b2, a.ln3.z, d, true, false, Mt, d, f, st));
     RC(residual_ln(m, a.ln3.z, a.out2_32, p.ln3g, p.ln3b, w.dec_x32[l + 1], w.dec_x16[l + 1], a.ln3, Mt, site_dec(l, 2), st));
   }
@@ -359,11 +364,11 @@ int residual_ln_back(M* m, const float* g_in, const LnSave& s, int64_t g_off, in
 }
 
 // FFN backward: dy16 = d(ffn output); x16 = ffn input; accumulates d(input) into g (fp32)
-int ffn_back(M* m, const Ffn& p, const bf16* x16, const bf16* h, float* g, int64_t rows, cudaStream_t st) {
+int ffn_back(M* m, const Ffn& p, const bf16* x16, const bf16* h, const uint64_t* hbits, float* g, int64_t rows, cudaStream_t st) {
   const int d = m->lo.d, f = m->lo.f;
   Work& w = m->w;
   RC(linear_wgrad(h, f, w.dy16, d, m->G + p.W2, d, nullptr, rows, d, f, st));                 // db2: from the LN backward
-  RC(linear_dgrad(w.dy16, d, m->Sh + p.W2, d, w.dh, f, false, false, h, f, rows, d, f, st));     // dh = (dy . W2^T) o [h > 0]
+  RC(linear_dgrad(w.dy16, d, m->Sh + p.W2, d, w.dh, f, false, false, h, f, rows, d, f, st, hbits));     // dh = (dy . W2^T) o [h > 0]
   RC(linear_wgrad(x16, d, w.dh, f, m->G + p.W1, f, m->G + p.b1, rows, f, d, st));
   RC(linear_dgrad(w.dh, f, m->Sh + p.W1, f, g, d, true, true, nullptr, 0, rows, f, d, st));
   return 0;
@@ -414,7 +419,7 @@ int backward_decoder(M* m, cudaStream_t st) {
     DecAct& a = w.dec[l];
     // out3 = LN3(out2 + drop(ffn(out2)))
     RC(residual_ln_back(m, g_in, a.ln3, p.ln3g, p.ln3b, p.ffn.b2, g_out, Mt, site_dec(l, 2), st));
-    RC(ffn_back(m, p.ffn, a.out2_16, a.h, g_out, Mt, st));
+    RC(ffn_back(m, p.ffn, a.out2_16, a.h, a.hbits, g_out, Mt, st));
     std::swap(g_in, g_out);
     // out2 = LN2(out1 + drop(mha2(enc_out, enc_out, out1)))
     RC(residual_ln_back(m, g_in, a.ln2, p.ln2g, p.ln2b, p.mha2.bo, g_out, Mt, site_dec(l, 1), st));
@@ -456,7 +461,7 @@ int backward_encoder(M* m, cudaStream_t st) {
     const EncLayerP& p = lo.enc[l];
     EncAct& a = w.enc[l];
     RC(residual_ln_back(m, g_in, a.ln2, p.ln2g, p.ln2b, p.ffn.b2, g_out, Ms, site_enc(l, 1), st));
-    RC(ffn_back(m, p.ffn, a.out1_16, a.h, g_out, Ms, st));
+    RC(ffn_back(m, p.ffn, a.out1_16, a.h, a.hbits, g_out, Ms, st));
     { float* t = g_in; g_in = g_out; g_out = (t == w.d_enc_out) ? spare : t; }
     RC(residual_ln_back(m, g_in, a.ln1, p.ln1g, p.ln1b, p.mha.bo, g_out, Ms, site_enc(l, 0), st));
     RC(self_attn_back(m, p.mha, w.enc_x16[l], a.qkv, a.attn_o, a.lse, em, g_out, S, st));
