@@ -29,6 +29,8 @@ long long b200xf_launch_count(void);
 /* optional CUDA-event timing of every tensor-core kernel launch (used by bench.py for the live roofline numbers):
  * categories 0 = GEMM, 1 = attention forward, 2 = attention backward; after synchronising the stream,
  * b200xf_prof_collect fills out[cat*3 + {0,1,2}] = {total ms, total algorithmic flops, launches} and resets. */
+/* debug: CTA (0,0,0) of the attention kernels writes clock64 stamps into this device buffer (>= 128 int64; NULL = off) */
+int b200xf_debug_set_timeline(long long* dev_ptr);
 void b200xf_prof_enable(int on);
 int b200xf_prof_collect(double* out, int ncat);
 

@@ -69,6 +69,7 @@ _SIGS = {
     "b200xf_version": [],
     "b200xf_launch_count": [],
     "b200xf_prof_enable": [_I],
+    "b200xf_debug_set_timeline": [_P],
     "b200xf_gemm_force_cta_group": [_I],
     "b200xf_prof_collect": [C.POINTER(C.c_double), _I],
 }

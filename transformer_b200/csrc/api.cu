@@ -12,6 +12,7 @@ const char* b200xf_last_error(void) { return bx::last_error(); }
 int b200xf_version(void) { return 100; }
 long long b200xf_launch_count(void) { return bx::launch_count(); }
 void b200xf_prof_enable(int on) { bx::prof_enable(on); }
+int b200xf_debug_set_timeline(long long* dev_ptr) { return bx::set_timeline(dev_ptr); }
 void b200xf_gemm_force_cta_group(int cg) { bx::gemm_force_cta_group(cg); }
 int b200xf_prof_collect(double* out, int ncat) { return bx::prof_collect(out, ncat); }
 

@@ -16,6 +16,16 @@
 
 namespace bx {
 
+// optional debug timeline: clock64 stamps written by CTA (0,0,0) when a buffer has been registered
+__device__ long long* g_timeline = nullptr;
+__device__ __forceinline__ void tl_stamp(int slot) {
+  if (g_timeline != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) g_timeline[slot] = clock64();
+}
+int set_timeline(long long* dev_ptr) {
+  BX_CHECK_CUDA(cudaMemcpyToSymbol(g_timeline, &dev_ptr, sizeof(dev_ptr)));
+  return 0;
+}
+
 constexpr float kLog2e = 1.4426950408889634f;
 constexpr float kMaskVal = -1e9f;
 
@@ -78,6 +88,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 16);
 
   const uint32_t warp = warp_idx(), lane = lane_idx();
+  if (threadIdx.x == 64) tl_stamp(0);
   const int b = blockIdx.z, h = blockIdx.y;
   const int q0 = blockIdx.x * 256;
   const int n_slots = (q0 + 128 < Sq) ? 2 : 1;
@@ -112,6 +123,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   __syncthreads();
   tcgen05_after_thread_sync();
   const uint32_t tmem_base = *tmem_ptr;
+  if (threadIdx.x == 64) tl_stamp(1);
   const uint32_t tS[2] = {tmem_base, tmem_base + 128};
   const uint32_t tO[2] = {tmem_base + 256, tmem_base + 256 + DK};
 
@@ -212,8 +224,11 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
           oobbits[c] = __ballot_sync(0xffffffffu, oob);
         }
         const bool diag = mask.causal && (kv0 + 127 > q0 + s * 128);   // tile touches the causal boundary
+        const bool tl = (s == 0 && wg_tid == 0);
+        if (tl) tl_stamp(8 + j * 8 + 0);
         mbar_wait(&s_full[s], j & 1);
         tcgen05_after_thread_sync();
+        if (tl) tl_stamp(8 + j * 8 + 1);
 
         auto logit = [&](float raw, uint32_t pb, uint32_t ob, int c, int e) -> float {
           const int kv = kv0 + c * 32 + e;
@@ -257,6 +272,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         }
         const float alpha = fast_exp2((m_run - m_new) * kLog2e);   // first tile: exp2(-inf) = 0
         const float mb = m_new * kLog2e;
+        if (tl) tl_stamp(8 + j * 8 + 2);
         // pass 2: p = exp(t - m), row sum (fp32), P -> bf16 -> smem (K-major SWIZZLE_128B, two 64-key panels)
         float rsum = 0.f;
 #pragma unroll 1
@@ -291,14 +307,17 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
                            pack_bf16x2(p[8 * g + 6], p[8 * g + 7]));
           }
         }
+        if (tl) tl_stamp(8 + j * 8 + 3);
         fence_proxy_async_smem();
         tcgen05_before_thread_sync();
         mbar_arrive(&p_full[s]);
         l_run = l_run * alpha + rsum;
         m_run = m_new;
         // accumulate this tile's P.V
+        if (tl) tl_stamp(8 + j * 8 + 4);
         mbar_wait(&o_full[s], j & 1);
         tcgen05_after_thread_sync();
+        if (tl) tl_stamp(8 + j * 8 + 5);
         {
           uint32_t ro[DK / 32][32];
 #pragma unroll
@@ -312,6 +331,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         tcgen05_before_thread_sync();
       }
       // finalise: O = acc / l -> bf16 -> smem (reuse this slot's P buffer) -> TMA store ; lse = m + ln(l)
+      if (s == 0 && wg_tid == 0) tl_stamp(2);
       const float inv = 1.f / l_run;
 #pragma unroll
       for (int g = 0; g < DK / 8; ++g)
@@ -326,6 +346,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         tma_store_3d(&tmO, smem + L::OFF_P + s * C::P_BYTES, h * DK, q0 + s * 128, b);
         tma_store_commit();
         tma_store_wait_all<0>();
+        if (s == 0) tl_stamp(3);
       }
     }
   }
@@ -379,6 +400,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   float* rowbuf = reinterpret_cast<float*>(smem + L::OFF_ROW);
 
   const uint32_t warp = warp_idx(), lane = lane_idx();
+  if (threadIdx.x == 64) tl_stamp(60);
   const int b = blockIdx.z, h = blockIdx.y, jt = blockIdx.x;
   const int kv0 = jt * 128;
   const int nq = (Sq + 127) / 128;
@@ -503,12 +525,14 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         if (ctid < 128) rb[ctid] = qq < Sq ? lse[off] * kLog2e : INFINITY;
         else rb[ctid] = qq < Sq ? delta[off] : 0.f;
       }
-      if (ctid == 0) tma_store_wait_read<0>();      // previous tile's dQ reduce has finished reading its staging
+      if (ctid == 0) { tl_stamp(64 + n * 8 + 0); tma_store_wait_read<0>(); }      // previous tile's dQ reduce has finished reading its staging
       named_bar_sync(1, 256);
+      if (ctid == 0) tl_stamp(64 + n * 8 + 1);
       const bool diag = mask.causal && (qt0 < kv0 + 128);   // tile touches the causal boundary (some q < kv)
       const bool plain = rows_clean && !diag && mask.maskf == nullptr;   // no mask logic needed in this tile
       mbar_wait(sdp_full, n & 1);
       tcgen05_after_thread_sync();
+      if (ctid == 0) tl_stamp(64 + n * 8 + 2);
 #pragma unroll 1
       for (int c = 0; c < 2; ++c) {
         const int col0 = half * 64 + c * 32;
@@ -549,6 +573,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
                        pack_bf16x2(ds[8 * g + 4], ds[8 * g + 5]), pack_bf16x2(ds[8 * g + 6], ds[8 * g + 7]));
         }
       }
+      if (ctid == 0) tl_stamp(64 + n * 8 + 3);
       fence_proxy_async_smem();
       tcgen05_before_thread_sync();
       mbar_arrive(pds_full);
@@ -556,6 +581,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       // (cp.reduce.async.bulk.tensor .add.f32 into the caller-zeroed accumulator; rows >= Sq are clipped by TMA)
       mbar_wait(dq_full, n & 1);
       tcgen05_after_thread_sync();
+      if (ctid == 0) tl_stamp(64 + n * 8 + 4);
       {
         constexpr int HC = DK / 2;
         const uint32_t stg = sDQ + half * C::TILE_BYTES;
@@ -579,6 +605,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
           tma_reduce_add_3d(&tmdQ, smem + L::OFF_DQ, h * DK, qt0, b);
           tma_reduce_add_3d(&tmdQ, smem + L::OFF_DQ + C::TILE_BYTES, h * DK + HC, qt0, b);
           tma_store_commit();
+          tl_stamp(64 + n * 8 + 5);
         }
       }
     }
@@ -614,10 +641,12 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       fence_proxy_async_smem();
       named_bar_sync(1, 256);
       if (ctid == 0) {
+        tl_stamp(61);
         tma_store_3d(&tmdV, smem + L::OFF_PT, h * DK, kv0, b);
         tma_store_3d(&tmdK, smem + L::OFF_DST, h * DK, kv0, b);
         tma_store_commit();
         tma_store_wait_all<0>();
+        tl_stamp(62);
       }
     }
   }

@@ -11,6 +11,8 @@ int gemm_bf16(const void* A, long long lda, int a_major, const void* B, long lon
 
 void gemm_force_cta_group(int cg);   // 0 = heuristic, 1 / 2 = force single-CTA / CTA-pair tiles (tests, benchmarks)
 
+int set_timeline(long long* dev_ptr);   // debug: register a device buffer of >= 128 int64 clock stamps (nullptr disables)
+
 int attn_fwd(const void* Q, long long ld_q, const void* K, long long ld_k, const void* V, long long ld_v, void* O,
              long long ld_o, float* lse, const uint8_t* kpad, int causal, const float* maskf, long long mask_sb,
              long long mask_sq, int B, int H, int Sq, int Sk, int dk, cudaStream_t st);
