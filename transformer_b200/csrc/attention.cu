@@ -62,10 +62,15 @@ struct FwdSmem {
   static constexpr uint32_t OFF_V = OFF_K + 2 * C::TILE_BYTES;          // 2 stages
   static constexpr uint32_t OFF_P = OFF_V + 2 * C::TILE_BYTES;          // 2 slots
   static constexpr uint32_t OFF_BAR = OFF_P + 2 * C::P_BYTES;
-  static constexpr uint32_t BYTES = OFF_BAR + 256 + 1024;
+  static constexpr uint32_t OFF_PADW = OFF_BAR + 256;                   // key-padding bit words: [2 slots][kMaxPadTiles][4]
+  static constexpr uint32_t BYTES = OFF_PADW + 2 * 64 * 4 * 4 + 1024;
 };
+constexpr int kMaxPadTiles = 64;       // kv tiles whose pad bits are preloaded (Sk <= 8192); longer rows load per tile
 
-constexpr int ATTN_FWD_THREADS = 320;  // w0 TMA, w1 MMA(+TMEM alloc), w2-5 softmax slot 0, w6-9 softmax slot 1
+// warpgroup 0: w0 TMA, w1 MMA (+TMEM alloc), w2-3 idle; warpgroup 1: softmax of q slot 0; warpgroup 2: slot 1.
+// setmaxnreg moves registers from warpgroup 0 (48) to the softmax warpgroups (232): a thread keeps a whole
+// 128-column S row in registers (single pass over TMEM).
+constexpr int ATTN_FWD_THREADS = 384;
 
 template <int DK>
 __global__ void __launch_bounds__(ATTN_FWD_THREADS, 1)
@@ -127,6 +132,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   const uint32_t tS[2] = {tmem_base, tmem_base + 128};
   const uint32_t tO[2] = {tmem_base + 256, tmem_base + 256 + DK};
 
+  if (warp < 4) {
+  setmaxnreg_dec<48>();
   if (warp == 0) {
     if (lane == 0) {
       // ===================================== TMA producer =====================================
@@ -179,7 +186,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         for (int k = 0; k < 8; ++k) {
           const uint64_t ad = make_smem_desc(sP + s * C::P_BYTES + (k >> 2) * 16384 + (k & 3) * 32, 0, 1024, kSwz128);
           const uint64_t bd = make_smem_desc(sV + st * C::TILE_BYTES + k * C::KSTEP_MN, C::TILE_BYTES, C::SBO, C::SWZ);
-          umma_f16(tO[s], ad, bd, idescO, k > 0 ? 1u : 0u);
+          umma_f16(tO[s], ad, bd, idescO, (j > 0 || k > 0) ? 1u : 0u);   // O accumulates in TMEM over the kv tiles
         }
         umma_commit(&o_full[s]);
         const bool last_user = (s == 1) || !(j < nt[1]);
@@ -195,157 +202,171 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         if (j + 1 < nt[s]) issue_S(s, j + 1);
       }
     }
+  }
   } else {
+    setmaxnreg_inc<232>();
     // ===================================== softmax warps =====================================
-    const int s = (warp - 2) >> 2;               // q slot
+    const int s = (warp - 4) >> 2;               // q slot
     const uint32_t quad = warp & 3u;             // TMEM lane quadrant
     const uint32_t row = quad * 32u + lane;
     const int q = q0 + s * 128 + (int)row;       // global query index
-    const int wg_tid = (int)threadIdx.x - 64 - s * 128;
+    const int wg_tid = (int)threadIdx.x - 128 - s * 128;
     if (s < n_slots) {
       const uint32_t lane_sel = (quad * 32u) << 16;
       const uint32_t sPs = smem_u32(smem + L::OFF_P + s * C::P_BYTES);
       const float* mrow = mask.maskf ? mask.maskf + (long long)b * mask.sb + (long long)min(q, Sq - 1) * mask.sq : nullptr;
-      float m_run = -INFINITY, l_run = 0.f;
-      float acc[DK];
+      const float sl2 = scale * kLog2e;
+      // ---- key-padding bits of every kv tile this slot visits: loaded ONCE into smem (a global load per tile on the
+      //      critical path costs ~1000 cycles); bit e of word 4*tile+c <-> key 128*tile + 32*c + e
+      uint32_t* padw = reinterpret_cast<uint32_t*>(smem + L::OFF_PADW) + s * (kMaxPadTiles * 4);
+      const bool pad_pre = mask.kpad != nullptr && nt[s] <= kMaxPadTiles;
+      if (pad_pre) {
+        const int nwords = nt[s] * 4;
+        for (int w0 = (int)quad; w0 < nwords; w0 += 16) {       // 4 independent loads in flight per warp
+          uint8_t v[4];
 #pragma unroll
-      for (int i = 0; i < DK; ++i) acc[i] = 0.f;
+          for (int u = 0; u < 4; ++u) {
+            const int kv = (w0 + 4 * u) * 32 + (int)lane;
+            v[u] = (w0 + 4 * u < nwords && kv < Sk) ? mask.kpad[(long long)b * Sk + kv] : (uint8_t)0;
+          }
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const uint32_t bits = __ballot_sync(0xffffffffu, v[u] != 0);
+            if (lane == 0 && w0 + 4 * u < nwords) padw[w0 + 4 * u] = bits;
+          }
+        }
+        named_bar_sync(1 + s, 128);
+      }
+      // running state.  The subtracted maximum `m_used` is STALE by design: it is only raised (and O, l rescaled) when
+      // the tile maximum exceeds it by more than 2^8, so P stays <= 256 and the per-tile O correction is rare.
+      float m_used = -INFINITY, l_run = 0.f;
 
       for (int j = 0; j < nt[s]; ++j) {
         const int kv0 = j * 128;
-        // key flags for this tile as 4 x 32-bit ballots: bit e of word c <-> key kv0 + 32c + e
         uint32_t padbits[4], oobbits[4];
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
-          const int kv = kv0 + c * 32 + (int)lane;
-          const bool oob = kv >= Sk;
-          const bool pad = !oob && mask.kpad != nullptr && mask.kpad[(long long)b * Sk + kv] != 0;
-          padbits[c] = __ballot_sync(0xffffffffu, pad);
-          oobbits[c] = __ballot_sync(0xffffffffu, oob);
+          const int k0 = kv0 + c * 32;
+          oobbits[c] = k0 + 32 <= Sk ? 0u : (k0 >= Sk ? 0xffffffffu : (0xffffffffu << (Sk - k0)));
+          if (mask.kpad == nullptr) padbits[c] = 0u;
+          else if (pad_pre) padbits[c] = padw[j * 4 + c];
+          else {
+            const int kv = k0 + (int)lane;
+            padbits[c] = __ballot_sync(0xffffffffu, kv < Sk && mask.kpad[(long long)b * Sk + kv] != 0);
+          }
         }
         const bool diag = mask.causal && (kv0 + 127 > q0 + s * 128);   // tile touches the causal boundary
+        // a tile with no padded / out-of-range key, off the causal boundary and without a float mask needs no
+        // per-element mask logic: the common case for every tile but the diagonal / tail ones
+        const bool plain = !diag && mrow == nullptr &&
+                           ((padbits[0] | padbits[1] | padbits[2] | padbits[3] | oobbits[0] | oobbits[1] | oobbits[2] | oobbits[3]) == 0u);
         const bool tl = (s == 0 && wg_tid == 0);
         if (tl) tl_stamp(8 + j * 8 + 0);
         mbar_wait(&s_full[s], j & 1);
         tcgen05_after_thread_sync();
         if (tl) tl_stamp(8 + j * 8 + 1);
-
-        auto logit = [&](float raw, uint32_t pb, uint32_t ob, int c, int e) -> float {
-          const int kv = kv0 + c * 32 + e;
-          float t = raw * scale;
-          const bool masked = ((pb >> e) & 1u) || (diag && kv > q);
-          if (masked) t = kMaskVal;
-          if (mrow != nullptr && kv < Sk) t += mrow[kv] * kMaskVal;
-          if ((ob >> e) & 1u) t = -INFINITY;
-          return t;
-        };
-        auto sel4 = [](const uint32_t (&a)[4], int c) -> uint32_t {
-          return c == 0 ? a[0] : (c == 1 ? a[1] : (c == 2 ? a[2] : a[3]));
-        };
-        // a tile with no padded / out-of-range key, off the causal boundary and without a float mask needs no
-        // per-element mask logic: the common case for every tile but the diagonal / tail ones
-        const bool plain = !diag && mrow == nullptr &&
-                           ((padbits[0] | padbits[1] | padbits[2] | padbits[3] | oobbits[0] | oobbits[1] | oobbits[2] | oobbits[3]) == 0u);
-        const float sl2 = scale * kLog2e;
-        // pass 1: row max   (TMEM loads are issued two 32-column chunks at a time, one wait per pair)
-        float m_new = m_run;
-#pragma unroll 1
-        for (int c2 = 0; c2 < 2; ++c2) {
-          uint32_t ra[32], rb2[32];
-          tmem_ld_x32(tS[s] + lane_sel + c2 * 64, ra);
-          tmem_ld_x32(tS[s] + lane_sel + c2 * 64 + 32, rb2);
-          tmem_ld_wait();
-          if (plain) {
-            float mx = -INFINITY;
+        // ---- the whole 128-column S row of this thread, ONE pass over TMEM
+        uint32_t r[4][32];
 #pragma unroll
-            for (int e = 0; e < 32; ++e) mx = fmaxf(mx, fmaxf(__uint_as_float(ra[e]), __uint_as_float(rb2[e])));
-            m_new = fmaxf(m_new, mx * scale);
-          } else {
-            const uint32_t pa = sel4(padbits, 2 * c2), oa = sel4(oobbits, 2 * c2);
-            const uint32_t pb = sel4(padbits, 2 * c2 + 1), ob = sel4(oobbits, 2 * c2 + 1);
+        for (int c = 0; c < 4; ++c) tmem_ld_x32(tS[s] + lane_sel + c * 32, r[c]);
+        tmem_ld_wait();
+        float mx[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+        if (plain) {
+#pragma unroll
+          for (int c = 0; c < 4; ++c)
+#pragma unroll
+            for (int e = 0; e < 32; ++e) mx[e & 3] = fmaxf(mx[e & 3], __uint_as_float(r[c][e]));
+#pragma unroll
+          for (int u = 0; u < 4; ++u) mx[u] *= scale;
+        } else {
+          // masked tile: turn raw scores into logits in place (reference semantics: masked = -1e9, finite)
+#pragma unroll
+          for (int c = 0; c < 4; ++c)
 #pragma unroll
             for (int e = 0; e < 32; ++e) {
-              m_new = fmaxf(m_new, logit(__uint_as_float(ra[e]), pa, oa, 2 * c2, e));
-              m_new = fmaxf(m_new, logit(__uint_as_float(rb2[e]), pb, ob, 2 * c2 + 1, e));
+              const int kv = kv0 + c * 32 + e;
+              float t = __uint_as_float(r[c][e]) * scale;
+              if (((padbits[c] >> e) & 1u) || (diag && kv > q)) t = kMaskVal;
+              if (mrow != nullptr && kv < Sk) t += mrow[kv] * kMaskVal;
+              if ((oobbits[c] >> e) & 1u) t = -INFINITY;
+              r[c][e] = __float_as_uint(t);
+              mx[e & 3] = fmaxf(mx[e & 3], t);
             }
-          }
         }
-        const float alpha = fast_exp2((m_run - m_new) * kLog2e);   // first tile: exp2(-inf) = 0
-        const float mb = m_new * kLog2e;
+        const float m_tile = fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3]));
         if (tl) tl_stamp(8 + j * 8 + 2);
-        // pass 2: p = exp(t - m), row sum (fp32), P -> bf16 -> smem (K-major SWIZZLE_128B, two 64-key panels)
-        float rsum = 0.f;
-#pragma unroll 1
-        for (int c2 = 0; c2 < 2; ++c2) {
-          uint32_t rr[2][32];
-          tmem_ld_x32(tS[s] + lane_sel + c2 * 64, rr[0]);
-          tmem_ld_x32(tS[s] + lane_sel + c2 * 64 + 32, rr[1]);
-          tmem_ld_wait();
-          const uint32_t panel = sPs + c2 * 16384;
+        // ---- lazy rescale
+        const bool need = (j > 0) && ((m_tile - m_used) * kLog2e > 8.f);
+        if (j == 0) m_used = m_tile;
+        if (__any_sync(0xffffffffu, need)) {
+          const float alpha = need ? fast_exp2((m_used - m_tile) * kLog2e) : 1.f;
+          if (need) { m_used = m_tile; l_run *= alpha; }
+          mbar_wait(&o_full[s], (j - 1) & 1);            // P.V of the previous tile has landed in TMEM
+          tcgen05_after_thread_sync();
 #pragma unroll
-          for (int hc = 0; hc < 2; ++hc) {
-            const int c = 2 * c2 + hc;
-            float p[32];
-            if (plain) {
+          for (int c = 0; c < DK / 32; ++c) {
+            uint32_t ro[32];
+            tmem_ld_x32(tO[s] + lane_sel + c * 32, ro);
+            tmem_ld_wait();
 #pragma unroll
-              for (int e = 0; e < 32; ++e) {
-                p[e] = fast_exp2(__uint_as_float(rr[hc][e]) * sl2 - mb);
-                rsum += p[e];
-              }
-            } else {
-              const uint32_t pb = sel4(padbits, c), ob = sel4(oobbits, c);
-#pragma unroll
-              for (int e = 0; e < 32; ++e) {
-                p[e] = fast_exp2(logit(__uint_as_float(rr[hc][e]), pb, ob, c, e) * kLog2e - mb);
-                rsum += p[e];
-              }
-            }
-#pragma unroll
-            for (int g = 0; g < 4; ++g)
-              st_shared_v4(panel + swz128_off(row, hc * 4 + g), pack_bf16x2(p[8 * g], p[8 * g + 1]),
-                           pack_bf16x2(p[8 * g + 2], p[8 * g + 3]), pack_bf16x2(p[8 * g + 4], p[8 * g + 5]),
-                           pack_bf16x2(p[8 * g + 6], p[8 * g + 7]));
+            for (int e = 0; e < 32; ++e) ro[e] = __float_as_uint(__uint_as_float(ro[e]) * alpha);
+            tmem_st_x32(tO[s] + lane_sel + c * 32, ro);
           }
+          tmem_st_wait();
         }
+        const float mb = m_used * kLog2e;
+        // ---- p = exp(t - m_used) in place, row sum (fp32, 4 partial sums), P -> bf16 -> smem (two 64-key panels)
+        float rs4[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          float p[32];
+          if (plain) {
+#pragma unroll
+            for (int e = 0; e < 32; ++e) { p[e] = fast_exp2(__uint_as_float(r[c][e]) * sl2 - mb); rs4[e & 3] += p[e]; }
+          } else {
+#pragma unroll
+            for (int e = 0; e < 32; ++e) { p[e] = fast_exp2(__uint_as_float(r[c][e]) * kLog2e - mb); rs4[e & 3] += p[e]; }
+          }
+          const uint32_t panel = sPs + (c >> 1) * 16384;
+#pragma unroll
+          for (int g = 0; g < 4; ++g)
+            st_shared_v4(panel + swz128_off(row, (c & 1) * 4 + g), pack_bf16x2(p[8 * g], p[8 * g + 1]),
+                         pack_bf16x2(p[8 * g + 2], p[8 * g + 3]), pack_bf16x2(p[8 * g + 4], p[8 * g + 5]),
+                         pack_bf16x2(p[8 * g + 6], p[8 * g + 7]));
+        }
+        l_run += (rs4[0] + rs4[1]) + (rs4[2] + rs4[3]);
         if (tl) tl_stamp(8 + j * 8 + 3);
         fence_proxy_async_smem();
         tcgen05_before_thread_sync();
         mbar_arrive(&p_full[s]);
-        l_run = l_run * alpha + rsum;
-        m_run = m_new;
-        // accumulate this tile's P.V
         if (tl) tl_stamp(8 + j * 8 + 4);
-        mbar_wait(&o_full[s], j & 1);
-        tcgen05_after_thread_sync();
-        if (tl) tl_stamp(8 + j * 8 + 5);
-        {
-          uint32_t ro[DK / 32][32];
-#pragma unroll
-          for (int c = 0; c < DK / 32; ++c) tmem_ld_x32(tO[s] + lane_sel + c * 32, ro[c]);
-          tmem_ld_wait();
-#pragma unroll
-          for (int c = 0; c < DK / 32; ++c)
-#pragma unroll
-            for (int e = 0; e < 32; ++e) acc[c * 32 + e] = acc[c * 32 + e] * alpha + __uint_as_float(ro[c][e]);
-        }
-        tcgen05_before_thread_sync();
       }
-      // finalise: O = acc / l -> bf16 -> smem (reuse this slot's P buffer) -> TMA store ; lse = m + ln(l)
+      // finalise: O (TMEM) / l -> bf16 -> smem (reuse this slot's P buffer) -> TMA store ; lse = m_used + ln(l)
+      mbar_wait(&o_full[s], (nt[s] - 1) & 1);
+      tcgen05_after_thread_sync();
       if (s == 0 && wg_tid == 0) tl_stamp(2);
       const float inv = 1.f / l_run;
 #pragma unroll
-      for (int g = 0; g < DK / 8; ++g)
-        st_shared_v4(sPs + swz_off<DK>(row, g), pack_bf16x2(acc[8 * g] * inv, acc[8 * g + 1] * inv),
-                     pack_bf16x2(acc[8 * g + 2] * inv, acc[8 * g + 3] * inv),
-                     pack_bf16x2(acc[8 * g + 4] * inv, acc[8 * g + 5] * inv),
-                     pack_bf16x2(acc[8 * g + 6] * inv, acc[8 * g + 7] * inv));
-      if (q < Sq) lse_out[((long long)b * H + h) * Sq + q] = m_run + __logf(l_run);
+      for (int c = 0; c < DK / 32; ++c) {
+        uint32_t ro[32];
+        tmem_ld_x32(tO[s] + lane_sel + c * 32, ro);
+        tmem_ld_wait();
+#pragma unroll
+        for (int g = 0; g < 4; ++g)
+          st_shared_v4(sPs + swz_off<DK>(row, c * 4 + g),
+                       pack_bf16x2(__uint_as_float(ro[8 * g]) * inv, __uint_as_float(ro[8 * g + 1]) * inv),
+                       pack_bf16x2(__uint_as_float(ro[8 * g + 2]) * inv, __uint_as_float(ro[8 * g + 3]) * inv),
+                       pack_bf16x2(__uint_as_float(ro[8 * g + 4]) * inv, __uint_as_float(ro[8 * g + 5]) * inv),
+                       pack_bf16x2(__uint_as_float(ro[8 * g + 6]) * inv, __uint_as_float(ro[8 * g + 7]) * inv));
+      }
+      if (q < Sq) lse_out[((long long)b * H + h) * Sq + q] = m_used + __logf(l_run);
+      tcgen05_before_thread_sync();
       fence_proxy_async_smem();
       named_bar_sync(1 + s, 128);
       if (wg_tid == 0) {
         tma_store_3d(&tmO, smem + L::OFF_P + s * C::P_BYTES, h * DK, q0 + s * 128, b);
         tma_store_commit();
-        tma_store_wait_all<0>();
+        tma_store_wait_read<0>();          // smem may be released; the write itself completes before the grid does
         if (s == 0) tl_stamp(3);
       }
     }
@@ -515,16 +536,21 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     const uint32_t sDQ = smem_u32(smem + L::OFF_DQ);
     // no padded / out-of-range key among this warp's rows (fixed for the whole CTA)
     const bool rows_clean = !__any_sync(0xffffffffu, kv_pad || !kv_valid);
+    // lse (x log2 e) / delta of a query tile: thread ctid < 128 fetches lse[q], the others delta[q].  The value for the
+    // NEXT tile is fetched one tile ahead so the global-load latency is off the critical path.
+    auto load_row = [&](int i) -> float {
+      const int qq = i * 128 + (ctid & 127);
+      const long long off = ((long long)b * H + h) * Sq + qq;
+      if (ctid < 128) return qq < Sq ? lse[off] * kLog2e : INFINITY;    // +inf for out-of-range queries -> p = 0
+      return qq < Sq ? delta[off] : 0.f;
+    };
+    float row_next = load_row(i_start);
     int n = 0;
     for (int i = i_start; i < nq; ++i, ++n) {
       const int qt0 = i * 128;
       float* rb = rowbuf + (n & 1) * 256;
-      {  // stage lse / delta of this query tile (lse = +inf for out-of-range queries -> p = 0)
-        const int qq = qt0 + (ctid & 127);
-        const long long off = ((long long)b * H + h) * Sq + qq;
-        if (ctid < 128) rb[ctid] = qq < Sq ? lse[off] * kLog2e : INFINITY;
-        else rb[ctid] = qq < Sq ? delta[off] : 0.f;
-      }
+      rb[ctid] = row_next;
+      if (i + 1 < nq) row_next = load_row(i + 1);
       if (ctid == 0) { tl_stamp(64 + n * 8 + 0); tma_store_wait_read<0>(); }      // previous tile's dQ reduce has finished reading its staging
       named_bar_sync(1, 256);
       if (ctid == 0) tl_stamp(64 + n * 8 + 1);
