@@ -68,7 +68,7 @@ struct FwdSmem {
 constexpr int kMaxPadTiles = 64;       // kv tiles whose pad bits are preloaded (Sk <= 8192); longer rows load per tile
 
 // warpgroup 0: w0 TMA, w1 MMA (+TMEM alloc), w2-3 idle; warpgroup 1: softmax of q slot 0; warpgroup 2: slot 1.
-// setmaxnreg moves registers from warpgroup 0 (48) to the softmax warpgroups (232): a thread keeps a whole
+// setmaxnreg moves registers from warpgroup 0 (40) to the softmax warpgroups (232; 128*40 + 256*232 = 64512 <= 65536): a thread keeps a whole
 // 128-column S row in registers (single pass over TMEM).
 constexpr int ATTN_FWD_THREADS = 384;
 
@@ -133,7 +133,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   const uint32_t tO[2] = {tmem_base + 256, tmem_base + 256 + DK};
 
   if (warp < 4) {
-  setmaxnreg_dec<48>();
+  setmaxnreg_dec<40>();
   if (warp == 0) {
     if (lane == 0) {
       // ===================================== TMA producer =====================================
