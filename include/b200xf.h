@@ -103,6 +103,15 @@ int b200xf_colsum_bf16(const void* X, int64_t ld, float* out, int64_t rows, int 
 int b200xf_adam_step(float* p, float* m, float* v, const float* g, void* shadow_bf16, int64_t n, float alpha,
                      float beta1, float beta2, float eps, b200xf_stream_t stream);
 
+/*      Graph-replayable form: the per-step scalars live on the device.  b200xf_step_params (one thread) reads and
+ *      increments state[0] = keras optimizer.iterations and writes seed = base_seed + iterations, lr =
+ *      CustomSchedule(iterations) (train.py:21-34; const_lr >= 0 overrides) and the TF-form alpha;
+ *      b200xf_adam_step_dev reads alpha from the device.                                                        */
+int b200xf_step_params(int64_t* state, uint64_t base_seed, float d_model, float warmup_steps, float const_lr, float beta1,
+                       float beta2, uint64_t* seed_out, float* alpha_out, float* lr_out, b200xf_stream_t stream);
+int b200xf_adam_step_dev(float* p, float* m, float* v, const float* g, void* shadow_bf16, int64_t n, const float* alpha_dev,
+                         float beta1, float beta2, float eps, b200xf_stream_t stream);
+
 /* ---- casts / masks */
 int b200xf_cast_f32_bf16(const float* in, void* out, int64_t n, b200xf_stream_t stream);
 int b200xf_cast_bf16_f32(const void* in, float* out, int64_t n, b200xf_stream_t stream);
@@ -138,6 +147,9 @@ int b200xf_model_create(const b200xf_model_config* cfg, float* params, float* gr
                         void* shadow, const float* pos_in, const float* pos_tgt, void* workspace,
                         b200xf_model** out);
 void b200xf_model_destroy(b200xf_model* m);
+/* when seed_dev != NULL the dropout seed of forward/backward is read from this device word (b200xf_step_params output)
+ * instead of the `seed` argument -- required for CUDA-graph replays */
+void b200xf_model_set_seed_ptr(b200xf_model* m, const uint64_t* seed_dev);
 /* refresh the bf16 shadow from the fp32 params (after loading / initialising weights) */
 int b200xf_model_sync_shadow(b200xf_model* m, b200xf_stream_t stream);
 

@@ -11,5 +11,5 @@ for l in sys.stdin:
     except Exception: print(l[:300]); continue
     print({k:j[k] for k in ('value','ms_per_step','gpu_launches','clocks')}); r=j['roofline']; print({k:r[k] for k in ('achieved','frac','share_of_step','launches_per_step')}, r['attention_fwd'], r['attention_bwd'])
 "
-timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 900 --csv --log-file gpurun_out/launches_r1.csv python bench.py --steps 1 --warmup 3 --no-cpu-baseline > gpurun_out/bench_under_ncu.log 2>&1
-python tools/summarize_launches.py gpurun_out/launches_r1.csv | head -22
+
+

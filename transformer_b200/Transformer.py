@@ -186,6 +186,7 @@ class Transformer:
         L.call("b200xf_model_create", C.byref(c), L.ptr(self.params), L.ptr(self.grads), L.ptr(self.adam_m), L.ptr(self.adam_v),
                L.ptr(self.shadow), L.ptr(self.pos_encoding_in), L.ptr(self.pos_encoding_tgt), L.ptr(self._workspace), C.byref(h))
         self._handle = h
+        self._handle_generation = getattr(self, "_handle_generation", 0) + 1      # captured CUDA graphs of older handles are stale
         self._shadow_dirty = True
 
     def __del__(self):
@@ -196,8 +197,9 @@ class Transformer:
             pass
 
     # ------------------------------------------------------------------ forward
-    def _forward(self, inp, tar, tar_offset, T, training, seed=0, masks=None, want_logits=True):
-        """inp int64 (B,S); tar int64 (B, >= tar_offset+T) -- the decoder input is tar[:, tar_offset:tar_offset+T]."""
+    def _forward(self, inp, tar, tar_offset, T, training, seed=0, masks=None, want_logits=True, seed_dev=None):
+        """inp int64 (B,S); tar int64 (B, >= tar_offset+T) -- the decoder input is tar[:, tar_offset:tar_offset+T].
+        ``seed_dev``: optional device uint64 holding the dropout seed (graph-replayable steps); else ``seed``."""
         if inp.dtype != torch.int64 or tar.dtype != torch.int64:
             inp, tar = inp.to(torch.int64), tar.to(torch.int64)
         inp = inp.to(self.device).contiguous()
@@ -228,7 +230,8 @@ class Transformer:
             logits = torch.empty((B * T, ld), dtype=torch.float32, device=self.device)
         self._generation += 1
         self._last_shape = (B, S, T)
-        self._keepalive = (inp, tar, enc_m, la_m, dec_m)      # the library keeps raw pointers until the next forward
+        self._keepalive = (inp, tar, enc_m, la_m, dec_m, seed_dev)      # the library keeps raw pointers until the next forward
+        L.load().b200xf_model_set_seed_ptr(self._handle, L.ptr(seed_dev))
         L.call("b200xf_model_forward", self._handle, L.ptr(inp), L.ptr(tar), tar.shape[1], tar_offset, B, S, T, int(bool(training)),
                int(seed), L.ptr(enc_m), L.ptr(la_m), la_bs, L.ptr(dec_m), L.ptr(logits), ld, L.stream_ptr())
         weights = LazyAttentionWeights(self, self.num_layers, B, self.num_heads, T, S, self._generation)

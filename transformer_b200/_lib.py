@@ -48,6 +48,9 @@ _SIGS = {
     "b200xf_xent": [_P, _I, _I64, _P, _I, _I, _I, _P, _I64, _P, _P, _I64, _I, _F, _P],
     "b200xf_colsum_bf16": [_P, _I64, _P, _I64, _I, _P],
     "b200xf_adam_step": [_P, _P, _P, _P, _P, _I64, _F, _F, _F, _F, _P],
+    "b200xf_adam_step_dev": [_P, _P, _P, _P, _P, _I64, _P, _F, _F, _F, _P],
+    "b200xf_step_params": [_P, _U64, _F, _F, _F, _F, _F, _P, _P, _P, _P],
+    "b200xf_model_set_seed_ptr": [_P, _P],
     "b200xf_cast_f32_bf16": [_P, _P, _I64, _P],
     "b200xf_cast_bf16_f32": [_P, _P, _I64, _P],
     "b200xf_cast_f32_bf16_strided": [_P, _P, _I64, _I, _I64, _P],
@@ -75,7 +78,7 @@ _SIGS = {
 }
 _RESTYPES = {"b200xf_last_error": C.c_char_p, "b200xf_launch_count": C.c_longlong,
              "b200xf_model_param_count": _I64, "b200xf_model_workspace_bytes": _I64,
-             "b200xf_model_destroy": None, "b200xf_prof_enable": None, "b200xf_gemm_force_cta_group": None}
+             "b200xf_model_destroy": None, "b200xf_model_set_seed_ptr": None, "b200xf_prof_enable": None, "b200xf_gemm_force_cta_group": None}
 
 EXPORTED_SYMBOLS = tuple(_SIGS)
 

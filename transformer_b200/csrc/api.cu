@@ -81,6 +81,15 @@ int b200xf_adam_step(float* p, float* m, float* v, const float* g, void* shadow_
                      float beta1, float beta2, float eps, b200xf_stream_t stream) {
   return bx::adam_step(p, m, v, g, shadow_bf16, n, alpha, beta1, beta2, eps, ST(stream));
 }
+int b200xf_adam_step_dev(float* p, float* m, float* v, const float* g, void* shadow_bf16, int64_t n, const float* alpha_dev,
+                         float beta1, float beta2, float eps, b200xf_stream_t stream) {
+  return bx::adam_step(p, m, v, g, shadow_bf16, n, 0.f, beta1, beta2, eps, ST(stream), alpha_dev);
+}
+int b200xf_step_params(int64_t* state, uint64_t base_seed, float d_model, float warmup_steps, float const_lr, float beta1,
+                       float beta2, uint64_t* seed_out, float* alpha_out, float* lr_out, b200xf_stream_t stream) {
+  return bx::step_params(reinterpret_cast<long long*>(state), base_seed, d_model, warmup_steps, const_lr, beta1, beta2,
+                         reinterpret_cast<unsigned long long*>(seed_out), alpha_out, lr_out, ST(stream));
+}
 int b200xf_cast_f32_bf16(const float* in, void* out, int64_t n, b200xf_stream_t stream) {
   return bx::cast_f32_bf16(in, out, n, ST(stream));
 }

@@ -51,7 +51,8 @@ __global__ void embed_fwd_kernel(const long long* __restrict__ ids, const float*
                                  const float* __restrict__ pos, float* __restrict__ out_f32,
                                  __nv_bfloat16* __restrict__ out_bf16, long long rows, int S, int id_stride,
                                  int id_offset, int d, long long V, float scale, float rate, unsigned long long seed,
-                                 uint32_t site) {
+                                 uint32_t site, const unsigned long long* __restrict__ seed_dev) {
+  if (seed_dev != nullptr) seed = *seed_dev;      // CUDA-graph replays: the per-step seed lives on the device
   const int d4 = d >> 2;
   const long long total = rows * d4;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
@@ -74,7 +75,9 @@ __global__ void embed_fwd_kernel(const long long* __restrict__ ids, const float*
 // backward: dTable[id] += dx * sqrt(d) * dropmask   (dense-equivalent IndexedSlices sum, Appendix A.8)
 __global__ void embed_bwd_kernel(const long long* __restrict__ ids, const float* __restrict__ dx,
                                  float* __restrict__ dtable, long long rows, int S, int id_stride, int id_offset, int d,
-                                 long long V, float scale, float rate, unsigned long long seed, uint32_t site) {
+                                 long long V, float scale, float rate, unsigned long long seed, uint32_t site,
+                                 const unsigned long long* __restrict__ seed_dev) {
+  if (seed_dev != nullptr) seed = *seed_dev;
   const int d4 = d >> 2;
   const long long total = rows * d4;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
@@ -107,7 +110,8 @@ residual_ln_fwd_kernel(float* __restrict__ y_z, const float* __restrict__ x, con
                        const float* __restrict__ beta, float* __restrict__ out_f32,
                        __nv_bfloat16* __restrict__ out_bf16, float* __restrict__ mean_out,
                        float* __restrict__ rstd_out, long long rows, int d, float eps, float rate,
-                       unsigned long long seed, uint32_t site) {
+                       unsigned long long seed, uint32_t site, const unsigned long long* __restrict__ seed_dev) {
+  if (seed_dev != nullptr) seed = *seed_dev;
   const int lane = threadIdx.x & 31;
   const long long warp_global = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
   const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
@@ -172,7 +176,8 @@ residual_ln_bwd_kernel(const float* __restrict__ dout, const float* __restrict__
                        const float* __restrict__ rstd_in, const float* __restrict__ gamma, float* __restrict__ dz,
                        __nv_bfloat16* __restrict__ dy_sub, float* __restrict__ dgamma, float* __restrict__ dbeta,
                        float* __restrict__ dbias, long long rows, int d, float rate, unsigned long long seed,
-                       uint32_t site) {
+                       uint32_t site, const unsigned long long* __restrict__ seed_dev) {
+  if (seed_dev != nullptr) seed = *seed_dev;
   extern __shared__ float red[];  // [3][d]: dgamma, dbeta, dbias partials of this block (shared-memory atomics)
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, nw = blockDim.x >> 5;
   const long long warp_global = (long long)blockIdx.x * nw + wib;
@@ -414,7 +419,9 @@ colsum_bf16_kernel(const __nv_bfloat16* __restrict__ X, long long ld, float* __r
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
 adam_kernel(float* __restrict__ p, float* __restrict__ m, float* __restrict__ v, const float* __restrict__ g,
-            __nv_bfloat16* __restrict__ shadow, long long n4, float alpha, float b1, float b2, float eps) {
+            __nv_bfloat16* __restrict__ shadow, long long n4, float alpha, float b1, float b2, float eps,
+            const float* __restrict__ alpha_dev) {
+  if (alpha_dev != nullptr) alpha = *alpha_dev;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
     float4 pv = reinterpret_cast<float4*>(p)[i], mv = reinterpret_cast<float4*>(m)[i], vv = reinterpret_cast<float4*>(v)[i];
     const float4 gv = reinterpret_cast<const float4*>(g)[i];
@@ -429,6 +436,29 @@ adam_kernel(float* __restrict__ p, float* __restrict__ m, float* __restrict__ v,
     reinterpret_cast<float4*>(v)[i] = vv;
     if (shadow) reinterpret_cast<uint2*>(shadow)[i] = make_uint2(pack_bf16x2(pv.x, pv.y), pack_bf16x2(pv.z, pv.w));
   }
+}
+
+// per-step scalars derived ON THE DEVICE from the iteration counter, so a captured CUDA graph can be replayed:
+//   state[0] = keras `optimizer.iterations` (0-based; incremented here, i.e. once per training step)
+//   out: seed = base_seed + iterations ; lr = CustomSchedule(iterations) (train.py:21-34, fp32) or const_lr ;
+//        alpha = lr * sqrt(1 - b2^t) / (1 - b1^t), t = iterations + 1      (TF-form Adam)
+__global__ void step_params_kernel(long long* state, unsigned long long base_seed, float d_model, float warmup, float const_lr,
+                                   float b1, float b2, unsigned long long* seed_out, float* alpha_out, float* lr_out) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  const long long it = state[0];
+  float lr = const_lr;
+  if (const_lr < 0.f) {
+    const float step = (float)it;
+    const float arg1 = 1.0f / sqrtf(step);                                  // rsqrt(0) = inf on the first step
+    const float arg2 = step * (float)pow((double)warmup, -1.5);
+    lr = (1.0f / sqrtf(d_model)) * fminf(arg1, arg2);
+  }
+  const double t = (double)(it + 1);
+  const double alpha = (double)lr * sqrt(1.0 - pow((double)b2, t)) / (1.0 - pow((double)b1, t));
+  *seed_out = base_seed + (unsigned long long)it;
+  *alpha_out = (float)alpha;
+  *lr_out = lr;
+  state[0] = it + 1;
 }
 
 __global__ void __launch_bounds__(256)
@@ -502,18 +532,19 @@ static inline int grid_for(long long work, int threads, int max_blocks_per_sm = 
 
 int embed_fwd(const long long* ids, int id_stride, int id_offset, const float* table, const float* pos, float* out_f32,
               void* out_bf16, long long rows, int S, int d, long long V, float rate, unsigned long long seed, unsigned site,
-              cudaStream_t st) {
+              cudaStream_t st, const unsigned long long* seed_dev) {
   BX_REQUIRE(d % 4 == 0, "embed: d_model %% 4 != 0");
   embed_fwd_kernel<<<grid_for(rows * (d / 4), 256), 256, 0, st>>>(ids, table, pos, out_f32, (__nv_bfloat16*)out_bf16, rows, S,
-                                                                 id_stride, id_offset, d, V, sqrtf((float)d), rate, seed, site);
+                                                                 id_stride, id_offset, d, V, sqrtf((float)d), rate, seed, site, seed_dev);
   BX_POST_LAUNCH();
   return 0;
 }
 int embed_bwd(const long long* ids, int id_stride, int id_offset, const float* dx, float* dtable, long long rows, int S,
-              int d, long long V, float rate, unsigned long long seed, unsigned site, cudaStream_t st) {
+              int d, long long V, float rate, unsigned long long seed, unsigned site, cudaStream_t st,
+              const unsigned long long* seed_dev) {
   BX_REQUIRE(d % 4 == 0, "embed: d_model %% 4 != 0");
   embed_bwd_kernel<<<grid_for(rows * (d / 4), 256), 256, 0, st>>>(ids, dx, dtable, rows, S, id_stride, id_offset, d, V,
-                                                                 sqrtf((float)d), rate, seed, site);
+                                                                 sqrtf((float)d), rate, seed, site, seed_dev);
   BX_POST_LAUNCH();
   return 0;
 }
@@ -526,22 +557,22 @@ int embed_bwd(const long long* ids, int id_stride, int id_offset, const float* d
 
 int residual_ln_fwd(float* y_z, const float* x, const float* gamma, const float* beta, float* out_f32, void* out_bf16,
                     float* mean, float* rstd, long long rows, int d, float eps, float rate, unsigned long long seed,
-                    unsigned site, cudaStream_t st) {
+                    unsigned site, cudaStream_t st, const unsigned long long* seed_dev) {
   BX_REQUIRE(d % 4 == 0 && d <= 1024, "layernorm: need d %% 4 == 0 and d <= 1024 (got %d)", d);
   const int grid = grid_for(rows * 32, 256);
   BX_LN_DISPATCH(residual_ln_fwd_kernel, <<<grid, 256, 0, st>>>(y_z, x, gamma, beta, out_f32, (__nv_bfloat16*)out_bf16, mean, rstd,
-                                                               rows, d, eps, rate, seed, site))
+                                                               rows, d, eps, rate, seed, site, seed_dev))
   BX_POST_LAUNCH();
   return 0;
 }
 int residual_ln_bwd(const float* dout, const float* z, const float* mean, const float* rstd, const float* gamma,
                     float* dz, void* dy_sub, float* dgamma, float* dbeta, float* dbias, long long rows, int d, float rate,
-                    unsigned long long seed, unsigned site, cudaStream_t st) {
+                    unsigned long long seed, unsigned site, cudaStream_t st, const unsigned long long* seed_dev) {
   BX_REQUIRE(d % 4 == 0 && d <= 1024, "layernorm: need d %% 4 == 0 and d <= 1024 (got %d)", d);
   const int grid = grid_for(rows * 32, 256, 3);
   const size_t smem = (size_t)3 * d * sizeof(float);
   BX_LN_DISPATCH(residual_ln_bwd_kernel, <<<grid, 256, smem, st>>>(dout, z, mean, rstd, gamma, dz, (__nv_bfloat16*)dy_sub, dgamma,
-                                                                  dbeta, dbias, rows, d, rate, seed, site))
+                                                                  dbeta, dbias, rows, d, rate, seed, site, seed_dev))
   BX_POST_LAUNCH();
   return 0;
 }
@@ -574,10 +605,16 @@ int colsum_bf16(const void* X, long long ld, float* out, long long rows, int N, 
   return 0;
 }
 
+int step_params(long long* state, unsigned long long base_seed, float d_model, float warmup, float const_lr, float b1, float b2,
+                unsigned long long* seed_out, float* alpha_out, float* lr_out, cudaStream_t st) {
+  step_params_kernel<<<1, 32, 0, st>>>(state, base_seed, d_model, warmup, const_lr, b1, b2, seed_out, alpha_out, lr_out);
+  BX_POST_LAUNCH();
+  return 0;
+}
 int adam_step(float* p, float* m, float* v, const float* g, void* shadow, long long n, float alpha, float b1, float b2,
-              float eps, cudaStream_t st) {
+              float eps, cudaStream_t st, const float* alpha_dev) {
   BX_REQUIRE(n % 4 == 0, "adam: arena length must be a multiple of 4");
-  adam_kernel<<<grid_for(n / 4, 256), 256, 0, st>>>(p, m, v, g, (__nv_bfloat16*)shadow, n / 4, alpha, b1, b2, eps);
+  adam_kernel<<<grid_for(n / 4, 256), 256, 0, st>>>(p, m, v, g, (__nv_bfloat16*)shadow, n / 4, alpha, b1, b2, eps, alpha_dev);
   BX_POST_LAUNCH();
   return 0;
 }

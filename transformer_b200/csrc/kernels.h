@@ -29,21 +29,24 @@ int attn_delta(const void* O, long long ld_o, const void* dO, long long ld_do, f
 // ids of row r = (b, s) are read at ids[b * id_stride + id_offset + s]  (tar[:, :-1] without a copy)
 int embed_fwd(const long long* ids, int id_stride, int id_offset, const float* table, const float* pos, float* out_f32,
               void* out_bf16, long long rows, int S, int d, long long V, float rate, unsigned long long seed, unsigned site,
-              cudaStream_t st);
+              cudaStream_t st, const unsigned long long* seed_dev = nullptr);   // seed_dev != NULL overrides `seed` (graph replays)
 int embed_bwd(const long long* ids, int id_stride, int id_offset, const float* dx, float* dtable, long long rows, int S,
-              int d, long long V, float rate, unsigned long long seed, unsigned site, cudaStream_t st);
+              int d, long long V, float rate, unsigned long long seed, unsigned site, cudaStream_t st,
+              const unsigned long long* seed_dev = nullptr);
 int residual_ln_fwd(float* y_z, const float* x, const float* gamma, const float* beta, float* out_f32, void* out_bf16,
                     float* mean, float* rstd, long long rows, int d, float eps, float rate, unsigned long long seed,
-                    unsigned site, cudaStream_t st);
+                    unsigned site, cudaStream_t st, const unsigned long long* seed_dev = nullptr);
 int residual_ln_bwd(const float* dout, const float* z, const float* mean, const float* rstd, const float* gamma,
                     float* dz, void* dy_sub, float* dgamma, float* dbeta, float* dbias, long long rows, int d, float rate,
-                    unsigned long long seed, unsigned site, cudaStream_t st);
+                    unsigned long long seed, unsigned site, cudaStream_t st, const unsigned long long* seed_dev = nullptr);
 int xent(const void* logits, int logits_f32, long long ld, const long long* labels, int label_stride, int label_offset,
          int T_len, void* dlogits, long long ld_d, float* row_loss, double* stats, long long rows, int V, float inv_batch,
          cudaStream_t st);
 int colsum_bf16(const void* X, long long ld, float* out, long long rows, int N, cudaStream_t st);
 int adam_step(float* p, float* m, float* v, const float* g, void* shadow, long long n, float alpha, float b1, float b2,
-              float eps, cudaStream_t st);
+              float eps, cudaStream_t st, const float* alpha_dev = nullptr);
+int step_params(long long* state, unsigned long long base_seed, float d_model, float warmup, float const_lr, float b1, float b2,
+                unsigned long long* seed_out, float* alpha_out, float* lr_out, cudaStream_t st);
 int cast_f32_bf16(const float* in, void* out, long long n, cudaStream_t st);
 int cast_bf16_f32(const void* in, float* out, long long n, cudaStream_t st);
 int cast_f32_bf16_strided(const float* in, void* out, long long rows, int d, long long ld_out, cudaStream_t st);

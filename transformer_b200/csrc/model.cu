@@ -218,6 +218,7 @@ struct b200xf_model {
   // state of the last forward
   int B = 0, S = 0, T = 0, training = 0;
   uint64_t seed = 0;
+  const unsigned long long* seed_dev = nullptr;   // when set, kernels read the dropout seed from the device (graph replays)
   const int64_t *inp = nullptr, *tar = nullptr;
   int tar_stride = 0, tar_offset = 0;
   const float *enc_mask = nullptr, *la_mask = nullptr, *dec_mask = nullptr;
@@ -285,7 +286,7 @@ int residual_ln(M* m, float* y_z, const float* x, int64_t g_off, int64_t b_off, 
                 int64_t rows, uint32_t site, cudaStream_t st) {
   const float rate = m->training ? m->cfg.dropout_rate : 0.f;
   return bx::residual_ln_fwd(y_z, x, m->P + g_off, m->P + b_off, out32, out16, s.mean, s.rstd, rows, m->lo.d, m->cfg.ln_eps, rate,
-                             m->seed, site, st);
+                             m->seed, site, st, m->seed_dev);
 }
 
 int forward_impl(M* m, float* logits_out, int64_t ld_logits, cudaStream_t st) {
@@ -302,7 +303,7 @@ int forward_impl(M* m, float* logits_out, int64_t ld_logits, cudaStream_t st) {
 
   // ---------------- encoder (Encoder.py:48-60) ----------------
   RC(bx::embed_fwd(reinterpret_cast<const long long*>(m->inp), S, 0, m->P + lo.enc_emb, m->pos_in, w.enc_x32[0], w.enc_x16[0], Ms, S, d,
-                   lo.Vin, rate, m->seed, site_enc_embed(), st));
+                   lo.Vin, rate, m->seed, site_enc_embed(), st, m->seed_dev));
   const MaskSpec em = enc_self_mask(m);
   for (int l = 0; l < L; ++l) {
     const EncLayerP& p = lo.enc[l];
@@ -322,7 +323,7 @@ int forward_impl(M* m, float* logits_out, int64_t ld_logits, cudaStream_t st) {
 
   // ---------------- decoder (Decoder.py:59-79) ----------------
   RC(bx::embed_fwd(reinterpret_cast<const long long*>(m->tar), m->tar_stride, m->tar_offset, m->P + lo.dec_emb, m->pos_tgt, w.dec_x32[0],
-                   w.dec_x16[0], Mt, T, d, lo.Vtgt, rate, m->seed, site_dec_embed(), st));
+                   w.dec_x16[0], Mt, T, d, lo.Vtgt, rate, m->seed, site_dec_embed(), st, m->seed_dev));
   const MaskSpec sm = dec_self_mask(m), cm = dec_cross_mask(m);
   for (int l = 0; l < L; ++l) {
     const DecLayerP& p = lo.dec[l];
@@ -360,7 +361,7 @@ int residual_ln_back(M* m, const float* g_in, const LnSave& s, int64_t g_off, in
                      uint32_t site, cudaStream_t st) {
   const float rate = m->training ? m->cfg.dropout_rate : 0.f;
   return bx::residual_ln_bwd(g_in, s.z, s.mean, s.rstd, m->P + g_off, g_out, m->w.dy16, m->G + g_off, m->G + b_off, m->G + bias_off, rows,
-                             m->lo.d, rate, m->seed, site, st);
+                             m->lo.d, rate, m->seed, site, st, m->seed_dev);
 }
 
 // FFN backward: dy16 = d(ffn output); x16 = ffn input; accumulates d(input) into g (fp32)
@@ -442,7 +443,7 @@ int backward_decoder(M* m, cudaStream_t st) {
     std::swap(g_in, g_out);
   }
   RC(bx::embed_bwd(reinterpret_cast<const long long*>(m->tar), m->tar_stride, m->tar_offset, g_in, m->G + lo.dec_emb, Mt, T, d, lo.Vtgt,
-                   rate, m->seed, site_dec_embed(), st));
+                   rate, m->seed, site_dec_embed(), st, m->seed_dev));
   return 0;
 }
 
@@ -468,7 +469,7 @@ int backward_encoder(M* m, cudaStream_t st) {
     std::swap(g_in, g_out);
   }
   RC(bx::embed_bwd(reinterpret_cast<const long long*>(m->inp), S, 0, g_in, m->G + lo.enc_emb, Ms, S, d, lo.Vin, rate, m->seed,
-                   site_enc_embed(), st));
+                   site_enc_embed(), st, m->seed_dev));
   return 0;
 }
 
@@ -522,6 +523,10 @@ int b200xf_model_create(const b200xf_model_config* cfg, float* params, float* gr
   return 0;
 }
 void b200xf_model_destroy(b200xf_model* m) { delete m; }
+
+void b200xf_model_set_seed_ptr(b200xf_model* m, const uint64_t* seed_dev) {
+  m->seed_dev = reinterpret_cast<const unsigned long long*>(seed_dev);
+}
 
 int b200xf_model_sync_shadow(b200xf_model* m, b200xf_stream_t stream) {
   return bx::cast_f32_bf16(m->P, m->Sh, m->lo.total, reinterpret_cast<cudaStream_t>(stream));

@@ -10,6 +10,7 @@ train.py:134).  No host synchronisation happens inside a step; metrics are read 
 from __future__ import annotations
 
 import math
+import os
 import time
 
 import numpy as np
@@ -71,6 +72,21 @@ class Adam:
         lr = self.learning_rate
         return float(lr(self.iterations)) if callable(lr) else float(lr)
 
+    def schedule_args(self):
+        """(d_model, warmup_steps, const_lr) for the device-side schedule (b200xf_step_params)."""
+        lr = self.learning_rate
+        if isinstance(lr, CustomSchedule):
+            return float(lr.d_model), float(lr.warmup_steps), -1.0
+        if callable(lr):
+            return None                      # arbitrary Python schedule: host-computed alpha only (no graph replay)
+        return 1.0, 1.0, float(lr)
+
+    def apply_gradients_dev(self, transformer, alpha_dev):
+        """same update with alpha read from the device (written by b200xf_step_params); graph-replayable."""
+        L.call("b200xf_adam_step_dev", L.ptr(transformer.params), L.ptr(transformer.adam_m), L.ptr(transformer.adam_v),
+               L.ptr(transformer.grads), L.ptr(transformer.shadow), transformer._n, L.ptr(alpha_dev), self.beta_1, self.beta_2,
+               self.epsilon, L.stream_ptr())
+
     def apply_gradients(self, transformer):
         t = self.iterations + 1
         lr_t = self.current_lr()                                              # evaluated at the 0-based iteration count
@@ -92,7 +108,7 @@ class Train(object):
     """
 
     def __init__(self, epochs, enable_function, transformer, src_tokenizer, tgt_tokenizer, batch_size, train_log_dir,
-                 test_log_dir, max_ckpt_keep, ckpt_path, d_model, warmup_steps=60000, seed=0):
+                 test_log_dir, max_ckpt_keep, ckpt_path, d_model, warmup_steps=60000, seed=0, cuda_graph=None):
         self.epochs = epochs
         self.enable_function = enable_function
         self.transformer = transformer
@@ -111,6 +127,18 @@ class Train(object):
         self._stats = torch.zeros(4, dtype=torch.float64, device=dev)          # per-step {loss_sum, correct, positions, nonpad}
         self._seed = int(seed)
         self.last_lr = 0.0
+        # per-step scalars live on the device (iteration counter -> dropout seed, lr, Adam alpha), so a whole step can be
+        # captured ONCE per batch shape as a CUDA graph and replayed: ~400 kernel launches become one graph launch.
+        self._it_dev = torch.zeros(1, dtype=torch.int64, device=dev)
+        self._seed_dev = torch.zeros(1, dtype=torch.int64, device=dev)
+        self._alpha_dev = torch.zeros(1, dtype=torch.float32, device=dev)
+        self._lr_dev = torch.zeros(1, dtype=torch.float32, device=dev)
+        if cuda_graph is None:
+            cuda_graph = os.environ.get("B200XF_CUDA_GRAPH", "1") != "0"
+        self.cuda_graph = bool(cuda_graph) and self.optimizer.schedule_args() is not None
+        self._graphs = {}
+        self._shape_seen = {}
+        self._graph_handle_generation = None
 
     # -- train.py:83-88 on materialised predictions (API parity; train_step uses the fused path) ---------------------
     def loss_function(self, real, pred):
@@ -132,30 +160,80 @@ class Train(object):
     def _finish_gradients(self):
         pass
 
-    def _step_core(self, src, tar, training):
+    def _step_core(self, src, tar, training, seed_dev=None):
         tr = self.transformer
         src = src.to(tr.device, torch.int64).contiguous()
         tar = tar.to(tr.device, torch.int64).contiguous()
         T = tar.shape[1] - 1                                                   # tar_inp = tar[:, :-1]; tar_real = tar[:, 1:]
         self._stats.zero_()
         seed = self._seed + self.optimizer.iterations
-        tr._forward(src, tar, 0, T, training, seed=seed, want_logits=False)
+        tr._forward(src, tar, 0, T, training, seed=seed, want_logits=False, seed_dev=seed_dev)
         L.call("b200xf_model_loss", tr._handle, L.ptr(tar), tar.shape[1], 1, 1.0 / self.batch_size, L.ptr(self._stats),
                int(training), L.stream_ptr())
+
+    def _train_step_body(self, src, tar):
+        """every device operation of one training step, in launch order (this is what gets captured into a CUDA graph)"""
+        tr = self.transformer
+        sched = self.optimizer.schedule_args()
+        tr.zero_grads()
+        if sched is not None:
+            L.call("b200xf_step_params", L.ptr(self._it_dev), self._seed, sched[0], sched[1], sched[2], self.optimizer.beta_1,
+                   self.optimizer.beta_2, L.ptr(self._seed_dev), L.ptr(self._alpha_dev), L.ptr(self._lr_dev), L.stream_ptr())
+        self._step_core(src, tar, True, seed_dev=self._seed_dev if sched is not None else None)
+        for stage in (0, 1, 2):                                                # final layer | decoder | encoder
+            L.call("b200xf_model_backward", tr._handle, stage, L.stream_ptr())
+            self._reduce_gradients(stage)
+        self._finish_gradients()
+        if sched is not None:
+            self.optimizer.apply_gradients_dev(tr, self._alpha_dev)
+        else:
+            self.optimizer.apply_gradients(tr)
+            self.optimizer.iterations -= 1                                     # bookkeeping happens in train_step
+        self.train_loss(self._stats[0] * (1.0 / self.batch_size))
+        self.train_accuracy.add_(self._stats[1], self._stats[2])
 
     def train_step(self, inputs):
         """One training step (train.py:124-141).  inputs: (src (B,S) int64, tar (B,T+1) int64)."""
         src, tar = inputs
         tr = self.transformer
-        tr.zero_grads()
-        self._step_core(src, tar, True)
-        for stage in (0, 1, 2):                                                # final layer | decoder | encoder
-            L.call("b200xf_model_backward", tr._handle, stage, L.stream_ptr())
-            self._reduce_gradients(stage)
-        self._finish_gradients()
-        self.last_lr = self.optimizer.apply_gradients(tr)
-        self.train_loss(self._stats[0] * (1.0 / self.batch_size))
-        self.train_accuracy.add_(self._stats[1], self._stats[2])
+        src = src.to(tr.device, torch.int64, non_blocking=True).contiguous()
+        tar = tar.to(tr.device, torch.int64, non_blocking=True).contiguous()
+        self.last_lr = self.optimizer.current_lr()
+        key = (tuple(src.shape), tuple(tar.shape))
+        if self._graph_handle_generation != getattr(tr, "_handle_generation", 0):
+            self._graphs.clear()                                               # workspace was re-created: old graphs are stale
+            self._graph_handle_generation = getattr(tr, "_handle_generation", 0)
+        entry = self._graphs.get(key) if self.cuda_graph else None
+        if self.cuda_graph and entry is None and self._shape_seen.get(key, 0) >= 1:
+            entry = self._capture(key, src, tar)                               # second time this shape shows up
+        if entry is None:
+            self._shape_seen[key] = self._shape_seen.get(key, 0) + 1
+            self._train_step_body(src, tar)                                    # eager (also the warm-up before a capture)
+        else:
+            graph, g_src, g_tar = entry
+            g_src.copy_(src, non_blocking=True)
+            g_tar.copy_(tar, non_blocking=True)
+            graph.replay()
+        self.optimizer.iterations += 1
+
+    def _capture(self, key, src, tar):
+        tr = self.transformer
+        tr._ensure_workspace(src.shape[0], src.shape[1], tar.shape[1] - 1)
+        self._graph_handle_generation = getattr(tr, "_handle_generation", 0)
+        g_src, g_tar = src.clone(), tar.clone()
+        graph = torch.cuda.CUDAGraph()
+        try:
+            torch.cuda.synchronize(tr.device)
+            with torch.cuda.graph(graph):
+                self._train_step_body(g_src, g_tar)
+        except Exception as e:                                                 # e.g. a collective that cannot be captured
+            import warnings
+            warnings.warn(f"CUDA-graph capture of train_step failed ({type(e).__name__}: {e}); staying eager")
+            self.cuda_graph = False
+            torch.cuda.synchronize(tr.device)
+            return None
+        self._graphs[key] = (graph, g_src, g_tar)
+        return self._graphs[key]
 
     def test_step(self, inputs):
         """One test step (train.py:144-156)."""
