@@ -27,10 +27,10 @@ for causal in (0, 1):
     print(f"FWD causal={causal}: alloc+init {f[1]-t0}; per tile [wait_S, pass1, pass2, (fence), wait_O, accO]; final {f[2]-t0} .. stored {f[3]-t0}")
     for j in range(4):
         e = f[8 + j * 8: 8 + j * 8 + 6]
-        if e[0]: print(f"   tile {j}: start {e[0]-t0:6d} | waitS {e[1]-e[0]:5d} pass1 {e[2]-e[1]:5d} pass2 {e[3]-e[2]:5d} fence {e[4]-e[3]:4d} waitO {e[5]-e[4]:5d}")
+        if e[0]: print(f"   tile {j}: start {e[0]-t0:6d} | waitS {e[1]-e[0]:5d} load+max {e[2]-e[1]:5d} exp+store {e[3]-e[2]:5d} fence {e[4]-e[3]:4d}")
     t0 = bw[60]
     print(f"BWD causal={causal}: epilogue start {bw[61]-t0} end {bw[62]-t0}")
     for n in range(4):
         e = bw[64 + n * 8: 64 + n * 8 + 6]
-        if e[0]: print(f"   tile {n}: start {e[0]-t0:6d} | bar {e[1]-e[0]:5d} waitSdP {e[2]-e[1]:5d} compute {e[3]-e[2]:5d} waitdQ {e[4]-e[3]:5d} dQepi {e[5]-e[4]:5d}")
+        if e[0]: print(f"   tile {n}: start {e[0]-t0:6d} | waitSdP {e[2]-e[0]:5d} compute+st {e[3]-e[2]:5d} | dq_full(n) seen at {e[4]-t0:6d} reduce issued {e[5]-t0:6d}")
 L.call("b200xf_debug_set_timeline", None)

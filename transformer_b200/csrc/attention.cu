@@ -389,9 +389,9 @@ struct BwdSmem {
   static constexpr uint32_t OFF_V = OFF_K + C::TILE_BYTES;
   static constexpr uint32_t OFF_Q = OFF_V + C::TILE_BYTES;          // 2 stages
   static constexpr uint32_t OFF_DO = OFF_Q + 2 * C::TILE_BYTES;     // 2 stages
-  static constexpr uint32_t OFF_PT = OFF_DO + 2 * C::TILE_BYTES;    // P^T   [kv 128][q 128] bf16, two panels
-  static constexpr uint32_t OFF_DST = OFF_PT + C::P_BYTES;          // dS^T
-  static constexpr uint32_t OFF_DQ = OFF_DST + C::P_BYTES;          // dQ tile fp32 [128 x DK] as two [128 x DK/2] boxes (TMA reduce-add staging)
+  static constexpr uint32_t OFF_DST = OFF_DO + 2 * C::TILE_BYTES;   // dS^T [kv 128][q 128] bf16, two panels, DOUBLE buffered
+                                                                    // (P^T lives in tensor memory, not in smem)
+  static constexpr uint32_t OFF_DQ = OFF_DST + 2 * C::P_BYTES;      // dQ tile fp32 [128 x DK] as two [128 x DK/2] boxes (TMA reduce-add staging)
   static constexpr uint32_t OFF_ROW = OFF_DQ + 2 * C::TILE_BYTES;   // lse/delta: 2 buffers x (128 + 128) floats
   static constexpr uint32_t OFF_BAR = OFF_ROW + 2 * 256 * 4;
   static constexpr uint32_t BYTES = OFF_BAR + 256 + 1024;
@@ -417,7 +417,9 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   uint64_t* sdp_full = bars + 5;     // [1]
   uint64_t* pds_full = bars + 6;     // [1] count 256
   uint64_t* dq_full = bars + 7;      // [1]
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 8);
+  uint64_t* pt_free = bars + 8;      // [1] dV MMAs have finished reading P^T from tensor memory
+  uint64_t* dq_free = bars + 9;      // [1] count 256: the compute warps have read the dQ tile out of tensor memory
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 10);
   float* rowbuf = reinterpret_cast<float*>(smem + L::OFF_ROW);
 
   const uint32_t warp = warp_idx(), lane = lane_idx();
@@ -433,7 +435,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     prefetch_tmap(&tmdK); prefetch_tmap(&tmdV); prefetch_tmap(&tmdQ);
     mbar_init(kv_full, 1);
     for (int i = 0; i < 2; ++i) { mbar_init(&qdo_full[i], 1); mbar_init(&qdo_empty[i], 1); }
-    mbar_init(sdp_full, 1); mbar_init(pds_full, 256); mbar_init(dq_full, 1);
+    mbar_init(sdp_full, 1); mbar_init(pds_full, 256); mbar_init(dq_full, 1); mbar_init(pt_free, 1); mbar_init(dq_free, 256);
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc<512>(tmem_ptr);
@@ -441,8 +443,9 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   __syncthreads();
   tcgen05_after_thread_sync();
   const uint32_t tmem_base = *tmem_ptr;
+  // tensor memory (512 columns): S^T 128 | dP^T 128 | dV dk | dK dk | dQ dk | P^T (bf16 pairs) 64
   const uint32_t tSt = tmem_base, tdPt = tmem_base + 128, tdV = tmem_base + 256, tdK = tmem_base + 256 + DK,
-                 tdQ = tmem_base + 256 + 2 * DK;
+                 tdQ = tmem_base + 256 + 2 * DK, tPt = tmem_base + 256 + 3 * DK;
 
   if (warp == 0) {
     if (lane == 0) {
@@ -465,7 +468,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     constexpr uint32_t idescKV = make_idesc_bf16(128, DK, 0, 1);    // [kv, dk] = P^T/dS^T (K-major) . dO/Q (MN-major)
     constexpr uint32_t idescQ = make_idesc_bf16(128, DK, 1, 1);     // [q, dk]  = dS (MN-major view of dS^T) . K (MN-major)
     const uint32_t sK = smem_u32(smem + L::OFF_K), sV = smem_u32(smem + L::OFF_V), sQ = smem_u32(smem + L::OFF_Q),
-                   sdO = smem_u32(smem + L::OFF_DO), sPt = smem_u32(smem + L::OFF_PT), sdSt = smem_u32(smem + L::OFF_DST);
+                   sdO = smem_u32(smem + L::OFF_DO), sdSt = smem_u32(smem + L::OFF_DST);
     auto issue_sdp = [&](int n) {
       const int st = n & 1;
       mbar_wait(&qdo_full[st], (n >> 1) & 1);
@@ -490,26 +493,36 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     mbar_wait(kv_full, 0);
     const int ntile = nq - i_start;
     issue_sdp(0);
+    // per tile the tensor core runs   dV(n) | S^T,dP^T(n+1) | dK(n), dQ(n)   so the compute warps can start on tile n+1
+    // (their S^T/dP^T are ready after the first two groups) while dK/dQ of tile n are still executing
     for (int n = 0; n < ntile; ++n) {
       const int st = n & 1;
+      const uint32_t sdS = sdSt + (n & 1) * C::P_BYTES;
       mbar_wait(pds_full, n & 1);
       tcgen05_after_thread_sync();
       if (lane == 0) {
 #pragma unroll
-        for (int k = 0; k < 8; ++k) {   // dV += P^T . dO     (K = 128 queries)
-          const uint64_t ad = make_smem_desc(sPt + (k >> 2) * 16384 + (k & 3) * 32, 0, 1024, kSwz128);
+        for (int k = 0; k < 8; ++k) {   // dV += P^T . dO     (K = 128 queries; A = P^T in tensor memory, 8 columns per k16)
           const uint64_t bd = make_smem_desc(sdO + st * C::TILE_BYTES + k * C::KSTEP_MN, C::TILE_BYTES, C::SBO, C::SWZ);
-          umma_f16(tdV, ad, bd, idescKV, (n > 0 || k > 0) ? 1u : 0u);
+          umma_f16_ts(tdV, tPt + k * 8, bd, idescKV, (n > 0 || k > 0) ? 1u : 0u);
         }
+        umma_commit(pt_free);
+      }
+      __syncwarp();
+      if (n + 1 < ntile) issue_sdp(n + 1);
+      if (lane == 0) {
 #pragma unroll
         for (int k = 0; k < 8; ++k) {   // dK += dS^T . Q
-          const uint64_t ad = make_smem_desc(sdSt + (k >> 2) * 16384 + (k & 3) * 32, 0, 1024, kSwz128);
+          const uint64_t ad = make_smem_desc(sdS + (k >> 2) * 16384 + (k & 3) * 32, 0, 1024, kSwz128);
           const uint64_t bd = make_smem_desc(sQ + st * C::TILE_BYTES + k * C::KSTEP_MN, C::TILE_BYTES, C::SBO, C::SWZ);
           umma_f16(tdK, ad, bd, idescKV, (n > 0 || k > 0) ? 1u : 0u);
         }
+      }
+      if (n > 0) { mbar_wait(dq_free, (n - 1) & 1); tcgen05_after_thread_sync(); }   // dQ(n-1) has been read out of TMEM
+      if (lane == 0) {
 #pragma unroll
         for (int k = 0; k < 8; ++k) {   // dQ = dS . K        (K = 128 keys; A = MN-major view of dS^T)
-          const uint64_t ad = make_smem_desc(sdSt + k * 2048, 16384, 1024, kSwz128);
+          const uint64_t ad = make_smem_desc(sdS + k * 2048, 16384, 1024, kSwz128);
           const uint64_t bd = make_smem_desc(sK + k * C::KSTEP_MN, C::TILE_BYTES, C::SBO, C::SWZ);
           umma_f16(tdQ, ad, bd, idescQ, k > 0 ? 1u : 0u);
         }
@@ -517,7 +530,6 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         umma_commit(dq_full);
       }
       __syncwarp();
-      if (n + 1 < ntile) issue_sdp(n + 1);
     }
   } else {
     // ===================================== compute warps =====================================
@@ -530,10 +542,11 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     const int kv = kv0 + (int)row;
     const bool kv_valid = kv < Sk;
     const bool kv_pad = kv_valid && mask.kpad != nullptr && mask.kpad[(long long)b * Sk + kv] != 0;
-    const uint32_t sPt = smem_u32(smem + L::OFF_PT), sdSt = smem_u32(smem + L::OFF_DST);
+    const uint32_t sdSt = smem_u32(smem + L::OFF_DST);
     const float sl2 = scale * kLog2e;
     const float inv_sk = 1.f / (float)Sk;
     const uint32_t sDQ = smem_u32(smem + L::OFF_DQ);
+    constexpr int HC = DK / 2;
     // no padded / out-of-range key among this warp's rows (fixed for the whole CTA)
     const bool rows_clean = !__any_sync(0xffffffffu, kv_pad || !kv_valid);
     // lse (x log2 e) / delta of a query tile: thread ctid < 128 fetches lse[q], the others delta[q].  The value for the
@@ -544,6 +557,38 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       if (ctid < 128) return qq < Sq ? lse[off] * kLog2e : INFINITY;    // +inf for out-of-range queries -> p = 0
       return qq < Sq ? delta[off] : 0.f;
     };
+    // dQ tile of query tile `qt`: row = query, this warp's half of the dk columns -> fp32 smem staging -> ONE TMA
+    // reduce-add per half (cp.reduce.async.bulk.tensor .add.f32; rows >= Sq are clipped by TMA)
+    auto dq_epilogue = [&](int n_done, int qt0) {
+      mbar_wait(dq_full, n_done & 1);
+      tcgen05_after_thread_sync();
+      if (ctid == 0) { tl_stamp(64 + (n_done & 7) * 8 + 4); tma_store_wait_read<0>(); }   // previous reduce has drained the staging
+      named_bar_sync(2, 256);
+      const uint32_t stg = sDQ + half * C::TILE_BYTES;
+      if (HC == 32) {
+        uint32_t r[32];
+        tmem_ld_x32(tdQ + lane_sel + half * HC, r);
+        tmem_ld_wait();
+#pragma unroll
+        for (int g = 0; g < 8; ++g) st_shared_v4(stg + swz_off<DK>(row, g), r[4 * g], r[4 * g + 1], r[4 * g + 2], r[4 * g + 3]);
+      } else {
+        uint32_t r[16];
+        tmem_ld_x16(tdQ + lane_sel + half * HC, r);
+        tmem_ld_wait();
+#pragma unroll
+        for (int g = 0; g < 4; ++g) st_shared_v4(stg + swz_off<DK>(row, g), r[4 * g], r[4 * g + 1], r[4 * g + 2], r[4 * g + 3]);
+      }
+      tcgen05_before_thread_sync();
+      mbar_arrive(dq_free);                      // the dQ accumulator may be overwritten by the next tile's MMA
+      fence_proxy_async_smem();
+      named_bar_sync(3, 256);
+      if (ctid == 0) {
+        tma_reduce_add_3d(&tmdQ, smem + L::OFF_DQ, h * DK, qt0, b);
+        tma_reduce_add_3d(&tmdQ, smem + L::OFF_DQ + C::TILE_BYTES, h * DK + HC, qt0, b);
+        tma_store_commit();
+        tl_stamp(64 + (n_done & 7) * 8 + 5);
+      }
+    };
     float row_next = load_row(i_start);
     int n = 0;
     for (int i = i_start; i < nq; ++i, ++n) {
@@ -551,15 +596,16 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       float* rb = rowbuf + (n & 1) * 256;
       rb[ctid] = row_next;
       if (i + 1 < nq) row_next = load_row(i + 1);
-      if (ctid == 0) { tl_stamp(64 + n * 8 + 0); tma_store_wait_read<0>(); }      // previous tile's dQ reduce has finished reading its staging
+      if (ctid == 0) tl_stamp(64 + (n & 7) * 8 + 0);
       named_bar_sync(1, 256);
-      if (ctid == 0) tl_stamp(64 + n * 8 + 1);
       const bool diag = mask.causal && (qt0 < kv0 + 128);   // tile touches the causal boundary (some q < kv)
       const bool plain = rows_clean && !diag && mask.maskf == nullptr;   // no mask logic needed in this tile
       mbar_wait(sdp_full, n & 1);
       tcgen05_after_thread_sync();
-      if (ctid == 0) tl_stamp(64 + n * 8 + 2);
-#pragma unroll 1
+      if (ctid == 0) tl_stamp(64 + (n & 7) * 8 + 2);
+      const uint32_t sdS = sdSt + (n & 1) * C::P_BYTES + half * 16384;   // this tile's dS^T buffer, this warp's 64-query panel
+      uint32_t pw[32];                                                    // P^T row of this thread, 64 queries as bf16 pairs
+#pragma unroll
       for (int c = 0; c < 2; ++c) {
         const int col0 = half * 64 + c * 32;
         uint32_t rs[32], rp[32];
@@ -573,71 +619,44 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
             p[e] = fast_exp2(__uint_as_float(rs[e]) * sl2 - rb[col0 + e]);
             ds[e] = p[e] * (__uint_as_float(rp[e]) - rb[128 + col0 + e]) * scale;
           }
-        } else
+        } else {
 #pragma unroll
-        for (int e = 0; e < 32; ++e) {
-          const int qi = qt0 + col0 + e;
-          float t2 = __uint_as_float(rs[e]) * sl2;                        // logit * log2(e)
-          const bool masked = kv_pad || (diag && kv > qi);
-          if (masked) t2 = kMaskVal * kLog2e;
-          if (mask.maskf != nullptr && kv_valid && qi < Sq)
-            t2 += mask.maskf[(long long)b * mask.sb + (long long)qi * mask.sq + kv] * (kMaskVal * kLog2e);
-          const float l2 = rb[col0 + e];
-          float pe = fast_exp2(t2 - l2);
-          if (l2 < -1e8f) pe *= inv_sk;     // fully-masked query row: lse == -1e9 in fp32 (ln Sk absorbed) -> uniform 1/Sk
-          if (!kv_valid) pe = 0.f;
-          p[e] = pe;
-          ds[e] = pe * (__uint_as_float(rp[e]) - rb[128 + col0 + e]) * scale;
+          for (int e = 0; e < 32; ++e) {
+            const int qi = qt0 + col0 + e;
+            float t2 = __uint_as_float(rs[e]) * sl2;                        // logit * log2(e)
+            const bool masked = kv_pad || (diag && kv > qi);
+            if (masked) t2 = kMaskVal * kLog2e;
+            if (mask.maskf != nullptr && kv_valid && qi < Sq)
+              t2 += mask.maskf[(long long)b * mask.sb + (long long)qi * mask.sq + kv] * (kMaskVal * kLog2e);
+            const float l2 = rb[col0 + e];
+            float pe = fast_exp2(t2 - l2);
+            if (l2 < -1e8f) pe *= inv_sk;     // fully-masked query row: lse == -1e9 in fp32 (ln Sk absorbed) -> uniform 1/Sk
+            if (!kv_valid) pe = 0.f;
+            p[e] = pe;
+            ds[e] = pe * (__uint_as_float(rp[e]) - rb[128 + col0 + e]) * scale;
+          }
         }
-        const uint32_t po = half * 16384;
 #pragma unroll
-        for (int g = 0; g < 4; ++g) {
-          const uint32_t off = po + swz128_off(row, c * 4 + g);
-          st_shared_v4(sPt + off, pack_bf16x2(p[8 * g], p[8 * g + 1]), pack_bf16x2(p[8 * g + 2], p[8 * g + 3]),
-                       pack_bf16x2(p[8 * g + 4], p[8 * g + 5]), pack_bf16x2(p[8 * g + 6], p[8 * g + 7]));
-          st_shared_v4(sdSt + off, pack_bf16x2(ds[8 * g], ds[8 * g + 1]), pack_bf16x2(ds[8 * g + 2], ds[8 * g + 3]),
+        for (int g = 0; g < 16; ++g) pw[c * 16 + g] = pack_bf16x2(p[2 * g], p[2 * g + 1]);
+#pragma unroll
+        for (int g = 0; g < 4; ++g)
+          st_shared_v4(sdS + swz128_off(row, c * 4 + g), pack_bf16x2(ds[8 * g], ds[8 * g + 1]), pack_bf16x2(ds[8 * g + 2], ds[8 * g + 3]),
                        pack_bf16x2(ds[8 * g + 4], ds[8 * g + 5]), pack_bf16x2(ds[8 * g + 6], ds[8 * g + 7]));
-        }
       }
-      if (ctid == 0) tl_stamp(64 + n * 8 + 3);
+      // P^T -> tensor memory (A operand of the dV MMA), once the previous tile's dV MMAs have finished reading it
+      if (n > 0) { mbar_wait(pt_free, (n - 1) & 1); tcgen05_after_thread_sync(); }
+      tmem_st_x32(tPt + lane_sel + half * 32, pw);
+      tmem_st_wait();
+      if (ctid == 0) tl_stamp(64 + (n & 7) * 8 + 3);
       fence_proxy_async_smem();
       tcgen05_before_thread_sync();
       mbar_arrive(pds_full);
-      // dQ tile: row = query, this warp's half of the dk columns -> fp32 smem staging -> ONE TMA reduce-add per half
-      // (cp.reduce.async.bulk.tensor .add.f32 into the caller-zeroed accumulator; rows >= Sq are clipped by TMA)
-      mbar_wait(dq_full, n & 1);
-      tcgen05_after_thread_sync();
-      if (ctid == 0) tl_stamp(64 + n * 8 + 4);
-      {
-        constexpr int HC = DK / 2;
-        const uint32_t stg = sDQ + half * C::TILE_BYTES;
-        if (HC == 32) {
-          uint32_t r[32];
-          tmem_ld_x32(tdQ + lane_sel + half * HC, r);
-          tmem_ld_wait();
-#pragma unroll
-          for (int g = 0; g < 8; ++g) st_shared_v4(stg + swz_off<DK>(row, g), r[4 * g], r[4 * g + 1], r[4 * g + 2], r[4 * g + 3]);
-        } else {
-          uint32_t r[16];
-          tmem_ld_x16(tdQ + lane_sel + half * HC, r);
-          tmem_ld_wait();
-#pragma unroll
-          for (int g = 0; g < 4; ++g) st_shared_v4(stg + swz_off<DK>(row, g), r[4 * g], r[4 * g + 1], r[4 * g + 2], r[4 * g + 3]);
-        }
-        tcgen05_before_thread_sync();
-        fence_proxy_async_smem();
-        named_bar_sync(2, 256);
-        if (ctid == 0) {
-          tma_reduce_add_3d(&tmdQ, smem + L::OFF_DQ, h * DK, qt0, b);
-          tma_reduce_add_3d(&tmdQ, smem + L::OFF_DQ + C::TILE_BYTES, h * DK + HC, qt0, b);
-          tma_store_commit();
-          tl_stamp(64 + n * 8 + 5);
-        }
-      }
+      // the PREVIOUS tile's dQ is drained while the tensor core works on this tile's dV and the next tile's S^T/dP^T
+      if (n > 0) dq_epilogue(n - 1, qt0 - 128);
     }
-    // epilogue: dV, dK (TMEM) -> bf16 -> smem (reuse P^T / dS^T buffers) -> TMA store
+    dq_epilogue(n - 1, (nq - 1) * 128);
+    // epilogue: dV, dK (TMEM) -> bf16 -> smem (the two dS^T buffers, free once the last dq_full has fired) -> TMA store
     {
-      constexpr int HC = DK / 2;
       float v[HC], k[HC];
       if (HC == 32) {
         uint32_t r[32];
@@ -659,19 +678,19 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
 #pragma unroll
       for (int g = 0; g < HC / 8; ++g) {
         const uint32_t off = swz_off<DK>(row, half * (HC / 8) + g);
-        st_shared_v4(sPt + off, pack_bf16x2(v[8 * g], v[8 * g + 1]), pack_bf16x2(v[8 * g + 2], v[8 * g + 3]),
+        st_shared_v4(sdSt + off, pack_bf16x2(v[8 * g], v[8 * g + 1]), pack_bf16x2(v[8 * g + 2], v[8 * g + 3]),
                      pack_bf16x2(v[8 * g + 4], v[8 * g + 5]), pack_bf16x2(v[8 * g + 6], v[8 * g + 7]));
-        st_shared_v4(sdSt + off, pack_bf16x2(k[8 * g], k[8 * g + 1]), pack_bf16x2(k[8 * g + 2], k[8 * g + 3]),
+        st_shared_v4(sdSt + C::P_BYTES + off, pack_bf16x2(k[8 * g], k[8 * g + 1]), pack_bf16x2(k[8 * g + 2], k[8 * g + 3]),
                      pack_bf16x2(k[8 * g + 4], k[8 * g + 5]), pack_bf16x2(k[8 * g + 6], k[8 * g + 7]));
       }
       fence_proxy_async_smem();
       named_bar_sync(1, 256);
       if (ctid == 0) {
         tl_stamp(61);
-        tma_store_3d(&tmdV, smem + L::OFF_PT, h * DK, kv0, b);
-        tma_store_3d(&tmdK, smem + L::OFF_DST, h * DK, kv0, b);
+        tma_store_3d(&tmdV, smem + L::OFF_DST, h * DK, kv0, b);
+        tma_store_3d(&tmdK, smem + L::OFF_DST + C::P_BYTES, h * DK, kv0, b);
         tma_store_commit();
-        tma_store_wait_all<0>();
+        tma_store_wait_read<0>();
         tl_stamp(62);
       }
     }
