@@ -90,7 +90,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   uint64_t* s_full = bars + 10;     // [2]
   uint64_t* p_full = bars + 12;     // [2]
   uint64_t* o_full = bars + 14;     // [2]
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 16);
+  uint64_t* s_free = bars + 16;     // [2] count 128: the softmax warps hold the S tile in registers, TMEM S may be overwritten
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 18);
 
   const uint32_t warp = warp_idx(), lane = lane_idx();
   if (threadIdx.x == 64) tl_stamp(0);
@@ -119,7 +120,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     for (int i = 0; i < 2; ++i) {
       mbar_init(&q_full[i], 1); mbar_init(&k_full[i], 1); mbar_init(&v_full[i], 1);
       mbar_init(&k_empty[i], 1); mbar_init(&v_empty[i], 1);
-      mbar_init(&s_full[i], 1); mbar_init(&p_full[i], 128); mbar_init(&o_full[i], 1);
+      mbar_init(&s_full[i], 1); mbar_init(&p_full[i], 128); mbar_init(&o_full[i], 1); mbar_init(&s_free[i], 128);
     }
     fence_barrier_init();
   }
@@ -196,11 +197,17 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     };
     for (int s = 0; s < 2; ++s)
       if (0 < nt[s]) issue_S(s, 0);
+    // S(j+1) is issued as soon as the softmax warps have pulled S(j) into registers (s_free) -- it then runs on the tensor
+    // core while they exponentiate tile j -- and P.V(j) once P(j) is in smem.
     for (int j = 0; j < ntiles; ++j) {
-      for (int s = 0; s < 2; ++s) {
+      for (int s = 0; s < 2; ++s)
+        if (j + 1 < nt[s]) {
+          mbar_wait(&s_free[s], j & 1);
+          tcgen05_after_thread_sync();
+          issue_S(s, j + 1);
+        }
+      for (int s = 0; s < 2; ++s)
         if (j < nt[s]) issue_PV(s, j);
-        if (j + 1 < nt[s]) issue_S(s, j + 1);
-      }
     }
   }
   } else {
@@ -270,6 +277,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
 #pragma unroll
         for (int c = 0; c < 4; ++c) tmem_ld_x32(tS[s] + lane_sel + c * 32, r[c]);
         tmem_ld_wait();
+        tcgen05_before_thread_sync();
+        mbar_arrive(&s_free[s]);                       // the next tile's S may overwrite tensor memory now
         float mx[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
         if (plain) {
 #pragma unroll
@@ -555,7 +564,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       const int qq = i * 128 + (ctid & 127);
       const long long off = ((long long)b * H + h) * Sq + qq;
       if (ctid < 128) return qq < Sq ? lse[off] * kLog2e : INFINITY;    // +inf for out-of-range queries -> p = 0
-      return qq < Sq ? delta[off] : 0.f;
+      return qq < Sq ? delta[off] * scale : 0.f;                        // delta pre-multiplied by 1/sqrt(dk)
     };
     // dQ tile of query tile `qt`: row = query, this warp's half of the dk columns -> fp32 smem staging -> ONE TMA
     // reduce-add per half (cp.reduce.async.bulk.tensor .add.f32; rows >= Sq are clipped by TMA)
@@ -617,7 +626,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
 #pragma unroll
           for (int e = 0; e < 32; ++e) {
             p[e] = fast_exp2(__uint_as_float(rs[e]) * sl2 - rb[col0 + e]);
-            ds[e] = p[e] * (__uint_as_float(rp[e]) - rb[128 + col0 + e]) * scale;
+            ds[e] = p[e] * (__uint_as_float(rp[e]) * scale - rb[128 + col0 + e]);      // = p (dP - delta) / sqrt(dk)
           }
         } else {
 #pragma unroll
@@ -633,7 +642,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
             if (l2 < -1e8f) pe *= inv_sk;     // fully-masked query row: lse == -1e9 in fp32 (ln Sk absorbed) -> uniform 1/Sk
             if (!kv_valid) pe = 0.f;
             p[e] = pe;
-            ds[e] = pe * (__uint_as_float(rp[e]) - rb[128 + col0 + e]) * scale;
+            ds[e] = pe * (__uint_as_float(rp[e]) * scale - rb[128 + col0 + e]);
           }
         }
 #pragma unroll
