@@ -324,8 +324,9 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
           tmem_st_wait();
         }
         const float mb = m_used * kLog2e;
-        // ---- p = exp(t - m_used) in place, row sum (fp32, 4 partial sums), P -> bf16 -> smem (two 64-key panels)
+        // ---- p = exp(t - m_used), row sum (fp32, 4 partial sums), P -> bf16 pairs in registers
         float rs4[4] = {0.f, 0.f, 0.f, 0.f};
+        uint32_t pk[4][16];
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
           float p[32];
@@ -336,12 +337,18 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
 #pragma unroll
             for (int e = 0; e < 32; ++e) { p[e] = fast_exp2(__uint_as_float(r[c][e]) * kLog2e - mb); rs4[e & 3] += p[e]; }
           }
+#pragma unroll
+          for (int g = 0; g < 16; ++g) pk[c][g] = pack_bf16x2(p[2 * g], p[2 * g + 1]);
+        }
+        // the P smem tile of this slot is still being read by P.V of the previous kv tile until o_full fires
+        // (S(j) was issued BEFORE that P.V, so s_full alone does not order them)
+        if (j > 0) { mbar_wait(&o_full[s], (j - 1) & 1); tcgen05_after_thread_sync(); }
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
           const uint32_t panel = sPs + (c >> 1) * 16384;
 #pragma unroll
           for (int g = 0; g < 4; ++g)
-            st_shared_v4(panel + swz128_off(row, (c & 1) * 4 + g), pack_bf16x2(p[8 * g], p[8 * g + 1]),
-                         pack_bf16x2(p[8 * g + 2], p[8 * g + 3]), pack_bf16x2(p[8 * g + 4], p[8 * g + 5]),
-                         pack_bf16x2(p[8 * g + 6], p[8 * g + 7]));
+            st_shared_v4(panel + swz128_off(row, (c & 1) * 4 + g), pk[c][4 * g], pk[c][4 * g + 1], pk[c][4 * g + 2], pk[c][4 * g + 3]);
         }
         l_run += (rs4[0] + rs4[1]) + (rs4[2] + rs4[3]);
         if (tl) tl_stamp(8 + j * 8 + 3);
