@@ -175,8 +175,8 @@ __global__ void __launch_bounds__(256, NV >= 8 ? 1 : 3)
 residual_ln_bwd_kernel(const float* __restrict__ dout, const float* __restrict__ z, const float* __restrict__ mean_in,
                        const float* __restrict__ rstd_in, const float* __restrict__ gamma, float* __restrict__ dz,
                        __nv_bfloat16* __restrict__ dy_sub, float* __restrict__ dgamma, float* __restrict__ dbeta,
-                       float* __restrict__ dbias, long long rows, int d, float rate, unsigned long long seed,
-                       uint32_t site, const unsigned long long* __restrict__ seed_dev) {
+                       float* __restrict__ dbias, float* __restrict__ partial, long long rows, int d, float rate,
+                       unsigned long long seed, uint32_t site, const unsigned long long* __restrict__ seed_dev) {
   if (seed_dev != nullptr) seed = *seed_dev;
   extern __shared__ float red[];  // [3][d]: dgamma, dbeta, dbias partials of this block (shared-memory atomics)
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, nw = blockDim.x >> 5;
@@ -246,11 +246,35 @@ residual_ln_bwd_kernel(const float* __restrict__ dout, const float* __restrict__
     }
   }
   __syncthreads();
+  if (partial != nullptr) {
+    // per-block partials; ln_partials_reduce_kernel sums them (hundreds of blocks hitting the same 3d addresses with
+    // global atomics serialise in L2 and cost ~20 us per call)
+    for (int c = threadIdx.x; c < 3 * d; c += blockDim.x) partial[(size_t)blockIdx.x * 3 * d + c] = red[c];
+    return;
+  }
   for (int c = threadIdx.x; c < d; c += blockDim.x) {
     atomicAdd(dgamma + c, red[c]);
     atomicAdd(dbeta + c, red[d + c]);
     if (dbias != nullptr) atomicAdd(dbias + c, red[2 * d + c]);
   }
+}
+
+__global__ void __launch_bounds__(256)
+ln_partials_reduce_kernel(const float* __restrict__ partial, int nblocks, int d, float* __restrict__ dgamma,
+                          float* __restrict__ dbeta, float* __restrict__ dbias) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= 3 * d) return;
+  float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+  int k = 0;
+  for (; k + 3 < nblocks; k += 4) {
+    s0 += partial[(size_t)k * 3 * d + c]; s1 += partial[(size_t)(k + 1) * 3 * d + c];
+    s2 += partial[(size_t)(k + 2) * 3 * d + c]; s3 += partial[(size_t)(k + 3) * 3 * d + c];
+  }
+  for (; k < nblocks; ++k) s0 += partial[(size_t)k * 3 * d + c];
+  const float t = (s0 + s1) + (s2 + s3);
+  if (c < d) dgamma[c] += t;
+  else if (c < 2 * d) dbeta[c - d] += t;
+  else if (dbias != nullptr) dbias[c - 2 * d] += t;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -567,13 +591,19 @@ int residual_ln_fwd(float* y_z, const float* x, const float* gamma, const float*
 }
 int residual_ln_bwd(const float* dout, const float* z, const float* mean, const float* rstd, const float* gamma,
                     float* dz, void* dy_sub, float* dgamma, float* dbeta, float* dbias, long long rows, int d, float rate,
-                    unsigned long long seed, unsigned site, cudaStream_t st, const unsigned long long* seed_dev) {
+                    unsigned long long seed, unsigned site, cudaStream_t st, const unsigned long long* seed_dev, float* partial,
+                    long long partial_floats) {
   BX_REQUIRE(d % 4 == 0 && d <= 1024, "layernorm: need d %% 4 == 0 and d <= 1024 (got %d)", d);
   const int grid = grid_for(rows * 32, 256, 3);
   const size_t smem = (size_t)3 * d * sizeof(float);
+  const bool use_partial = partial != nullptr && partial_floats >= (long long)grid * 3 * d;
   BX_LN_DISPATCH(residual_ln_bwd_kernel, <<<grid, 256, smem, st>>>(dout, z, mean, rstd, gamma, dz, (__nv_bfloat16*)dy_sub, dgamma,
-                                                                  dbeta, dbias, rows, d, rate, seed, site, seed_dev))
+                                                                  dbeta, dbias, use_partial ? partial : nullptr, rows, d, rate, seed, site, seed_dev))
   BX_POST_LAUNCH();
+  if (use_partial) {
+    ln_partials_reduce_kernel<<<(3 * d + 255) / 256, 256, 0, st>>>(partial, grid, d, dgamma, dbeta, dbias);
+    BX_POST_LAUNCH();
+  }
   return 0;
 }
 

@@ -38,7 +38,8 @@ int residual_ln_fwd(float* y_z, const float* x, const float* gamma, const float*
                     unsigned site, cudaStream_t st, const unsigned long long* seed_dev = nullptr);
 int residual_ln_bwd(const float* dout, const float* z, const float* mean, const float* rstd, const float* gamma,
                     float* dz, void* dy_sub, float* dgamma, float* dbeta, float* dbias, long long rows, int d, float rate,
-                    unsigned long long seed, unsigned site, cudaStream_t st, const unsigned long long* seed_dev = nullptr);
+                    unsigned long long seed, unsigned site, cudaStream_t st, const unsigned long long* seed_dev = nullptr,
+                    float* partial = nullptr, long long partial_floats = 0);   // scratch for per-block dgamma/dbeta/dbias partials
 int xent(const void* logits, int logits_f32, long long ld, const long long* labels, int label_stride, int label_offset,
          int T_len, void* dlogits, long long ld_d, float* row_loss, double* stats, long long rows, int V, float inv_batch,
          cudaStream_t st);

@@ -149,6 +149,7 @@ struct Work {
   float* d_enc_out;                       // [Ms, d] accumulates cross-attention K/V gradients of all decoder layers
   bf16 *dy16, *dO16, *dqkv, *dh;          // [Mmax,d] [Mmax,d] [Mmax,3d] [Mmax,f]
   float *dq_acc, *delta;                  // [Mmax,d] [B,H,Smax]
+  float* ln_partial; int64_t ln_partial_floats;   // per-block LayerNorm-backward partial sums
   int64_t bytes;
 };
 
@@ -189,6 +190,7 @@ Work make_work(const b200xf_model_config& c, const Layout& lo, void* base) {
   w.gA = b.take<float>(Mx * d); w.gB = b.take<float>(Mx * d); w.d_enc_out = b.take<float>(Ms * d);
   w.dy16 = b.take<bf16>(Mx * d); w.dO16 = b.take<bf16>(Mx * d); w.dqkv = b.take<bf16>(Mx * 3 * d); w.dh = b.take<bf16>(Mx * f);
   w.dq_acc = b.take<float>(Mx * d); w.delta = b.take<float>(c.max_batch * H * Smax);
+  w.ln_partial_floats = (int64_t)1024 * 3 * d; w.ln_partial = b.take<float>(w.ln_partial_floats);
   w.bytes = b.cur;
   return w;
 }
@@ -361,7 +363,7 @@ int residual_ln_back(M* m, const float* g_in, const LnSave& s, int64_t g_off, in
                      uint32_t site, cudaStream_t st) {
   const float rate = m->training ? m->cfg.dropout_rate : 0.f;
   return bx::residual_ln_bwd(g_in, s.z, s.mean, s.rstd, m->P + g_off, g_out, m->w.dy16, m->G + g_off, m->G + b_off, m->G + bias_off, rows,
-                             m->lo.d, rate, m->seed, site, st, m->seed_dev);
+                             m->lo.d, rate, m->seed, site, st, m->seed_dev, m->w.ln_partial, m->w.ln_partial_floats);
 }
 
 // FFN backward: dy16 = d(ffn output); x16 = ffn input; accumulates d(input) into g (fp32)
