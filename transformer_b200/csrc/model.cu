@@ -363,7 +363,7 @@ int residual_ln_back(M* m, const float* g_in, const LnSave& s, int64_t g_off, in
                      uint32_t site, cudaStream_t st) {
   const float rate = m->training ? m->cfg.dropout_rate : 0.f;
   return bx::residual_ln_bwd(g_in, s.z, s.mean, s.rstd, m->P + g_off, g_out, m->w.dy16, m->G + g_off, m->G + b_off, m->G + bias_off, rows,
-                             m->lo.d, rate, m->seed, site, st, m->seed_dev, m->w.ln_partial, m->w.ln_partial_floats);
+                             m->lo.d, rate, m->seed, site, st, m->seed_dev);   // (a per-block-partials variant exists but measured slower than the atomics)
 }
 
 // FFN backward: dy16 = d(ffn output); x16 = ffn input; accumulates d(input) into g (fp32)
