@@ -255,10 +255,19 @@ def main():
         if N == 1 and not args.no_cpu_baseline:
             base, _ = cpu_reference_run(args.config, 2, 1, sample_batch=2)
             line["cpu_baseline"] = base
-        print(json.dumps(line))
+        print(json.dumps(line), flush=True)
     if world > 1:
+        # Tear-down: destroy_process_group() can block for minutes once NCCL collectives have been captured into CUDA
+        # graphs.  Everything is measured and printed: synchronise, meet at a barrier, then leave without destructors
+        # (a watchdog bounds even that).
+        def _bail():
+            time.sleep(60)
+            os._exit(0)
+        threading.Thread(target=_bail, daemon=True).start()
+        torch.cuda.synchronize()
         dist.barrier()
-        dist.destroy_process_group()
+        sys.stdout.flush()
+        os._exit(0)
 
 
 if __name__ == "__main__":
