@@ -60,6 +60,7 @@ def _worker(rank, world, port, q):
         q.put(dict(same=same))
     torch.cuda.synchronize()
     dist.barrier()
+    q.close(); q.join_thread()      # flush the result before leaving without destructors
     os._exit(0)       # destroy_process_group() can block once collectives were captured into CUDA graphs
 
 
