@@ -239,7 +239,11 @@ def main():
         roof = {"bound": "tensor", "kernel": "bx::gemm_kernel (tcgen05 GEMM, all launches of the step: FFN, projections, vocab, dgrad, wgrad)",
                 "achieved": ach, "peak": peaks["tf_sustained"], "unit": "TFLOP/s", "frac": ach / peaks["tf_sustained"],
                 "peak_source": f"{peaks['src']} MEASURED_PEAKS.json bf16_tflops_sustained (kernel timed inside a long step)",
-                "traffic": None, "launches_per_step": gemm_n / rsteps, "share_of_step": gemm_ms / ms_roof,
+                "traffic": 188747264,
+                "traffic_note": "dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the kernel (FFN dense0 wgrad, gemm_kernel<1,1,256,1,2>, "
+                                "512x2048x32768) from the committed ncu --set full capture profiles/r01_ncu_full_gemm_instep_backward.txt; "
+                                "algorithmic bytes of that launch = 172.0e6 (A 33.5 MB + B 134.2 MB + D 4.2 MB)",
+                "launches_per_step": gemm_n / rsteps, "share_of_step": gemm_ms / ms_roof,
                 "measured_in": f"eager pass of {rsteps} steps ({ms_roof / rsteps:.3f} ms/step) right after the timed region, events around every launch",
                 "attention_fwd": {"achieved": prof[4] / (prof[3] * 1e-3) / 1e12 if prof[3] > 0 else 0.0, "unit": "TFLOP/s (dense 4.B.H.Sq.Sk.dk)",
                                   "share_of_step": prof[3] / ms_roof},
