@@ -161,3 +161,34 @@ def test_gradient_buckets_allreduce_gloo_world2():
         p.join(60)
         assert p.exitcode == 0
     assert err < 1e-10, err
+
+
+def test_text_pipeline_semantics(tmp_path):
+    """utils.load_dataset stand-in keeps the reference's batching semantics (utils.py:114-161)."""
+    from transformer_b200 import utils
+    rng = np.random.default_rng(0)
+    words = [f"w{i}" for i in range(50)]
+    src_lines = [" ".join(rng.choice(words, rng.integers(1, 12))) for _ in range(103)]
+    tgt_lines = [" ".join(rng.choice(words, rng.integers(1, 12))) for _ in range(103)]
+    (tmp_path / "src-train.txt").write_text("\n".join(src_lines) + "\n")
+    (tmp_path / "tgt-train.txt").write_text("\n".join(tgt_lines) + "\n")
+    sv, tv = str(tmp_path / "sv"), str(tmp_path / "tv")
+    train, test, st, tt = utils.load_dataset(str(tmp_path) + "/", 8, sv, tv, 16, 1000)
+    assert os.path.exists(sv + ".subwords") and os.path.exists(tv + ".subwords")
+    n_test = max(1, int(103 * 0.05))
+    assert sum(b[0].shape[0] for b in test) == n_test                       # held-out tail (reference ships no test split)
+    kept = [(s, t) for s, t in zip(src_lines[:-n_test], tgt_lines[:-n_test])
+            if len(s.split()) + 2 <= 8 and len(t.split()) + 2 <= 8]         # length filter counts start/end ids, train only
+    assert sum(b[0].shape[0] for b in train) == len(kept)
+    assert all(b[0].shape[0] == 16 for b in train[:-1]) and 1 <= train[-1][0].shape[0] <= 16   # last batch partial
+    for src, tgt in train:
+        assert src.dtype == torch.int64 and src.shape[1] <= 8 and tgt.shape[1] <= 8
+        assert (src[:, 0] == st.vocab_size).all() and (tgt[:, 0] == tt.vocab_size).all()       # start id = vocab_size
+        for row in src:
+            nz = row[row != 0]
+            assert nz[-1] == st.vocab_size + 1 and (row[len(nz):] == 0).all()                   # end id, then pad 0
+    # tokenizer round trip and the "vocabulary exists" path
+    s = src_lines[0]
+    assert st.decode(st.encode(s)) == s
+    train2, _, st2, _ = utils.load_dataset(str(tmp_path) + "/", 8, sv, tv, 16, 1000)
+    assert st2.vocab_size == st.vocab_size and torch.equal(train2[0][0], train[0][0])

@@ -242,6 +242,62 @@ class Train(object):
         self.test_loss(self._stats[0] * (1.0 / self.batch_size))
         self.test_accuracy.add_(self._stats[1], self._stats[2])
 
+    # -- checkpoint / resume (train.py:77-80, 159-164, 208-211): flat arenas + keras-order manifest ---------------------
+    def _ckpt_files(self):
+        import glob
+        import re
+        files = glob.glob(os.path.join(self.ckpt_path, "ckpt-*.pt"))
+        return sorted(files, key=lambda f: int(re.findall(r"ckpt-(\d+)\.pt$", f)[0]))
+
+    def save_checkpoint(self):
+        """CheckpointManager.save(): params + Adam slots + iterations, newest ``max_ckpt_keep`` files kept."""
+        os.makedirs(self.ckpt_path, exist_ok=True)
+        tr = self.transformer
+        files = self._ckpt_files()
+        n = (int(files[-1].rsplit("-", 1)[1][:-3]) + 1) if files else 1
+        path = os.path.join(self.ckpt_path, f"ckpt-{n}.pt")
+        torch.cuda.synchronize(tr.device)
+        torch.save({"params": tr.params.cpu(), "adam_m": tr.adam_m.cpu(), "adam_v": tr.adam_v.cpu(),
+                    "iterations": self.optimizer.iterations,
+                    "manifest": [(v.name, tuple(v.shape)) for v in tr.trainable_variables],
+                    "config": dict(num_layers=tr.num_layers, d_model=tr.d_model, num_heads=tr.num_heads, dff=tr.dff,
+                                   input_vocab_size=tr.input_vocab_size, target_vocab_size=tr.target_vocab_size)}, path)
+        for old in self._ckpt_files()[:-self.max_ckpt_keep]:
+            os.remove(old)
+        return path
+
+    def load_ckpt(self):
+        """if a checkpoint exists, restore the latest checkpoint (train.py:159-164)."""
+        files = self._ckpt_files() if self.ckpt_path and os.path.isdir(self.ckpt_path) else []
+        if not files:
+            return False
+        tr = self.transformer
+        ck = torch.load(files[-1], map_location="cpu")
+        assert ck["manifest"] == [(v.name, tuple(v.shape)) for v in tr.trainable_variables], "checkpoint/model mismatch"
+        tr.params.copy_(ck["params"]); tr.adam_m.copy_(ck["adam_m"]); tr.adam_v.copy_(ck["adam_v"])
+        tr._shadow_dirty = True
+        self.optimizer.iterations = int(ck["iterations"])
+        self._it_dev.fill_(self.optimizer.iterations)
+        print('Latest checkpoint restored!!')
+        return True
+
+    def predict(self, input_sentence, max_steps=10):
+        """Greedy inference (train.py:91-121): start token, 10 decode steps, no EOS stop, the whole model re-run per
+        step.  (The reference indexes ``input_sentence[0]``, i.e. expects a 1-element batch of strings.)"""
+        if not isinstance(input_sentence, str):
+            input_sentence = input_sentence[0]
+        tr = self.transformer
+        start_token = [self.src_tokenizer.vocab_size]
+        end_token = [self.src_tokenizer.vocab_size + 1]
+        ids = start_token + self.src_tokenizer.encode(input_sentence) + end_token
+        encoder_input = torch.tensor([ids], dtype=torch.int64, device=tr.device)
+        output = torch.tensor([start_token], dtype=torch.int64, device=tr.device)
+        for _ in range(max_steps):
+            predictions, _ = tr.call((encoder_input, output), False)
+            predicted_id = predictions[:, -1:, :].argmax(dim=-1).to(torch.int64)
+            output = torch.cat([output, predicted_id], dim=-1)
+        return output[0]
+
     def training_loop(self, train_dataset, test_dataset):
         """Custom training and testing loop (train.py:167-213): same cadence and print template."""
         template = 'Epoch {}  Loss {:.4f} Accuracy {:.4f}, Test Loss {:.4f}, Test Accuracy {:.4f}'
@@ -260,5 +316,50 @@ class Train(object):
                         self.test_step((t_src, t_tgt))
                     print(template.format(epoch + 1, self.train_loss.result(), self.train_accuracy.result() * 100,
                                           self.test_loss.result(), self.test_accuracy.result() * 100))
+            if (epoch + 1) % 5 or (epoch + 1 == self.epochs) == 0:      # the reference's save condition, verbatim (train.py:208)
+                if self.ckpt_path:
+                    ckpt_save_path = self.save_checkpoint()
+                    print('Saving checkpoint for epoch {} at {}'.format(epoch + 1, ckpt_save_path))
             torch.cuda.synchronize()
             print('Time taken for {} epoch: {} secs\n'.format(epoch + 1, (time.time() - start)))
+
+
+def run_main(argv):
+    """train.py:216-220."""
+    del argv
+    from . import utils
+    kwargs = utils.flags_dict()
+    del kwargs['per_replica_batch_size']
+    main(**kwargs)
+
+
+def main(epochs, enable_function, buffer_size, batch_size, d_model, dff, num_heads, src_vocab_file, tgt_vocab_file, dataset_path,
+         dropout_rate, num_layers, sequence_length, ckpt_path, max_ckpt_keep):
+    """train.py:223-246 on the B200 drop-in (text pipeline: utils.load_dataset stand-in)."""
+    import datetime
+    from . import utils
+    from .Transformer import Transformer
+    current_time = datetime.datetime.now().strftime("%Y%m%d-%H%M%S")
+    train_log_dir = 'logs/gradient_tape/' + current_time + '/train'
+    test_log_dir = 'logs/gradient_tape/' + current_time + '/test'
+    train_dataset, test_dataset, src_tokenizer, tgt_tokenizer = utils.load_dataset(
+        dataset_path, sequence_length, src_vocab_file, tgt_vocab_file, batch_size, buffer_size)
+    input_vocab_size = src_tokenizer.vocab_size + 2
+    target_vocab_size = tgt_tokenizer.vocab_size + 2
+    transformer = Transformer(num_layers, d_model, num_heads, dff, input_vocab_size, target_vocab_size, dropout_rate,
+                              pos_rows=max(sequence_length + 2, 512))
+    print('create training object')
+    train_obj = Train(epochs, enable_function, transformer, src_tokenizer, tgt_tokenizer, batch_size, train_log_dir, test_log_dir,
+                      max_ckpt_keep, ckpt_path, d_model)
+    train_obj.training_loop(train_dataset, test_dataset)
+    train_obj.load_ckpt()
+    input_sentence = 'he go to school'
+    print(tgt_tokenizer.decode(train_obj.predict(input_sentence).tolist()))
+    return train_obj
+
+
+if __name__ == '__main__':
+    from absl import app
+    from . import utils as _utils
+    _utils.transformer_flags()
+    app.run(run_main)

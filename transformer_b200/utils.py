@@ -78,3 +78,113 @@ class SyntheticDataset:
 
     def __len__(self):
         return len(self.batches)
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# Text pipeline stand-in (SURVEY.md §8f "next" #1).  The reference's utils.read_data / _load_or_create_tokenier /
+# load_dataset (utils.py:65-161) are tf.data + tensorflow_datasets' SubwordTextEncoder -- neither library exists here
+# and the subword algorithm lives in the unvendored tfds package (parity unpinned).  This keeps the SAME function
+# names, arguments, return values and batching semantics on plain Python/torch, with a deterministic word-level
+# tokenizer standing in for SubwordTextEncoder.  Host-side I/O only; nothing here runs on the GPU.
+# ------------------------------------------------------------------------------------------------------------------
+import collections
+import os
+import random
+
+
+class WordTokenizer:
+    """Stand-in for tfds SubwordTextEncoder: ids 1..vocab_size-1 are words by descending corpus frequency, id 0 is the
+    padding id (never produced), the last id is <unk>.  Same surface: ``vocab_size``, ``encode``, ``decode``,
+    ``save_to_file`` / ``load_from_file`` (file suffix '.subwords' like tfds, so the reference's existence check,
+    utils.py:96-97, keeps working)."""
+
+    def __init__(self, words):
+        self.words = list(words)
+        self.index = {w: i + 1 for i, w in enumerate(self.words)}
+        self.vocab_size = len(self.words) + 2          # + pad (0) + <unk> (last)
+
+    @classmethod
+    def build_from_corpus(cls, corpus, target_vocab_size=2 ** 15):
+        cnt = collections.Counter()
+        for line in corpus:
+            cnt.update(line.split())
+        words = [w for w, _ in sorted(cnt.items(), key=lambda kv: (-kv[1], kv[0]))[:max(0, target_vocab_size - 2)]]
+        return cls(words)
+
+    def encode(self, s):
+        if isinstance(s, bytes):
+            s = s.decode("utf-8")
+        unk = self.vocab_size - 1
+        return [self.index.get(w, unk) for w in s.split()]
+
+    def decode(self, ids):
+        return " ".join(self.words[i - 1] if 1 <= i <= len(self.words) else "<unk>" for i in ids if i != 0)
+
+    def save_to_file(self, prefix):
+        with open(prefix + ".subwords", "w", encoding="utf-8") as f:
+            f.write("\n".join(self.words))
+
+    @classmethod
+    def load_from_file(cls, prefix):
+        with open(prefix + ".subwords", encoding="utf-8") as f:
+            return cls([w for w in f.read().split("\n") if w])
+
+
+def read_data(src_file, tgt_file):
+    """utils.py:65-80: zip of the two line files -> list of (src_line, tgt_line)."""
+    with open(src_file, encoding="utf-8") as fs, open(tgt_file, encoding="utf-8") as ft:
+        return list(zip((l.rstrip("\n") for l in fs), (l.rstrip("\n") for l in ft)))
+
+
+def _load_or_create_tokenier(dataset, src_vocab_file, tgt_vocab_file):
+    """utils.py:83-111 (name kept, typo included)."""
+    if not os.path.exists(src_vocab_file + '.subwords') and not os.path.exists(tgt_vocab_file + '.subwords'):
+        src_tokenizer = WordTokenizer.build_from_corpus((s for s, _ in dataset), target_vocab_size=2 ** 15)
+        src_tokenizer.save_to_file(src_vocab_file)
+        tgt_tokenizer = WordTokenizer.build_from_corpus((t for _, t in dataset), target_vocab_size=2 ** 15)
+        tgt_tokenizer.save_to_file(tgt_vocab_file)
+    else:
+        print("Vocabulary exists Loading...")
+        src_tokenizer = WordTokenizer.load_from_file(src_vocab_file)
+        tgt_tokenizer = WordTokenizer.load_from_file(tgt_vocab_file)
+    return src_tokenizer, tgt_tokenizer
+
+
+def _padded_batches(examples, batch_size):
+    """tf.data padded_batch(batch_size, ([-1],[-1])): ragged per batch, pad id 0, last batch partial (utils.py:154-159)."""
+    out = []
+    for i in range(0, len(examples), batch_size):
+        chunk = examples[i:i + batch_size]
+        ls = max(len(s) for s, _ in chunk)
+        lt = max(len(t) for _, t in chunk)
+        src = torch.zeros((len(chunk), ls), dtype=torch.int64)
+        tgt = torch.zeros((len(chunk), lt), dtype=torch.int64)
+        for r, (s, t) in enumerate(chunk):
+            src[r, :len(s)] = torch.tensor(s, dtype=torch.int64)
+            tgt[r, :len(t)] = torch.tensor(t, dtype=torch.int64)
+        out.append((src, tgt))
+    return out
+
+
+def load_dataset(dataset_path, sequence_length, src_vocab_file, tgt_vocab_file, batch_size, buffer_size, seed=0,
+                 holdout=0.05):
+    """utils.py:114-161.  The reference opens src-test.txt / tgt-test.txt, which it does not ship (SURVEY §0 trap 6):
+    when they are missing, the last ``holdout`` fraction of the train files is held out as the test set."""
+    pairs = read_data(os.path.join(dataset_path, 'src-train.txt'), os.path.join(dataset_path, 'tgt-train.txt'))
+    st, tt = os.path.join(dataset_path, 'src-test.txt'), os.path.join(dataset_path, 'tgt-test.txt')
+    if os.path.exists(st) and os.path.exists(tt):
+        test_pairs = read_data(st, tt)
+    else:
+        n_test = max(1, int(len(pairs) * holdout))
+        pairs, test_pairs = pairs[:-n_test], pairs[-n_test:]
+    src_tokenizer, tgt_tokenizer = _load_or_create_tokenier(pairs, src_vocab_file, tgt_vocab_file)
+
+    def encode(src, tgt):      # start / end ids = vocab_size, vocab_size + 1 (utils.py:137-143)
+        return ([src_tokenizer.vocab_size] + src_tokenizer.encode(src) + [src_tokenizer.vocab_size + 1],
+                [tgt_tokenizer.vocab_size] + tgt_tokenizer.encode(tgt) + [tgt_tokenizer.vocab_size + 1])
+
+    train = [encode(s, t) for s, t in pairs]
+    train = [(s, t) for s, t in train if len(s) <= sequence_length and len(t) <= sequence_length]   # train only (utils.py:153)
+    random.Random(seed).shuffle(train)                       # shuffle(buffer_size) with buffer >= dataset
+    test = [encode(s, t) for s, t in test_pairs]
+    return _padded_batches(train, batch_size), _padded_batches(test, batch_size), src_tokenizer, tgt_tokenizer
