@@ -341,10 +341,12 @@ def test_embed_fwd_bwd():
     assert (dt - dref).abs().max().item() < 1e-3
 
 
-@pytest.mark.parametrize("logits_f32", [1, 0])
-def test_xent_loss_grad_accuracy(logits_f32):
-    B, T, V = 4, 9, 1003
-    ld = 1008
+@pytest.mark.parametrize("logits_f32,V,ld,inplace", [(1, 1003, 1008, False), (0, 1003, 1008, False), (0, 1003, 1008, True),
+                                                     (0, 8190, 8192, True), (0, 32768, 32768, True), (0, 20001, 20008, False),
+                                                     (0, 40000, 40000, True)])
+def test_xent_loss_grad_accuracy(logits_f32, V, ld, inplace):
+    """two-pass kernel (fp32 logits, V > 32768) and the register-resident row kernel (bf16, KV 4 / 16), also in place."""
+    B, T = 4, 9
     g = torch.Generator().manual_seed(1)
     logits = torch.randn(B * T, ld, generator=g).to(dev()) * 3
     tar = torch.randint(1, V, (B, T + 1), generator=g); tar[1, 5:] = 0; tar[3, 1:] = 0
@@ -356,7 +358,7 @@ def test_xent_loss_grad_accuracy(logits_f32):
     per = (lse - torch.gather(lref, -1, real[..., None]).squeeze(-1)) * (real != 0)
     loss = per.sum() / B
     loss.backward()
-    dl = torch.full((B * T, ld), float("nan"), dtype=torch.bfloat16, device=dev())
+    dl = lg if inplace else torch.full((B * T, ld), float("nan"), dtype=torch.bfloat16, device=dev())
     stats = torch.zeros(4, dtype=torch.float64, device=dev())
     row_loss = torch.empty(B * T, device=dev())
     L.call("b200xf_xent", L.ptr(lg), logits_f32, ld, L.ptr(tar), T + 1, 1, T, L.ptr(dl), ld, L.ptr(row_loss), L.ptr(stats), B * T, V, 1.0 / B, sp())

@@ -171,7 +171,7 @@ residual_ln_fwd_kernel(float* __restrict__ y_z, const float* __restrict__ x, con
 //   dy_sub = dz * dropmask/(1-rate)                                      (bf16, gradient to the sublayer output)
 //   dgamma += sum_rows dy*xhat ; dbeta += sum_rows dy                    (block partials -> atomicAdd)
 template <int NV>
-__global__ void __launch_bounds__(256, NV >= 8 ? 1 : 3)
+__global__ void __launch_bounds__(256, 1)
 residual_ln_bwd_kernel(const float* __restrict__ dout, const float* __restrict__ z, const float* __restrict__ mean_in,
                        const float* __restrict__ rstd_in, const float* __restrict__ gamma, float* __restrict__ dz,
                        __nv_bfloat16* __restrict__ dy_sub, float* __restrict__ dgamma, float* __restrict__ dbeta,
@@ -188,19 +188,35 @@ residual_ln_bwd_kernel(const float* __restrict__ dout, const float* __restrict__
   float4 ag[NV], ab[NV], ac[NV];
 #pragma unroll
   for (int i = 0; i < NV; ++i) { ag[i] = make_float4(0, 0, 0, 0); ab[i] = make_float4(0, 0, 0, 0); ac[i] = make_float4(0, 0, 0, 0); }
-  for (long long r = warp_global; r < rows; r += nwarps) {
-    const float mean = mean_in[r], rstd = rstd_in[r];
-    float s1 = 0.f, s2 = 0.f;
-    // phase 1: row statistics + dgamma/dbeta partials.  xhat / gamma*dy are NOT kept in registers (3 CTAs per SM);
-    // phase 2 re-reads the row, which is still in L1.
+  // software pipeline: the NEXT row's dout / z are in flight (registers) while the current row is reduced and written
+  float4 nd[NV], nz[NV];
+  float nmean = 0.f, nrstd = 0.f;
+  auto fetch = [&](long long r) {
 #pragma unroll
     for (int i = 0; i < NV; ++i) {
       const int c4 = lane + 32 * i;
       if (c4 < d4) {
-        const long long idx = r * d4 + c4;
-        const float4 dyv = reinterpret_cast<const float4*>(dout)[idx];
-        const float4 zv = reinterpret_cast<const float4*>(z)[idx];
-        const float4 g = __ldg(reinterpret_cast<const float4*>(gamma) + c4);
+        nd[i] = reinterpret_cast<const float4*>(dout)[r * d4 + c4];
+        nz[i] = reinterpret_cast<const float4*>(z)[r * d4 + c4];
+      } else { nd[i] = make_float4(0, 0, 0, 0); nz[i] = make_float4(0, 0, 0, 0); }
+    }
+    nmean = mean_in[r]; nrstd = rstd_in[r];
+  };
+  if (warp_global < rows) fetch(warp_global);
+  float4 gm[NV];
+#pragma unroll
+  for (int i = 0; i < NV; ++i) gm[i] = (lane + 32 * i < d4) ? __ldg(reinterpret_cast<const float4*>(gamma) + lane + 32 * i) : make_float4(0, 0, 0, 0);
+  for (long long r = warp_global; r < rows; r += nwarps) {
+    float4 cd[NV], cz[NV];
+#pragma unroll
+    for (int i = 0; i < NV; ++i) { cd[i] = nd[i]; cz[i] = nz[i]; }
+    const float mean = nmean, rstd = nrstd;
+    if (r + nwarps < rows) fetch(r + nwarps);
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      if (lane + 32 * i < d4) {
+        const float4 dyv = cd[i], zv = cz[i], g = gm[i];
         const float4 xh = make_float4((zv.x - mean) * rstd, (zv.y - mean) * rstd, (zv.z - mean) * rstd, (zv.w - mean) * rstd);
         const float4 gd = make_float4(g.x * dyv.x, g.y * dyv.y, g.z * dyv.z, g.w * dyv.w);
         s1 += gd.x + gd.y + gd.z + gd.w;
@@ -215,9 +231,7 @@ residual_ln_bwd_kernel(const float* __restrict__ dout, const float* __restrict__
       const int c4 = lane + 32 * i;
       if (c4 < d4) {
         const long long idx = r * d4 + c4;
-        const float4 dyv = reinterpret_cast<const float4*>(dout)[idx];
-        const float4 zv = reinterpret_cast<const float4*>(z)[idx];
-        const float4 g = __ldg(reinterpret_cast<const float4*>(gamma) + c4);
+        const float4 dyv = cd[i], zv = cz[i], g = gm[i];
         float4 o;
         o.x = rstd * (g.x * dyv.x - m1 - (zv.x - mean) * rstd * m2);
         o.y = rstd * (g.y * dyv.y - m1 - (zv.y - mean) * rstd * m2);
@@ -369,10 +383,10 @@ xent_kernel(const T* logits, long long ld, const long long* __restrict__ labels,
   if (threadIdx.x == 0) {
     const float loss = nonpad ? (lse - s_lab) : 0.f;
     if (row_loss) row_loss[r] = loss;
-    atomicAdd(&stats[0], (double)loss);
-    atomicAdd(&stats[1], (double)((long long)am == raw_label ? 1.0 : 0.0));
+    if (nonpad) atomicAdd(&stats[0], (double)loss);
+    if ((long long)am == raw_label) atomicAdd(&stats[1], 1.0);
     atomicAdd(&stats[2], 1.0);
-    atomicAdd(&stats[3], nonpad ? 1.0 : 0.0);
+    if (nonpad) atomicAdd(&stats[3], 1.0);
   }
   if (dlogits == nullptr) return;
   // pass 2: gradient (row re-read hits L1/L2); padded columns [V, ld_d) are zeroed
@@ -523,24 +537,27 @@ __global__ void pad_mask_kernel(const long long* __restrict__ ids, uint8_t* __re
 __global__ void __launch_bounds__(256)
 attn_delta_kernel(const __nv_bfloat16* __restrict__ O, long long ld_o, const __nv_bfloat16* __restrict__ dO,
                   long long ld_do, float* __restrict__ delta, int B, int S, int H, int dk) {
+  // dk/8 adjacent lanes share one (row, head): every lane reads 16 contiguous bytes of O and dO, so a warp reads
+  // 512 contiguous bytes of each; a sub-warp shuffle finishes the dot product
+  const int lph = dk >> 3;                                              // lanes per head: 4 (dk 32) or 8 (dk 64)
   const long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-  const long long total = (long long)B * H * S;
-  if (idx >= total) return;
-  const int q = (int)(idx % S);
-  const long long bh = idx / S;
-  const int h = (int)(bh % H);
-  const long long b = bh / H;
-  const __nv_bfloat16* o = O + (b * S + q) * ld_o + h * dk;
-  const __nv_bfloat16* g = dO + (b * S + q) * ld_do + h * dk;
-  float s = 0.f;
-  for (int c = 0; c < dk; c += 8) {
-    const uint4 a = __ldg(reinterpret_cast<const uint4*>(o + c));
-    const uint4 d = __ldg(reinterpret_cast<const uint4*>(g + c));
-    const float2 a0 = unpack_bf16x2(a.x), a1 = unpack_bf16x2(a.y), a2 = unpack_bf16x2(a.z), a3 = unpack_bf16x2(a.w);
-    const float2 d0 = unpack_bf16x2(d.x), d1 = unpack_bf16x2(d.y), d2 = unpack_bf16x2(d.z), d3 = unpack_bf16x2(d.w);
-    s += a0.x * d0.x + a0.y * d0.y + a1.x * d1.x + a1.y * d1.y + a2.x * d2.x + a2.y * d2.y + a3.x * d3.x + a3.y * d3.y;
+  const long long total = (long long)B * S * H * lph;
+  const bool live = idx < total;
+  const long long i = live ? idx : total - 1;
+  const int l = (int)(i % lph);
+  const int h = (int)((i / lph) % H);
+  const long long row = i / ((long long)lph * H);                       // b * S + q
+  const uint4 a = __ldg(reinterpret_cast<const uint4*>(O + row * ld_o + h * dk + l * 8));
+  const uint4 d = __ldg(reinterpret_cast<const uint4*>(dO + row * ld_do + h * dk + l * 8));
+  const float2 a0 = unpack_bf16x2(a.x), a1 = unpack_bf16x2(a.y), a2 = unpack_bf16x2(a.z), a3 = unpack_bf16x2(a.w);
+  const float2 d0 = unpack_bf16x2(d.x), d1 = unpack_bf16x2(d.y), d2 = unpack_bf16x2(d.z), d3 = unpack_bf16x2(d.w);
+  float s = a0.x * d0.x + a0.y * d0.y + a1.x * d1.x + a1.y * d1.y + a2.x * d2.x + a2.y * d2.y + a3.x * d3.x + a3.y * d3.y;
+  for (int o = lph >> 1; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if (live && l == 0) {
+    const long long b = row / S;
+    const int q = (int)(row % S);
+    delta[(b * H + h) * S + q] = s;
   }
-  delta[idx] = s;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -594,7 +611,7 @@ int residual_ln_bwd(const float* dout, const float* z, const float* mean, const 
                     unsigned long long seed, unsigned site, cudaStream_t st, const unsigned long long* seed_dev, float* partial,
                     long long partial_floats) {
   BX_REQUIRE(d % 4 == 0 && d <= 1024, "layernorm: need d %% 4 == 0 and d <= 1024 (got %d)", d);
-  const int grid = grid_for(rows * 32, 256, 3);
+  const int grid = grid_for(rows * 32, 256, 1);
   const size_t smem = (size_t)3 * d * sizeof(float);
   const bool use_partial = partial != nullptr && partial_floats >= (long long)grid * 3 * d;
   BX_LN_DISPATCH(residual_ln_bwd_kernel, <<<grid, 256, smem, st>>>(dout, z, mean, rstd, gamma, dz, (__nv_bfloat16*)dy_sub, dgamma,
@@ -672,8 +689,8 @@ int pad_mask(const long long* ids, int id_stride, int id_offset, uint8_t* mask, 
 }
 int attn_delta(const void* O, long long ld_o, const void* dO, long long ld_do, float* delta, int B, int S, int H, int dk,
                cudaStream_t st) {
-  BX_REQUIRE(dk % 8 == 0 && ld_o % 8 == 0 && ld_do % 8 == 0, "attn_delta: dk and leading dimensions must be multiples of 8");
-  const long long n = (long long)B * S * H;
+  BX_REQUIRE((dk == 32 || dk == 64) && ld_o % 8 == 0 && ld_do % 8 == 0, "attn_delta: depth must be 32 or 64, leading dimensions multiples of 8");
+  const long long n = (long long)B * S * H * (dk / 8);
   attn_delta_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>((const __nv_bfloat16*)O, ld_o, (const __nv_bfloat16*)dO, ld_do, delta, B,
                                                                  S, H, dk);
   BX_POST_LAUNCH();
