@@ -75,18 +75,25 @@ int b200xf_attn_probs(const void* Q, int64_t ld_q, const void* K, int64_t ld_k, 
 int b200xf_embed_fwd(const int64_t* ids, int id_stride, int id_offset, const float* table, const float* pos,
                      float* out_f32, void* out_bf16, int64_t rows, int S, int d, int64_t V, float rate, uint64_t seed,
                      uint32_t site, b200xf_stream_t stream);
-int b200xf_embed_bwd(const int64_t* ids, int id_stride, int id_offset, const float* dx, float* dtable, int64_t rows,
-                     int S, int d, int64_t V, float rate, uint64_t seed, uint32_t site, b200xf_stream_t stream);
+/*      out_f32 may be NULL (the training path keeps only the bf16 stream).
+ *      backward: the gradient of the embedding output is g1 + g2 (bf16 [rows, d]; g2 may be NULL).                 */
+int b200xf_embed_bwd(const int64_t* ids, int id_stride, int id_offset, const void* g1_bf16, const void* g2_bf16, float* dtable,
+                     int64_t rows, int S, int d, int64_t V, float rate, uint64_t seed, uint32_t site, b200xf_stream_t stream);
 
 /* ---- Dropout + residual add + LayerNormalization(eps) (Encoder.py:22-23,26-27; Decoder.py:30-31,35-36,39-40).
- *      y_z: in = sublayer output y, out = z = x + dropout(y) (kept for backward).                                 */
-int b200xf_residual_ln_fwd(float* y_z, const float* x, const float* gamma, const float* beta, float* out_f32,
+ *      y (sublayer output), x (residual input), z = x + dropout(y) (kept for backward) and out = LN(z) are bf16
+ *      [rows, d] streams in HBM; statistics and normalisation are fp32 on the unrounded z.                          */
+int b200xf_residual_ln_fwd(const void* y_bf16, const void* x_bf16, const float* gamma, const float* beta, void* z_bf16,
                            void* out_bf16, float* mean, float* rstd, int64_t rows, int d, float eps, float rate,
                            uint64_t seed, uint32_t site, b200xf_stream_t stream);
-int b200xf_residual_ln_bwd(const float* dout, const float* z, const float* mean, const float* rstd, const float* gamma,
-                           float* dz, void* dy_sub_bf16, float* dgamma, float* dbeta, float* dbias, int64_t rows, int d,
-                           float rate, uint64_t seed, uint32_t site, b200xf_stream_t stream);
-/*      dbias (may be NULL) += column sums of dy_sub: the bias gradient of the sublayer's last Dense, for free */
+/*      backward: incoming gradient of `out` = g1 (fp32 if g1_is_f32 else bf16) + g2 (bf16, may be NULL), summed in fp32.
+ *      dz (bf16) = gradient of z = of the residual input; dy_sub (bf16, may be NULL when rate == 0: equals dz) =
+ *      gradient of the sublayer output; dgamma/dbeta += ; dbias (may be NULL) += column sums of dy_sub: the bias
+ *      gradient of the sublayer's last Dense, for free                                                              */
+int b200xf_residual_ln_bwd(const void* g1, int g1_is_f32, const void* g2_bf16, const void* z_bf16, const float* mean,
+                           const float* rstd, const float* gamma, void* dz_bf16, void* dy_sub_bf16, float* dgamma,
+                           float* dbeta, float* dbias, int64_t rows, int d, float rate, uint64_t seed, uint32_t site,
+                           b200xf_stream_t stream);
 
 /* ---- Train.loss_function + SparseCategoricalAccuracy (train.py:83-88, 141) and d(loss)/d(logits).
  *      row r = (b, t) reads label labels[b*label_stride + label_offset + t] (tar[:, 1:] without a copy).

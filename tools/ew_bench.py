@@ -37,22 +37,23 @@ def main():
     flush = torch.zeros(64 << 20, device=dev)   # 256 MB
     out = []
     f = lambda *s: torch.randn(*s, device=dev)
-    y, x, g, bta = f(rows, d), f(rows, d), f(d), f(d)
-    z, o32 = y.clone(), torch.empty_like(y)
-    o16 = torch.empty(rows, d, device=dev, dtype=torch.bfloat16)
+    h16 = lambda *s: torch.randn(*s, device=dev).bfloat16()
+    y, x, g, bta = h16(rows, d), h16(rows, d), f(d), f(d)
+    z, o16 = torch.empty_like(y), torch.empty_like(y)
     mean, rstd = torch.empty(rows, device=dev), torch.empty(rows, device=dev)
 
     def ln_fwd():
-        L.call("b200xf_residual_ln_fwd", L.ptr(z), L.ptr(x), L.ptr(g), L.ptr(bta), L.ptr(o32), L.ptr(o16), L.ptr(mean), L.ptr(rstd),
+        L.call("b200xf_residual_ln_fwd", L.ptr(y), L.ptr(x), L.ptr(g), L.ptr(bta), L.ptr(z), L.ptr(o16), L.ptr(mean), L.ptr(rstd),
                rows, d, 1e-6, 0.1, 1, 3, sp)
-    out.append(("residual_ln_fwd", timeit(ln_fwd, flush=flush), rows * d * (4 + 4 + 4 + 4 + 2)))
-    dz = torch.empty_like(y); dy = torch.empty_like(o16)
+    out.append(("residual_ln_fwd", timeit(ln_fwd, flush=flush), rows * d * 2 * 4))
+    g1, g2 = h16(rows, d), h16(rows, d)
+    dz = torch.empty_like(y); dy = torch.empty_like(y)
     dg, db, dbias = torch.zeros(d, device=dev), torch.zeros(d, device=dev), torch.zeros(d, device=dev)
 
     def ln_bwd():
-        L.call("b200xf_residual_ln_bwd", L.ptr(y), L.ptr(z), L.ptr(mean), L.ptr(rstd), L.ptr(g), L.ptr(dz), L.ptr(dy), L.ptr(dg), L.ptr(db),
-               L.ptr(dbias), rows, d, 0.1, 1, 3, sp)
-    out.append(("residual_ln_bwd", timeit(ln_bwd, flush=flush), rows * d * (4 + 4 + 4 + 2)))
+        L.call("b200xf_residual_ln_bwd", L.ptr(g1), 0, L.ptr(g2), L.ptr(z), L.ptr(mean), L.ptr(rstd), L.ptr(g), L.ptr(dz), L.ptr(dy),
+               L.ptr(dg), L.ptr(db), L.ptr(dbias), rows, d, 0.1, 1, 3, sp)
+    out.append(("residual_ln_bwd", timeit(ln_bwd, flush=flush), rows * d * 2 * 5))
 
     logits = (torch.randn(rows, V, device=dev) * 2).bfloat16()
     tar = torch.randint(1, V, (B, S + 1), device=dev)

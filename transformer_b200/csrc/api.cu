@@ -51,22 +51,23 @@ int b200xf_embed_fwd(const int64_t* ids, int id_stride, int id_offset, const flo
   return bx::embed_fwd(reinterpret_cast<const long long*>(ids), id_stride, id_offset, table, pos, out_f32, out_bf16, rows,
                        S, d, V, rate, seed, site, ST(stream));
 }
-int b200xf_embed_bwd(const int64_t* ids, int id_stride, int id_offset, const float* dx, float* dtable, int64_t rows,
-                     int S, int d, int64_t V, float rate, uint64_t seed, uint32_t site, b200xf_stream_t stream) {
-  return bx::embed_bwd(reinterpret_cast<const long long*>(ids), id_stride, id_offset, dx, dtable, rows, S, d, V, rate,
+int b200xf_embed_bwd(const int64_t* ids, int id_stride, int id_offset, const void* g1_bf16, const void* g2_bf16, float* dtable,
+                     int64_t rows, int S, int d, int64_t V, float rate, uint64_t seed, uint32_t site, b200xf_stream_t stream) {
+  return bx::embed_bwd(reinterpret_cast<const long long*>(ids), id_stride, id_offset, g1_bf16, g2_bf16, dtable, rows, S, d, V, rate,
                        seed, site, ST(stream));
 }
-int b200xf_residual_ln_fwd(float* y_z, const float* x, const float* gamma, const float* beta, float* out_f32,
+int b200xf_residual_ln_fwd(const void* y_bf16, const void* x_bf16, const float* gamma, const float* beta, void* z_bf16,
                            void* out_bf16, float* mean, float* rstd, int64_t rows, int d, float eps, float rate,
                            uint64_t seed, uint32_t site, b200xf_stream_t stream) {
-  return bx::residual_ln_fwd(y_z, x, gamma, beta, out_f32, out_bf16, mean, rstd, rows, d, eps, rate, seed, site,
+  return bx::residual_ln_fwd(y_bf16, x_bf16, gamma, beta, z_bf16, out_bf16, mean, rstd, rows, d, eps, rate, seed, site,
                              ST(stream));
 }
-int b200xf_residual_ln_bwd(const float* dout, const float* z, const float* mean, const float* rstd, const float* gamma,
-                           float* dz, void* dy_sub_bf16, float* dgamma, float* dbeta, float* dbias, int64_t rows, int d,
-                           float rate, uint64_t seed, uint32_t site, b200xf_stream_t stream) {
-  return bx::residual_ln_bwd(dout, z, mean, rstd, gamma, dz, dy_sub_bf16, dgamma, dbeta, dbias, rows, d, rate, seed, site,
-                             ST(stream));
+int b200xf_residual_ln_bwd(const void* g1, int g1_is_f32, const void* g2_bf16, const void* z_bf16, const float* mean,
+                           const float* rstd, const float* gamma, void* dz_bf16, void* dy_sub_bf16, float* dgamma,
+                           float* dbeta, float* dbias, int64_t rows, int d, float rate, uint64_t seed, uint32_t site,
+                           b200xf_stream_t stream) {
+  return bx::residual_ln_bwd(g1, g1_is_f32, g2_bf16, z_bf16, mean, rstd, gamma, dz_bf16, dy_sub_bf16, dgamma, dbeta, dbias, rows,
+                             d, rate, seed, site, ST(stream));
 }
 int b200xf_xent(const void* logits, int logits_f32, int64_t ld, const int64_t* labels, int label_stride,
                 int label_offset, int T, void* dlogits, int64_t ld_d, float* row_loss, double* stats, int64_t rows,

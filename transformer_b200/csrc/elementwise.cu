@@ -44,8 +44,30 @@ __device__ __forceinline__ float warp_max(float v) {
 }
 
 // ------------------------------------------------------------------------------------------------
+// 8-wide bf16 helpers: the activation and gradient streams between sublayers are bf16 in HBM (half the traffic of
+// fp32 streams); all arithmetic below is fp32 in registers.
+// ------------------------------------------------------------------------------------------------
+struct F8 { float v[8]; };
+__device__ __forceinline__ F8 unpack8(const uint4 u) {
+  const float2 a = unpack_bf16x2(u.x), b = unpack_bf16x2(u.y), c = unpack_bf16x2(u.z), d = unpack_bf16x2(u.w);
+  F8 f;
+  f.v[0] = a.x; f.v[1] = a.y; f.v[2] = b.x; f.v[3] = b.y; f.v[4] = c.x; f.v[5] = c.y; f.v[6] = d.x; f.v[7] = d.y;
+  return f;
+}
+__device__ __forceinline__ uint4 pack8(const F8& f) {
+  return make_uint4(pack_bf16x2(f.v[0], f.v[1]), pack_bf16x2(f.v[2], f.v[3]), pack_bf16x2(f.v[4], f.v[5]), pack_bf16x2(f.v[6], f.v[7]));
+}
+// keep-scale factors of the 8 consecutive elements starting at flat element index idx8*8 (same stream as dropout_scale4)
+__device__ __forceinline__ F8 dropout_scale8(unsigned long long seed, uint32_t site, unsigned long long idx8, float rate) {
+  const float4 a = dropout_scale4(seed, site, 2ull * idx8, rate), b = dropout_scale4(seed, site, 2ull * idx8 + 1ull, rate);
+  F8 k;
+  k.v[0] = a.x; k.v[1] = a.y; k.v[2] = a.z; k.v[3] = a.w; k.v[4] = b.x; k.v[5] = b.y; k.v[6] = b.z; k.v[7] = b.w;
+  return k;
+}
+
+// ------------------------------------------------------------------------------------------------
 // K6  embedding * sqrt(d) + pos_encoding[:, :S] (+ dropout)      Encoder.py:51-55, Decoder.py:65-69
-//   ids int64 [rows] (rows = B*S), table fp32 [V, d], pos fp32 [P, d]  ->  x fp32 [rows, d] and bf16 copy
+//   ids int64 [rows] (rows = B*S), table fp32 [V, d], pos fp32 [P, d]  ->  x bf16 [rows, d] (+ optional fp32 copy)
 // ------------------------------------------------------------------------------------------------
 __global__ void embed_fwd_kernel(const long long* __restrict__ ids, const float* __restrict__ table,
                                  const float* __restrict__ pos, float* __restrict__ out_f32,
@@ -67,16 +89,17 @@ __global__ void embed_fwd_kernel(const long long* __restrict__ ids, const float*
       const float4 k = dropout_scale4(seed, site, (unsigned long long)i, rate);
       o.x *= k.x; o.y *= k.y; o.z *= k.z; o.w *= k.w;
     }
-    reinterpret_cast<float4*>(out_f32)[i] = o;
+    if (out_f32 != nullptr) reinterpret_cast<float4*>(out_f32)[i] = o;
     reinterpret_cast<uint2*>(out_bf16)[i] = make_uint2(pack_bf16x2(o.x, o.y), pack_bf16x2(o.z, o.w));
   }
 }
 
-// backward: dTable[id] += dx * sqrt(d) * dropmask   (dense-equivalent IndexedSlices sum, Appendix A.8)
-__global__ void embed_bwd_kernel(const long long* __restrict__ ids, const float* __restrict__ dx,
-                                 float* __restrict__ dtable, long long rows, int S, int id_stride, int id_offset, int d,
-                                 long long V, float scale, float rate, unsigned long long seed, uint32_t site,
-                                 const unsigned long long* __restrict__ seed_dev) {
+// backward: dTable[id] += (g1 + g2) * sqrt(d) * dropmask   (dense-equivalent IndexedSlices sum, Appendix A.8)
+//   the gradient of the embedding output arrives as two bf16 streams (residual path + first sublayer's dgrad)
+__global__ void embed_bwd_kernel(const long long* __restrict__ ids, const __nv_bfloat16* __restrict__ g1,
+                                 const __nv_bfloat16* __restrict__ g2, float* __restrict__ dtable, long long rows, int S,
+                                 int id_stride, int id_offset, int d, long long V, float scale, float rate,
+                                 unsigned long long seed, uint32_t site, const unsigned long long* __restrict__ seed_dev) {
   if (seed_dev != nullptr) seed = *seed_dev;
   const int d4 = d >> 2;
   const long long total = rows * d4;
@@ -85,7 +108,14 @@ __global__ void embed_bwd_kernel(const long long* __restrict__ ids, const float*
     const int c4 = (int)(i - r * d4);
     long long id = ids[(r / S) * id_stride + id_offset + (r % S)];
     id = id < 0 ? 0 : (id >= V ? V - 1 : id);
-    float4 g = reinterpret_cast<const float4*>(dx)[i];
+    const uint2 a = reinterpret_cast<const uint2*>(g1)[i];
+    const float2 a0 = unpack_bf16x2(a.x), a1 = unpack_bf16x2(a.y);
+    float4 g = make_float4(a0.x, a0.y, a1.x, a1.y);
+    if (g2 != nullptr) {
+      const uint2 b = reinterpret_cast<const uint2*>(g2)[i];
+      const float2 b0 = unpack_bf16x2(b.x), b1 = unpack_bf16x2(b.y);
+      g.x += b0.x; g.y += b0.y; g.z += b1.x; g.w += b1.y;
+    }
     if (rate > 0.f) {
       const float4 k = dropout_scale4(seed, site, (unsigned long long)i, rate);
       g.x *= k.x; g.y *= k.y; g.z *= k.z; g.w *= k.w;
@@ -101,194 +131,210 @@ __global__ void embed_bwd_kernel(const long long* __restrict__ ids, const float*
 // ------------------------------------------------------------------------------------------------
 // K3/K4 epilogue (stand-alone form) + K5:  z = x + dropout(y);  out = LayerNorm(z)   (eps 1e-6, biased var)
 //   Encoder.py:22-23,26-27  Decoder.py:30-31,35-36,39-40 ; LN formula SURVEY Appendix A.4
-//   one warp per row; NV = ceil(d/128) float4 per lane kept in registers.
-//   y (fp32, sublayer output) is overwritten in place by z (kept for backward).
+//   y (sublayer output), x (residual input), z (kept for backward) and out are bf16 [rows, d]; statistics and the
+//   normalisation use the unrounded fp32 z.  One warp per row, NV = ceil(d/256) 16-byte vectors per lane; the next
+//   row's loads are issued before the current row is reduced (software pipeline).
 // ------------------------------------------------------------------------------------------------
 template <int NV>
 __global__ void __launch_bounds__(256)
-residual_ln_fwd_kernel(float* __restrict__ y_z, const float* __restrict__ x, const float* __restrict__ gamma,
-                       const float* __restrict__ beta, float* __restrict__ out_f32,
-                       __nv_bfloat16* __restrict__ out_bf16, float* __restrict__ mean_out,
-                       float* __restrict__ rstd_out, long long rows, int d, float eps, float rate,
-                       unsigned long long seed, uint32_t site, const unsigned long long* __restrict__ seed_dev) {
+residual_ln_fwd_kernel(const __nv_bfloat16* __restrict__ y, const __nv_bfloat16* __restrict__ x,
+                       const float* __restrict__ gamma, const float* __restrict__ beta, __nv_bfloat16* __restrict__ z_out,
+                       __nv_bfloat16* __restrict__ out, float* __restrict__ mean_out, float* __restrict__ rstd_out,
+                       long long rows, int d, float eps, float rate, unsigned long long seed, uint32_t site,
+                       const unsigned long long* __restrict__ seed_dev) {
   if (seed_dev != nullptr) seed = *seed_dev;
   const int lane = threadIdx.x & 31;
   const long long warp_global = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
   const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
-  const int d4 = d >> 2;
+  const int d8 = d >> 3;
+  uint4 ny[NV], nx[NV];
+  auto fetch = [&](long long r) {
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int c8 = lane + 32 * i;
+      if (c8 < d8) {
+        ny[i] = reinterpret_cast<const uint4*>(y)[r * d8 + c8];
+        nx[i] = reinterpret_cast<const uint4*>(x)[r * d8 + c8];
+      } else { ny[i] = make_uint4(0, 0, 0, 0); nx[i] = make_uint4(0, 0, 0, 0); }
+    }
+  };
+  if (warp_global < rows) fetch(warp_global);
   for (long long r = warp_global; r < rows; r += nwarps) {
-    float4 z[NV];
+    F8 z[NV];
     float s = 0.f;
 #pragma unroll
     for (int i = 0; i < NV; ++i) {
-      const int c4 = lane + 32 * i;
-      z[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (c4 < d4) {
-        const long long idx = r * d4 + c4;
-        float4 yv = reinterpret_cast<const float4*>(y_z)[idx];
-        const float4 xv = reinterpret_cast<const float4*>(x)[idx];
-        if (rate > 0.f) {
-          const float4 k = dropout_scale4(seed, site, (unsigned long long)idx, rate);
-          yv.x *= k.x; yv.y *= k.y; yv.z *= k.z; yv.w *= k.w;
-        }
-        z[i] = make_float4(xv.x + yv.x, xv.y + yv.y, xv.z + yv.z, xv.w + yv.w);
-        reinterpret_cast<float4*>(y_z)[idx] = z[i];
-        s += z[i].x + z[i].y + z[i].z + z[i].w;
+      const int c8 = lane + 32 * i;
+      F8 yv = unpack8(ny[i]);
+      const F8 xv = unpack8(nx[i]);
+      if (rate > 0.f && c8 < d8) {
+        const F8 k = dropout_scale8(seed, site, (unsigned long long)(r * d8 + c8), rate);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) yv.v[e] *= k.v[e];
       }
+#pragma unroll
+      for (int e = 0; e < 8; ++e) { z[i].v[e] = xv.v[e] + yv.v[e]; s += z[i].v[e]; }
     }
+    if (r + nwarps < rows) fetch(r + nwarps);
     const float mean = warp_sum(s) / d;
     float v = 0.f;
 #pragma unroll
     for (int i = 0; i < NV; ++i) {
-      if (lane + 32 * i < d4) {
-        const float a = z[i].x - mean, b = z[i].y - mean, c = z[i].z - mean, e = z[i].w - mean;
-        v += a * a + b * b + c * c + e * e;
+      if (lane + 32 * i < d8) {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) { const float a = z[i].v[e] - mean; v += a * a; }
       }
     }
     const float rstd = rsqrtf(warp_sum(v) / d + eps);
     if (lane == 0) { mean_out[r] = mean; rstd_out[r] = rstd; }
 #pragma unroll
     for (int i = 0; i < NV; ++i) {
-      const int c4 = lane + 32 * i;
-      if (c4 < d4) {
-        const float4 g = __ldg(reinterpret_cast<const float4*>(gamma) + c4);
-        const float4 b = __ldg(reinterpret_cast<const float4*>(beta) + c4);
-        float4 o;
-        o.x = (z[i].x - mean) * rstd * g.x + b.x;
-        o.y = (z[i].y - mean) * rstd * g.y + b.y;
-        o.z = (z[i].z - mean) * rstd * g.z + b.z;
-        o.w = (z[i].w - mean) * rstd * g.w + b.w;
-        const long long idx = r * d4 + c4;
-        reinterpret_cast<float4*>(out_f32)[idx] = o;
-        reinterpret_cast<uint2*>(out_bf16)[idx] = make_uint2(pack_bf16x2(o.x, o.y), pack_bf16x2(o.z, o.w));
+      const int c8 = lane + 32 * i;
+      if (c8 < d8) {
+        const long long idx = r * d8 + c8;
+        reinterpret_cast<uint4*>(z_out)[idx] = pack8(z[i]);
+        const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma) + 2 * c8), g1 = __ldg(reinterpret_cast<const float4*>(gamma) + 2 * c8 + 1);
+        const float4 b0 = __ldg(reinterpret_cast<const float4*>(beta) + 2 * c8), b1 = __ldg(reinterpret_cast<const float4*>(beta) + 2 * c8 + 1);
+        const float g[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+        const float b[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+        F8 o;
+#pragma unroll
+        for (int e = 0; e < 8; ++e) o.v[e] = (z[i].v[e] - mean) * rstd * g[e] + b[e];
+        reinterpret_cast<uint4*>(out)[idx] = pack8(o);
       }
     }
   }
 }
 
-// backward of out = LN(z), z = x + dropout(y):
-//   dz = rstd * (g*dy - mean(g*dy) - xhat * mean(g*dy*xhat))            (fp32, gradient to the residual input x)
-//   dy_sub = dz * dropmask/(1-rate)                                      (bf16, gradient to the sublayer output)
-//   dgamma += sum_rows dy*xhat ; dbeta += sum_rows dy                    (block partials -> atomicAdd)
-template <int NV>
+// backward of out = LN(z), z = x + dropout(y); the incoming gradient is g1 (+ g2): the residual-path gradient and the
+// previous sublayer's dgrad output arrive as separate streams and are summed here in fp32 (no read-modify-write
+// accumulation in a GEMM epilogue, no intermediate bf16 rounding of the sum):
+//   dz = rstd * (g*dy - mean(g*dy) - xhat * mean(g*dy*xhat))            (bf16, gradient to the residual input x)
+//   dy_sub = dz * dropmask/(1-rate)                                      (bf16, gradient to the sublayer output;
+//                                                                         NULL when rate == 0: it equals dz)
+//   dgamma += sum_rows dy*xhat ; dbeta += sum_rows dy ; dbias += sum_rows dy_sub   (block partials -> atomicAdd)
+template <int NV, bool kG1F32>
 __global__ void __launch_bounds__(256, 1)
-residual_ln_bwd_kernel(const float* __restrict__ dout, const float* __restrict__ z, const float* __restrict__ mean_in,
-                       const float* __restrict__ rstd_in, const float* __restrict__ gamma, float* __restrict__ dz,
-                       __nv_bfloat16* __restrict__ dy_sub, float* __restrict__ dgamma, float* __restrict__ dbeta,
-                       float* __restrict__ dbias, float* __restrict__ partial, long long rows, int d, float rate,
+residual_ln_bwd_kernel(const void* __restrict__ g1v, const __nv_bfloat16* __restrict__ g2, const __nv_bfloat16* __restrict__ z,
+                       const float* __restrict__ mean_in, const float* __restrict__ rstd_in, const float* __restrict__ gamma,
+                       __nv_bfloat16* __restrict__ dz, __nv_bfloat16* __restrict__ dy_sub, float* __restrict__ dgamma,
+                       float* __restrict__ dbeta, float* __restrict__ dbias, long long rows, int d, float rate,
                        unsigned long long seed, uint32_t site, const unsigned long long* __restrict__ seed_dev) {
   if (seed_dev != nullptr) seed = *seed_dev;
   extern __shared__ float red[];  // [3][d]: dgamma, dbeta, dbias partials of this block (shared-memory atomics)
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, nw = blockDim.x >> 5;
   const long long warp_global = (long long)blockIdx.x * nw + wib;
   const long long nwarps = (long long)gridDim.x * nw;
-  const int d4 = d >> 2;
+  const int d8 = d >> 3;
   for (int c = threadIdx.x; c < 3 * d; c += blockDim.x) red[c] = 0.f;
   __syncthreads();
-  float4 ag[NV], ab[NV], ac[NV];
+  F8 ag[NV], ab[NV], ac[NV], gm[NV];
 #pragma unroll
-  for (int i = 0; i < NV; ++i) { ag[i] = make_float4(0, 0, 0, 0); ab[i] = make_float4(0, 0, 0, 0); ac[i] = make_float4(0, 0, 0, 0); }
-  // software pipeline: the NEXT row's dout / z are in flight (registers) while the current row is reduced and written
-  float4 nd[NV], nz[NV];
+  for (int i = 0; i < NV; ++i) {
+#pragma unroll
+    for (int e = 0; e < 8; ++e) { ag[i].v[e] = 0.f; ab[i].v[e] = 0.f; ac[i].v[e] = 0.f; gm[i].v[e] = 0.f; }
+    const int c8 = lane + 32 * i;
+    if (c8 < d8) {
+      const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma) + 2 * c8), g1 = __ldg(reinterpret_cast<const float4*>(gamma) + 2 * c8 + 1);
+      gm[i].v[0] = g0.x; gm[i].v[1] = g0.y; gm[i].v[2] = g0.z; gm[i].v[3] = g0.w;
+      gm[i].v[4] = g1.x; gm[i].v[5] = g1.y; gm[i].v[6] = g1.z; gm[i].v[7] = g1.w;
+    }
+  }
+  // software pipeline: the NEXT row's gradient / z vectors are in flight while the current row is reduced and written
+  constexpr int G1V = kG1F32 ? 2 : 1;
+  uint4 n1[NV][G1V], n2[NV], nz[NV];
   float nmean = 0.f, nrstd = 0.f;
   auto fetch = [&](long long r) {
 #pragma unroll
     for (int i = 0; i < NV; ++i) {
-      const int c4 = lane + 32 * i;
-      if (c4 < d4) {
-        nd[i] = reinterpret_cast<const float4*>(dout)[r * d4 + c4];
-        nz[i] = reinterpret_cast<const float4*>(z)[r * d4 + c4];
-      } else { nd[i] = make_float4(0, 0, 0, 0); nz[i] = make_float4(0, 0, 0, 0); }
+      const int c8 = lane + 32 * i;
+      if (c8 < d8) {
+        const long long idx = r * d8 + c8;
+        if (kG1F32) {
+          n1[i][0] = reinterpret_cast<const uint4*>(g1v)[2 * idx];
+          n1[i][G1V - 1] = reinterpret_cast<const uint4*>(g1v)[2 * idx + 1];
+        } else {
+          n1[i][0] = reinterpret_cast<const uint4*>(g1v)[idx];
+        }
+        n2[i] = g2 != nullptr ? reinterpret_cast<const uint4*>(g2)[idx] : make_uint4(0, 0, 0, 0);
+        nz[i] = reinterpret_cast<const uint4*>(z)[idx];
+      } else {
+#pragma unroll
+        for (int k = 0; k < G1V; ++k) n1[i][k] = make_uint4(0, 0, 0, 0);
+        n2[i] = make_uint4(0, 0, 0, 0); nz[i] = make_uint4(0, 0, 0, 0);
+      }
     }
     nmean = mean_in[r]; nrstd = rstd_in[r];
   };
   if (warp_global < rows) fetch(warp_global);
-  float4 gm[NV];
-#pragma unroll
-  for (int i = 0; i < NV; ++i) gm[i] = (lane + 32 * i < d4) ? __ldg(reinterpret_cast<const float4*>(gamma) + lane + 32 * i) : make_float4(0, 0, 0, 0);
   for (long long r = warp_global; r < rows; r += nwarps) {
-    float4 cd[NV], cz[NV];
-#pragma unroll
-    for (int i = 0; i < NV; ++i) { cd[i] = nd[i]; cz[i] = nz[i]; }
+    F8 dy[NV], xh[NV];
     const float mean = nmean, rstd = nrstd;
-    if (r + nwarps < rows) fetch(r + nwarps);
     float s1 = 0.f, s2 = 0.f;
 #pragma unroll
     for (int i = 0; i < NV; ++i) {
-      if (lane + 32 * i < d4) {
-        const float4 dyv = cd[i], zv = cz[i], g = gm[i];
-        const float4 xh = make_float4((zv.x - mean) * rstd, (zv.y - mean) * rstd, (zv.z - mean) * rstd, (zv.w - mean) * rstd);
-        const float4 gd = make_float4(g.x * dyv.x, g.y * dyv.y, g.z * dyv.z, g.w * dyv.w);
-        s1 += gd.x + gd.y + gd.z + gd.w;
-        s2 += gd.x * xh.x + gd.y * xh.y + gd.z * xh.z + gd.w * xh.w;
-        ag[i].x += dyv.x * xh.x; ag[i].y += dyv.y * xh.y; ag[i].z += dyv.z * xh.z; ag[i].w += dyv.w * xh.w;
-        ab[i].x += dyv.x; ab[i].y += dyv.y; ab[i].z += dyv.z; ab[i].w += dyv.w;
+      if (kG1F32) {
+        dy[i].v[0] = __uint_as_float(n1[i][0].x); dy[i].v[1] = __uint_as_float(n1[i][0].y);
+        dy[i].v[2] = __uint_as_float(n1[i][0].z); dy[i].v[3] = __uint_as_float(n1[i][0].w);
+        dy[i].v[4] = __uint_as_float(n1[i][G1V - 1].x); dy[i].v[5] = __uint_as_float(n1[i][G1V - 1].y);
+        dy[i].v[6] = __uint_as_float(n1[i][G1V - 1].z); dy[i].v[7] = __uint_as_float(n1[i][G1V - 1].w);
+      } else {
+        dy[i] = unpack8(n1[i][0]);
+      }
+      const F8 b = unpack8(n2[i]);
+      const F8 zv = unpack8(nz[i]);
+      const bool live = lane + 32 * i < d8;
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        dy[i].v[e] += b.v[e];
+        xh[i].v[e] = live ? (zv.v[e] - mean) * rstd : 0.f;
+        const float gd = gm[i].v[e] * dy[i].v[e];
+        s1 += gd;
+        s2 += gd * xh[i].v[e];
+        ag[i].v[e] += dy[i].v[e] * xh[i].v[e];
+        ab[i].v[e] += dy[i].v[e];
       }
     }
+    if (r + nwarps < rows) fetch(r + nwarps);
     const float m1 = warp_sum(s1) / d, m2 = warp_sum(s2) / d;
 #pragma unroll
     for (int i = 0; i < NV; ++i) {
-      const int c4 = lane + 32 * i;
-      if (c4 < d4) {
-        const long long idx = r * d4 + c4;
-        const float4 dyv = cd[i], zv = cz[i], g = gm[i];
-        float4 o;
-        o.x = rstd * (g.x * dyv.x - m1 - (zv.x - mean) * rstd * m2);
-        o.y = rstd * (g.y * dyv.y - m1 - (zv.y - mean) * rstd * m2);
-        o.z = rstd * (g.z * dyv.z - m1 - (zv.z - mean) * rstd * m2);
-        o.w = rstd * (g.w * dyv.w - m1 - (zv.w - mean) * rstd * m2);
-        reinterpret_cast<float4*>(dz)[idx] = o;
+      const int c8 = lane + 32 * i;
+      if (c8 < d8) {
+        const long long idx = r * d8 + c8;
+        F8 o;
+#pragma unroll
+        for (int e = 0; e < 8; ++e) o.v[e] = rstd * (gm[i].v[e] * dy[i].v[e] - m1 - xh[i].v[e] * m2);
+        reinterpret_cast<uint4*>(dz)[idx] = pack8(o);
         if (rate > 0.f) {
-          const float4 k = dropout_scale4(seed, site, (unsigned long long)idx, rate);
-          o.x *= k.x; o.y *= k.y; o.z *= k.z; o.w *= k.w;
+          const F8 k = dropout_scale8(seed, site, (unsigned long long)idx, rate);
+#pragma unroll
+          for (int e = 0; e < 8; ++e) o.v[e] *= k.v[e];
         }
-        ac[i].x += o.x; ac[i].y += o.y; ac[i].z += o.z; ac[i].w += o.w;     // bias grad of the sublayer's last Dense
-        reinterpret_cast<uint2*>(dy_sub)[idx] = make_uint2(pack_bf16x2(o.x, o.y), pack_bf16x2(o.z, o.w));
+#pragma unroll
+        for (int e = 0; e < 8; ++e) ac[i].v[e] += o.v[e];       // bias grad of the sublayer's last Dense
+        if (dy_sub != nullptr) reinterpret_cast<uint4*>(dy_sub)[idx] = pack8(o);
       }
     }
   }
 #pragma unroll
   for (int i = 0; i < NV; ++i) {
-    const int c = (lane + 32 * i) * 4;
+    const int c = (lane + 32 * i) * 8;
     if (c < d) {
-      atomicAdd(red + c + 0, ag[i].x); atomicAdd(red + c + 1, ag[i].y); atomicAdd(red + c + 2, ag[i].z); atomicAdd(red + c + 3, ag[i].w);
-      atomicAdd(red + d + c + 0, ab[i].x); atomicAdd(red + d + c + 1, ab[i].y); atomicAdd(red + d + c + 2, ab[i].z); atomicAdd(red + d + c + 3, ab[i].w);
-      if (dbias != nullptr) {
-        atomicAdd(red + 2 * d + c + 0, ac[i].x); atomicAdd(red + 2 * d + c + 1, ac[i].y);
-        atomicAdd(red + 2 * d + c + 2, ac[i].z); atomicAdd(red + 2 * d + c + 3, ac[i].w);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        atomicAdd(red + c + e, ag[i].v[e]);
+        atomicAdd(red + d + c + e, ab[i].v[e]);
+        if (dbias != nullptr) atomicAdd(red + 2 * d + c + e, ac[i].v[e]);
       }
     }
   }
   __syncthreads();
-  if (partial != nullptr) {
-    // per-block partials; ln_partials_reduce_kernel sums them (hundreds of blocks hitting the same 3d addresses with
-    // global atomics serialise in L2 and cost ~20 us per call)
-    for (int c = threadIdx.x; c < 3 * d; c += blockDim.x) partial[(size_t)blockIdx.x * 3 * d + c] = red[c];
-    return;
-  }
   for (int c = threadIdx.x; c < d; c += blockDim.x) {
     atomicAdd(dgamma + c, red[c]);
     atomicAdd(dbeta + c, red[d + c]);
     if (dbias != nullptr) atomicAdd(dbias + c, red[2 * d + c]);
   }
-}
-
-__global__ void __launch_bounds__(256)
-ln_partials_reduce_kernel(const float* __restrict__ partial, int nblocks, int d, float* __restrict__ dgamma,
-                          float* __restrict__ dbeta, float* __restrict__ dbias) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= 3 * d) return;
-  float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
-  int k = 0;
-  for (; k + 3 < nblocks; k += 4) {
-    s0 += partial[(size_t)k * 3 * d + c]; s1 += partial[(size_t)(k + 1) * 3 * d + c];
-    s2 += partial[(size_t)(k + 2) * 3 * d + c]; s3 += partial[(size_t)(k + 3) * 3 * d + c];
-  }
-  for (; k < nblocks; ++k) s0 += partial[(size_t)k * 3 * d + c];
-  const float t = (s0 + s1) + (s2 + s3);
-  if (c < d) dgamma[c] += t;
-  else if (c < 2 * d) dbeta[c - d] += t;
-  else if (dbias != nullptr) dbias[c - 2 * d] += t;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -580,47 +626,55 @@ int embed_fwd(const long long* ids, int id_stride, int id_offset, const float* t
   BX_POST_LAUNCH();
   return 0;
 }
-int embed_bwd(const long long* ids, int id_stride, int id_offset, const float* dx, float* dtable, long long rows, int S,
-              int d, long long V, float rate, unsigned long long seed, unsigned site, cudaStream_t st,
+int embed_bwd(const long long* ids, int id_stride, int id_offset, const void* g1, const void* g2, float* dtable, long long rows,
+              int S, int d, long long V, float rate, unsigned long long seed, unsigned site, cudaStream_t st,
               const unsigned long long* seed_dev) {
   BX_REQUIRE(d % 4 == 0, "embed: d_model %% 4 != 0");
-  embed_bwd_kernel<<<grid_for(rows * (d / 4), 256), 256, 0, st>>>(ids, dx, dtable, rows, S, id_stride, id_offset, d, V,
-                                                                 sqrtf((float)d), rate, seed, site, seed_dev);
+  embed_bwd_kernel<<<grid_for(rows * (d / 4), 256), 256, 0, st>>>(ids, (const __nv_bfloat16*)g1, (const __nv_bfloat16*)g2, dtable, rows,
+                                                                 S, id_stride, id_offset, d, V, sqrtf((float)d), rate, seed, site,
+                                                                 seed_dev);
   BX_POST_LAUNCH();
   return 0;
 }
 
-#define BX_LN_DISPATCH(NAME, ...)                                       \
-  if (d <= 128) NAME<1> __VA_ARGS__;                                    \
-  else if (d <= 256) NAME<2> __VA_ARGS__;                               \
-  else if (d <= 512) NAME<4> __VA_ARGS__;                               \
-  else NAME<8> __VA_ARGS__;
+#define BX_LN_DISPATCH(NAME, ...)                                         \
+  if (d <= 256) NAME<1 BX_LN_EXTRA> __VA_ARGS__;                          \
+  else if (d <= 512) NAME<2 BX_LN_EXTRA> __VA_ARGS__;                     \
+  else NAME<4 BX_LN_EXTRA> __VA_ARGS__;
 
-int residual_ln_fwd(float* y_z, const float* x, const float* gamma, const float* beta, float* out_f32, void* out_bf16,
-                    float* mean, float* rstd, long long rows, int d, float eps, float rate, unsigned long long seed,
-                    unsigned site, cudaStream_t st, const unsigned long long* seed_dev) {
-  BX_REQUIRE(d % 4 == 0 && d <= 1024, "layernorm: need d %% 4 == 0 and d <= 1024 (got %d)", d);
+int residual_ln_fwd(const void* y, const void* x, const float* gamma, const float* beta, void* z, void* out, float* mean,
+                    float* rstd, long long rows, int d, float eps, float rate, unsigned long long seed, unsigned site,
+                    cudaStream_t st, const unsigned long long* seed_dev) {
+  BX_REQUIRE(d % 8 == 0 && d <= 1024, "layernorm: need d %% 8 == 0 and d <= 1024 (got %d)", d);
   const int grid = grid_for(rows * 32, 256);
-  BX_LN_DISPATCH(residual_ln_fwd_kernel, <<<grid, 256, 0, st>>>(y_z, x, gamma, beta, out_f32, (__nv_bfloat16*)out_bf16, mean, rstd,
-                                                               rows, d, eps, rate, seed, site, seed_dev))
+#define BX_LN_EXTRA
+  BX_LN_DISPATCH(residual_ln_fwd_kernel, <<<grid, 256, 0, st>>>((const __nv_bfloat16*)y, (const __nv_bfloat16*)x, gamma, beta,
+                                                               (__nv_bfloat16*)z, (__nv_bfloat16*)out, mean, rstd, rows, d, eps, rate,
+                                                               seed, site, seed_dev))
+#undef BX_LN_EXTRA
   BX_POST_LAUNCH();
   return 0;
 }
-int residual_ln_bwd(const float* dout, const float* z, const float* mean, const float* rstd, const float* gamma,
-                    float* dz, void* dy_sub, float* dgamma, float* dbeta, float* dbias, long long rows, int d, float rate,
-                    unsigned long long seed, unsigned site, cudaStream_t st, const unsigned long long* seed_dev, float* partial,
-                    long long partial_floats) {
-  BX_REQUIRE(d % 4 == 0 && d <= 1024, "layernorm: need d %% 4 == 0 and d <= 1024 (got %d)", d);
+int residual_ln_bwd(const void* g1, int g1_f32, const void* g2, const void* z, const float* mean, const float* rstd,
+                    const float* gamma, void* dz, void* dy_sub, float* dgamma, float* dbeta, float* dbias, long long rows, int d,
+                    float rate, unsigned long long seed, unsigned site, cudaStream_t st, const unsigned long long* seed_dev) {
+  BX_REQUIRE(d % 8 == 0 && d <= 1024, "layernorm: need d %% 8 == 0 and d <= 1024 (got %d)", d);
   const int grid = grid_for(rows * 32, 256, 1);
   const size_t smem = (size_t)3 * d * sizeof(float);
-  const bool use_partial = partial != nullptr && partial_floats >= (long long)grid * 3 * d;
-  BX_LN_DISPATCH(residual_ln_bwd_kernel, <<<grid, 256, smem, st>>>(dout, z, mean, rstd, gamma, dz, (__nv_bfloat16*)dy_sub, dgamma,
-                                                                  dbeta, dbias, use_partial ? partial : nullptr, rows, d, rate, seed, site, seed_dev))
-  BX_POST_LAUNCH();
-  if (use_partial) {
-    ln_partials_reduce_kernel<<<(3 * d + 255) / 256, 256, 0, st>>>(partial, grid, d, dgamma, dbeta, dbias);
-    BX_POST_LAUNCH();
+  if (g1_f32) {
+#define BX_LN_EXTRA , true
+    BX_LN_DISPATCH(residual_ln_bwd_kernel, <<<grid, 256, smem, st>>>(g1, (const __nv_bfloat16*)g2, (const __nv_bfloat16*)z, mean, rstd,
+                                                                    gamma, (__nv_bfloat16*)dz, (__nv_bfloat16*)dy_sub, dgamma, dbeta,
+                                                                    dbias, rows, d, rate, seed, site, seed_dev))
+#undef BX_LN_EXTRA
+  } else {
+#define BX_LN_EXTRA , false
+    BX_LN_DISPATCH(residual_ln_bwd_kernel, <<<grid, 256, smem, st>>>(g1, (const __nv_bfloat16*)g2, (const __nv_bfloat16*)z, mean, rstd,
+                                                                    gamma, (__nv_bfloat16*)dz, (__nv_bfloat16*)dy_sub, dgamma, dbeta,
+                                                                    dbias, rows, d, rate, seed, site, seed_dev))
+#undef BX_LN_EXTRA
   }
+  BX_POST_LAUNCH();
   return 0;
 }
 

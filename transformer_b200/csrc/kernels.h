@@ -30,16 +30,17 @@ int attn_delta(const void* O, long long ld_o, const void* dO, long long ld_do, f
 int embed_fwd(const long long* ids, int id_stride, int id_offset, const float* table, const float* pos, float* out_f32,
               void* out_bf16, long long rows, int S, int d, long long V, float rate, unsigned long long seed, unsigned site,
               cudaStream_t st, const unsigned long long* seed_dev = nullptr);   // seed_dev != NULL overrides `seed` (graph replays)
-int embed_bwd(const long long* ids, int id_stride, int id_offset, const float* dx, float* dtable, long long rows, int S,
-              int d, long long V, float rate, unsigned long long seed, unsigned site, cudaStream_t st,
-              const unsigned long long* seed_dev = nullptr);
-int residual_ln_fwd(float* y_z, const float* x, const float* gamma, const float* beta, float* out_f32, void* out_bf16,
-                    float* mean, float* rstd, long long rows, int d, float eps, float rate, unsigned long long seed,
-                    unsigned site, cudaStream_t st, const unsigned long long* seed_dev = nullptr);
-int residual_ln_bwd(const float* dout, const float* z, const float* mean, const float* rstd, const float* gamma,
-                    float* dz, void* dy_sub, float* dgamma, float* dbeta, float* dbias, long long rows, int d, float rate,
-                    unsigned long long seed, unsigned site, cudaStream_t st, const unsigned long long* seed_dev = nullptr,
-                    float* partial = nullptr, long long partial_floats = 0);   // scratch for per-block dgamma/dbeta/dbias partials
+int embed_bwd(const long long* ids, int id_stride, int id_offset, const void* g1, const void* g2, float* dtable, long long rows,
+              int S, int d, long long V, float rate, unsigned long long seed, unsigned site, cudaStream_t st,
+              const unsigned long long* seed_dev = nullptr);   // gradient of the embedding output = g1 (+ g2), bf16 streams
+// y, x, z, out: bf16 [rows, d]
+int residual_ln_fwd(const void* y, const void* x, const float* gamma, const float* beta, void* z, void* out, float* mean,
+                    float* rstd, long long rows, int d, float eps, float rate, unsigned long long seed, unsigned site,
+                    cudaStream_t st, const unsigned long long* seed_dev = nullptr);
+// incoming gradient = g1 (fp32 if g1_f32 else bf16) + g2 (bf16, may be NULL); dz, dy_sub bf16 (dy_sub NULL: not written)
+int residual_ln_bwd(const void* g1, int g1_f32, const void* g2, const void* z, const float* mean, const float* rstd,
+                    const float* gamma, void* dz, void* dy_sub, float* dgamma, float* dbeta, float* dbias, long long rows, int d,
+                    float rate, unsigned long long seed, unsigned site, cudaStream_t st, const unsigned long long* seed_dev = nullptr);
 int xent(const void* logits, int logits_f32, long long ld, const long long* labels, int label_stride, int label_offset,
          int T_len, void* dlogits, long long ld_d, float* row_loss, double* stats, long long rows, int V, float inv_batch,
          cudaStream_t st);

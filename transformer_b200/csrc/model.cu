@@ -130,26 +130,26 @@ Layout make_layout(const b200xf_model_config& c) {
 }
 
 // ---- workspace (activations kept for backward + gradient scratch), carved from one caller-owned buffer ----
-struct LnSave { float *z, *mean, *rstd; };
-struct EncAct { bf16* qkv; bf16* attn_o; float* lse; LnSave ln1; float* out1_32; bf16* out1_16; bf16* h; uint64_t* hbits; LnSave ln2; };
+struct LnSave { bf16* z; float *mean, *rstd; };   // z = x + dropout(y) (bf16) and the row statistics
+struct EncAct { bf16* qkv; bf16* attn_o; float* lse; LnSave ln1; bf16* out1_16; bf16* h; uint64_t* hbits; LnSave ln2; };
 struct DecAct {
-  bf16* qkv1; bf16* attn1_o; float* lse1; LnSave ln1; float* out1_32; bf16* out1_16;
-  bf16* q2; bf16* kv2; bf16* attn2_o; float* lse2; LnSave ln2; float* out2_32; bf16* out2_16;
+  bf16* qkv1; bf16* attn1_o; float* lse1; LnSave ln1; bf16* out1_16;
+  bf16* q2; bf16* kv2; bf16* attn2_o; float* lse2; LnSave ln2; bf16* out2_16;
   bf16* h; uint64_t* hbits; LnSave ln3;
 };
 struct Work {
-  std::vector<float*> enc_x32, dec_x32;   // [L+1] layer inputs/outputs (index 0 = embedding output)
-  std::vector<bf16*> enc_x16, dec_x16;
+  std::vector<bf16*> enc_x16, dec_x16;    // [L+1] layer inputs/outputs (index 0 = embedding output); the streams are bf16
+  bf16* y16;                              // [Mmax, d] sublayer output on its way into the residual LayerNorm
   std::vector<EncAct> enc;
   std::vector<DecAct> dec;
   bf16* logits;                           // [Mt, Vp] bf16, overwritten in place by dlogits
   uint8_t *kpad_in, *kpad_tar;
   // backward scratch
-  float *gA, *gB;                         // [Mmax, d] gradient stream (ping-pong)
-  float* d_enc_out;                       // [Ms, d] accumulates cross-attention K/V gradients of all decoder layers
+  bf16 *gR0, *gR1;                        // [Mmax, d] residual-path gradient (dz of the last LayerNorm backward), ping-pong
+  bf16* gD;                               // [Mmax, d] dgrad output of the last sublayer; the stream gradient is gR + gD
+  float* d_enc_out;                       // [Ms, d] fp32: accumulates cross-attention K/V gradients of all decoder layers
   bf16 *dy16, *dO16, *dqkv, *dh;          // [Mmax,d] [Mmax,d] [Mmax,3d] [Mmax,f]
   float *dq_acc, *delta;                  // [Mmax,d] [B,H,Smax]
-  float* ln_partial; int64_t ln_partial_floats;   // per-block LayerNorm-backward partial sums
   int64_t bytes;
 };
 
@@ -169,28 +169,28 @@ Work make_work(const b200xf_model_config& c, const Layout& lo, void* base) {
   const int64_t Ms = (int64_t)c.max_batch * c.max_src_len, Mt = (int64_t)c.max_batch * c.max_tgt_len;
   const int64_t Mx = Ms > Mt ? Ms : Mt;
   const int64_t Smax = c.max_src_len > c.max_tgt_len ? c.max_src_len : c.max_tgt_len;
-  auto ln = [&](int64_t M) { LnSave s; s.z = b.take<float>(M * d); s.mean = b.take<float>(M); s.rstd = b.take<float>(M); return s; };
-  w.enc_x32.resize(L + 1); w.enc_x16.resize(L + 1); w.dec_x32.resize(L + 1); w.dec_x16.resize(L + 1);
-  for (int i = 0; i <= L; ++i) { w.enc_x32[i] = b.take<float>(Ms * d); w.enc_x16[i] = b.take<bf16>(Ms * d); }
-  for (int i = 0; i <= L; ++i) { w.dec_x32[i] = b.take<float>(Mt * d); w.dec_x16[i] = b.take<bf16>(Mt * d); }
+  auto ln = [&](int64_t M) { LnSave s; s.z = b.take<bf16>(M * d); s.mean = b.take<float>(M); s.rstd = b.take<float>(M); return s; };
+  w.enc_x16.resize(L + 1); w.dec_x16.resize(L + 1);
+  for (int i = 0; i <= L; ++i) w.enc_x16[i] = b.take<bf16>(Ms * d);
+  for (int i = 0; i <= L; ++i) w.dec_x16[i] = b.take<bf16>(Mt * d);
+  w.y16 = b.take<bf16>(Mx * d);
   w.enc.resize(L); w.dec.resize(L);
   for (auto& a : w.enc) {
     a.qkv = b.take<bf16>(Ms * 3 * d); a.attn_o = b.take<bf16>(Ms * d); a.lse = b.take<float>(c.max_batch * H * c.max_src_len);
-    a.ln1 = ln(Ms); a.out1_32 = b.take<float>(Ms * d); a.out1_16 = b.take<bf16>(Ms * d); a.h = b.take<bf16>(Ms * f); a.hbits = b.take<uint64_t>(Ms * ((f + 63) / 64)); a.ln2 = ln(Ms);
+    a.ln1 = ln(Ms); a.out1_16 = b.take<bf16>(Ms * d); a.h = b.take<bf16>(Ms * f); a.hbits = b.take<uint64_t>(Ms * ((f + 63) / 64)); a.ln2 = ln(Ms);
   }
   for (auto& a : w.dec) {
     a.qkv1 = b.take<bf16>(Mt * 3 * d); a.attn1_o = b.take<bf16>(Mt * d); a.lse1 = b.take<float>(c.max_batch * H * c.max_tgt_len);
-    a.ln1 = ln(Mt); a.out1_32 = b.take<float>(Mt * d); a.out1_16 = b.take<bf16>(Mt * d);
+    a.ln1 = ln(Mt); a.out1_16 = b.take<bf16>(Mt * d);
     a.q2 = b.take<bf16>(Mt * d); a.kv2 = b.take<bf16>(Ms * 2 * d); a.attn2_o = b.take<bf16>(Mt * d);
     a.lse2 = b.take<float>(c.max_batch * H * c.max_tgt_len);
-    a.ln2 = ln(Mt); a.out2_32 = b.take<float>(Mt * d); a.out2_16 = b.take<bf16>(Mt * d); a.h = b.take<bf16>(Mt * f); a.hbits = b.take<uint64_t>(Mt * ((f + 63) / 64)); a.ln3 = ln(Mt);
+    a.ln2 = ln(Mt); a.out2_16 = b.take<bf16>(Mt * d); a.h = b.take<bf16>(Mt * f); a.hbits = b.take<uint64_t>(Mt * ((f + 63) / 64)); a.ln3 = ln(Mt);
   }
   w.logits = b.take<bf16>(Mt * lo.Vp);
   w.kpad_in = b.take<uint8_t>(Ms); w.kpad_tar = b.take<uint8_t>(Mt);
-  w.gA = b.take<float>(Mx * d); w.gB = b.take<float>(Mx * d); w.d_enc_out = b.take<float>(Ms * d);
+  w.gR0 = b.take<bf16>(Mx * d); w.gR1 = b.take<bf16>(Mx * d); w.gD = b.take<bf16>(Mx * d); w.d_enc_out = b.take<float>(Ms * d);
   w.dy16 = b.take<bf16>(Mx * d); w.dO16 = b.take<bf16>(Mx * d); w.dqkv = b.take<bf16>(Mx * 3 * d); w.dh = b.take<bf16>(Mx * f);
   w.dq_acc = b.take<float>(Mx * d); w.delta = b.take<float>(c.max_batch * H * Smax);
-  w.ln_partial_floats = (int64_t)1024 * 3 * d; w.ln_partial = b.take<float>(w.ln_partial_floats);
   w.bytes = b.cur;
   return w;
 }
@@ -284,10 +284,11 @@ MaskSpec dec_cross_mask(const M* m) {
   return {m->w.kpad_in, 0, nullptr, 0, 0};
 }
 
-int residual_ln(M* m, float* y_z, const float* x, int64_t g_off, int64_t b_off, float* out32, bf16* out16, const LnSave& s,
-                int64_t rows, uint32_t site, cudaStream_t st) {
+// out = LayerNorm(x + dropout(y)); y is the sublayer output in w.y16
+int residual_ln(M* m, const bf16* x, int64_t g_off, int64_t b_off, bf16* out16, const LnSave& s, int64_t rows, uint32_t site,
+                cudaStream_t st) {
   const float rate = m->training ? m->cfg.dropout_rate : 0.f;
-  return bx::residual_ln_fwd(y_z, x, m->P + g_off, m->P + b_off, out32, out16, s.mean, s.rstd, rows, m->lo.d, m->cfg.ln_eps, rate,
+  return bx::residual_ln_fwd(m->w.y16, x, m->P + g_off, m->P + b_off, s.z, out16, s.mean, s.rstd, rows, m->lo.d, m->cfg.ln_eps, rate,
                              m->seed, site, st, m->seed_dev);
 }
 
@@ -304,7 +305,7 @@ int forward_impl(M* m, float* logits_out, int64_t ld_logits, cudaStream_t st) {
   RC(bx::pad_mask(reinterpret_cast<const long long*>(m->tar), m->tar_stride, m->tar_offset, w.kpad_tar, B, T, st));
 
   // ---------------- encoder (Encoder.py:48-60) ----------------
-  RC(bx::embed_fwd(reinterpret_cast<const long long*>(m->inp), S, 0, m->P + lo.enc_emb, m->pos_in, w.enc_x32[0], w.enc_x16[0], Ms, S, d,
+  RC(bx::embed_fwd(reinterpret_cast<const long long*>(m->inp), S, 0, m->P + lo.enc_emb, m->pos_in, nullptr, w.enc_x16[0], Ms, S, d,
                    lo.Vin, rate, m->seed, site_enc_embed(), st, m->seed_dev));
   const MaskSpec em = enc_self_mask(m);
   for (int l = 0; l < L; ++l) {
@@ -314,17 +315,17 @@ int forward_impl(M* m, float* logits_out, int64_t ld_logits, cudaStream_t st) {
     RC(linear_fwd(w.enc_x16[l], d, Sh + p.mha.Wqkv, 3 * d, m->P + p.mha.bqkv, a.qkv, 3 * d, false, false, Ms, 3 * d, d, st));
     RC(bx::attn_fwd(a.qkv, 3 * d, a.qkv + d, 3 * d, a.qkv + 2 * d, 3 * d, a.attn_o, d, a.lse, em.kpad, em.causal, em.maskf, em.sb,
                     em.sq, B, H, S, S, dk, st));
-    RC(linear_fwd(a.attn_o, d, Sh + p.mha.Wo, d, m->P + p.mha.bo, a.ln1.z, d, true, false, Ms, d, d, st));
-    RC(residual_ln(m, a.ln1.z, w.enc_x32[l], p.ln1g, p.ln1b, a.out1_32, a.out1_16, a.ln1, Ms, site_enc(l, 0), st));   // Encoder.py:22-23
+    RC(linear_fwd(a.attn_o, d, Sh + p.mha.Wo, d, m->P + p.mha.bo, w.y16, d, false, false, Ms, d, d, st));
+    RC(residual_ln(m, w.enc_x16[l], p.ln1g, p.ln1b, a.out1_16, a.ln1, Ms, site_enc(l, 0), st));   // Encoder.py:22-23
     // point_wise_feed_forward_network (point_ffn.py:3-7)
     RC(linear_fwd(a.out1_16, d, Sh + p.ffn.W1, f, m->P + p.ffn.b1, a.h, f, false, true, Ms, f, d, st, a.hbits));
-    RC(linear_fwd(a.h, f, Sh + p.ffn.W2, d, m->P + p.ffn.b2, a.ln2.z, d, true, false, Ms, d, f, st));
-    RC(residual_ln(m, a.ln2.z, a.out1_32, p.ln2g, p.ln2b, w.enc_x32[l + 1], w.enc_x16[l + 1], a.ln2, Ms, site_enc(l, 1), st));   // Encoder.py:26-27
+    RC(linear_fwd(a.h, f, Sh + p.ffn.W2, d, m->P + p.ffn.b2, w.y16, d, false, false, Ms, d, f, st));
+    RC(residual_ln(m, a.out1_16, p.ln2g, p.ln2b, w.enc_x16[l + 1], a.ln2, Ms, site_enc(l, 1), st));   // Encoder.py:26-27
   }
   const bf16* enc_out16 = w.enc_x16[L];
 
   // ---------------- decoder (Decoder.py:59-79) ----------------
-  RC(bx::embed_fwd(reinterpret_cast<const long long*>(m->tar), m->tar_stride, m->tar_offset, m->P + lo.dec_emb, m->pos_tgt, w.dec_x32[0],
+  RC(bx::embed_fwd(reinterpret_cast<const long long*>(m->tar), m->tar_stride, m->tar_offset, m->P + lo.dec_emb, m->pos_tgt, nullptr,
                    w.dec_x16[0], Mt, T, d, lo.Vtgt, rate, m->seed, site_dec_embed(), st, m->seed_dev));
   const MaskSpec sm = dec_self_mask(m), cm = dec_cross_mask(m);
   for (int l = 0; l < L; ++l) {
@@ -334,19 +335,19 @@ int forward_impl(M* m, float* logits_out, int64_t ld_logits, cudaStream_t st) {
     RC(linear_fwd(w.dec_x16[l], d, Sh + p.mha1.Wqkv, 3 * d, m->P + p.mha1.bqkv, a.qkv1, 3 * d, false, false, Mt, 3 * d, d, st));
     RC(bx::attn_fwd(a.qkv1, 3 * d, a.qkv1 + d, 3 * d, a.qkv1 + 2 * d, 3 * d, a.attn1_o, d, a.lse1, sm.kpad, sm.causal, sm.maskf, sm.sb,
                     sm.sq, B, H, T, T, dk, st));
-    RC(linear_fwd(a.attn1_o, d, Sh + p.mha1.Wo, d, m->P + p.mha1.bo, a.ln1.z, d, true, false, Mt, d, d, st));
-    RC(residual_ln(m, a.ln1.z, w.dec_x32[l], p.ln1g, p.ln1b, a.out1_32, a.out1_16, a.ln1, Mt, site_dec(l, 0), st));
+    RC(linear_fwd(a.attn1_o, d, Sh + p.mha1.Wo, d, m->P + p.mha1.bo, w.y16, d, false, false, Mt, d, d, st));
+    RC(residual_ln(m, w.dec_x16[l], p.ln1g, p.ln1b, a.out1_16, a.ln1, Mt, site_dec(l, 0), st));
     // mha2: q from the decoder stream, k = v = enc_output, encoder padding mask (Decoder.py:33-36)
     RC(linear_fwd(a.out1_16, d, Sh + p.mha2.Wq, d, m->P + p.mha2.bq, a.q2, d, false, false, Mt, d, d, st));
     RC(linear_fwd(enc_out16, d, Sh + p.mha2.Wkv, 2 * d, m->P + p.mha2.bkv, a.kv2, 2 * d, false, false, Ms, 2 * d, d, st));
     RC(bx::attn_fwd(a.q2, d, a.kv2, 2 * d, a.kv2 + d, 2 * d, a.attn2_o, d, a.lse2, cm.kpad, cm.causal, cm.maskf, cm.sb, cm.sq, B, H, T, S,
                     dk, st));
-    RC(linear_fwd(a.attn2_o, d, Sh + p.mha2.Wo, d, m->P + p.mha2.bo, a.ln2.z, d, true, false, Mt, d, d, st));
-    RC(residual_ln(m, a.ln2.z, a.out1_32, p.ln2g, p.ln2b, a.out2_32, a.out2_16, a.ln2, Mt, site_dec(l, 1), st));
+    RC(linear_fwd(a.attn2_o, d, Sh + p.mha2.Wo, d, m->P + p.mha2.bo, w.y16, d, false, false, Mt, d, d, st));
+    RC(residual_ln(m, a.out1_16, p.ln2g, p.ln2b, a.out2_16, a.ln2, Mt, site_dec(l, 1), st));
     // ffn (Decoder.py:38-40)
     RC(linear_fwd(a.out2_16, d, Sh + p.ffn.W1, f, m->P + p.ffn.b1, a.h, f, false, true, Mt, f, d, st, a.hbits));
-    RC(linear_fwd(a.h, f, Sh + p.ffn.W2, d, m->P + p.ffn.b2, a.ln3.z, d, true, false, Mt, d, f, st));
-    RC(residual_ln(m, a.ln3.z, a.out2_32, p.ln3g, p.ln3b, w.dec_x32[l + 1], w.dec_x16[l + 1], a.ln3, Mt, site_dec(l, 2), st));
+    RC(linear_fwd(a.h, f, Sh + p.ffn.W2, d, m->P + p.ffn.b2, w.y16, d, false, false, Mt, d, f, st));
+    RC(residual_ln(m, a.out2_16, p.ln3g, p.ln3b, w.dec_x16[l + 1], a.ln3, Mt, site_dec(l, 2), st));
   }
   // ---------------- final_layer (Transformer.py:30) ----------------
   if (logits_out != nullptr)
@@ -356,42 +357,49 @@ int forward_impl(M* m, float* logits_out, int64_t ld_logits, cudaStream_t st) {
   return 0;
 }
 
-// LayerNorm + dropout + residual backward: g_in (gradient of the LN output) -> g_out (gradient of z, i.e. of the
-// residual input) and dy16 (gradient of the sublayer output, bf16)
-// `bias_off`: bias of the sublayer's last Dense -- its gradient (column sums of dy16) falls out of this kernel for free
-int residual_ln_back(M* m, const float* g_in, const LnSave& s, int64_t g_off, int64_t b_off, int64_t bias_off, float* g_out, int64_t rows,
-                     uint32_t site, cudaStream_t st) {
+// The gradient of a stream tensor travels as a pair: `r` (residual path: dz of the LayerNorm backward that consumed it,
+// or the fp32 d_enc_out) plus `dg` (dgrad output of the sublayer that consumed it, may be NULL); the next LayerNorm
+// backward (or the embedding backward) sums the two in fp32.
+struct StreamGrad { const void* r; bool r_f32; const bf16* dg; };
+
+// LayerNorm + dropout + residual backward: g (gradient of the LN output) -> dz (gradient of z = of the residual input,
+// bf16) and *dy (gradient of the sublayer output, bf16: w.dy16 under dropout, else dz itself).
+// `bias_off`: bias of the sublayer's last Dense -- its gradient (column sums of dy) falls out of this kernel for free
+int residual_ln_back(M* m, const StreamGrad& g, const LnSave& s, int64_t g_off, int64_t b_off, int64_t bias_off, bf16* dz,
+                     const bf16** dy, int64_t rows, uint32_t site, cudaStream_t st) {
   const float rate = m->training ? m->cfg.dropout_rate : 0.f;
-  return bx::residual_ln_bwd(g_in, s.z, s.mean, s.rstd, m->P + g_off, g_out, m->w.dy16, m->G + g_off, m->G + b_off, m->G + bias_off, rows,
-                             m->lo.d, rate, m->seed, site, st, m->seed_dev);   // (a per-block-partials variant exists but measured slower than the atomics)
+  bf16* dy_buf = rate > 0.f ? m->w.dy16 : nullptr;
+  *dy = rate > 0.f ? m->w.dy16 : dz;
+  return bx::residual_ln_bwd(g.r, g.r_f32 ? 1 : 0, g.dg, s.z, s.mean, s.rstd, m->P + g_off, dz, dy_buf, m->G + g_off, m->G + b_off,
+                             m->G + bias_off, rows, m->lo.d, rate, m->seed, site, st, m->seed_dev);
 }
 
-// FFN backward: dy16 = d(ffn output); x16 = ffn input; accumulates d(input) into g (fp32)
-int ffn_back(M* m, const Ffn& p, const bf16* x16, const bf16* h, const uint64_t* hbits, float* g, int64_t rows, cudaStream_t st) {
+// FFN backward: dy = d(ffn output); x16 = ffn input; writes d(input) (sublayer path only) to w.gD
+int ffn_back(M* m, const Ffn& p, const bf16* x16, const bf16* h, const uint64_t* hbits, const bf16* dy, int64_t rows, cudaStream_t st) {
   const int d = m->lo.d, f = m->lo.f;
   Work& w = m->w;
-  RC(linear_wgrad(h, f, w.dy16, d, m->G + p.W2, d, nullptr, rows, d, f, st));                 // db2: from the LN backward
-  RC(linear_dgrad(w.dy16, d, m->Sh + p.W2, d, w.dh, f, false, false, h, f, rows, d, f, st, hbits));     // dh = (dy . W2^T) o [h > 0]
+  RC(linear_wgrad(h, f, dy, d, m->G + p.W2, d, nullptr, rows, d, f, st));                     // db2: from the LN backward
+  RC(linear_dgrad(dy, d, m->Sh + p.W2, d, w.dh, f, false, false, h, f, rows, d, f, st, hbits));         // dh = (dy . W2^T) o [h > 0]
   RC(linear_wgrad(x16, d, w.dh, f, m->G + p.W1, f, m->G + p.b1, rows, f, d, st));
-  RC(linear_dgrad(w.dh, f, m->Sh + p.W1, f, g, d, true, true, nullptr, 0, rows, f, d, st));
+  RC(linear_dgrad(w.dh, f, m->Sh + p.W1, f, w.gD, d, false, false, nullptr, 0, rows, f, d, st));
   return 0;
 }
 
-// self-attention block backward (packed QKV).  dy16 = d(out-projection output); accumulates d(x) into g.
+// self-attention block backward (packed QKV).  dy = d(out-projection output); writes d(x) (sublayer path) to w.gD
 int self_attn_back(M* m, const MhaSelf& p, const bf16* x16, const bf16* qkv, const bf16* attn_o, const float* lse, const MaskSpec& mk,
-                   float* g, int S, cudaStream_t st) {
+                   const bf16* dy, int S, cudaStream_t st) {
   const int d = m->lo.d, H = m->lo.H, dk = d / H, B = m->B;
   const int64_t rows = (int64_t)B * S;
   Work& w = m->w;
-  RC(linear_wgrad(attn_o, d, w.dy16, d, m->G + p.Wo, d, nullptr, rows, d, d, st));             // dbo: from the LN backward
-  RC(linear_dgrad(w.dy16, d, m->Sh + p.Wo, d, w.dO16, d, false, false, nullptr, 0, rows, d, d, st));
+  RC(linear_wgrad(attn_o, d, dy, d, m->G + p.Wo, d, nullptr, rows, d, d, st));                 // dbo: from the LN backward
+  RC(linear_dgrad(dy, d, m->Sh + p.Wo, d, w.dO16, d, false, false, nullptr, 0, rows, d, d, st));
   RC(bx::attn_delta(attn_o, d, w.dO16, d, w.delta, B, S, H, dk, st));
   BX_CHECK_CUDA(cudaMemsetAsync(w.dq_acc, 0, rows * d * sizeof(float), st));
   RC(bx::attn_bwd(qkv, 3 * d, qkv + d, 3 * d, qkv + 2 * d, 3 * d, w.dO16, d, lse, w.delta, w.dq_acc, d, w.dqkv + d, 3 * d, w.dqkv + 2 * d,
                   3 * d, mk.kpad, mk.causal, mk.maskf, mk.sb, mk.sq, B, H, S, S, dk, st));
   RC(bx::cast_f32_bf16_strided(w.dq_acc, w.dqkv, rows, d, 3 * d, st));
   RC(linear_wgrad(x16, d, w.dqkv, 3 * d, m->G + p.Wqkv, 3 * d, m->G + p.bqkv, rows, 3 * d, d, st));
-  RC(linear_dgrad(w.dqkv, 3 * d, m->Sh + p.Wqkv, 3 * d, g, d, true, true, nullptr, 0, rows, 3 * d, d, st));
+  RC(linear_dgrad(w.dqkv, 3 * d, m->Sh + p.Wqkv, 3 * d, w.gD, d, false, false, nullptr, 0, rows, 3 * d, d, st));
   return 0;
 }
 
@@ -400,9 +408,9 @@ int backward_final(M* m, cudaStream_t st) {
   Work& w = m->w;
   const int d = lo.d, L = lo.L;
   const int64_t Mt = (int64_t)m->B * m->T;
-  // dlogits (bf16, in w.logits) -> final_layer grads and d(dec_output) in gA
+  // dlogits (bf16, in w.logits) -> final_layer grads and d(dec_output) in gD
   RC(linear_wgrad(w.dec_x16[L], d, w.logits, lo.Vp, m->G + lo.Wf, lo.Vp, m->G + lo.bf, Mt, lo.Vtgt, d, st));
-  RC(linear_dgrad(w.logits, lo.Vp, m->Sh + lo.Wf, lo.Vp, w.gA, d, true, false, nullptr, 0, Mt, lo.Vtgt, d, st));
+  RC(linear_dgrad(w.logits, lo.Vp, m->Sh + lo.Wf, lo.Vp, w.gD, d, false, false, nullptr, 0, Mt, lo.Vtgt, d, st));
   return 0;
 }
 
@@ -415,19 +423,22 @@ int backward_decoder(M* m, cudaStream_t st) {
   const float rate = m->training ? m->cfg.dropout_rate : 0.f;
   const MaskSpec sm = dec_self_mask(m), cm = dec_cross_mask(m);
   BX_CHECK_CUDA(cudaMemsetAsync(w.d_enc_out, 0, Ms * d * sizeof(float), st));
-  float* g_in = w.gA;    // gradient of the current layer's output
-  float* g_out = w.gB;
+  StreamGrad g{w.gD, false, nullptr};    // gradient of the current layer's output: the vocabulary dgrad wrote it to gD
+  bf16* dz = w.gR0;
+  bf16* dz_other = w.gR1;
+  const bf16* dy = nullptr;
+  auto advance = [&]() { g = StreamGrad{dz, false, w.gD}; std::swap(dz, dz_other); };
   for (int l = L - 1; l >= 0; --l) {
     const DecLayerP& p = lo.dec[l];
     DecAct& a = w.dec[l];
     // out3 = LN3(out2 + drop(ffn(out2)))
-    RC(residual_ln_back(m, g_in, a.ln3, p.ln3g, p.ln3b, p.ffn.b2, g_out, Mt, site_dec(l, 2), st));
-    RC(ffn_back(m, p.ffn, a.out2_16, a.h, a.hbits, g_out, Mt, st));
-    std::swap(g_in, g_out);
+    RC(residual_ln_back(m, g, a.ln3, p.ln3g, p.ln3b, p.ffn.b2, dz, &dy, Mt, site_dec(l, 2), st));
+    RC(ffn_back(m, p.ffn, a.out2_16, a.h, a.hbits, dy, Mt, st));
+    advance();
     // out2 = LN2(out1 + drop(mha2(enc_out, enc_out, out1)))
-    RC(residual_ln_back(m, g_in, a.ln2, p.ln2g, p.ln2b, p.mha2.bo, g_out, Mt, site_dec(l, 1), st));
-    RC(linear_wgrad(a.attn2_o, d, w.dy16, d, m->G + p.mha2.Wo, d, nullptr, Mt, d, d, st));
-    RC(linear_dgrad(w.dy16, d, m->Sh + p.mha2.Wo, d, w.dO16, d, false, false, nullptr, 0, Mt, d, d, st));
+    RC(residual_ln_back(m, g, a.ln2, p.ln2g, p.ln2b, p.mha2.bo, dz, &dy, Mt, site_dec(l, 1), st));
+    RC(linear_wgrad(a.attn2_o, d, dy, d, m->G + p.mha2.Wo, d, nullptr, Mt, d, d, st));
+    RC(linear_dgrad(dy, d, m->Sh + p.mha2.Wo, d, w.dO16, d, false, false, nullptr, 0, Mt, d, d, st));
     RC(bx::attn_delta(a.attn2_o, d, w.dO16, d, w.delta, B, T, H, dk, st));
     BX_CHECK_CUDA(cudaMemsetAsync(w.dq_acc, 0, Mt * d * sizeof(float), st));
     // dK/dV of the encoder memory go to dqkv[:, 0:2d) viewed as [Ms, 2d]
@@ -437,15 +448,15 @@ int backward_decoder(M* m, cudaStream_t st) {
     RC(linear_dgrad(w.dqkv, 2 * d, m->Sh + p.mha2.Wkv, 2 * d, w.d_enc_out, d, true, true, nullptr, 0, Ms, 2 * d, d, st));
     RC(bx::cast_f32_bf16(w.dq_acc, w.dO16, Mt * d, st));   // dq2 (bf16) reuses dO16
     RC(linear_wgrad(a.out1_16, d, w.dO16, d, m->G + p.mha2.Wq, d, m->G + p.mha2.bq, Mt, d, d, st));
-    RC(linear_dgrad(w.dO16, d, m->Sh + p.mha2.Wq, d, g_out, d, true, true, nullptr, 0, Mt, d, d, st));
-    std::swap(g_in, g_out);
+    RC(linear_dgrad(w.dO16, d, m->Sh + p.mha2.Wq, d, w.gD, d, false, false, nullptr, 0, Mt, d, d, st));
+    advance();
     // out1 = LN1(x + drop(mha1(x, x, x)))
-    RC(residual_ln_back(m, g_in, a.ln1, p.ln1g, p.ln1b, p.mha1.bo, g_out, Mt, site_dec(l, 0), st));
-    RC(self_attn_back(m, p.mha1, w.dec_x16[l], a.qkv1, a.attn1_o, a.lse1, sm, g_out, T, st));
-    std::swap(g_in, g_out);
+    RC(residual_ln_back(m, g, a.ln1, p.ln1g, p.ln1b, p.mha1.bo, dz, &dy, Mt, site_dec(l, 0), st));
+    RC(self_attn_back(m, p.mha1, w.dec_x16[l], a.qkv1, a.attn1_o, a.lse1, sm, dy, T, st));
+    advance();
   }
-  RC(bx::embed_bwd(reinterpret_cast<const long long*>(m->tar), m->tar_stride, m->tar_offset, g_in, m->G + lo.dec_emb, Mt, T, d, lo.Vtgt,
-                   rate, m->seed, site_dec_embed(), st, m->seed_dev));
+  RC(bx::embed_bwd(reinterpret_cast<const long long*>(m->tar), m->tar_stride, m->tar_offset, g.r, g.dg, m->G + lo.dec_emb, Mt, T, d,
+                   lo.Vtgt, rate, m->seed, site_dec_embed(), st, m->seed_dev));
   return 0;
 }
 
@@ -457,20 +468,22 @@ int backward_encoder(M* m, cudaStream_t st) {
   const int64_t Ms = (int64_t)B * S;
   const float rate = m->training ? m->cfg.dropout_rate : 0.f;
   const MaskSpec em = enc_self_mask(m);
-  float* g_in = w.d_enc_out;
-  float* g_out = w.gA;
-  float* spare = w.gB;
+  StreamGrad g{w.d_enc_out, true, nullptr};   // fp32 sum of the cross-attention K/V gradients of all decoder layers
+  bf16* dz = w.gR0;
+  bf16* dz_other = w.gR1;
+  const bf16* dy = nullptr;
+  auto advance = [&]() { g = StreamGrad{dz, false, w.gD}; std::swap(dz, dz_other); };
   for (int l = L - 1; l >= 0; --l) {
     const EncLayerP& p = lo.enc[l];
     EncAct& a = w.enc[l];
-    RC(residual_ln_back(m, g_in, a.ln2, p.ln2g, p.ln2b, p.ffn.b2, g_out, Ms, site_enc(l, 1), st));
-    RC(ffn_back(m, p.ffn, a.out1_16, a.h, a.hbits, g_out, Ms, st));
-    { float* t = g_in; g_in = g_out; g_out = (t == w.d_enc_out) ? spare : t; }
-    RC(residual_ln_back(m, g_in, a.ln1, p.ln1g, p.ln1b, p.mha.bo, g_out, Ms, site_enc(l, 0), st));
-    RC(self_attn_back(m, p.mha, w.enc_x16[l], a.qkv, a.attn_o, a.lse, em, g_out, S, st));
-    std::swap(g_in, g_out);
+    RC(residual_ln_back(m, g, a.ln2, p.ln2g, p.ln2b, p.ffn.b2, dz, &dy, Ms, site_enc(l, 1), st));
+    RC(ffn_back(m, p.ffn, a.out1_16, a.h, a.hbits, dy, Ms, st));
+    advance();
+    RC(residual_ln_back(m, g, a.ln1, p.ln1g, p.ln1b, p.mha.bo, dz, &dy, Ms, site_enc(l, 0), st));
+    RC(self_attn_back(m, p.mha, w.enc_x16[l], a.qkv, a.attn_o, a.lse, em, dy, S, st));
+    advance();
   }
-  RC(bx::embed_bwd(reinterpret_cast<const long long*>(m->inp), S, 0, g_in, m->G + lo.enc_emb, Ms, S, d, lo.Vin, rate, m->seed,
+  RC(bx::embed_bwd(reinterpret_cast<const long long*>(m->inp), S, 0, g.r, g.dg, m->G + lo.enc_emb, Ms, S, d, lo.Vin, rate, m->seed,
                    site_enc_embed(), st, m->seed_dev));
   return 0;
 }
@@ -588,16 +601,15 @@ int b200xf_model_attention_weights(b200xf_model* m, int layer, int block, float*
 int b200xf_model_tap(b200xf_model* m, const char* name, float* out, b200xf_stream_t stream) {
   BX_REQUIRE(m->B > 0, "tap: no forward has run");
   const int d = m->lo.d, L = m->lo.L;
-  const float* src = nullptr;
+  const bf16* src = nullptr;
   int64_t rows = 0;
   int idx = -1;
-  if (!strcmp(name, "enc_embed")) { src = m->w.enc_x32[0]; rows = (int64_t)m->B * m->S; }
-  else if (!strcmp(name, "dec_embed")) { src = m->w.dec_x32[0]; rows = (int64_t)m->B * m->T; }
-  else if (sscanf(name, "enc_layer%d", &idx) == 1 && idx >= 0 && idx < L) { src = m->w.enc_x32[idx + 1]; rows = (int64_t)m->B * m->S; }
-  else if (sscanf(name, "dec_layer%d", &idx) == 1 && idx >= 0 && idx < L) { src = m->w.dec_x32[idx + 1]; rows = (int64_t)m->B * m->T; }
+  if (!strcmp(name, "enc_embed")) { src = m->w.enc_x16[0]; rows = (int64_t)m->B * m->S; }
+  else if (!strcmp(name, "dec_embed")) { src = m->w.dec_x16[0]; rows = (int64_t)m->B * m->T; }
+  else if (sscanf(name, "enc_layer%d", &idx) == 1 && idx >= 0 && idx < L) { src = m->w.enc_x16[idx + 1]; rows = (int64_t)m->B * m->S; }
+  else if (sscanf(name, "dec_layer%d", &idx) == 1 && idx >= 0 && idx < L) { src = m->w.dec_x16[idx + 1]; rows = (int64_t)m->B * m->T; }
   BX_REQUIRE(src != nullptr, "tap: unknown activation '%s'", name);
-  BX_CHECK_CUDA(cudaMemcpyAsync(out, src, rows * d * sizeof(float), cudaMemcpyDeviceToDevice, reinterpret_cast<cudaStream_t>(stream)));
-  return 0;
+  return bx::cast_bf16_f32(src, out, rows * d, reinterpret_cast<cudaStream_t>(stream));   // the streams are bf16 in HBM
 }
 
 }  // extern "C"
