@@ -84,16 +84,19 @@ int b200xf_embed_bwd(const int64_t* ids, int id_stride, int id_offset, const voi
  *      y (sublayer output), x (residual input), z = x + dropout(y) (kept for backward) and out = LN(z) are bf16
  *      [rows, d] streams in HBM; statistics and normalisation are fp32 on the unrounded z.                          */
 int b200xf_residual_ln_fwd(const void* y_bf16, const void* x_bf16, const float* gamma, const float* beta, void* z_bf16,
-                           void* out_bf16, float* mean, float* rstd, int64_t rows, int d, float eps, float rate,
-                           uint64_t seed, uint32_t site, b200xf_stream_t stream);
+                           void* out_bf16, float* mean, float* rstd, void* keep_bits, int64_t rows, int d, float eps,
+                           float rate, uint64_t seed, uint32_t site, b200xf_stream_t stream);
+/*      keep_bits (uint8 [rows, d/8], may be NULL): the dropout keep mask, bit e of byte j = element 8j+e, written
+ *      when rate > 0 so that the backward pass reads it back instead of re-running the counter-based RNG.         */
 /*      backward: incoming gradient of `out` = g1 (fp32 if g1_is_f32 else bf16) + g2 (bf16, may be NULL), summed in fp32.
  *      dz (bf16) = gradient of z = of the residual input; dy_sub (bf16, may be NULL when rate == 0: equals dz) =
  *      gradient of the sublayer output; dgamma/dbeta += ; dbias (may be NULL) += column sums of dy_sub: the bias
  *      gradient of the sublayer's last Dense, for free                                                              */
 int b200xf_residual_ln_bwd(const void* g1, int g1_is_f32, const void* g2_bf16, const void* z_bf16, const float* mean,
                            const float* rstd, const float* gamma, void* dz_bf16, void* dy_sub_bf16, float* dgamma,
-                           float* dbeta, float* dbias, int64_t rows, int d, float rate, uint64_t seed, uint32_t site,
-                           b200xf_stream_t stream);
+                           float* dbeta, float* dbias, const void* keep_bits, int64_t rows, int d, float rate,
+                           uint64_t seed, uint32_t site, b200xf_stream_t stream);
+/*      keep_bits: the mask the forward stored, or NULL to regenerate it from (seed, site).                          */
 
 /* ---- Train.loss_function + SparseCategoricalAccuracy (train.py:83-88, 141) and d(loss)/d(logits).
  *      row r = (b, t) reads label labels[b*label_stride + label_offset + t] (tar[:, 1:] without a copy).

@@ -273,7 +273,7 @@ def test_residual_layernorm_fwd_bwd(d, g1_f32, two):
     out_ref = torch.nn.functional.layer_norm(z_ref, (d,), gamma, beta, 1e-6)
     z16 = torch.empty_like(y); o16 = torch.empty_like(y)
     mean = torch.empty(rows, device=dev()); rstd = torch.empty(rows, device=dev())
-    L.call("b200xf_residual_ln_fwd", L.ptr(y), L.ptr(x), L.ptr(gamma), L.ptr(beta), L.ptr(z16), L.ptr(o16), L.ptr(mean), L.ptr(rstd),
+    L.call("b200xf_residual_ln_fwd", L.ptr(y), L.ptr(x), L.ptr(gamma), L.ptr(beta), L.ptr(z16), L.ptr(o16), L.ptr(mean), L.ptr(rstd), None,
            rows, d, 1e-6, 0.0, 0, 0, sp())
     torch.cuda.synchronize()
     assert torch.equal(z16, z_ref.bfloat16())                                     # z is the correctly rounded fp32 sum
@@ -290,7 +290,7 @@ def test_residual_layernorm_fwd_bwd(d, g1_f32, two):
     dz = torch.empty_like(y); dy16 = torch.full_like(y, float("nan"))
     dg = torch.zeros(d, device=dev()); db = torch.zeros(d, device=dev()); dbias = torch.zeros(d, device=dev())
     L.call("b200xf_residual_ln_bwd", L.ptr(g1), g1_f32, L.ptr(g2) if two else None, L.ptr(z16), L.ptr(mean), L.ptr(rstd), L.ptr(gamma),
-           L.ptr(dz), L.ptr(dy16) if two else None, L.ptr(dg), L.ptr(db), L.ptr(dbias), rows, d, 0.0, 0, 0, sp())
+           L.ptr(dz), L.ptr(dy16) if two else None, L.ptr(dg), L.ptr(db), L.ptr(dbias), None, rows, d, 0.0, 0, 0, sp())
     torch.cuda.synchronize()
     scale = max(1.0, zs.grad.abs().max().item())
     assert (dz.float() - zs.grad).abs().max().item() < 1.2e-2 * scale           # bf16 output rounding + rounded-z statistics
@@ -308,10 +308,13 @@ def test_dropout_fwd_bwd_consistent():
     gamma = torch.ones(d, device=dev()); beta = torch.zeros(d, device=dev())
     z = torch.empty_like(y); o16 = torch.empty_like(y)
     mean = torch.empty(rows, device=dev()); rstd = torch.empty(rows, device=dev())
-    L.call("b200xf_residual_ln_fwd", L.ptr(y), L.ptr(x), L.ptr(gamma), L.ptr(beta), L.ptr(z), L.ptr(o16), L.ptr(mean), L.ptr(rstd),
+    bits = torch.zeros(rows, d // 8, dtype=torch.uint8, device=dev())
+    L.call("b200xf_residual_ln_fwd", L.ptr(y), L.ptr(x), L.ptr(gamma), L.ptr(beta), L.ptr(z), L.ptr(o16), L.ptr(mean), L.ptr(rstd), L.ptr(bits),
            rows, d, 1e-6, rate, 1234, 7, sp())
     torch.cuda.synchronize()
     keep = z != 0
+    unpacked = ((bits[:, :, None].int() >> torch.arange(8, device=dev())) & 1).bool().view(rows, d)
+    assert torch.equal(unpacked, keep)                               # stored keep mask: bit e of byte j = element 8j+e
     frac = keep.float().mean().item()
     assert abs(frac - (1 - rate)) < 0.01, frac                      # keep probability
     assert torch.allclose(z[keep].float(), torch.full_like(z[keep].float(), 1 / (1 - rate)), rtol=4e-3)    # inverted-dropout scale
@@ -319,14 +322,16 @@ def test_dropout_fwd_bwd_consistent():
     dout = (torch.ones(rows, d, device=dev()) * (torch.arange(d, device=dev()) % 64)).bfloat16()
     dz = torch.empty_like(y); dy16 = torch.empty_like(y)
     dg = torch.zeros(d, device=dev()); db = torch.zeros(d, device=dev())
-    L.call("b200xf_residual_ln_bwd", L.ptr(dout), 0, None, L.ptr(z), L.ptr(mean), L.ptr(rstd), L.ptr(gamma), L.ptr(dz), L.ptr(dy16),
-           L.ptr(dg), L.ptr(db), None, rows, d, rate, 1234, 7, sp())
-    torch.cuda.synchronize()
-    want = dz.float() * keep / (1 - rate)
-    assert (dy16.float() - want).abs().max().item() <= 0.02 * want.abs().max().item() + 1e-3
+    for kb in (None, bits):       # mask regenerated from (seed, site), or read back from the bits the forward stored
+        dy16.fill_(float("nan"))
+        L.call("b200xf_residual_ln_bwd", L.ptr(dout), 0, None, L.ptr(z), L.ptr(mean), L.ptr(rstd), L.ptr(gamma), L.ptr(dz), L.ptr(dy16),
+               L.ptr(dg), L.ptr(db), None, L.ptr(kb) if kb is not None else None, rows, d, rate, 1234, 7, sp())
+        torch.cuda.synchronize()
+        want = dz.float() * keep / (1 - rate)
+        assert (dy16.float() - want).abs().max().item() <= 0.02 * want.abs().max().item() + 1e-3
     # a different site gives a different mask
     z2 = torch.empty_like(y)
-    L.call("b200xf_residual_ln_fwd", L.ptr(y), L.ptr(x), L.ptr(gamma), L.ptr(beta), L.ptr(z2), L.ptr(o16), L.ptr(mean), L.ptr(rstd),
+    L.call("b200xf_residual_ln_fwd", L.ptr(y), L.ptr(x), L.ptr(gamma), L.ptr(beta), L.ptr(z2), L.ptr(o16), L.ptr(mean), L.ptr(rstd), None,
            rows, d, 1e-6, rate, 1234, 8, sp())
     torch.cuda.synchronize()
     assert (z2 != z).any()

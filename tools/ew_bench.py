@@ -41,10 +41,11 @@ def main():
     y, x, g, bta = h16(rows, d), h16(rows, d), f(d), f(d)
     z, o16 = torch.empty_like(y), torch.empty_like(y)
     mean, rstd = torch.empty(rows, device=dev), torch.empty(rows, device=dev)
+    keep = torch.zeros(rows, d // 8, dtype=torch.uint8, device=dev)
 
     def ln_fwd():
         L.call("b200xf_residual_ln_fwd", L.ptr(y), L.ptr(x), L.ptr(g), L.ptr(bta), L.ptr(z), L.ptr(o16), L.ptr(mean), L.ptr(rstd),
-               rows, d, 1e-6, 0.1, 1, 3, sp)
+               L.ptr(keep), rows, d, 1e-6, 0.1, 1, 3, sp)
     out.append(("residual_ln_fwd", timeit(ln_fwd, flush=flush), rows * d * 2 * 4))
     g1, g2 = h16(rows, d), h16(rows, d)
     dz = torch.empty_like(y); dy = torch.empty_like(y)
@@ -52,7 +53,7 @@ def main():
 
     def ln_bwd():
         L.call("b200xf_residual_ln_bwd", L.ptr(g1), 0, L.ptr(g2), L.ptr(z), L.ptr(mean), L.ptr(rstd), L.ptr(g), L.ptr(dz), L.ptr(dy),
-               L.ptr(dg), L.ptr(db), L.ptr(dbias), rows, d, 0.1, 1, 3, sp)
+               L.ptr(dg), L.ptr(db), L.ptr(dbias), L.ptr(keep), rows, d, 0.1, 1, 3, sp)
     out.append(("residual_ln_bwd", timeit(ln_bwd, flush=flush), rows * d * 2 * 5))
 
     logits = (torch.randn(rows, V, device=dev) * 2).bfloat16()

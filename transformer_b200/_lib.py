@@ -43,8 +43,8 @@ _SIGS = {
     "b200xf_attn_probs": [_P, _I64, _P, _I64, _P, _P, _P, _I, _P, _I64, _I64, _I, _I, _I, _I, _I, _P],
     "b200xf_embed_fwd": [_P, _I, _I, _P, _P, _P, _P, _I64, _I, _I, _I64, _F, _U64, _U32, _P],
     "b200xf_embed_bwd": [_P, _I, _I, _P, _P, _P, _I64, _I, _I, _I64, _F, _U64, _U32, _P],
-    "b200xf_residual_ln_fwd": [_P, _P, _P, _P, _P, _P, _P, _P, _I64, _I, _F, _F, _U64, _U32, _P],
-    "b200xf_residual_ln_bwd": [_P, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I64, _I, _F, _U64, _U32, _P],
+    "b200xf_residual_ln_fwd": [_P, _P, _P, _P, _P, _P, _P, _P, _P, _I64, _I, _F, _F, _U64, _U32, _P],
+    "b200xf_residual_ln_bwd": [_P, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I64, _I, _F, _U64, _U32, _P],
     "b200xf_xent": [_P, _I, _I64, _P, _I, _I, _I, _P, _I64, _P, _P, _I64, _I, _F, _P],
     "b200xf_colsum_bf16": [_P, _I64, _P, _I64, _I, _P],
     "b200xf_adam_step": [_P, _P, _P, _P, _P, _I64, _F, _F, _F, _F, _P],

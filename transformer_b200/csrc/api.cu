@@ -57,17 +57,17 @@ int b200xf_embed_bwd(const int64_t* ids, int id_stride, int id_offset, const voi
                        seed, site, ST(stream));
 }
 int b200xf_residual_ln_fwd(const void* y_bf16, const void* x_bf16, const float* gamma, const float* beta, void* z_bf16,
-                           void* out_bf16, float* mean, float* rstd, int64_t rows, int d, float eps, float rate,
+                           void* out_bf16, float* mean, float* rstd, void* keep_bits, int64_t rows, int d, float eps, float rate,
                            uint64_t seed, uint32_t site, b200xf_stream_t stream) {
-  return bx::residual_ln_fwd(y_bf16, x_bf16, gamma, beta, z_bf16, out_bf16, mean, rstd, rows, d, eps, rate, seed, site,
+  return bx::residual_ln_fwd(y_bf16, x_bf16, gamma, beta, z_bf16, out_bf16, mean, rstd, keep_bits, rows, d, eps, rate, seed, site,
                              ST(stream));
 }
 int b200xf_residual_ln_bwd(const void* g1, int g1_is_f32, const void* g2_bf16, const void* z_bf16, const float* mean,
                            const float* rstd, const float* gamma, void* dz_bf16, void* dy_sub_bf16, float* dgamma,
-                           float* dbeta, float* dbias, int64_t rows, int d, float rate, uint64_t seed, uint32_t site,
-                           b200xf_stream_t stream) {
-  return bx::residual_ln_bwd(g1, g1_is_f32, g2_bf16, z_bf16, mean, rstd, gamma, dz_bf16, dy_sub_bf16, dgamma, dbeta, dbias, rows,
-                             d, rate, seed, site, ST(stream));
+                           float* dbeta, float* dbias, const void* keep_bits, int64_t rows, int d, float rate, uint64_t seed,
+                           uint32_t site, b200xf_stream_t stream) {
+  return bx::residual_ln_bwd(g1, g1_is_f32, g2_bf16, z_bf16, mean, rstd, gamma, dz_bf16, dy_sub_bf16, dgamma, dbeta, dbias, keep_bits,
+                             rows, d, rate, seed, site, ST(stream));
 }
 int b200xf_xent(const void* logits, int logits_f32, int64_t ld, const int64_t* labels, int label_stride,
                 int label_offset, int T, void* dlogits, int64_t ld_d, float* row_loss, double* stats, int64_t rows,

@@ -57,12 +57,21 @@ __device__ __forceinline__ F8 unpack8(const uint4 u) {
 __device__ __forceinline__ uint4 pack8(const F8& f) {
   return make_uint4(pack_bf16x2(f.v[0], f.v[1]), pack_bf16x2(f.v[2], f.v[3]), pack_bf16x2(f.v[4], f.v[5]), pack_bf16x2(f.v[6], f.v[7]));
 }
-// keep-scale factors of the 8 consecutive elements starting at flat element index idx8*8 (same stream as dropout_scale4)
-__device__ __forceinline__ F8 dropout_scale8(unsigned long long seed, uint32_t site, unsigned long long idx8, float rate) {
-  const float4 a = dropout_scale4(seed, site, 2ull * idx8, rate), b = dropout_scale4(seed, site, 2ull * idx8 + 1ull, rate);
-  F8 k;
-  k.v[0] = a.x; k.v[1] = a.y; k.v[2] = a.z; k.v[3] = a.w; k.v[4] = b.x; k.v[5] = b.y; k.v[6] = b.z; k.v[7] = b.w;
-  return k;
+// keep bits (bit e = element e kept) of the 8 consecutive elements starting at flat element index idx8*8: ONE Philox
+// call per 8 elements, 16 random bits each (keep iff u16 >= rate * 65536) -- the RNG was half of the instructions of
+// the LayerNorm kernels when it ran once per 4 elements
+__device__ __forceinline__ uint32_t dropout_keep8(unsigned long long seed, uint32_t site, unsigned long long idx8, float rate) {
+  const uint4 r = philox4x32_10(make_uint4((uint32_t)idx8, (uint32_t)(idx8 >> 32), site, 0x8u),
+                                make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)));
+  const uint32_t thr = (uint32_t)(rate * 65536.f);
+  const uint32_t w[4] = {r.x, r.y, r.z, r.w};
+  uint32_t bits = 0;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    bits |= ((w[j] & 0xFFFFu) >= thr ? 1u : 0u) << (2 * j);
+    bits |= ((w[j] >> 16) >= thr ? 1u : 0u) << (2 * j + 1);
+  }
+  return bits;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -140,13 +149,14 @@ __global__ void __launch_bounds__(256)
 residual_ln_fwd_kernel(const __nv_bfloat16* __restrict__ y, const __nv_bfloat16* __restrict__ x,
                        const float* __restrict__ gamma, const float* __restrict__ beta, __nv_bfloat16* __restrict__ z_out,
                        __nv_bfloat16* __restrict__ out, float* __restrict__ mean_out, float* __restrict__ rstd_out,
-                       long long rows, int d, float eps, float rate, unsigned long long seed, uint32_t site,
+                       uint8_t* __restrict__ keep_out, long long rows, int d, float eps, float rate, unsigned long long seed, uint32_t site,
                        const unsigned long long* __restrict__ seed_dev) {
   if (seed_dev != nullptr) seed = *seed_dev;
   const int lane = threadIdx.x & 31;
   const long long warp_global = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
   const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
   const int d8 = d >> 3;
+  const float inv_keep = 1.f / (1.f - rate);
   uint4 ny[NV], nx[NV];
   auto fetch = [&](long long r) {
 #pragma unroll
@@ -168,9 +178,10 @@ residual_ln_fwd_kernel(const __nv_bfloat16* __restrict__ y, const __nv_bfloat16*
       F8 yv = unpack8(ny[i]);
       const F8 xv = unpack8(nx[i]);
       if (rate > 0.f && c8 < d8) {
-        const F8 k = dropout_scale8(seed, site, (unsigned long long)(r * d8 + c8), rate);
+        const uint32_t keep = dropout_keep8(seed, site, (unsigned long long)(r * d8 + c8), rate);
+        if (keep_out != nullptr) keep_out[r * d8 + c8] = (uint8_t)keep;     // the backward pass reads the bits back: no RNG there
 #pragma unroll
-        for (int e = 0; e < 8; ++e) yv.v[e] *= k.v[e];
+        for (int e = 0; e < 8; ++e) yv.v[e] = ((keep >> e) & 1u) ? yv.v[e] * inv_keep : 0.f;
       }
 #pragma unroll
       for (int e = 0; e < 8; ++e) { z[i].v[e] = xv.v[e] + yv.v[e]; s += z[i].v[e]; }
@@ -218,7 +229,7 @@ __global__ void __launch_bounds__(256, 1)
 residual_ln_bwd_kernel(const void* __restrict__ g1v, const __nv_bfloat16* __restrict__ g2, const __nv_bfloat16* __restrict__ z,
                        const float* __restrict__ mean_in, const float* __restrict__ rstd_in, const float* __restrict__ gamma,
                        __nv_bfloat16* __restrict__ dz, __nv_bfloat16* __restrict__ dy_sub, float* __restrict__ dgamma,
-                       float* __restrict__ dbeta, float* __restrict__ dbias, long long rows, int d, float rate,
+                       float* __restrict__ dbeta, float* __restrict__ dbias, const uint8_t* __restrict__ keep_in, long long rows, int d, float rate,
                        unsigned long long seed, uint32_t site, const unsigned long long* __restrict__ seed_dev) {
   if (seed_dev != nullptr) seed = *seed_dev;
   extern __shared__ float red[];  // [3][d]: dgamma, dbeta, dbias partials of this block (shared-memory atomics)
@@ -243,6 +254,8 @@ residual_ln_bwd_kernel(const void* __restrict__ g1v, const __nv_bfloat16* __rest
   // software pipeline: the NEXT row's gradient / z vectors are in flight while the current row is reduced and written
   constexpr int G1V = kG1F32 ? 2 : 1;
   uint4 n1[NV][G1V], n2[NV], nz[NV];
+  uint32_t nkeep[NV], nk[NV];
+  const float inv_keep = 1.f / (1.f - rate);
   float nmean = 0.f, nrstd = 0.f;
   auto fetch = [&](long long r) {
 #pragma unroll
@@ -258,10 +271,11 @@ residual_ln_bwd_kernel(const void* __restrict__ g1v, const __nv_bfloat16* __rest
         }
         n2[i] = g2 != nullptr ? reinterpret_cast<const uint4*>(g2)[idx] : make_uint4(0, 0, 0, 0);
         nz[i] = reinterpret_cast<const uint4*>(z)[idx];
+        nkeep[i] = keep_in != nullptr ? keep_in[idx] : 0u;
       } else {
 #pragma unroll
         for (int k = 0; k < G1V; ++k) n1[i][k] = make_uint4(0, 0, 0, 0);
-        n2[i] = make_uint4(0, 0, 0, 0); nz[i] = make_uint4(0, 0, 0, 0);
+        n2[i] = make_uint4(0, 0, 0, 0); nz[i] = make_uint4(0, 0, 0, 0); nkeep[i] = 0u;
       }
     }
     nmean = mean_in[r]; nrstd = rstd_in[r];
@@ -284,6 +298,7 @@ residual_ln_bwd_kernel(const void* __restrict__ g1v, const __nv_bfloat16* __rest
       const F8 b = unpack8(n2[i]);
       const F8 zv = unpack8(nz[i]);
       const bool live = lane + 32 * i < d8;
+      nk[i] = nkeep[i];
 #pragma unroll
       for (int e = 0; e < 8; ++e) {
         dy[i].v[e] += b.v[e];
@@ -307,9 +322,9 @@ residual_ln_bwd_kernel(const void* __restrict__ g1v, const __nv_bfloat16* __rest
         for (int e = 0; e < 8; ++e) o.v[e] = rstd * (gm[i].v[e] * dy[i].v[e] - m1 - xh[i].v[e] * m2);
         reinterpret_cast<uint4*>(dz)[idx] = pack8(o);
         if (rate > 0.f) {
-          const F8 k = dropout_scale8(seed, site, (unsigned long long)idx, rate);
+          const uint32_t keep = keep_in != nullptr ? nk[i] : dropout_keep8(seed, site, (unsigned long long)idx, rate);
 #pragma unroll
-          for (int e = 0; e < 8; ++e) o.v[e] *= k.v[e];
+          for (int e = 0; e < 8; ++e) o.v[e] = ((keep >> e) & 1u) ? o.v[e] * inv_keep : 0.f;
         }
 #pragma unroll
         for (int e = 0; e < 8; ++e) ac[i].v[e] += o.v[e];       // bias grad of the sublayer's last Dense
@@ -386,13 +401,17 @@ xent_kernel(const T* logits, long long ld, const long long* __restrict__ labels,
     float x[8];
     LogitVec<T>::load(row + (long long)i * VEC, x);
     const int c0 = i * VEC;
-    float vmax = -INFINITY;
+    if (c0 + VEC > V) {                       // ragged last vector only: columns >= V are not logits
 #pragma unroll
-    for (int e = 0; e < VEC; ++e) {
-      if (c0 + e >= V) x[e] = -INFINITY;
-      if (c0 + e == label) s_lab = x[e];     // captured now: pass 2 may overwrite the (aliased) row in place
-      if (x[e] > vmax) vmax = x[e];
+      for (int e = 0; e < VEC; ++e) if (c0 + e >= V) x[e] = -INFINITY;
     }
+    if ((unsigned)(label - c0) < (unsigned)VEC) {       // captured now: pass 2 may overwrite the (aliased) row in place
+#pragma unroll
+      for (int e = 0; e < VEC; ++e) if (c0 + e == label) s_lab = x[e];
+    }
+    float vmax = x[0];
+#pragma unroll
+    for (int e = 1; e < VEC; ++e) vmax = fmaxf(vmax, x[e]);
     if (vmax > m) {
       int first = 0;
 #pragma unroll
@@ -445,10 +464,14 @@ xent_kernel(const T* logits, long long ld, const long long* __restrict__ labels,
     const int c0 = i * VEC;
     float g[8];
 #pragma unroll
-    for (int e = 0; e < VEC; ++e) {
-      float v = fast_exp2(x[e] * L2E - lb);
-      if (c0 + e == label) v -= 1.f;
-      g[e] = (c0 + e < V) ? v * gscale : 0.f;
+    for (int e = 0; e < VEC; ++e) g[e] = fast_exp2(x[e] * L2E - lb) * gscale;
+    if ((unsigned)(label - c0) < (unsigned)VEC) {
+#pragma unroll
+      for (int e = 0; e < VEC; ++e) if (c0 + e == label) g[e] -= gscale;
+    }
+    if (c0 + VEC > V) {
+#pragma unroll
+      for (int e = 0; e < VEC; ++e) if (c0 + e >= V) g[e] = 0.f;
     }
     if (VEC == 8) {
       *reinterpret_cast<uint4*>(drow + c0) = make_uint4(pack_bf16x2(g[0], g[1]), pack_bf16x2(g[2], g[3]), pack_bf16x2(g[4], g[5]),
@@ -643,21 +666,22 @@ int embed_bwd(const long long* ids, int id_stride, int id_offset, const void* g1
   else NAME<4 BX_LN_EXTRA> __VA_ARGS__;
 
 int residual_ln_fwd(const void* y, const void* x, const float* gamma, const float* beta, void* z, void* out, float* mean,
-                    float* rstd, long long rows, int d, float eps, float rate, unsigned long long seed, unsigned site,
+                    float* rstd, void* keep_bits, long long rows, int d, float eps, float rate, unsigned long long seed, unsigned site,
                     cudaStream_t st, const unsigned long long* seed_dev) {
   BX_REQUIRE(d % 8 == 0 && d <= 1024, "layernorm: need d %% 8 == 0 and d <= 1024 (got %d)", d);
   const int grid = grid_for(rows * 32, 256);
 #define BX_LN_EXTRA
   BX_LN_DISPATCH(residual_ln_fwd_kernel, <<<grid, 256, 0, st>>>((const __nv_bfloat16*)y, (const __nv_bfloat16*)x, gamma, beta,
-                                                               (__nv_bfloat16*)z, (__nv_bfloat16*)out, mean, rstd, rows, d, eps, rate,
-                                                               seed, site, seed_dev))
+                                                               (__nv_bfloat16*)z, (__nv_bfloat16*)out, mean, rstd, (uint8_t*)keep_bits,
+                                                               rows, d, eps, rate, seed, site, seed_dev))
 #undef BX_LN_EXTRA
   BX_POST_LAUNCH();
   return 0;
 }
 int residual_ln_bwd(const void* g1, int g1_f32, const void* g2, const void* z, const float* mean, const float* rstd,
-                    const float* gamma, void* dz, void* dy_sub, float* dgamma, float* dbeta, float* dbias, long long rows, int d,
-                    float rate, unsigned long long seed, unsigned site, cudaStream_t st, const unsigned long long* seed_dev) {
+                    const float* gamma, void* dz, void* dy_sub, float* dgamma, float* dbeta, float* dbias, const void* keep_bits,
+                    long long rows, int d, float rate, unsigned long long seed, unsigned site, cudaStream_t st,
+                    const unsigned long long* seed_dev) {
   BX_REQUIRE(d % 8 == 0 && d <= 1024, "layernorm: need d %% 8 == 0 and d <= 1024 (got %d)", d);
   const int grid = grid_for(rows * 32, 256, 1);
   const size_t smem = (size_t)3 * d * sizeof(float);
@@ -665,13 +689,13 @@ int residual_ln_bwd(const void* g1, int g1_f32, const void* g2, const void* z, c
 #define BX_LN_EXTRA , true
     BX_LN_DISPATCH(residual_ln_bwd_kernel, <<<grid, 256, smem, st>>>(g1, (const __nv_bfloat16*)g2, (const __nv_bfloat16*)z, mean, rstd,
                                                                     gamma, (__nv_bfloat16*)dz, (__nv_bfloat16*)dy_sub, dgamma, dbeta,
-                                                                    dbias, rows, d, rate, seed, site, seed_dev))
+                                                                    dbias, (const uint8_t*)keep_bits, rows, d, rate, seed, site, seed_dev))
 #undef BX_LN_EXTRA
   } else {
 #define BX_LN_EXTRA , false
     BX_LN_DISPATCH(residual_ln_bwd_kernel, <<<grid, 256, smem, st>>>(g1, (const __nv_bfloat16*)g2, (const __nv_bfloat16*)z, mean, rstd,
                                                                     gamma, (__nv_bfloat16*)dz, (__nv_bfloat16*)dy_sub, dgamma, dbeta,
-                                                                    dbias, rows, d, rate, seed, site, seed_dev))
+                                                                    dbias, (const uint8_t*)keep_bits, rows, d, rate, seed, site, seed_dev))
 #undef BX_LN_EXTRA
   }
   BX_POST_LAUNCH();

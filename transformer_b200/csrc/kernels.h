@@ -34,13 +34,16 @@ int embed_bwd(const long long* ids, int id_stride, int id_offset, const void* g1
               int S, int d, long long V, float rate, unsigned long long seed, unsigned site, cudaStream_t st,
               const unsigned long long* seed_dev = nullptr);   // gradient of the embedding output = g1 (+ g2), bf16 streams
 // y, x, z, out: bf16 [rows, d]
+// keep_bits: uint8 [rows, d/8] dropout keep mask (bit e of byte c8 = element 8*c8+e); written by fwd when rate > 0 and
+// non-NULL, read back by bwd (NULL there: the mask is regenerated from (seed, site))
 int residual_ln_fwd(const void* y, const void* x, const float* gamma, const float* beta, void* z, void* out, float* mean,
-                    float* rstd, long long rows, int d, float eps, float rate, unsigned long long seed, unsigned site,
-                    cudaStream_t st, const unsigned long long* seed_dev = nullptr);
+                    float* rstd, void* keep_bits, long long rows, int d, float eps, float rate, unsigned long long seed,
+                    unsigned site, cudaStream_t st, const unsigned long long* seed_dev = nullptr);
 // incoming gradient = g1 (fp32 if g1_f32 else bf16) + g2 (bf16, may be NULL); dz, dy_sub bf16 (dy_sub NULL: not written)
 int residual_ln_bwd(const void* g1, int g1_f32, const void* g2, const void* z, const float* mean, const float* rstd,
-                    const float* gamma, void* dz, void* dy_sub, float* dgamma, float* dbeta, float* dbias, long long rows, int d,
-                    float rate, unsigned long long seed, unsigned site, cudaStream_t st, const unsigned long long* seed_dev = nullptr);
+                    const float* gamma, void* dz, void* dy_sub, float* dgamma, float* dbeta, float* dbias, const void* keep_bits,
+                    long long rows, int d, float rate, unsigned long long seed, unsigned site, cudaStream_t st,
+                    const unsigned long long* seed_dev = nullptr);
 int xent(const void* logits, int logits_f32, long long ld, const long long* labels, int label_stride, int label_offset,
          int T_len, void* dlogits, long long ld_d, float* row_loss, double* stats, long long rows, int V, float inv_batch,
          cudaStream_t st);

@@ -130,7 +130,7 @@ Layout make_layout(const b200xf_model_config& c) {
 }
 
 // ---- workspace (activations kept for backward + gradient scratch), carved from one caller-owned buffer ----
-struct LnSave { bf16* z; float *mean, *rstd; };   // z = x + dropout(y) (bf16) and the row statistics
+struct LnSave { bf16* z; float *mean, *rstd; uint8_t* keep; };   // z = x + dropout(y) (bf16) and the row statistics
 struct EncAct { bf16* qkv; bf16* attn_o; float* lse; LnSave ln1; bf16* out1_16; bf16* h; uint64_t* hbits; LnSave ln2; };
 struct DecAct {
   bf16* qkv1; bf16* attn1_o; float* lse1; LnSave ln1; bf16* out1_16;
@@ -169,7 +169,10 @@ Work make_work(const b200xf_model_config& c, const Layout& lo, void* base) {
   const int64_t Ms = (int64_t)c.max_batch * c.max_src_len, Mt = (int64_t)c.max_batch * c.max_tgt_len;
   const int64_t Mx = Ms > Mt ? Ms : Mt;
   const int64_t Smax = c.max_src_len > c.max_tgt_len ? c.max_src_len : c.max_tgt_len;
-  auto ln = [&](int64_t M) { LnSave s; s.z = b.take<bf16>(M * d); s.mean = b.take<float>(M); s.rstd = b.take<float>(M); return s; };
+  auto ln = [&](int64_t M) {
+    LnSave s; s.z = b.take<bf16>(M * d); s.mean = b.take<float>(M); s.rstd = b.take<float>(M); s.keep = b.take<uint8_t>(M * (d / 8));
+    return s;
+  };
   w.enc_x16.resize(L + 1); w.dec_x16.resize(L + 1);
   for (int i = 0; i <= L; ++i) w.enc_x16[i] = b.take<bf16>(Ms * d);
   for (int i = 0; i <= L; ++i) w.dec_x16[i] = b.take<bf16>(Mt * d);
@@ -288,7 +291,7 @@ MaskSpec dec_cross_mask(const M* m) {
 int residual_ln(M* m, const bf16* x, int64_t g_off, int64_t b_off, bf16* out16, const LnSave& s, int64_t rows, uint32_t site,
                 cudaStream_t st) {
   const float rate = m->training ? m->cfg.dropout_rate : 0.f;
-  return bx::residual_ln_fwd(m->w.y16, x, m->P + g_off, m->P + b_off, s.z, out16, s.mean, s.rstd, rows, m->lo.d, m->cfg.ln_eps, rate,
+  return bx::residual_ln_fwd(m->w.y16, x, m->P + g_off, m->P + b_off, s.z, out16, s.mean, s.rstd, s.keep, rows, m->lo.d, m->cfg.ln_eps, rate,
                              m->seed, site, st, m->seed_dev);
 }
 
@@ -371,7 +374,7 @@ int residual_ln_back(M* m, const StreamGrad& g, const LnSave& s, int64_t g_off, 
   bf16* dy_buf = rate > 0.f ? m->w.dy16 : nullptr;
   *dy = rate > 0.f ? m->w.dy16 : dz;
   return bx::residual_ln_bwd(g.r, g.r_f32 ? 1 : 0, g.dg, s.z, s.mean, s.rstd, m->P + g_off, dz, dy_buf, m->G + g_off, m->G + b_off,
-                             m->G + bias_off, rows, m->lo.d, rate, m->seed, site, st, m->seed_dev);
+                             m->G + bias_off, s.keep, rows, m->lo.d, rate, m->seed, site, st, m->seed_dev);
 }
 
 // FFN backward: dy = d(ffn output); x16 = ffn input; writes d(input) (sublayer path only) to w.gD
