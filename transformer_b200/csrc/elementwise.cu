@@ -224,8 +224,9 @@ residual_ln_fwd_kernel(const __nv_bfloat16* __restrict__ y, const __nv_bfloat16*
 //   dy_sub = dz * dropmask/(1-rate)                                      (bf16, gradient to the sublayer output;
 //                                                                         NULL when rate == 0: it equals dz)
 //   dgamma += sum_rows dy*xhat ; dbeta += sum_rows dy ; dbias += sum_rows dy_sub   (block partials -> atomicAdd)
-template <int NV, bool kG1F32>
-__global__ void __launch_bounds__(256, 1)
+// kRegen: the dropout mask is regenerated with Philox (no stored bits); that variant needs the registers of a 256-thread block
+template <int NV, bool kG1F32, bool kRegen>
+__global__ void __launch_bounds__((NV <= 2 && !kRegen) ? 512 : 256, 1)
 residual_ln_bwd_kernel(const void* __restrict__ g1v, const __nv_bfloat16* __restrict__ g2, const __nv_bfloat16* __restrict__ z,
                        const float* __restrict__ mean_in, const float* __restrict__ rstd_in, const float* __restrict__ gamma,
                        __nv_bfloat16* __restrict__ dz, __nv_bfloat16* __restrict__ dy_sub, float* __restrict__ dgamma,
@@ -239,17 +240,11 @@ residual_ln_bwd_kernel(const void* __restrict__ g1v, const __nv_bfloat16* __rest
   const int d8 = d >> 3;
   for (int c = threadIdx.x; c < 3 * d; c += blockDim.x) red[c] = 0.f;
   __syncthreads();
-  F8 ag[NV], ab[NV], ac[NV], gm[NV];
+  F8 ag[NV], ab[NV], ac[NV];      // gamma is re-read per row (L1-resident) instead of living in 8*NV registers
 #pragma unroll
   for (int i = 0; i < NV; ++i) {
 #pragma unroll
-    for (int e = 0; e < 8; ++e) { ag[i].v[e] = 0.f; ab[i].v[e] = 0.f; ac[i].v[e] = 0.f; gm[i].v[e] = 0.f; }
-    const int c8 = lane + 32 * i;
-    if (c8 < d8) {
-      const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma) + 2 * c8), g1 = __ldg(reinterpret_cast<const float4*>(gamma) + 2 * c8 + 1);
-      gm[i].v[0] = g0.x; gm[i].v[1] = g0.y; gm[i].v[2] = g0.z; gm[i].v[3] = g0.w;
-      gm[i].v[4] = g1.x; gm[i].v[5] = g1.y; gm[i].v[6] = g1.z; gm[i].v[7] = g1.w;
-    }
+    for (int e = 0; e < 8; ++e) { ag[i].v[e] = 0.f; ab[i].v[e] = 0.f; ac[i].v[e] = 0.f; }
   }
   // software pipeline: the NEXT row's gradient / z vectors are in flight while the current row is reduced and written
   constexpr int G1V = kG1F32 ? 2 : 1;
@@ -271,7 +266,7 @@ residual_ln_bwd_kernel(const void* __restrict__ g1v, const __nv_bfloat16* __rest
         }
         n2[i] = g2 != nullptr ? reinterpret_cast<const uint4*>(g2)[idx] : make_uint4(0, 0, 0, 0);
         nz[i] = reinterpret_cast<const uint4*>(z)[idx];
-        nkeep[i] = keep_in != nullptr ? keep_in[idx] : 0u;
+        nkeep[i] = (!kRegen && keep_in != nullptr) ? keep_in[idx] : 0u;
       } else {
 #pragma unroll
         for (int k = 0; k < G1V; ++k) n1[i][k] = make_uint4(0, 0, 0, 0);
@@ -282,32 +277,37 @@ residual_ln_bwd_kernel(const void* __restrict__ g1v, const __nv_bfloat16* __rest
   };
   if (warp_global < rows) fetch(warp_global);
   for (long long r = warp_global; r < rows; r += nwarps) {
-    F8 dy[NV], xh[NV];
+    F8 gd[NV], xh[NV];              // gamma * dy and xhat of this row
     const float mean = nmean, rstd = nrstd;
     float s1 = 0.f, s2 = 0.f;
 #pragma unroll
     for (int i = 0; i < NV; ++i) {
+      F8 dy;
       if (kG1F32) {
-        dy[i].v[0] = __uint_as_float(n1[i][0].x); dy[i].v[1] = __uint_as_float(n1[i][0].y);
-        dy[i].v[2] = __uint_as_float(n1[i][0].z); dy[i].v[3] = __uint_as_float(n1[i][0].w);
-        dy[i].v[4] = __uint_as_float(n1[i][G1V - 1].x); dy[i].v[5] = __uint_as_float(n1[i][G1V - 1].y);
-        dy[i].v[6] = __uint_as_float(n1[i][G1V - 1].z); dy[i].v[7] = __uint_as_float(n1[i][G1V - 1].w);
+        dy.v[0] = __uint_as_float(n1[i][0].x); dy.v[1] = __uint_as_float(n1[i][0].y);
+        dy.v[2] = __uint_as_float(n1[i][0].z); dy.v[3] = __uint_as_float(n1[i][0].w);
+        dy.v[4] = __uint_as_float(n1[i][G1V - 1].x); dy.v[5] = __uint_as_float(n1[i][G1V - 1].y);
+        dy.v[6] = __uint_as_float(n1[i][G1V - 1].z); dy.v[7] = __uint_as_float(n1[i][G1V - 1].w);
       } else {
-        dy[i] = unpack8(n1[i][0]);
+        dy = unpack8(n1[i][0]);
       }
       const F8 b = unpack8(n2[i]);
       const F8 zv = unpack8(nz[i]);
-      const bool live = lane + 32 * i < d8;
+      const int c8 = lane + 32 * i;
+      const bool live = c8 < d8;
+      const int cg = live ? c8 : 0;
+      const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma) + 2 * cg), g1 = __ldg(reinterpret_cast<const float4*>(gamma) + 2 * cg + 1);
+      const float gm[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
       nk[i] = nkeep[i];
 #pragma unroll
       for (int e = 0; e < 8; ++e) {
-        dy[i].v[e] += b.v[e];
+        const float dv = dy.v[e] + b.v[e];
         xh[i].v[e] = live ? (zv.v[e] - mean) * rstd : 0.f;
-        const float gd = gm[i].v[e] * dy[i].v[e];
-        s1 += gd;
-        s2 += gd * xh[i].v[e];
-        ag[i].v[e] += dy[i].v[e] * xh[i].v[e];
-        ab[i].v[e] += dy[i].v[e];
+        gd[i].v[e] = live ? gm[e] * dv : 0.f;
+        s1 += gd[i].v[e];
+        s2 += gd[i].v[e] * xh[i].v[e];
+        ag[i].v[e] += dv * xh[i].v[e];
+        ab[i].v[e] += dv;
       }
     }
     if (r + nwarps < rows) fetch(r + nwarps);
@@ -319,10 +319,10 @@ residual_ln_bwd_kernel(const void* __restrict__ g1v, const __nv_bfloat16* __rest
         const long long idx = r * d8 + c8;
         F8 o;
 #pragma unroll
-        for (int e = 0; e < 8; ++e) o.v[e] = rstd * (gm[i].v[e] * dy[i].v[e] - m1 - xh[i].v[e] * m2);
+        for (int e = 0; e < 8; ++e) o.v[e] = rstd * (gd[i].v[e] - m1 - xh[i].v[e] * m2);
         reinterpret_cast<uint4*>(dz)[idx] = pack8(o);
         if (rate > 0.f) {
-          const uint32_t keep = keep_in != nullptr ? nk[i] : dropout_keep8(seed, site, (unsigned long long)idx, rate);
+          const uint32_t keep = kRegen ? dropout_keep8(seed, site, (unsigned long long)idx, rate) : nk[i];
 #pragma unroll
           for (int e = 0; e < 8; ++e) o.v[e] = ((keep >> e) & 1u) ? o.v[e] * inv_keep : 0.f;
         }
@@ -485,22 +485,22 @@ xent_kernel(const T* logits, long long ld, const long long* __restrict__ labels,
 
 // ------------------------------------------------------------------------------------------------
 // column sums: out[n] += sum_m X[m, n]   (bias gradients = reduce of dY over tokens)
-//   block = 16 column groups (8 bf16 = 16 bytes each) x 16 row lanes; grid.y splits the rows.
+//   block = 32 column groups (8 bf16 = 16 bytes each: one warp = 512 contiguous bytes) x 8 row lanes; grid.y splits the rows.
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
 colsum_bf16_kernel(const __nv_bfloat16* __restrict__ X, long long ld, float* __restrict__ out, long long rows, int N,
                    int rows_per_block) {
-  __shared__ float sm[16][132];
-  const int cg = threadIdx.x & 15, rl = threadIdx.x >> 4;
-  const int c0 = blockIdx.x * 128 + cg * 8;
+  __shared__ float sm[8][264];
+  const int cg = threadIdx.x & 31, rl = threadIdx.x >> 5;        // a warp reads 512 contiguous bytes of one row
+  const int c0 = blockIdx.x * 256 + cg * 8;
   const long long r0 = (long long)blockIdx.y * rows_per_block;
   const long long r1 = r0 + rows_per_block < rows ? r0 + rows_per_block : rows;
   float acc[8];
 #pragma unroll
   for (int e = 0; e < 8; ++e) acc[e] = 0.f;
   if (c0 < N) {
-#pragma unroll 4
-    for (long long r = r0 + rl; r < r1; r += 16) {
+#pragma unroll 8
+    for (long long r = r0 + rl; r < r1; r += 8) {
       const uint4 v = __ldg(reinterpret_cast<const uint4*>(X + r * ld + c0));
       const float2 a = unpack_bf16x2(v.x), b = unpack_bf16x2(v.y), c = unpack_bf16x2(v.z), d = unpack_bf16x2(v.w);
       acc[0] += a.x; acc[1] += a.y; acc[2] += b.x; acc[3] += b.y; acc[4] += c.x; acc[5] += c.y; acc[6] += d.x; acc[7] += d.y;
@@ -509,14 +509,12 @@ colsum_bf16_kernel(const __nv_bfloat16* __restrict__ X, long long ld, float* __r
 #pragma unroll
   for (int e = 0; e < 8; ++e) sm[rl][cg * 8 + e] = acc[e];
   __syncthreads();
-  if (threadIdx.x < 128) {
-    const int c = blockIdx.x * 128 + threadIdx.x;
-    if (c < N) {
-      float t = 0.f;
+  const int c = blockIdx.x * 256 + threadIdx.x;
+  if (c < N) {
+    float t = 0.f;
 #pragma unroll
-      for (int k = 0; k < 16; ++k) t += sm[k][threadIdx.x];
-      atomicAdd(out + c, t);
-    }
+    for (int k = 0; k < 8; ++k) t += sm[k][threadIdx.x];
+    atomicAdd(out + c, t);
   }
 }
 
@@ -683,21 +681,33 @@ int residual_ln_bwd(const void* g1, int g1_f32, const void* g2, const void* z, c
                     long long rows, int d, float rate, unsigned long long seed, unsigned site, cudaStream_t st,
                     const unsigned long long* seed_dev) {
   BX_REQUIRE(d % 8 == 0 && d <= 1024, "layernorm: need d %% 8 == 0 and d <= 1024 (got %d)", d);
-  const int grid = grid_for(rows * 32, 256, 1);
+  const bool regen = rate > 0.f && keep_bits == nullptr;
+  const int threads = (d <= 512 && !regen) ? 512 : 256;
+  const int grid = grid_for(rows * 32, threads, 1);
   const size_t smem = (size_t)3 * d * sizeof(float);
-  if (g1_f32) {
-#define BX_LN_EXTRA , true
-    BX_LN_DISPATCH(residual_ln_bwd_kernel, <<<grid, 256, smem, st>>>(g1, (const __nv_bfloat16*)g2, (const __nv_bfloat16*)z, mean, rstd,
-                                                                    gamma, (__nv_bfloat16*)dz, (__nv_bfloat16*)dy_sub, dgamma, dbeta,
-                                                                    dbias, (const uint8_t*)keep_bits, rows, d, rate, seed, site, seed_dev))
+#define BX_LN_BWD_GO(F32, REGEN)                                                                                                   \
+  BX_LN_DISPATCH(residual_ln_bwd_kernel, <<<grid, threads, smem, st>>>(g1, (const __nv_bfloat16*)g2, (const __nv_bfloat16*)z, mean, \
+                                                                      rstd, gamma, (__nv_bfloat16*)dz, (__nv_bfloat16*)dy_sub,      \
+                                                                      dgamma, dbeta, dbias, (const uint8_t*)keep_bits, rows, d,     \
+                                                                      rate, seed, site, seed_dev))
+  if (g1_f32 && regen) {
+#define BX_LN_EXTRA , true, true
+    BX_LN_BWD_GO(true, true)
+#undef BX_LN_EXTRA
+  } else if (g1_f32) {
+#define BX_LN_EXTRA , true, false
+    BX_LN_BWD_GO(true, false)
+#undef BX_LN_EXTRA
+  } else if (regen) {
+#define BX_LN_EXTRA , false, true
+    BX_LN_BWD_GO(false, true)
 #undef BX_LN_EXTRA
   } else {
-#define BX_LN_EXTRA , false
-    BX_LN_DISPATCH(residual_ln_bwd_kernel, <<<grid, 256, smem, st>>>(g1, (const __nv_bfloat16*)g2, (const __nv_bfloat16*)z, mean, rstd,
-                                                                    gamma, (__nv_bfloat16*)dz, (__nv_bfloat16*)dy_sub, dgamma, dbeta,
-                                                                    dbias, (const uint8_t*)keep_bits, rows, d, rate, seed, site, seed_dev))
+#define BX_LN_EXTRA , false, false
+    BX_LN_BWD_GO(false, false)
 #undef BX_LN_EXTRA
   }
+#undef BX_LN_BWD_GO
   BX_POST_LAUNCH();
   return 0;
 }
@@ -719,7 +729,7 @@ int xent(const void* logits, int logits_f32, long long ld, const long long* labe
 
 int colsum_bf16(const void* X, long long ld, float* out, long long rows, int N, cudaStream_t st) {
   BX_REQUIRE(ld % 8 == 0 && (reinterpret_cast<uintptr_t>(X) & 15) == 0, "colsum: X must be 16-byte aligned with ld %% 8 == 0");
-  const int bx_ = (N + 127) / 128;
+  const int bx_ = (N + 255) / 256;
   long long by = (long long)sm_count() * 6 / bx_;
   if (by < 1) by = 1;
   long long rpb = (rows + by - 1) / by;
