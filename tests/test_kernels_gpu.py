@@ -226,12 +226,20 @@ def attn_case(B, H, Sq, Sk, dk, kind, seed=0, backward=True):
     dq_acc = torch.zeros(B * Sq, d, dtype=torch.float32, device=dev())
     dKV = torch.full((B * Sk, 2 * d), float("nan"), dtype=torch.bfloat16, device=dev())
     dKs = dKV[:, :d]; dVs = dKV[:, d:]
-    L.call("b200xf_attn_bwd", L.ptr(Qs), ldq, L.ptr(Ks), ldq, L.ptr(Vs), ldq, L.ptr(dO), d, L.ptr(lse), L.ptr(delta), L.ptr(dq_acc), d,
+    L.call("b200xf_attn_bwd", L.ptr(Qs), ldq, L.ptr(Ks), ldq, L.ptr(Vs), ldq, L.ptr(dO), d, L.ptr(lse), L.ptr(delta), L.ptr(dq_acc), d, 0,
            L.ptr(dKs), 2 * d, L.ptr(dVs), 2 * d, L.ptr(kpad), causal, L.ptr(maskf), msb, msq, B, H, Sq, Sk, dk, sp())
+    # the same with dQ reduce-added in bf16 into a strided (packed-QKV-gradient style) tensor
+    dq16 = torch.zeros(B * Sq, 3 * d, dtype=torch.bfloat16, device=dev())
+    dKV2 = torch.empty_like(dKV)
+    L.call("b200xf_attn_bwd", L.ptr(Qs), ldq, L.ptr(Ks), ldq, L.ptr(Vs), ldq, L.ptr(dO), d, L.ptr(lse), L.ptr(delta), L.ptr(dq16[:, d:2 * d]), 3 * d, 1,
+           L.ptr(dKV2[:, :d]), 2 * d, L.ptr(dKV2[:, d:]), 2 * d, L.ptr(kpad), causal, L.ptr(maskf), msb, msq, B, H, Sq, Sk, dk, sp())
     torch.cuda.synchronize()
+    assert torch.equal(dKV2, dKV)
+    assert (dq16[:, :d] == 0).all() and (dq16[:, 2 * d:] == 0).all()            # only the addressed column block is touched
     delta_ref = (o_ref.detach() * do4).sum(-1)
     assert (delta - delta_ref).abs().max().item() < 0.15
-    for name, got, ref, S in (("dq", dq_acc, q4.grad, Sq), ("dk", dKs.float(), k4.grad, Sk), ("dv", dVs.float(), v4.grad, Sk)):
+    for name, got, ref, S in (("dq", dq_acc, q4.grad, Sq), ("dq_bf16", dq16[:, d:2 * d].float(), q4.grad, Sq), ("dk", dKs.float(), k4.grad, Sk),
+                              ("dv", dVs.float(), v4.grad, Sk)):
         got4 = got.reshape(B, S, H, dk).permute(0, 2, 1, 3)
         assert torch.isfinite(got4).all(), f"{kind}: non-finite {name}"
         err = (got4 - ref).abs().max().item()

@@ -29,7 +29,7 @@ def bench(B, H, S, dk, causal, iters=10, bwd=True):
 
     def back():
         L.call("b200xf_attn_delta", L.ptr(O), d, L.ptr(dO), d, L.ptr(delta), B, S, H, dk, sp)
-        L.call("b200xf_attn_bwd", L.ptr(Q), 3 * d, L.ptr(K), 3 * d, L.ptr(V), 3 * d, L.ptr(dO), d, L.ptr(lse), L.ptr(delta), L.ptr(dq), d,
+        L.call("b200xf_attn_bwd", L.ptr(Q), 3 * d, L.ptr(K), 3 * d, L.ptr(V), 3 * d, L.ptr(dO), d, L.ptr(lse), L.ptr(delta), L.ptr(dqkv), 3 * d, 1,
                L.ptr(dqkv[:, d:2 * d]), 3 * d, L.ptr(dqkv[:, 2 * d:]), 3 * d, L.ptr(kpad), causal, None, 0, 0, B, H, S, S, dk, sp)
 
     out = {}

@@ -37,7 +37,7 @@ _U32 = C.c_uint32
 _SIGS = {
     "b200xf_gemm_bf16": [_P, _I64, _I, _P, _I64, _I, _P, _I64, _I, _P, _P, _I64, _I, _I, _I64, _I64, _I64, _P],
     "b200xf_attn_fwd": [_P, _I64, _P, _I64, _P, _I64, _P, _I64, _P, _P, _I, _P, _I64, _I64, _I, _I, _I, _I, _I, _P],
-    "b200xf_attn_bwd": [_P, _I64, _P, _I64, _P, _I64, _P, _I64, _P, _P, _P, _I64, _P, _I64, _P, _I64, _P, _I, _P, _I64,
+    "b200xf_attn_bwd": [_P, _I64, _P, _I64, _P, _I64, _P, _I64, _P, _P, _P, _I64, _I, _P, _I64, _P, _I64, _P, _I, _P, _I64,
                         _I64, _I, _I, _I, _I, _I, _P],
     "b200xf_attn_delta": [_P, _I64, _P, _I64, _P, _I, _I, _I, _I, _P],
     "b200xf_attn_probs": [_P, _I64, _P, _I64, _P, _P, _P, _I, _P, _I64, _I64, _I, _I, _I, _I, _I, _P],

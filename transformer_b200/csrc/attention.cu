@@ -415,7 +415,7 @@ struct BwdSmem {
 
 constexpr int ATTN_BWD_THREADS = 320;  // w0 TMA, w1 MMA(+TMEM alloc), w2-9 compute (rows x 2 column halves)
 
-template <int DK>
+template <int DK, bool kDqBf16>
 __global__ void __launch_bounds__(ATTN_BWD_THREADS, 1)
 attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                 const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmdO,
@@ -581,7 +581,26 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       if (ctid == 0) { tl_stamp(64 + (n_done & 7) * 8 + 4); tma_store_wait_read<0>(); }   // previous reduce has drained the staging
       named_bar_sync(2, 256);
       const uint32_t stg = sDQ + half * C::TILE_BYTES;
-      if (HC == 32) {
+      if (kDqBf16) {
+        // bf16 dQ: one [128 x DK] bf16 staging tile (this warp's half of the columns), reduce-added by TMA straight into
+        // the bf16 dQ tensor (cp.reduce.async.bulk.tensor .add on a bf16 tensor map) -- no fp32 accumulator, no cast pass
+        float v[HC];
+        if (HC == 32) {
+          uint32_t r[32];
+          tmem_ld_x32(tdQ + lane_sel + half * HC, r); tmem_ld_wait();
+#pragma unroll
+          for (int e = 0; e < HC; ++e) v[e] = __uint_as_float(r[e]);
+        } else {
+          uint32_t r[16];
+          tmem_ld_x16(tdQ + lane_sel + half * HC, r); tmem_ld_wait();
+#pragma unroll
+          for (int e = 0; e < HC; ++e) v[e] = __uint_as_float(r[e]);
+        }
+#pragma unroll
+        for (int g = 0; g < HC / 8; ++g)
+          st_shared_v4(sDQ + swz_off<DK>(row, half * (HC / 8) + g), pack_bf16x2(v[8 * g], v[8 * g + 1]), pack_bf16x2(v[8 * g + 2], v[8 * g + 3]),
+                       pack_bf16x2(v[8 * g + 4], v[8 * g + 5]), pack_bf16x2(v[8 * g + 6], v[8 * g + 7]));
+      } else if (HC == 32) {
         uint32_t r[32];
         tmem_ld_x32(tdQ + lane_sel + half * HC, r);
         tmem_ld_wait();
@@ -600,7 +619,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       named_bar_sync(3, 256);
       if (ctid == 0) {
         tma_reduce_add_3d(&tmdQ, smem + L::OFF_DQ, h * DK, qt0, b);
-        tma_reduce_add_3d(&tmdQ, smem + L::OFF_DQ + C::TILE_BYTES, h * DK + HC, qt0, b);
+        if (!kDqBf16) tma_reduce_add_3d(&tmdQ, smem + L::OFF_DQ + C::TILE_BYTES, h * DK + HC, qt0, b);
         tma_store_commit();
         tl_stamp(64 + (n_done & 7) * 8 + 5);
       }
@@ -778,9 +797,9 @@ static int attn_fwd_launch(const void* Q, long long ld_q, const void* K, long lo
   return 0;
 }
 
-template <int DK>
+template <int DK, bool kDqBf16>
 static int attn_bwd_launch(const void* Q, long long ld_q, const void* K, long long ld_k, const void* V, long long ld_v,
-                           const void* dO, long long ld_do, const float* lse, const float* delta, float* dq_acc,
+                           const void* dO, long long ld_do, const float* lse, const float* delta, void* dq_acc,
                            long long ld_dq, void* dK, long long ld_dk, void* dV, long long ld_dv, const AttnMask& mask,
                            int B, int H, int Sq, int Sk, cudaStream_t st) {
   using L = BwdSmem<DK>;
@@ -793,8 +812,10 @@ static int attn_bwd_launch(const void* Q, long long ld_q, const void* K, long lo
   if ((rc = encode_tmap_3d(&tmdO, 0, dO, (uint64_t)H * DK, Sq, B, ld_do, (uint64_t)Sq * ld_do, DK, 128, 1, swz))) return rc;
   if ((rc = encode_tmap_3d(&tmdK, 0, dK, (uint64_t)H * DK, Sk, B, ld_dk, (uint64_t)Sk * ld_dk, DK, 128, 1, swz))) return rc;
   if ((rc = encode_tmap_3d(&tmdV, 0, dV, (uint64_t)H * DK, Sk, B, ld_dv, (uint64_t)Sk * ld_dv, DK, 128, 1, swz))) return rc;
-  if ((rc = encode_tmap_3d(&tmdQ, 1, dq_acc, (uint64_t)H * DK, Sq, B, ld_dq, (uint64_t)Sq * ld_dq, DK / 2, 128, 1, swz))) return rc;
-  auto kern = attn_bwd_kernel<DK>;
+  if (kDqBf16) rc = encode_tmap_3d(&tmdQ, 0, dq_acc, (uint64_t)H * DK, Sq, B, ld_dq, (uint64_t)Sq * ld_dq, DK, 128, 1, swz);
+  else rc = encode_tmap_3d(&tmdQ, 1, dq_acc, (uint64_t)H * DK, Sq, B, ld_dq, (uint64_t)Sq * ld_dq, DK / 2, 128, 1, swz);
+  if (rc) return rc;
+  auto kern = attn_bwd_kernel<DK, kDqBf16>;
   static bool attr_done = false;
   if (!attr_done) {
     BX_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::BYTES));
@@ -826,16 +847,17 @@ int attn_fwd(const void* Q, long long ld_q, const void* K, long long ld_k, const
 }
 
 int attn_bwd(const void* Q, long long ld_q, const void* K, long long ld_k, const void* V, long long ld_v, const void* dO,
-             long long ld_do, const float* lse, const float* delta, float* dq_acc, long long ld_dq, void* dK,
+             long long ld_do, const float* lse, const float* delta, void* dq_acc, long long ld_dq, int dq_bf16, void* dK,
              long long ld_dk, void* dV, long long ld_dv, const uint8_t* kpad, int causal, const float* maskf,
              long long mask_sb, long long mask_sq, int B, int H, int Sq, int Sk, int dk, cudaStream_t st) {
   if (int rc = check_attn_args(B, H, Sq, Sk, dk, causal)) return rc;
-  BX_REQUIRE(ld_dq % 4 == 0 && (reinterpret_cast<uintptr_t>(dq_acc) & 15) == 0, "attention: dq accumulator alignment");
+  BX_REQUIRE(ld_dq % 8 == 0 && (reinterpret_cast<uintptr_t>(dq_acc) & 15) == 0, "attention: dq accumulator alignment");
   AttnMask m{kpad, maskf, mask_sb, mask_sq, causal};
-  return dk == 64 ? attn_bwd_launch<64>(Q, ld_q, K, ld_k, V, ld_v, dO, ld_do, lse, delta, dq_acc, ld_dq, dK, ld_dk, dV,
-                                        ld_dv, m, B, H, Sq, Sk, st)
-                  : attn_bwd_launch<32>(Q, ld_q, K, ld_k, V, ld_v, dO, ld_do, lse, delta, dq_acc, ld_dq, dK, ld_dk, dV,
-                                        ld_dv, m, B, H, Sq, Sk, st);
+#define BX_BWD_GO(D, BF) \
+  return attn_bwd_launch<D, BF>(Q, ld_q, K, ld_k, V, ld_v, dO, ld_do, lse, delta, dq_acc, ld_dq, dK, ld_dk, dV, ld_dv, m, B, H, Sq, Sk, st)
+  if (dk == 64) { if (dq_bf16) BX_BWD_GO(64, true); else BX_BWD_GO(64, false); }
+  if (dq_bf16) BX_BWD_GO(32, true); else BX_BWD_GO(32, false);
+#undef BX_BWD_GO
 }
 
 int attn_probs(const void* Q, long long ld_q, const void* K, long long ld_k, const float* lse, float* P,

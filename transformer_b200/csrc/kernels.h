@@ -17,7 +17,7 @@ int attn_fwd(const void* Q, long long ld_q, const void* K, long long ld_k, const
              long long ld_o, float* lse, const uint8_t* kpad, int causal, const float* maskf, long long mask_sb,
              long long mask_sq, int B, int H, int Sq, int Sk, int dk, cudaStream_t st);
 int attn_bwd(const void* Q, long long ld_q, const void* K, long long ld_k, const void* V, long long ld_v, const void* dO,
-             long long ld_do, const float* lse, const float* delta, float* dq_acc, long long ld_dq, void* dK,
+             long long ld_do, const float* lse, const float* delta, void* dq_acc, long long ld_dq, int dq_bf16, void* dK,
              long long ld_dk, void* dV, long long ld_dv, const uint8_t* kpad, int causal, const float* maskf,
              long long mask_sb, long long mask_sq, int B, int H, int Sq, int Sk, int dk, cudaStream_t st);
 int attn_probs(const void* Q, long long ld_q, const void* K, long long ld_k, const float* lse, float* P,

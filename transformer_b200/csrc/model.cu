@@ -149,7 +149,8 @@ struct Work {
   bf16* gD;                               // [Mmax, d] dgrad output of the last sublayer; the stream gradient is gR + gD
   float* d_enc_out;                       // [Ms, d] fp32: accumulates cross-attention K/V gradients of all decoder layers
   bf16 *dy16, *dO16, *dqkv, *dh;          // [Mmax,d] [Mmax,d] [Mmax,3d] [Mmax,f]
-  float *dq_acc, *delta;                  // [Mmax,d] [B,H,Smax]
+  bf16* dq16;                             // [Mmax,d] cross-attention dQ (bf16, TMA reduce-add target)
+  float* delta;                           // [B,H,Smax]
   int64_t bytes;
 };
 
@@ -193,7 +194,7 @@ Work make_work(const b200xf_model_config& c, const Layout& lo, void* base) {
   w.kpad_in = b.take<uint8_t>(Ms); w.kpad_tar = b.take<uint8_t>(Mt);
   w.gR0 = b.take<bf16>(Mx * d); w.gR1 = b.take<bf16>(Mx * d); w.gD = b.take<bf16>(Mx * d); w.d_enc_out = b.take<float>(Ms * d);
   w.dy16 = b.take<bf16>(Mx * d); w.dO16 = b.take<bf16>(Mx * d); w.dqkv = b.take<bf16>(Mx * 3 * d); w.dh = b.take<bf16>(Mx * f);
-  w.dq_acc = b.take<float>(Mx * d); w.delta = b.take<float>(c.max_batch * H * Smax);
+  w.dq16 = b.take<bf16>(Mx * d); w.delta = b.take<float>(c.max_batch * H * Smax);
   w.bytes = b.cur;
   return w;
 }
@@ -397,10 +398,10 @@ int self_attn_back(M* m, const MhaSelf& p, const bf16* x16, const bf16* qkv, con
   RC(linear_wgrad(attn_o, d, dy, d, m->G + p.Wo, d, nullptr, rows, d, d, st));                 // dbo: from the LN backward
   RC(linear_dgrad(dy, d, m->Sh + p.Wo, d, w.dO16, d, false, false, nullptr, 0, rows, d, d, st));
   RC(bx::attn_delta(attn_o, d, w.dO16, d, w.delta, B, S, H, dk, st));
-  BX_CHECK_CUDA(cudaMemsetAsync(w.dq_acc, 0, rows * d * sizeof(float), st));
-  RC(bx::attn_bwd(qkv, 3 * d, qkv + d, 3 * d, qkv + 2 * d, 3 * d, w.dO16, d, lse, w.delta, w.dq_acc, d, w.dqkv + d, 3 * d, w.dqkv + 2 * d,
-                  3 * d, mk.kpad, mk.causal, mk.maskf, mk.sb, mk.sq, B, H, S, S, dk, st));
-  RC(bx::cast_f32_bf16_strided(w.dq_acc, w.dqkv, rows, d, 3 * d, st));
+  // dQ is reduce-added (bf16, TMA) straight into the first d columns of the packed QKV gradient: zero them first
+  BX_CHECK_CUDA(cudaMemset2DAsync(w.dqkv, (size_t)3 * d * sizeof(bf16), 0, (size_t)d * sizeof(bf16), rows, st));
+  RC(bx::attn_bwd(qkv, 3 * d, qkv + d, 3 * d, qkv + 2 * d, 3 * d, w.dO16, d, lse, w.delta, w.dqkv, 3 * d, 1, w.dqkv + d, 3 * d,
+                  w.dqkv + 2 * d, 3 * d, mk.kpad, mk.causal, mk.maskf, mk.sb, mk.sq, B, H, S, S, dk, st));
   RC(linear_wgrad(x16, d, w.dqkv, 3 * d, m->G + p.Wqkv, 3 * d, m->G + p.bqkv, rows, 3 * d, d, st));
   RC(linear_dgrad(w.dqkv, 3 * d, m->Sh + p.Wqkv, 3 * d, w.gD, d, false, false, nullptr, 0, rows, 3 * d, d, st));
   return 0;
@@ -443,15 +444,14 @@ int backward_decoder(M* m, cudaStream_t st) {
     RC(linear_wgrad(a.attn2_o, d, dy, d, m->G + p.mha2.Wo, d, nullptr, Mt, d, d, st));
     RC(linear_dgrad(dy, d, m->Sh + p.mha2.Wo, d, w.dO16, d, false, false, nullptr, 0, Mt, d, d, st));
     RC(bx::attn_delta(a.attn2_o, d, w.dO16, d, w.delta, B, T, H, dk, st));
-    BX_CHECK_CUDA(cudaMemsetAsync(w.dq_acc, 0, Mt * d * sizeof(float), st));
-    // dK/dV of the encoder memory go to dqkv[:, 0:2d) viewed as [Ms, 2d]
-    RC(bx::attn_bwd(a.q2, d, a.kv2, 2 * d, a.kv2 + d, 2 * d, w.dO16, d, a.lse2, w.delta, w.dq_acc, d, w.dqkv, 2 * d, w.dqkv + d, 2 * d,
+    BX_CHECK_CUDA(cudaMemsetAsync(w.dq16, 0, Mt * d * sizeof(bf16), st));
+    // dK/dV of the encoder memory go to dqkv[:, 0:2d) viewed as [Ms, 2d]; dQ (bf16, TMA reduce-add) to dq16
+    RC(bx::attn_bwd(a.q2, d, a.kv2, 2 * d, a.kv2 + d, 2 * d, w.dO16, d, a.lse2, w.delta, w.dq16, d, 1, w.dqkv, 2 * d, w.dqkv + d, 2 * d,
                     cm.kpad, cm.causal, cm.maskf, cm.sb, cm.sq, B, H, T, S, dk, st));
     RC(linear_wgrad(w.enc_x16[L], d, w.dqkv, 2 * d, m->G + p.mha2.Wkv, 2 * d, m->G + p.mha2.bkv, Ms, 2 * d, d, st));
     RC(linear_dgrad(w.dqkv, 2 * d, m->Sh + p.mha2.Wkv, 2 * d, w.d_enc_out, d, true, true, nullptr, 0, Ms, 2 * d, d, st));
-    RC(bx::cast_f32_bf16(w.dq_acc, w.dO16, Mt * d, st));   // dq2 (bf16) reuses dO16
-    RC(linear_wgrad(a.out1_16, d, w.dO16, d, m->G + p.mha2.Wq, d, m->G + p.mha2.bq, Mt, d, d, st));
-    RC(linear_dgrad(w.dO16, d, m->Sh + p.mha2.Wq, d, w.gD, d, false, false, nullptr, 0, Mt, d, d, st));
+    RC(linear_wgrad(a.out1_16, d, w.dq16, d, m->G + p.mha2.Wq, d, m->G + p.mha2.bq, Mt, d, d, st));
+    RC(linear_dgrad(w.dq16, d, m->Sh + p.mha2.Wq, d, w.gD, d, false, false, nullptr, 0, Mt, d, d, st));
     advance();
     // out1 = LN1(x + drop(mha1(x, x, x)))
     RC(residual_ln_back(m, g, a.ln1, p.ln1g, p.ln1b, p.mha1.bo, dz, &dy, Mt, site_dec(l, 0), st));
