@@ -265,8 +265,14 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         const bool diag = mask.causal && (kv0 + 127 > q0 + s * 128);   // tile touches the causal boundary
         // a tile with no padded / out-of-range key, off the causal boundary and without a float mask needs no
         // per-element mask logic: the common case for every tile but the diagonal / tail ones
-        const bool plain = !diag && mrow == nullptr &&
+        const bool clean = mrow == nullptr &&
                            ((padbits[0] | padbits[1] | padbits[2] | padbits[3] | oobbits[0] | oobbits[1] | oobbits[2] | oobbits[3]) == 0u);
+        const bool plain = !diag && clean;
+        // the aligned diagonal tile of a look-ahead mask with nothing else to mask: key c*32+e is hidden from query
+        // `row` iff c*32+e > row.  Per warp (rows 32w..32w+31) that is uniform for 3 of the 4 32-key chunks: c < w fully
+        // visible (plain), c > w fully hidden (p = exp(-1e9 - m) = 0 exactly: no loads, no exponentials), c == w mixed.
+        const bool diag_fast = diag && clean && (kv0 == q0 + s * 128);
+        const int wq = (int)(row >> 5), lq = (int)(row & 31u);
         const bool tl = (s == 0 && wg_tid == 0);
         if (tl) tl_stamp(8 + j * 8 + 0);
         mbar_wait(&s_full[s], j & 1);
@@ -275,7 +281,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         // ---- the whole 128-column S row of this thread, ONE pass over TMEM
         uint32_t r[4][32];
 #pragma unroll
-        for (int c = 0; c < 4; ++c) tmem_ld_x32(tS[s] + lane_sel + c * 32, r[c]);
+        for (int c = 0; c < 4; ++c)
+          if (!diag_fast || c <= wq) tmem_ld_x32(tS[s] + lane_sel + c * 32, r[c]);
         tmem_ld_wait();
         tcgen05_before_thread_sync();
         mbar_arrive(&s_free[s]);                       // the next tile's S may overwrite tensor memory now
@@ -287,6 +294,19 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
             for (int e = 0; e < 32; ++e) mx[e & 3] = fmaxf(mx[e & 3], __uint_as_float(r[c][e]));
 #pragma unroll
           for (int u = 0; u < 4; ++u) mx[u] *= scale;
+        } else if (diag_fast) {
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            if (c < wq) {
+#pragma unroll
+              for (int e = 0; e < 32; ++e) mx[e & 3] = fmaxf(mx[e & 3], __uint_as_float(r[c][e]));
+            } else if (c == wq) {
+#pragma unroll
+              for (int e = 0; e < 32; ++e) mx[e & 3] = fmaxf(mx[e & 3], e <= lq ? __uint_as_float(r[c][e]) : -INFINITY);
+            }
+          }
+#pragma unroll
+          for (int u = 0; u < 4; ++u) mx[u] *= scale;       // scale > 0; the diagonal key is always visible: finite max
         } else {
           // masked tile: turn raw scores into logits in place (reference semantics: masked = -1e9, finite)
 #pragma unroll
@@ -333,6 +353,20 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
           if (plain) {
 #pragma unroll
             for (int e = 0; e < 32; ++e) { p[e] = fast_exp2(__uint_as_float(r[c][e]) * sl2 - mb); rs4[e & 3] += p[e]; }
+          } else if (diag_fast) {
+            if (c < wq) {
+#pragma unroll
+              for (int e = 0; e < 32; ++e) { p[e] = fast_exp2(__uint_as_float(r[c][e]) * sl2 - mb); rs4[e & 3] += p[e]; }
+            } else if (c == wq) {
+#pragma unroll
+              for (int e = 0; e < 32; ++e) {
+                p[e] = e <= lq ? fast_exp2(__uint_as_float(r[c][e]) * sl2 - mb) : 0.f;
+                rs4[e & 3] += p[e];
+              }
+            } else {
+#pragma unroll
+              for (int e = 0; e < 32; ++e) p[e] = 0.f;
+            }
           } else {
 #pragma unroll
             for (int e = 0; e < 32; ++e) { p[e] = fast_exp2(__uint_as_float(r[c][e]) * kLog2e - mb); rs4[e & 3] += p[e]; }
@@ -565,6 +599,13 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     constexpr int HC = DK / 2;
     // no padded / out-of-range key among this warp's rows (fixed for the whole CTA)
     const bool rows_clean = !__any_sync(0xffffffffu, kv_pad || !kv_valid);
+    // ... and among ALL 128 keys of this CTA's tile (every lane looks at 4 of them)
+    bool dirty = kv0 + 128 > Sk;
+    if (!dirty && mask.kpad != nullptr) {
+      const uint8_t* kp = mask.kpad + (long long)b * Sk + kv0 + (int)lane * 4;
+      dirty = (kp[0] | kp[1] | kp[2] | kp[3]) != 0;
+    }
+    const bool tile_clean = !__any_sync(0xffffffffu, dirty);
     // lse (x log2 e) / delta of a query tile: thread ctid < 128 fetches lse[q], the others delta[q].  The value for the
     // NEXT tile is fetched one tile ahead so the global-load latency is off the critical path.
     auto load_row = [&](int i) -> float {
@@ -635,6 +676,12 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       named_bar_sync(1, 256);
       const bool diag = mask.causal && (qt0 < kv0 + 128);   // tile touches the causal boundary (some q < kv)
       const bool plain = rows_clean && !diag && mask.maskf == nullptr;   // no mask logic needed in this tile
+      // aligned diagonal tile of a look-ahead mask, nothing else to mask: query col is hidden from key `row` iff col < row.
+      // Per warp (keys 32w..32w+31) and 32-query chunk cc: cc > w plain, cc < w fully hidden (P = dS = 0: no loads, no
+      // exponentials), cc == w mixed.  With the WHOLE key tile clean every query of the tile sees at least its own key, so
+      // no query row here is fully masked (those attend uniformly to all keys, hidden ones included: general path).
+      const bool diag_fast = diag && tile_clean && mask.maskf == nullptr && qt0 == kv0;
+      const int wk = (int)(row >> 5), lk = (int)(row & 31u);
       mbar_wait(sdp_full, n & 1);
       tcgen05_after_thread_sync();
       if (ctid == 0) tl_stamp(64 + (n & 7) * 8 + 2);
@@ -644,11 +691,24 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       for (int c = 0; c < 2; ++c) {
         const int col0 = half * 64 + c * 32;
         uint32_t rs[32], rp[32];
-        tmem_ld_x32(tSt + lane_sel + col0, rs);
-        tmem_ld_x32(tdPt + lane_sel + col0, rp);
-        tmem_ld_wait();
+        const int cc = half * 2 + c;
+        const bool hidden = diag_fast && cc < wk;
         float p[32], ds[32];
-        if (plain) {
+        if (!hidden) {
+          tmem_ld_x32(tSt + lane_sel + col0, rs);
+          tmem_ld_x32(tdPt + lane_sel + col0, rp);
+          tmem_ld_wait();
+        }
+        if (hidden) {
+#pragma unroll
+          for (int e = 0; e < 32; ++e) { p[e] = 0.f; ds[e] = 0.f; }
+        } else if (diag_fast && cc == wk) {
+#pragma unroll
+          for (int e = 0; e < 32; ++e) {
+            p[e] = e >= lk ? fast_exp2(__uint_as_float(rs[e]) * sl2 - rb[col0 + e]) : 0.f;
+            ds[e] = p[e] * (__uint_as_float(rp[e]) * scale - rb[128 + col0 + e]);
+          }
+        } else if (plain || diag_fast) {
 #pragma unroll
           for (int e = 0; e < 32; ++e) {
             p[e] = fast_exp2(__uint_as_float(rs[e]) * sl2 - rb[col0 + e]);
