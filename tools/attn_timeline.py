@@ -10,16 +10,17 @@ dq = torch.zeros(B * S, d, device=dev); dqkv = torch.empty(B * S, 3 * d, device=
 kpad = torch.zeros(B, S, dtype=torch.uint8, device=dev); sp = L.stream_ptr()
 Q, K, V = qkv[:, :d], qkv[:, d:2 * d], qkv[:, 2 * d:]
 tl = torch.zeros(256, dtype=torch.int64, device=dev)
+SEL = int(sys.argv[1]) if len(sys.argv) > 1 else -1      # blockIdx.x of the traced CTA (-1: last)
 for causal in (0, 1):
     for it in range(2):
         L.call("b200xf_debug_set_timeline", L.ptr(tl))
-        tl.zero_()
+        tl.zero_(); tl[255] = SEL
         L.call("b200xf_attn_fwd", L.ptr(Q), 3 * d, L.ptr(K), 3 * d, L.ptr(V), 3 * d, L.ptr(O), d, L.ptr(lse), L.ptr(kpad), causal, None, 0, 0, B, H, S, S, dk, sp)
         torch.cuda.synchronize()
         f = tl.cpu().tolist()
-        tl.zero_()
+        tl.zero_(); tl[255] = SEL
         L.call("b200xf_attn_delta", L.ptr(O), d, L.ptr(dO), d, L.ptr(delta), B, S, H, dk, sp)
-        L.call("b200xf_attn_bwd", L.ptr(Q), 3 * d, L.ptr(K), 3 * d, L.ptr(V), 3 * d, L.ptr(dO), d, L.ptr(lse), L.ptr(delta), L.ptr(dq), d,
+        L.call("b200xf_attn_bwd", L.ptr(Q), 3 * d, L.ptr(K), 3 * d, L.ptr(V), 3 * d, L.ptr(dO), d, L.ptr(lse), L.ptr(delta), L.ptr(dq), d, 0,
                L.ptr(dqkv[:, d:2 * d]), 3 * d, L.ptr(dqkv[:, 2 * d:]), 3 * d, L.ptr(kpad), causal, None, 0, 0, B, H, S, S, dk, sp)
         torch.cuda.synchronize()
         bw = tl.cpu().tolist()

@@ -16,10 +16,14 @@
 
 namespace bx {
 
-// optional debug timeline: clock64 stamps written by CTA (0,0,0) when a buffer has been registered
+// optional debug timeline: clock64 stamps written by the LAST CTA of the grid (last wave: warm instruction cache; with a
+// look-ahead mask the forward CTA with the most tiles) when a buffer has been registered
 __device__ long long* g_timeline = nullptr;
 __device__ __forceinline__ void tl_stamp(int slot) {
-  if (g_timeline != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) g_timeline[slot] = clock64();
+  if (g_timeline != nullptr && blockIdx.y == gridDim.y - 1 && blockIdx.z == gridDim.z - 1) {
+    const long long sel = g_timeline[255];              // which blockIdx.x to trace; < 0: the last one
+    if ((long long)blockIdx.x == (sel < 0 ? (long long)gridDim.x - 1 : sel)) g_timeline[slot] = clock64();
+  }
 }
 int set_timeline(long long* dev_ptr) {
   BX_CHECK_CUDA(cudaMemcpyToSymbol(g_timeline, &dev_ptr, sizeof(dev_ptr)));
@@ -72,7 +76,8 @@ constexpr int kMaxPadTiles = 64;       // kv tiles whose pad bits are preloaded 
 // 128-column S row in registers (single pass over TMEM).
 constexpr int ATTN_FWD_THREADS = 384;
 
-template <int DK>
+// kMaskF: an arbitrary float mask is given (its own instantiation: one more global load per score; every chunk "touched")
+template <int DK, bool kMaskF>
 __global__ void __launch_bounds__(ATTN_FWD_THREADS, 1)
 attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                 const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmO,
@@ -99,21 +104,9 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   const int q0 = blockIdx.x * 256;
   const int n_slots = (q0 + 128 < Sq) ? 2 : 1;
   const int nkv = (Sk + 127) / 128;
-  // tiles each slot must visit.  Causal rows only see keys <= query index -- unless key 0 of this batch row is
-  // padding, in which case some rows may be fully masked and (reference semantics) attend uniformly to ALL keys.
-  int nt[2];
-  {
-    const bool lead_pad = mask.causal && mask.kpad != nullptr && mask.kpad[(long long)b * Sk] != 0;
-    for (int s = 0; s < 2; ++s) {
-      int n = nkv;
-      if (mask.causal && !lead_pad) {
-        const int last_q = min(q0 + s * 128 + 127, Sq - 1);
-        n = min(nkv, last_q / 128 + 1);
-      }
-      nt[s] = s < n_slots ? n : 0;
-    }
-  }
-  const int ntiles = max(nt[0], nt[1]);
+  // key 0 of this batch row (look-ahead mask only): the load is in flight during the prologue below, its value is
+  // first needed for the tile counts after the block-wide sync
+  const uint8_t lead_byte = (mask.causal && mask.kpad != nullptr) ? mask.kpad[(long long)b * Sk] : (uint8_t)0;
 
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&tmQ); prefetch_tmap(&tmK); prefetch_tmap(&tmV); prefetch_tmap(&tmO);
@@ -130,6 +123,21 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   tcgen05_after_thread_sync();
   const uint32_t tmem_base = *tmem_ptr;
   if (threadIdx.x == 64) tl_stamp(1);
+  // tiles each slot must visit.  Causal rows only see keys <= query index -- unless key 0 of this batch row is
+  // padding, in which case some rows may be fully masked and (reference semantics) attend uniformly to ALL keys.
+  int nt[2];
+  {
+    const bool lead_pad = lead_byte != 0;
+    for (int s = 0; s < 2; ++s) {
+      int n = nkv;
+      if (mask.causal && !lead_pad) {
+        const int last_q = min(q0 + s * 128 + 127, Sq - 1);
+        n = min(nkv, last_q / 128 + 1);
+      }
+      nt[s] = s < n_slots ? n : 0;
+    }
+  }
+  const int ntiles = max(nt[0], nt[1]);
   const uint32_t tS[2] = {tmem_base, tmem_base + 128};
   const uint32_t tO[2] = {tmem_base + 256, tmem_base + 256 + DK};
 
@@ -221,7 +229,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     if (s < n_slots) {
       const uint32_t lane_sel = (quad * 32u) << 16;
       const uint32_t sPs = smem_u32(smem + L::OFF_P + s * C::P_BYTES);
-      const float* mrow = mask.maskf ? mask.maskf + (long long)b * mask.sb + (long long)min(q, Sq - 1) * mask.sq : nullptr;
+      const float* mrow = kMaskF ? mask.maskf + (long long)b * mask.sb + (long long)min(q, Sq - 1) * mask.sq : nullptr;
       const float sl2 = scale * kLog2e;
       // ---- key-padding bits of every kv tile this slot visits: loaded ONCE into smem (a global load per tile on the
       //      critical path costs ~1000 cycles); bit e of word 4*tile+c <-> key 128*tile + 32*c + e
@@ -244,35 +252,37 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         }
         named_bar_sync(1 + s, 128);
       }
-      // running state.  The subtracted maximum `m_used` is STALE by design: it is only raised (and O, l rescaled) when
-      // the tile maximum exceeds it by more than 2^8, so P stays <= 256 and the per-tile O correction is rare.
+      // running state, in the log2 domain (logit * log2 e).  The subtracted maximum `m_used` is STALE by design: it is only
+      // raised (and O, l rescaled) when the tile maximum exceeds it by more than 8 (a factor 2^8), so P stays <= 256 and
+      // the per-tile O correction is rare.
       float m_used = -INFINITY, l_run = 0.f;
+      // a hidden key holds the RAW score kMaskRaw: times scale it is the reference's finite -1e9 logit (Attention.py:25-26)
+      const float kMaskRaw = kMaskVal / scale;
 
       for (int j = 0; j < nt[s]; ++j) {
         const int kv0 = j * 128;
-        uint32_t padbits[4], oobbits[4];
+        // ---- per-thread mask words of this tile: bit e of bm[c] = key kv0+32c+e is hidden from this query (padding or
+        //      look-ahead: finite -1e9 logit), of bo[c] = the key does not exist (-inf).  ONE code path serves every mask
+        //      (three unrolled variants of the 128-element passes overflowed the instruction cache: icc hit rate 54 %,
+        //      "no instruction" the top stall); a 32-key chunk with no bit set in the whole warp takes the clean body.
+        uint32_t bm[4], bo[4];
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
           const int k0 = kv0 + c * 32;
-          oobbits[c] = k0 + 32 <= Sk ? 0u : (k0 >= Sk ? 0xffffffffu : (0xffffffffu << (Sk - k0)));
-          if (mask.kpad == nullptr) padbits[c] = 0u;
-          else if (pad_pre) padbits[c] = padw[j * 4 + c];
+          bo[c] = k0 + 32 <= Sk ? 0u : (k0 >= Sk ? 0xffffffffu : (0xffffffffu << (Sk - k0)));
+          uint32_t pb;
+          if (mask.kpad == nullptr) pb = 0u;
+          else if (pad_pre) pb = padw[j * 4 + c];
           else {
             const int kv = k0 + (int)lane;
-            padbits[c] = __ballot_sync(0xffffffffu, kv < Sk && mask.kpad[(long long)b * Sk + kv] != 0);
+            pb = __ballot_sync(0xffffffffu, kv < Sk && mask.kpad[(long long)b * Sk + kv] != 0);
           }
+          if (mask.causal) {                       // keys k0 + e > q are hidden
+            const int dq = q - k0;
+            pb |= dq >= 31 ? 0u : (dq < 0 ? 0xffffffffu : (0xfffffffeu << dq));
+          }
+          bm[c] = pb;
         }
-        const bool diag = mask.causal && (kv0 + 127 > q0 + s * 128);   // tile touches the causal boundary
-        // a tile with no padded / out-of-range key, off the causal boundary and without a float mask needs no
-        // per-element mask logic: the common case for every tile but the diagonal / tail ones
-        const bool clean = mrow == nullptr &&
-                           ((padbits[0] | padbits[1] | padbits[2] | padbits[3] | oobbits[0] | oobbits[1] | oobbits[2] | oobbits[3]) == 0u);
-        const bool plain = !diag && clean;
-        // the aligned diagonal tile of a look-ahead mask with nothing else to mask: key c*32+e is hidden from query
-        // `row` iff c*32+e > row.  Per warp (rows 32w..32w+31) that is uniform for 3 of the 4 32-key chunks: c < w fully
-        // visible (plain), c > w fully hidden (p = exp(-1e9 - m) = 0 exactly: no loads, no exponentials), c == w mixed.
-        const bool diag_fast = diag && clean && (kv0 == q0 + s * 128);
-        const int wq = (int)(row >> 5), lq = (int)(row & 31u);
         const bool tl = (s == 0 && wg_tid == 0);
         if (tl) tl_stamp(8 + j * 8 + 0);
         mbar_wait(&s_full[s], j & 1);
@@ -281,54 +291,39 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         // ---- the whole 128-column S row of this thread, ONE pass over TMEM
         uint32_t r[4][32];
 #pragma unroll
-        for (int c = 0; c < 4; ++c)
-          if (!diag_fast || c <= wq) tmem_ld_x32(tS[s] + lane_sel + c * 32, r[c]);
+        for (int c = 0; c < 4; ++c) tmem_ld_x32(tS[s] + lane_sel + c * 32, r[c]);
         tmem_ld_wait();
         tcgen05_before_thread_sync();
         mbar_arrive(&s_free[s]);                       // the next tile's S may overwrite tensor memory now
+        // ---- pass 1: apply the mask words to the raw scores (in place), row maximum
         float mx[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
-        if (plain) {
+        bool hidden[4];                                // the whole chunk is hidden for every row of this warp
 #pragma unroll
-          for (int c = 0; c < 4; ++c)
-#pragma unroll
-            for (int e = 0; e < 32; ++e) mx[e & 3] = fmaxf(mx[e & 3], __uint_as_float(r[c][e]));
-#pragma unroll
-          for (int u = 0; u < 4; ++u) mx[u] *= scale;
-        } else if (diag_fast) {
-#pragma unroll
-          for (int c = 0; c < 4; ++c) {
-            if (c < wq) {
-#pragma unroll
-              for (int e = 0; e < 32; ++e) mx[e & 3] = fmaxf(mx[e & 3], __uint_as_float(r[c][e]));
-            } else if (c == wq) {
-#pragma unroll
-              for (int e = 0; e < 32; ++e) mx[e & 3] = fmaxf(mx[e & 3], e <= lq ? __uint_as_float(r[c][e]) : -INFINITY);
-            }
-          }
-#pragma unroll
-          for (int u = 0; u < 4; ++u) mx[u] *= scale;       // scale > 0; the diagonal key is always visible: finite max
-        } else {
-          // masked tile: turn raw scores into logits in place (reference semantics: masked = -1e9, finite)
-#pragma unroll
-          for (int c = 0; c < 4; ++c)
+        for (int c = 0; c < 4; ++c) {
+          const bool touched = kMaskF || __any_sync(0xffffffffu, (bm[c] | bo[c]) != 0u);
+          hidden[c] = !kMaskF && __all_sync(0xffffffffu, bm[c] == 0xffffffffu);
+          if (touched) {
 #pragma unroll
             for (int e = 0; e < 32; ++e) {
-              const int kv = kv0 + c * 32 + e;
-              float t = __uint_as_float(r[c][e]) * scale;
-              if (((padbits[c] >> e) & 1u) || (diag && kv > q)) t = kMaskVal;
-              if (mrow != nullptr && kv < Sk) t += mrow[kv] * kMaskVal;
-              if ((oobbits[c] >> e) & 1u) t = -INFINITY;
+              float t = __uint_as_float(r[c][e]);
+              if (bm[c] & (1u << e)) t = kMaskRaw;
+              if (kMaskF) { const int kv = kv0 + c * 32 + e; if (kv < Sk) t += mrow[kv] * kMaskRaw; }
+              if (bo[c] & (1u << e)) t = -INFINITY;
               r[c][e] = __float_as_uint(t);
               mx[e & 3] = fmaxf(mx[e & 3], t);
             }
+          } else {
+#pragma unroll
+            for (int e = 0; e < 32; ++e) mx[e & 3] = fmaxf(mx[e & 3], __uint_as_float(r[c][e]));
+          }
         }
-        const float m_tile = fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3]));
+        const float m_tile = fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3])) * sl2;     // sl2 > 0
         if (tl) tl_stamp(8 + j * 8 + 2);
         // ---- lazy rescale
-        const bool need = (j > 0) && ((m_tile - m_used) * kLog2e > 8.f);
+        const bool need = (j > 0) && (m_tile - m_used > 8.f);
         if (j == 0) m_used = m_tile;
         if (__any_sync(0xffffffffu, need)) {
-          const float alpha = need ? fast_exp2((m_used - m_tile) * kLog2e) : 1.f;
+          const float alpha = need ? fast_exp2(m_used - m_tile) : 1.f;
           if (need) { m_used = m_tile; l_run *= alpha; }
           mbar_wait(&o_full[s], (j - 1) & 1);            // P.V of the previous tile has landed in TMEM
           tcgen05_after_thread_sync();
@@ -343,36 +338,24 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
           }
           tmem_st_wait();
         }
-        const float mb = m_used * kLog2e;
-        // ---- p = exp(t - m_used), row sum (fp32, 4 partial sums), P -> bf16 pairs in registers
+        // ---- p = 2^(raw * scale * log2 e - m_used), row sum (fp32, 4 partial sums), P -> bf16 pairs in registers.
+        //      A chunk hidden for the whole warp contributes exactly 0 (2^(-1.44e9 - m) underflows) unless some row of the
+        //      warp is fully masked so far (m_used is then the -1e9 level itself and those keys count: uniform attention)
+        const bool real_max = __all_sync(0xffffffffu, m_used > -1e8f);
         float rs4[4] = {0.f, 0.f, 0.f, 0.f};
         uint32_t pk[4][16];
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
-          float p[32];
-          if (plain) {
+          if (hidden[c] && real_max) {
 #pragma unroll
-            for (int e = 0; e < 32; ++e) { p[e] = fast_exp2(__uint_as_float(r[c][e]) * sl2 - mb); rs4[e & 3] += p[e]; }
-          } else if (diag_fast) {
-            if (c < wq) {
-#pragma unroll
-              for (int e = 0; e < 32; ++e) { p[e] = fast_exp2(__uint_as_float(r[c][e]) * sl2 - mb); rs4[e & 3] += p[e]; }
-            } else if (c == wq) {
-#pragma unroll
-              for (int e = 0; e < 32; ++e) {
-                p[e] = e <= lq ? fast_exp2(__uint_as_float(r[c][e]) * sl2 - mb) : 0.f;
-                rs4[e & 3] += p[e];
-              }
-            } else {
-#pragma unroll
-              for (int e = 0; e < 32; ++e) p[e] = 0.f;
-            }
+            for (int g = 0; g < 16; ++g) pk[c][g] = 0u;
           } else {
+            float p[32];
 #pragma unroll
-            for (int e = 0; e < 32; ++e) { p[e] = fast_exp2(__uint_as_float(r[c][e]) * kLog2e - mb); rs4[e & 3] += p[e]; }
+            for (int e = 0; e < 32; ++e) { p[e] = fast_exp2(__uint_as_float(r[c][e]) * sl2 - m_used); rs4[e & 3] += p[e]; }
+#pragma unroll
+            for (int g = 0; g < 16; ++g) pk[c][g] = pack_bf16x2(p[2 * g], p[2 * g + 1]);
           }
-#pragma unroll
-          for (int g = 0; g < 16; ++g) pk[c][g] = pack_bf16x2(p[2 * g], p[2 * g + 1]);
         }
         // the P smem tile of this slot is still being read by P.V of the previous kv tile until o_full fires
         // (S(j) was issued BEFORE that P.V, so s_full alone does not order them)
@@ -391,7 +374,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         mbar_arrive(&p_full[s]);
         if (tl) tl_stamp(8 + j * 8 + 4);
       }
-      // finalise: O (TMEM) / l -> bf16 -> smem (reuse this slot's P buffer) -> TMA store ; lse = m_used + ln(l)
+      // finalise: O (TMEM) / l -> bf16 -> smem (reuse this slot's P buffer) -> TMA store ; lse = (m_used + log2 l) ln 2
       mbar_wait(&o_full[s], (nt[s] - 1) & 1);
       tcgen05_after_thread_sync();
       if (s == 0 && wg_tid == 0) tl_stamp(2);
@@ -409,7 +392,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
                        pack_bf16x2(__uint_as_float(ro[8 * g + 4]) * inv, __uint_as_float(ro[8 * g + 5]) * inv),
                        pack_bf16x2(__uint_as_float(ro[8 * g + 6]) * inv, __uint_as_float(ro[8 * g + 7]) * inv));
       }
-      if (q < Sq) lse_out[((long long)b * H + h) * Sq + q] = m_used + __logf(l_run);
+      if (q < Sq) lse_out[((long long)b * H + h) * Sq + q] = (m_used + __log2f(l_run)) * 0.6931471805599453f;   // back to natural log
       tcgen05_before_thread_sync();
       fence_proxy_async_smem();
       named_bar_sync(1 + s, 128);
@@ -843,10 +826,11 @@ static int attn_fwd_launch(const void* Q, long long ld_q, const void* K, long lo
   if ((rc = encode_tmap_3d(&tmK, 0, K, (uint64_t)H * DK, Sk, B, ld_k, (uint64_t)Sk * ld_k, DK, 128, 1, swz))) return rc;
   if ((rc = encode_tmap_3d(&tmV, 0, V, (uint64_t)H * DK, Sk, B, ld_v, (uint64_t)Sk * ld_v, DK, 128, 1, swz))) return rc;
   if ((rc = encode_tmap_3d(&tmO, 0, O, (uint64_t)H * DK, Sq, B, ld_o, (uint64_t)Sq * ld_o, DK, 128, 1, swz))) return rc;
-  auto kern = attn_fwd_kernel<DK>;
+  auto kern = mask.maskf != nullptr ? attn_fwd_kernel<DK, true> : attn_fwd_kernel<DK, false>;
   static bool attr_done = false;
   if (!attr_done) {
-    BX_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::BYTES));
+    BX_CHECK_CUDA(cudaFuncSetAttribute(attn_fwd_kernel<DK, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::BYTES));
+    BX_CHECK_CUDA(cudaFuncSetAttribute(attn_fwd_kernel<DK, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::BYTES));
     attr_done = true;
   }
   dim3 grid((Sq + 255) / 256, H, B);
