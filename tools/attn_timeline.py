@@ -20,7 +20,7 @@ for causal in (0, 1):
         f = tl.cpu().tolist()
         tl.zero_(); tl[255] = SEL
         L.call("b200xf_attn_delta", L.ptr(O), d, L.ptr(dO), d, L.ptr(delta), B, S, H, dk, sp)
-        L.call("b200xf_attn_bwd", L.ptr(Q), 3 * d, L.ptr(K), 3 * d, L.ptr(V), 3 * d, L.ptr(dO), d, L.ptr(lse), L.ptr(delta), L.ptr(dq), d, 0,
+        L.call("b200xf_attn_bwd", L.ptr(Q), 3 * d, L.ptr(K), 3 * d, L.ptr(V), 3 * d, L.ptr(dO), d, L.ptr(lse), L.ptr(delta), L.ptr(dqkv), 3 * d, 1,
                L.ptr(dqkv[:, d:2 * d]), 3 * d, L.ptr(dqkv[:, 2 * d:]), 3 * d, L.ptr(kpad), causal, None, 0, 0, B, H, S, S, dk, sp)
         torch.cuda.synchronize()
         bw = tl.cpu().tolist()
@@ -32,6 +32,6 @@ for causal in (0, 1):
     t0 = bw[60]
     print(f"BWD causal={causal}: epilogue start {bw[61]-t0} end {bw[62]-t0}")
     for n in range(4):
-        e = bw[64 + n * 8: 64 + n * 8 + 6]
+        e = bw[64 + n * 8: 64 + n * 8 + 8]
         if e[0]: print(f"   tile {n}: start {e[0]-t0:6d} | waitSdP {e[2]-e[0]:5d} compute+st {e[3]-e[2]:5d} | dq_full(n) seen at {e[4]-t0:6d} reduce issued {e[5]-t0:6d}")
 L.call("b200xf_debug_set_timeline", None)

@@ -19,12 +19,15 @@ namespace bx {
 // optional debug timeline: clock64 stamps written by the LAST CTA of the grid (last wave: warm instruction cache; with a
 // look-ahead mask the forward CTA with the most tiles) when a buffer has been registered
 __device__ long long* g_timeline = nullptr;
-__device__ __forceinline__ void tl_stamp(int slot) {
-  if (g_timeline != nullptr && blockIdx.y == gridDim.y - 1 && blockIdx.z == gridDim.z - 1) {
-    const long long sel = g_timeline[255];              // which blockIdx.x to trace; < 0: the last one
-    if ((long long)blockIdx.x == (sel < 0 ? (long long)gridDim.x - 1 : sel)) g_timeline[slot] = clock64();
-  }
+// the pointer is fetched ONCE per thread at kernel entry (tl_begin): a stamp site then costs a register test, not a global
+// load inside the hot loops
+__device__ __forceinline__ long long* tl_begin() {
+  long long* t = g_timeline;
+  if (t == nullptr || blockIdx.y != gridDim.y - 1 || blockIdx.z != gridDim.z - 1) return nullptr;
+  const long long sel = t[255];                           // which blockIdx.x to trace; < 0: the last one
+  return (long long)blockIdx.x == (sel < 0 ? (long long)gridDim.x - 1 : sel) ? t : nullptr;
 }
+#define tl_stamp(slot) do { if (tlp != nullptr) tlp[slot] = clock64(); } while (0)
 int set_timeline(long long* dev_ptr) {
   BX_CHECK_CUDA(cudaMemcpyToSymbol(g_timeline, &dev_ptr, sizeof(dev_ptr)));
   return 0;
@@ -99,6 +102,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 18);
 
   const uint32_t warp = warp_idx(), lane = lane_idx();
+  long long* const tlp = tl_begin();
   if (threadIdx.x == 64) tl_stamp(0);
   const int b = blockIdx.z, h = blockIdx.y;
   const int q0 = blockIdx.x * 256;
@@ -438,7 +442,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
                 const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmdO,
                 const __grid_constant__ CUtensorMap tmdK, const __grid_constant__ CUtensorMap tmdV,
                 const __grid_constant__ CUtensorMap tmdQ, const float* __restrict__ lse, const float* __restrict__ delta,
-                AttnMask mask, int H, int Sq, int Sk, float scale) {
+                AttnMask mask, int H, int Sq, int Sk, float scale, __nv_bfloat16* dq16, long long ld_dq16) {
   using C = AttnCfg<DK>;
   using L = BwdSmem<DK>;
   extern __shared__ uint8_t smem_raw[];
@@ -456,6 +460,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   float* rowbuf = reinterpret_cast<float*>(smem + L::OFF_ROW);
 
   const uint32_t warp = warp_idx(), lane = lane_idx();
+  long long* const tlp = tl_begin();
   if (threadIdx.x == 64) tl_stamp(60);
   const int b = blockIdx.z, h = blockIdx.y, jt = blockIdx.x;
   const int kv0 = jt * 128;
@@ -591,23 +596,32 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     const bool tile_clean = !__any_sync(0xffffffffu, dirty);
     // lse (x log2 e) / delta of a query tile: thread ctid < 128 fetches lse[q], the others delta[q].  The value for the
     // NEXT tile is fetched one tile ahead so the global-load latency is off the critical path.
-    auto load_row = [&](int i) -> float {
+    // The value for the NEXT tile travels global -> shared memory by cp.async (no register in between: a register copy was
+    // multiplied / spilled right after the load, which made every thread wait out the whole global-load latency --
+    // ~1400 of ~4500 cycles per tile) and is scaled in place once it has landed, one tile later.
+    const float* const row_src = (ctid < 128 ? lse : delta) + ((long long)b * H + h) * Sq;
+    const float row_oob = ctid < 128 ? INFINITY : 0.f;                  // +inf lse for out-of-range queries -> p = 0
+    const float row_mul = ctid < 128 ? kLog2e : scale;                  // lse in the log2 domain; delta pre-multiplied by 1/sqrt(dk)
+    auto prefetch_row = [&](int i, float* buf) {
       const int qq = i * 128 + (ctid & 127);
-      const long long off = ((long long)b * H + h) * Sq + qq;
-      if (ctid < 128) return qq < Sq ? lse[off] * kLog2e : INFINITY;    // +inf for out-of-range queries -> p = 0
-      return qq < Sq ? delta[off] * scale : 0.f;                        // delta pre-multiplied by 1/sqrt(dk)
+      if (qq < Sq) {
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" :: "r"(smem_u32(buf + ctid)), "l"(row_src + qq) : "memory");
+      } else {
+        buf[ctid] = row_oob;
+      }
+      asm volatile("cp.async.commit_group;" ::: "memory");
     };
     // dQ tile of query tile `qt`: row = query, this warp's half of the dk columns -> fp32 smem staging -> ONE TMA
     // reduce-add per half (cp.reduce.async.bulk.tensor .add.f32; rows >= Sq are clipped by TMA)
     auto dq_epilogue = [&](int n_done, int qt0) {
       mbar_wait(dq_full, n_done & 1);
       tcgen05_after_thread_sync();
-      if (ctid == 0) { tl_stamp(64 + (n_done & 7) * 8 + 4); tma_store_wait_read<0>(); }   // previous reduce has drained the staging
-      named_bar_sync(2, 256);
-      const uint32_t stg = sDQ + half * C::TILE_BYTES;
+      if (ctid == 0) tl_stamp(64 + (n_done & 7) * 8 + 4);
       if (kDqBf16) {
-        // bf16 dQ: one [128 x DK] bf16 staging tile (this warp's half of the columns), reduce-added by TMA straight into
-        // the bf16 dQ tensor (cp.reduce.async.bulk.tensor .add on a bf16 tensor map) -- no fp32 accumulator, no cast pass
+        // bf16 dQ: straight from tensor memory to global memory.  This thread owns query row `row` and HC contiguous columns
+        // (2*HC bytes): red.global.add.noftz.v4.bf16x2 adds 16 bytes per instruction, fire-and-forget -- no smem staging,
+        // no block barrier, no TMA.  (One thread issuing a TMA reduce-add stalled ~1300 cycles at its next memory
+        // instruction, and the loop-top barrier passed that on to all 256 compute threads, every tile.)
         float v[HC];
         if (HC == 32) {
           uint32_t r[32];
@@ -620,11 +634,27 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
 #pragma unroll
           for (int e = 0; e < HC; ++e) v[e] = __uint_as_float(r[e]);
         }
+        tcgen05_before_thread_sync();
+        mbar_arrive(dq_free);                    // the dQ accumulator may be overwritten by the next tile's MMA
+        const int qq = qt0 + (int)row;
+        if (qq < Sq) {
+          __nv_bfloat16* dst = dq16 + ((long long)b * Sq + qq) * ld_dq16 + h * DK + half * HC;
 #pragma unroll
-        for (int g = 0; g < HC / 8; ++g)
-          st_shared_v4(sDQ + swz_off<DK>(row, half * (HC / 8) + g), pack_bf16x2(v[8 * g], v[8 * g + 1]), pack_bf16x2(v[8 * g + 2], v[8 * g + 3]),
-                       pack_bf16x2(v[8 * g + 4], v[8 * g + 5]), pack_bf16x2(v[8 * g + 6], v[8 * g + 7]));
-      } else if (HC == 32) {
+          for (int g = 0; g < HC / 8; ++g)
+            asm volatile("red.global.add.noftz.v4.bf16x2 [%0], {%1, %2, %3, %4};" ::"l"(dst + 8 * g), "r"(pack_bf16x2(v[8 * g], v[8 * g + 1])),
+                         "r"(pack_bf16x2(v[8 * g + 2], v[8 * g + 3])), "r"(pack_bf16x2(v[8 * g + 4], v[8 * g + 5])),
+                         "r"(pack_bf16x2(v[8 * g + 6], v[8 * g + 7]))
+                         : "memory");
+        }
+        if (ctid == 0) tl_stamp(64 + (n_done & 7) * 8 + 5);
+        return;
+      }
+      // fp32 dQ (tests, other callers): row = query, this warp's half of the dk columns -> fp32 smem staging -> one TMA
+      // reduce-add per half (cp.reduce.async.bulk.tensor .add.f32; rows >= Sq are clipped by TMA)
+      if (ctid == 0) tma_store_wait_read<0>();   // the previous reduce has drained the staging
+      named_bar_sync(2, 256);
+      const uint32_t stg = sDQ + half * C::TILE_BYTES;
+      if (HC == 32) {
         uint32_t r[32];
         tmem_ld_x32(tdQ + lane_sel + half * HC, r);
         tmem_ld_wait();
@@ -643,20 +673,21 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       named_bar_sync(3, 256);
       if (ctid == 0) {
         tma_reduce_add_3d(&tmdQ, smem + L::OFF_DQ, h * DK, qt0, b);
-        if (!kDqBf16) tma_reduce_add_3d(&tmdQ, smem + L::OFF_DQ + C::TILE_BYTES, h * DK + HC, qt0, b);
+        tma_reduce_add_3d(&tmdQ, smem + L::OFF_DQ + C::TILE_BYTES, h * DK + HC, qt0, b);
         tma_store_commit();
         tl_stamp(64 + (n_done & 7) * 8 + 5);
       }
     };
-    float row_next = load_row(i_start);
+    prefetch_row(i_start, rowbuf);
     int n = 0;
     for (int i = i_start; i < nq; ++i, ++n) {
       const int qt0 = i * 128;
       float* rb = rowbuf + (n & 1) * 256;
-      rb[ctid] = row_next;
-      if (i + 1 < nq) row_next = load_row(i + 1);
+      asm volatile("cp.async.wait_group 0;" ::: "memory");      // this thread's element of tile n has landed ...
+      rb[ctid] *= row_mul;                                      // ... scale it in place (inf / 0 stay what they are)
       if (ctid == 0) tl_stamp(64 + (n & 7) * 8 + 0);
-      named_bar_sync(1, 256);
+      named_bar_sync(1, 256);                                   // every thread is past tile n-1: its row buffer may be refilled
+      if (i + 1 < nq) prefetch_row(i + 1, rowbuf + ((n + 1) & 1) * 256);
       const bool diag = mask.causal && (qt0 < kv0 + 128);   // tile touches the causal boundary (some q < kv)
       const bool plain = rows_clean && !diag && mask.maskf == nullptr;   // no mask logic needed in this tile
       // aligned diagonal tile of a look-ahead mask, nothing else to mask: query col is hidden from key `row` iff col < row.
@@ -868,7 +899,7 @@ static int attn_bwd_launch(const void* Q, long long ld_q, const void* K, long lo
   dim3 grid((Sk + 127) / 128, H, B);
   void* pb = prof_on() ? prof_begin(st) : nullptr;
   kern<<<grid, ATTN_BWD_THREADS, L::BYTES, st>>>(tmQ, tmK, tmV, tmdO, tmdK, tmdV, tmdQ, lse, delta, mask, H, Sq, Sk,
-                                                 1.f / sqrtf((float)DK));
+                                                 1.f / sqrtf((float)DK), (__nv_bfloat16*)dq_acc, ld_dq);
   if (pb) prof_end(pb, 2, 8.0 * B * H * (double)Sq * Sk * DK, st);     // 2x the forward's 4.B.H.Sq.Sk.dk
   BX_POST_LAUNCH();
   return 0;
