@@ -192,3 +192,39 @@ def test_text_pipeline_semantics(tmp_path):
     assert st.decode(st.encode(s)) == s
     train2, _, st2, _ = utils.load_dataset(str(tmp_path) + "/", 8, sv, tv, 16, 1000)
     assert st2.vocab_size == st.vocab_size and torch.equal(train2[0][0], train[0][0])
+
+
+def _c_kind(decl):
+    """coarse kind of one C parameter declaration: 'p' pointer, 'f' float, 'i64' 64-bit integer, 'i' 32-bit integer"""
+    d = decl.strip()
+    if "*" in d or d.startswith("b200xf_stream_t"):
+        return "p"
+    t = " ".join(d.split()[:-1]) if len(d.split()) > 1 else d
+    if t in ("float",):
+        return "f"
+    if t in ("int64_t", "uint64_t", "long long", "unsigned long long"):
+        return "i64"
+    if t in ("int", "uint32_t", "int32_t", "unsigned", "unsigned int"):
+        return "i"
+    raise AssertionError(f"unclassified C parameter '{d}'")
+
+
+def test_ctypes_signatures_match_the_header():
+    """include/b200xf.h is the contract; transformer_b200/_lib.py must bind every entry with the same number of
+    parameters and the same kind (pointer / float / 32- / 64-bit integer) in every position -- an ABI drift between the
+    two would otherwise only show up as garbage arguments on the GPU box."""
+    header = open(os.path.join(ROOT, "include", "b200xf.h")).read()
+    header = re.sub(r"/\*.*?\*/", " ", header, flags=re.S)
+    protos = dict(re.findall(r"\b(b200xf_[a-z0-9_]+)\s*\(([^;{]*?)\)\s*;", header, flags=re.S))
+    kinds = {C.c_void_p: "p", C.c_char_p: "p", C.c_float: "f", C.c_int64: "i64", C.c_uint64: "i64", C.c_longlong: "i64",
+             C.c_int: "i", C.c_uint32: "i", C.c_int32: "i"}
+    checked = 0
+    for name, argtypes in L._SIGS.items():
+        assert name in protos, f"{name} bound in _lib.py but not declared in the header"
+        params = [a for a in protos[name].replace("\n", " ").split(",") if a.strip() and a.strip() != "void"]
+        assert len(params) == len(argtypes), f"{name}: header has {len(params)} parameters, _lib.py binds {len(argtypes)}"
+        for i, (decl, at) in enumerate(zip(params, argtypes)):
+            got = kinds.get(at, "p" if hasattr(at, "contents") or issubclass(at, C._Pointer) else None)   # POINTER(struct) etc.
+            assert _c_kind(decl) == got, f"{name} parameter {i} ('{decl.strip()}'): header {_c_kind(decl)} vs ctypes {got}"
+        checked += 1
+    assert checked >= 30
