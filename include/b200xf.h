@@ -57,8 +57,9 @@ int b200xf_attn_fwd(const void* Q, int64_t ld_q, const void* K, int64_t ld_k, co
                     int64_t ld_o, float* lse, const uint8_t* kpad, int causal, const float* maskf, int64_t mask_sb,
                     int64_t mask_sq, int B, int H, int Sq, int Sk, int dk, b200xf_stream_t stream);
 /*      delta: fp32 [B,H,Sq] = rowsum(dO o O) (b200xf_attn_delta); dq_acc: [B*Sq, ld_dq] ZEROED by the caller, fp32
- *      or (dq_is_bf16) bf16 -- every key tile's contribution is reduce-added by TMA (cp.reduce.async.bulk.tensor),
- *      in bf16 directly into the tensor the QKV weight-gradient GEMM reads; dK/dV: bf16 token-major like K/V.     */
+ *      (every key tile's contribution reduce-added by TMA, cp.reduce.async.bulk.tensor) or, with dq_is_bf16, bf16
+ *      (added with red.global.add.v4.bf16x2 directly into the tensor the QKV weight-gradient GEMM reads);
+ *      dK/dV: bf16 token-major like K/V.                                                                        */
 int b200xf_attn_bwd(const void* Q, int64_t ld_q, const void* K, int64_t ld_k, const void* V, int64_t ld_v,
                     const void* dO, int64_t ld_do, const float* lse, const float* delta, void* dq_acc, int64_t ld_dq,
                     int dq_is_bf16, void* dK, int64_t ld_dk, void* dV, int64_t ld_dv, const uint8_t* kpad, int causal,

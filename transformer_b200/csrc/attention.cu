@@ -417,7 +417,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
 // ================================================================================================
 // backward:  one CTA per (kv tile, head, batch); loops over query tiles.
 //   S^T = K.Q^T, dP^T = V.dO^T (TMEM)  ->  P^T = exp(S^T*scale - lse), dS^T = P^T o (dP^T - delta) * scale  (smem, bf16)
-//   dV += P^T.dO   dK += dS^T.Q   (TMEM accumulators over all query tiles)    dQ_tile = dS.K  -> red.add fp32
+//   dV += P^T.dO   dK += dS^T.Q   (TMEM accumulators over all query tiles)    dQ_tile = dS.K  -> added into global dQ (bf16: red.global.v4.bf16x2; fp32: TMA reduce-add)
 // ================================================================================================
 template <int DK>
 struct BwdSmem {
@@ -428,7 +428,7 @@ struct BwdSmem {
   static constexpr uint32_t OFF_DO = OFF_Q + 2 * C::TILE_BYTES;     // 2 stages
   static constexpr uint32_t OFF_DST = OFF_DO + 2 * C::TILE_BYTES;   // dS^T [kv 128][q 128] bf16, two panels, DOUBLE buffered
                                                                     // (P^T lives in tensor memory, not in smem)
-  static constexpr uint32_t OFF_DQ = OFF_DST + 2 * C::P_BYTES;      // dQ tile fp32 [128 x DK] as two [128 x DK/2] boxes (TMA reduce-add staging)
+  static constexpr uint32_t OFF_DQ = OFF_DST + 2 * C::P_BYTES;      // fp32-dQ variant only: dQ tile fp32 [128 x DK] as two [128 x DK/2] boxes (TMA reduce-add staging)
   static constexpr uint32_t OFF_ROW = OFF_DQ + 2 * C::TILE_BYTES;   // lse/delta: 2 buffers x (128 + 128) floats
   static constexpr uint32_t OFF_BAR = OFF_ROW + 2 * 256 * 4;
   static constexpr uint32_t BYTES = OFF_BAR + 256 + 1024;

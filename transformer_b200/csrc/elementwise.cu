@@ -6,7 +6,8 @@
 namespace bx {
 
 // ------------------------------------------------------------------------------------------------
-// counter-based dropout RNG (Philox-4x32-10); keep-mask regenerated in backward from (seed, site, element)
+// counter-based dropout RNG (Philox-4x32-10) keyed by (seed, site, element); the LayerNorm kernels store the keep mask
+// (1 bit per element) in forward and read it back in backward, the embedding kernels regenerate it
 // keras Dropout semantics: keep w.p. 1-rate, scale kept by 1/(1-rate).
 // ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ uint4 philox4x32_10(uint4 ctr, uint2 key) {

@@ -149,7 +149,7 @@ struct Work {
   bf16* gD;                               // [Mmax, d] dgrad output of the last sublayer; the stream gradient is gR + gD
   float* d_enc_out;                       // [Ms, d] fp32: accumulates cross-attention K/V gradients of all decoder layers
   bf16 *dy16, *dO16, *dqkv, *dh;          // [Mmax,d] [Mmax,d] [Mmax,3d] [Mmax,f]
-  bf16* dq16;                             // [Mmax,d] cross-attention dQ (bf16, TMA reduce-add target)
+  bf16* dq16;                             // [Mmax,d] cross-attention dQ (bf16, accumulated by red.global adds)
   float* delta;                           // [B,H,Smax]
   int64_t bytes;
 };
@@ -398,7 +398,7 @@ int self_attn_back(M* m, const MhaSelf& p, const bf16* x16, const bf16* qkv, con
   RC(linear_wgrad(attn_o, d, dy, d, m->G + p.Wo, d, nullptr, rows, d, d, st));                 // dbo: from the LN backward
   RC(linear_dgrad(dy, d, m->Sh + p.Wo, d, w.dO16, d, false, false, nullptr, 0, rows, d, d, st));
   RC(bx::attn_delta(attn_o, d, w.dO16, d, w.delta, B, S, H, dk, st));
-  // dQ is reduce-added (bf16, TMA) straight into the first d columns of the packed QKV gradient: zero them first
+  // dQ is accumulated (bf16 red.global adds) straight into the first d columns of the packed QKV gradient: zero them first
   BX_CHECK_CUDA(cudaMemset2DAsync(w.dqkv, (size_t)3 * d * sizeof(bf16), 0, (size_t)d * sizeof(bf16), rows, st));
   RC(bx::attn_bwd(qkv, 3 * d, qkv + d, 3 * d, qkv + 2 * d, 3 * d, w.dO16, d, lse, w.delta, w.dqkv, 3 * d, 1, w.dqkv + d, 3 * d,
                   w.dqkv + 2 * d, 3 * d, mk.kpad, mk.causal, mk.maskf, mk.sb, mk.sq, B, H, S, S, dk, st));
@@ -445,7 +445,7 @@ int backward_decoder(M* m, cudaStream_t st) {
     RC(linear_dgrad(dy, d, m->Sh + p.mha2.Wo, d, w.dO16, d, false, false, nullptr, 0, Mt, d, d, st));
     RC(bx::attn_delta(a.attn2_o, d, w.dO16, d, w.delta, B, T, H, dk, st));
     BX_CHECK_CUDA(cudaMemsetAsync(w.dq16, 0, Mt * d * sizeof(bf16), st));
-    // dK/dV of the encoder memory go to dqkv[:, 0:2d) viewed as [Ms, 2d]; dQ (bf16, TMA reduce-add) to dq16
+    // dK/dV of the encoder memory go to dqkv[:, 0:2d) viewed as [Ms, 2d]; dQ (bf16 red.global adds) to dq16
     RC(bx::attn_bwd(a.q2, d, a.kv2, 2 * d, a.kv2 + d, 2 * d, w.dO16, d, a.lse2, w.delta, w.dq16, d, 1, w.dqkv, 2 * d, w.dqkv + d, 2 * d,
                     cm.kpad, cm.causal, cm.maskf, cm.sb, cm.sq, B, H, T, S, dk, st));
     RC(linear_wgrad(w.enc_x16[L], d, w.dqkv, 2 * d, m->G + p.mha2.Wkv, 2 * d, m->G + p.mha2.bkv, Ms, 2 * d, d, st));
