@@ -4,13 +4,20 @@ This file is the *oracle*: an op-for-op restatement, in torch-CPU (fp32 or fp64)
 reference builds.  Only ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s ``cpu_baseline`` /
 ``--impl reference`` legs may import it.  The product path (``transformer_b200``) never does.
 
-PARITY UNPINNED: the reference ships no tests, golden vectors or fixtures and TensorFlow
-is not installable here, so this restatement cannot be checked against outputs of the reference itself --
-except ``positional_encoding``, whose NumPy body *does* run under a two-symbol TF stub
-(``oracle/make_golden.py`` -> ``tests/golden/posenc_*.npy``), and the closed-form known answers of
-SURVEY.md Appendix D (``tests/test_oracle.py``).  TF/Keras op semantics are restated from the TF 2.0-era
-public API (third-party ``tensorflow`` package, unpinned: ``assert tf.__version__.startswith('2')``,
-reference ``train.py:19``).
+PARITY PARTLY PINNED.  The reference ships no tests, golden vectors or fixtures and TensorFlow
+is not installable here, so nothing can be checked against the reference running on real TensorFlow: in that sense
+parity is UNPINNED for TensorFlow's own kernels, whose numerics are restated from the TF 2.x public API (third-party
+``tensorflow`` package, unpinned: ``assert tf.__version__.startswith('2')``, reference ``train.py:19``).  What IS
+pinned, against the reference's own source files executed unmodified on a NumPy stand-in for the TF symbols they touch
+(``oracle/tf_numpy_stub.py``, ``oracle/make_golden.py`` -> ``tests/golden/``):
+  * ``positional_encoding`` (bit-exact, ``posenc_*.npy``);
+  * ``create_masks`` (bit-exact), the whole inference-mode forward of a 2-layer ``Transformer`` -- logits and all four
+    attention-weight tensors -- ``Train.loss_function`` and ``CustomSchedule`` (fp32 rounding,
+    ``ref_model_on_numpy_stub.npz``, ``tests/test_oracle.py::test_oracle_matches_reference_code_on_numpy_stub``): i.e.
+    everything the reference itself wrote -- wiring, mask routing, scales, residual order, head split/merge, loss
+    masking and normalisation, the schedule formula;
+plus the closed-form known answers of SURVEY.md Appendix D (``tests/test_oracle.py``).  Not pinned: training-mode
+dropout streams, TF's autodiff (backward here is torch autograd over the restated graph) and Keras' Adam kernel.
 
 Every function cites the reference file:line it follows.
 """

@@ -6,6 +6,7 @@ identical weights and tokens.  Tolerances (bf16 tensor-core operands, fp32 accum
   100-step curve   : every step's loss within 1e-3 relative of the fp32 oracle trained in lock-step
 Run on a B200:  python -m pytest tests -m gpu -x -q"""
 import math
+import os
 
 import numpy as np
 import pytest
@@ -271,3 +272,25 @@ def test_checkpoint_roundtrip_and_predict(tmp_path):
     ids = torch.tensor([[tok.vocab_size] + tok.encode("w1 w2 w3") + [tok.vocab_size + 1]], device="cuda")
     logits, _ = model((ids, out[None, :-1]), training=False)
     assert torch.equal(logits.argmax(-1)[0], out[1:])
+
+
+def test_forward_matches_reference_code_on_numpy_stub(golden_dir):
+    """The CUDA forward against logits / attention weights produced by the reference's OWN Transformer code (run on
+    oracle/tf_numpy_stub.py, fixture tests/golden/ref_model_on_numpy_stub.npz): bf16-operand tolerance."""
+    import numpy as np
+    z = np.load(os.path.join(golden_dir, "ref_model_on_numpy_stub.npz"))
+    L_, d, H, f, Vin, Vt, B = (int(v) for v in z["cfg"])
+    P = {k[2:]: torch.from_numpy(z[k]) for k in z.files if k.startswith("w/")}
+    model = Transformer(L_, d, H, f, Vin, Vt, rate=0.1, pos_rows=64)
+    model.load_variables(P)
+    src, tar = torch.from_numpy(z["src"]), torch.from_numpy(z["tar"])
+    tar_inp = tar[:, :-1]
+    logits, attn = model((src.cuda(), tar_inp.cuda()), training=False)
+    torch.cuda.synchronize()
+    want = torch.from_numpy(z["logits"])
+    assert (logits.cpu() - want).abs().max().item() <= 3e-2 * max(1.0, want.abs().max().item())
+    for k in (k[5:] for k in z.files if k.startswith("attn/")):
+        assert (attn[k].cpu() - torch.from_numpy(z["attn/" + k])).abs().max().item() <= 2e-2, k
+    tr = make_trainer(model, B)
+    lf = tr.loss_function(tar[:, 1:], logits).item()
+    assert abs(lf - float(z["loss"])) <= 1e-3 * abs(float(z["loss"]))

@@ -132,3 +132,38 @@ def test_adam_tf_form_first_steps():
     assert out["lr"] > 0 and any(not torch.equal(before[k], P[k]) for k in P)
     # |update| of the first effective step is bounded by alpha (Adam property with m,v from 2 grads)
     assert st.iterations == 2
+
+
+def _load_reference_fixture(golden_dir):
+    """tests/golden/ref_model_on_numpy_stub.npz: outputs of the reference's OWN model / loss / schedule code executed on
+    oracle/tf_numpy_stub.py (oracle/make_golden.py).  -> (cfg tuple, P as torch fp32, z)"""
+    z = np.load(os.path.join(golden_dir, "ref_model_on_numpy_stub.npz"))
+    L, d, H, f, Vin, Vt, B = (int(v) for v in z["cfg"])
+    P = {k[2:]: torch.from_numpy(z[k]) for k in z.files if k.startswith("w/")}
+    return (L, d, H, f, Vin, Vt, B), P, z
+
+
+def test_oracle_matches_reference_code_on_numpy_stub(golden_dir):
+    """The restatement against the reference's own source files run on a NumPy stand-in for TensorFlow: masks bit-exact,
+    logits / attention weights / loss / schedule to fp32 rounding (the two sides order their fp32 sums differently)."""
+    (L, d, H, f, Vin, Vt, B), P, z = _load_reference_fixture(golden_dir)
+    assert sorted(P) == sorted(R.variable_names(L))                            # same variables, keras names
+    for name, v in P.items():
+        assert tuple(v.shape) == R.variable_shape(name, d, f, Vin, Vt), name
+    src, tar = torch.from_numpy(z["src"]), torch.from_numpy(z["tar"])
+    tar_inp, tar_real = tar[:, :-1], tar[:, 1:]
+    enc_m, comb_m, dec_m = R.create_masks(src, tar_inp)
+    assert np.array_equal(enc_m.numpy(), z["enc_padding_mask"]) and np.array_equal(dec_m.numpy(), z["dec_padding_mask"])
+    assert np.array_equal(comb_m.numpy(), z["combined_mask"])
+    cfg = R.make_cfg(L, d, H, f, Vin, Vt, rate=0.1)                            # pos-enc tables with vocab_size rows, like the reference
+    logits, attn = R.transformer(P, cfg, src, tar_inp, training=False)
+    scale = float(np.abs(z["logits"]).max())
+    assert np.abs(logits.numpy() - z["logits"]).max() <= 2e-5 * max(1.0, scale)
+    keys = sorted(k[5:] for k in z.files if k.startswith("attn/"))
+    assert keys == sorted(attn) and len(keys) == 2 * L
+    for k in keys:
+        assert np.abs(attn[k].numpy() - z["attn/" + k]).max() <= 2e-6, k
+    loss = R.loss_function(tar_real, logits, B).item()
+    assert abs(loss - float(z["loss"])) <= 2e-6 * abs(float(z["loss"]))
+    for step, lr in zip(z["schedule_steps"], z["schedule_lr_d512"]):
+        assert abs(float(R.custom_schedule(float(step), 512)) - float(lr)) <= 1e-6 * max(float(lr), 1e-12), step
