@@ -30,6 +30,13 @@ CONFIGS = {
 }
 
 
+def R_param_count(L, d, f, V):
+    """trainable parameters of the model (both embeddings, L encoder + L decoder layers, final layer)"""
+    mha = 4 * (d * d + d)
+    ffn = d * f + f + f * d + d
+    return 2 * V * d + L * (mha + ffn + 4 * d) + L * (2 * mha + ffn + 6 * d) + d * V + V
+
+
 def step_flops(L, d, f, V, B, S):
     """3 * [L*(24BSd^2 + 12BS^2d + 8BSdf) + 2BSdV]  (S = T)."""
     return 3.0 * (L * (24.0 * B * S * d * d + 12.0 * B * S * S * d + 8.0 * B * S * d * f) + 2.0 * B * S * d * V)
@@ -124,10 +131,15 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     N = max(args.gpus, 1)
-    config = {"workload": f"transformer-base train step {args.config}: {L_}L d{d} {H}h dff{f} V{V} seq_len {S}, {Bper} sequences per GPU"
+    family = {"base": "transformer-base", "big": "transformer-big", "tiny": "tiny transformer"}[args.config.split("_")[0]]
+    # bytes one step streams through HBM at least once: fp32 params/grads/Adam state + bf16 logits + saved activations (rough)
+    work_mb = (R_param_count(L_, d, f, V) * 18 + Bper * S * V * 2 + Bper * S * d * 2 * 20 * L_) / 1e6
+    config = {"workload": f"{family} train step {args.config}: {L_}L d{d} {H}h dff{f} V{V} seq_len {S}, {Bper} sequences per GPU"
                           f" (global batch {Bper * N}), synthetic tokens, dropout {args.dropout_rate}",
               "global_batch": Bper * N, "seq_len": S, "parallelism": f"dp{N}",
-              "l2": "per-step working set (activations+weights+grads >> 126 MB L2) is larger than L2; no explicit flush"}
+              "l2": (f"per-step working set ~{work_mb:.0f} MB (params+grads+Adam state, logits, saved activations) "
+                     + ("is larger than the 126 MB L2; no explicit flush" if work_mb > 126
+                        else "FITS the 126 MB L2: numbers of this config are L2-warm, it is a parity-test shape, not a bench line"))}
 
     if args.impl == "reference":
         if rank != 0:

@@ -228,3 +228,27 @@ def test_ctypes_signatures_match_the_header():
             assert _c_kind(decl) == got, f"{name} parameter {i} ('{decl.strip()}'): header {_c_kind(decl)} vs ctypes {got}"
         checked += 1
     assert checked >= 30
+
+
+def test_bench_reference_arm_contract_and_no_cpu_fallback():
+    """bench.py --impl reference (the oracle on host cores) prints ONE JSON line with the contract's keys; the product arm
+    has no CPU fallback: without a GPU it must fail loudly, never print a number."""
+    import json
+    import subprocess
+    import sys
+    env = dict(os.environ, CUDA_VISIBLE_DEVICES="")
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--config", "tiny_s40_b32", "--steps", "1",
+                          "--warmup", "1"], capture_output=True, text=True, timeout=300, env=env, cwd=ROOT)
+    assert out.returncode == 0, out.stderr[-500:]
+    lines = [l for l in out.stdout.splitlines() if l.startswith("{")]
+    assert len(lines) == 1
+    j = json.loads(lines[0])
+    for k in ("impl", "metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline",
+              "dtype", "data", "config", "e2e", "cpu_baseline"):
+        assert k in j, k
+    assert j["impl"] == "reference" and j["value"] > 0 and j["unit"] == "tokens/s" and "workload" in j["config"]
+    assert j["e2e"]["h2d_bytes_per_step"] == 0 and j["e2e"]["d2h_bytes_per_step"] == 0 and j["e2e"]["value"] == j["value"]
+    assert j["cpu_baseline"]["kind"] == "port" and j["cpu_baseline"]["cores"] >= 1
+    prod = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--config", "tiny_s40_b32", "--steps", "1", "--warmup", "1",
+                           "--no-cpu-baseline"], capture_output=True, text=True, timeout=300, env=env, cwd=ROOT)
+    assert prod.returncode != 0 and not any(l.startswith("{") for l in prod.stdout.splitlines())
