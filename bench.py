@@ -26,6 +26,7 @@ CONFIGS = {
     "base_s512_b64": (6, 512, 8, 2048, 32768, 512, 64),     # BASELINE.json configs[2] -- the metric's "seq512"
     "base_s128_b256": (6, 512, 8, 2048, 32768, 128, 256),   # configs[1]
     "big_s256_b16": (6, 1024, 16, 4096, 32768, 256, 16),    # configs[3] per-GPU share of the global batch 128
+    "big_s256_b128": (6, 1024, 16, 4096, 32768, 256, 128),  # configs[3] with --scaling strong: GLOBAL batch 128 split over N GPUs
     "tiny_s40_b32": (2, 128, 4, 512, 8192, 40, 32),         # configs[0] shape (synthetic tokens)
 }
 
@@ -117,6 +118,141 @@ def cpu_reference_run(cfg_name, steps, warmup, sample_batch):
                 sample=f"{steps} full train steps (fwd+loss+bwd+Adam) of {cfg_name} at batch {sample_batch} (of {CONFIGS[cfg_name][6]}), torch-CPU fp32 oracle, {cores} of {avail} host threads; TF2 not installable"), dt
 
 
+def ncu_traffic():
+    """dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the dominant GEMM from the newest committed per-round ncu
+    --set full summary (profiles/r*_traffic.json, written by tools/ncu_traffic.py from the .ncu-rep); None when absent."""
+    import glob
+    files = sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_traffic.json")))
+    if not files:
+        return None
+    try:
+        j = json.load(open(files[-1]))
+        return {"bytes": j["dram_bytes_per_launch"], "note": f"{os.path.basename(files[-1])}: {j.get('note', '')}"}
+    except Exception:
+        return None
+
+
+def dp_check(rank, world, dev):
+    """Evidence that the data-parallel step is CORRECT, not just running (printed with every N > 1 line):
+    (1) replica agreement: a hash of every rank's parameter arena after the timed steps, min == max over ranks;
+    (2) N-GPU step == 1-GPU step: a small model trained 3 steps on a global batch split over the N replicas (DistributedTrain)
+        against the same 3 steps on rank 0 alone (Train) -- relative weight difference and |loss_N - loss_1| / loss_1."""
+    import torch
+    import torch.distributed as dist
+    from transformer_b200.Transformer import Transformer
+    from transformer_b200.train import Train
+    from transformer_b200.distributed_train import DistributedTrain, MirroredStrategy
+    from transformer_b200.utils import synthetic_batch
+    L_, d, H, f, V = 2, 128, 2, 256, 1003
+    Bg = 4 * world
+    batches = [synthetic_batch(Bg, 40, 33, V, V, seed=50 + i, pad_tail=True) for i in range(3)]
+    strategy = MirroredStrategy()
+    model = Transformer(L_, d, H, f, V, V, rate=0.0, pos_rows=64, device=dev, seed=7 + rank)     # different init per rank:
+    tr = DistributedTrain(1, True, model, None, None, Bg, Bg // world, None, None, 5, "ckpt", d, warmup_steps=50)   # ...broadcast fixes it
+    init = model.params.clone()
+    it = iter(batches)
+    for _ in range(3):
+        strategy.experimental_run(tr.train_step, it)
+    torch.cuda.synchronize()
+    h = torch.stack([model.params.double().sum(), model.params.double().abs().sum(), (model.params.double() ** 2).sum()])
+    lo, hi = h.clone(), h.clone()
+    dist.all_reduce(lo, op=dist.ReduceOp.MIN)
+    dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+    out = {"replica_param_hash_equal": bool(torch.equal(lo, hi))}
+    loss_dp = torch.tensor([tr.train_loss._acc[0].item()], dtype=torch.float64, device=dev)
+    dist.all_reduce(loss_dp, op=dist.ReduceOp.SUM)                      # sum over replicas of the per-replica (local_sum / B_global) losses
+    if rank == 0:
+        single = Transformer(L_, d, H, f, V, V, rate=0.0, pos_rows=64, device=dev)
+        single.params.copy_(init); single._shadow_dirty = True
+        tr1 = Train(1, True, single, None, None, Bg, None, None, 5, "ckpt", d, warmup_steps=50)
+        for b in batches:
+            tr1.train_step(b)
+        torch.cuda.synchronize()
+        out["weights_rel_diff_vs_1gpu"] = (single.params - model.params).norm().item() / single.params.norm().item()
+        l1 = tr1.train_loss._acc[0].item()
+        out["loss_rel_diff_vs_1gpu"] = abs(loss_dp.item() - l1) / abs(l1)
+        out["what"] = f"2L d128 model, global batch {Bg} over {world} replicas, 3 steps, warmup 50 (weights move)"
+    return out
+
+
+def seq_len_sweep(args):
+    """BASELINE config C5: d_model 512, 8 heads (dk 64), S in {64..2048} with B*S = 32768 fixed, one GPU.  Per S: attention
+    forward / backward kernel time (CUDA events), algorithmic HBM bytes (Q,K,V read + O written, bf16; backward: Q,K,V,O,dO
+    read + dQ,dK,dV written) -> GB/s and fraction of the measured HBM peak, dense TFLOP/s and fraction of the tensor peak
+    (the bound that applies is marked), and the full training step in tokens/s."""
+    import torch
+    from transformer_b200 import _lib as L
+    from transformer_b200.Transformer import Transformer
+    from transformer_b200.train import Train
+    from transformer_b200.utils import synthetic_batch
+    peaks = measured_peaks()
+    dev = torch.device("cuda:0")
+    torch.cuda.set_device(dev)
+    H, dk, d, V = 8, 64, 512, 32768
+    ridge = peaks["tf_sustained"] * 1e12 / (peaks["hbm"] * 1e9)
+    rows = []
+    for S in (64, 128, 256, 512, 1024, 2048):
+        B = 32768 // S
+        qkv = torch.randn(B * S, 3 * d, device=dev).bfloat16()
+        O = torch.empty(B * S, d, device=dev, dtype=torch.bfloat16)
+        dO = torch.randn(B * S, d, device=dev).bfloat16()
+        lse = torch.empty(B, H, S, device=dev); delta = torch.empty(B, H, S, device=dev)
+        dqkv = torch.zeros(B * S, 3 * d, device=dev, dtype=torch.bfloat16)
+        kpad = torch.zeros(B, S, dtype=torch.uint8, device=dev)
+        flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)             # > 126 MB L2: flushed between timed launches
+        sp = L.stream_ptr()
+        Q, K, Vv = qkv[:, :d], qkv[:, d:2 * d], qkv[:, 2 * d:]
+        row = {"seq_len": S, "batch": B}
+        for causal in (0, 1):
+            def fwd():
+                L.call("b200xf_attn_fwd", L.ptr(Q), 3 * d, L.ptr(K), 3 * d, L.ptr(Vv), 3 * d, L.ptr(O), d, L.ptr(lse), L.ptr(kpad), causal, None, 0, 0,
+                       B, H, S, S, dk, sp)
+
+            def bwd():
+                L.call("b200xf_attn_bwd", L.ptr(Q), 3 * d, L.ptr(K), 3 * d, L.ptr(Vv), 3 * d, L.ptr(dO), d, L.ptr(lse), L.ptr(delta), L.ptr(dqkv), 3 * d, 1,
+                       L.ptr(dqkv[:, d:2 * d]), 3 * d, L.ptr(dqkv[:, 2 * d:]), 3 * d, L.ptr(kpad), causal, None, 0, 0, B, H, S, S, dk, sp)
+            fwd()
+            L.call("b200xf_attn_delta", L.ptr(O), d, L.ptr(dO), d, L.ptr(delta), B, S, H, dk, sp)
+            for name, fn, nbytes, flops in (("fwd", fwd, 4 * B * S * d * 2, 4.0 * B * H * S * S * dk),
+                                            ("bwd", bwd, 8 * B * S * d * 2, 8.0 * B * H * S * S * dk)):
+                fn(); torch.cuda.synchronize()
+                ts = []
+                for _ in range(5):
+                    flush.zero_()
+                    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    e0.record(); fn(); e1.record(); torch.cuda.synchronize()
+                    ts.append(e0.elapsed_time(e1))
+                ms = sorted(ts)[len(ts) // 2]
+                ai = flops / nbytes
+                gbs, tfs = nbytes / ms / 1e6, flops / ms / 1e9
+                row[f"{name}_{'causal' if causal else 'full'}"] = {
+                    "us": round(ms * 1e3, 2), "hbm_GBps": round(gbs, 1), "hbm_frac": round(gbs / peaks["hbm"], 3), "dense_TFLOPs": round(tfs, 1),
+                    "tensor_frac": round(tfs / peaks["tf_sustained"], 3), "bound": "hbm" if ai < ridge else "tensor"}
+        del qkv, O, dO, dqkv, flush
+        # full training step at this sequence length (transformer-base, dropout 0.1)
+        model = Transformer(6, d, H, 2048, V, V, rate=0.1, device=dev, max_batch=B, max_src_len=S, max_tgt_len=S, pos_rows=S + 1)
+        tr = Train(1, True, model, None, None, B, None, None, 5, "ckpt", d)
+        batch = tuple(t.to(dev) for t in synthetic_batch(B, S, S + 1, V, V, seed=1234))
+        for _ in range(4):
+            tr.train_step(batch)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        n = 8
+        e0.record()
+        for _ in range(n):
+            tr.train_step(batch)
+        e1.record(); torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / n
+        row["train_step"] = {"ms": round(ms, 3), "tokens_per_s": round(B * S / ms * 1e3), "model_TFLOPs": round(step_flops(6, d, 2048, V, B, S) / ms / 1e9, 1)}
+        del model, tr
+        torch.cuda.empty_cache()
+        rows.append(row)
+        print(json.dumps(row), flush=True)
+    print(json.dumps({"sweep": "C5 seq_len 64..2048, d_model 512, 8 heads, B*S = 32768", "peaks": peaks, "ridge_flop_per_byte": round(ridge, 1),
+                      "bytes": "algorithmic: fwd 4*B*S*d*2 (Q,K,V in, O out), bwd 8*B*S*d*2 (Q,K,V,O,dO in; dQ,dK,dV out), bf16; L2 flushed between launches",
+                      "rows": rows}))
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -126,11 +262,23 @@ def main():
     ap.add_argument("--config", default="base_s512_b64", choices=sorted(CONFIGS))
     ap.add_argument("--dropout_rate", type=float, default=0.1)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="weak: the config's batch PER GPU (default); strong: the config's batch is the GLOBAL batch, split over the "
+                         "GPUs -- the reference's semantics (distributed_train.py:154-158)")
+    ap.add_argument("--global-batch", type=int, default=0, help="with --scaling strong: override the global batch")
+    ap.add_argument("--sweep", action="store_true", help="BASELINE config C5: seq_len sweep 64..2048 at d_model 512 (B*S = 32768): "
+                                                         "attention kernels (us, HBM GB/s or TFLOP/s vs roofline) + full step")
     args = ap.parse_args()
+    if args.sweep:
+        return seq_len_sweep(args)
     L_, d, H, f, V, S, Bper = CONFIGS[args.config]
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     N = max(args.gpus, 1)
+    if args.scaling == "strong":
+        gb = args.global_batch or Bper
+        assert gb % N == 0, 'Batch size ({}) must be divisible by the number of replicas ({})'.format(gb, N)
+        Bper = gb // N
     family = {"base": "transformer-base", "big": "transformer-big", "tiny": "tiny transformer"}[args.config.split("_")[0]]
     # bytes one step streams through HBM at least once: fp32 params/grads/Adam state + bf16 logits + saved activations (rough)
     work_mb = (R_param_count(L_, d, f, V) * 18 + Bper * S * V * 2 + Bper * S * d * 2 * 20 * L_) / 1e6
@@ -147,7 +295,7 @@ def main():
         steps = max(1, min(args.steps, 3)); warm = max(1, min(args.warmup, 1))
         base, dt = cpu_reference_run(args.config, steps, warm, sample_batch=2)
         line = {"impl": "reference", "metric": "tokens/sec (target positions) of one training step", "value": base["value"], "unit": "tokens/s",
-                "n_gpus": N, "steps": steps, "warmup": warm, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak",
+                "n_gpus": N, "steps": steps, "warmup": warm, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": args.scaling,
                 "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config, "cpu_baseline": base,
                 "e2e": {"value": base["value"], "unit": "tokens/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
                 "gpu_launches": 0}
@@ -239,51 +387,62 @@ def main():
     lib.load().b200xf_prof_enable(1)
     ms_roof = timed(step_resident, rsteps)
     lib.load().b200xf_prof_enable(0)
-    prof = (C.c_double * 9)()
-    lib.load().b200xf_prof_collect(prof, 3)
+    prof = (C.c_double * 12)()
+    lib.load().b200xf_prof_collect(prof, 4)
     launches_per_step = (lib.launch_count() - launches0) / rsteps
     launches = int(round(launches_per_step * args.steps))
+    dp = dp_check(rank, world, dev) if world > 1 else None
 
     if rank == 0:
         peaks = measured_peaks()
-        gemm_ms, gemm_fl, gemm_n = prof[0], prof[1], prof[2]
+        # categories: 0 = projection / vocabulary / other GEMMs, 3 = the FFN GEMMs (dense0, dense1: fwd, dgrad, wgrad)
+        gemm_ms, gemm_fl, gemm_n = prof[0] + prof[9], prof[1] + prof[10], prof[2] + prof[11]
         ach = gemm_fl / (gemm_ms * 1e-3) / 1e12 if gemm_ms > 0 else 0.0
+        ffn_ach = prof[10] / (prof[9] * 1e-3) / 1e12 if prof[9] > 0 else 0.0
+        traffic = ncu_traffic()
         roof = {"bound": "tensor", "kernel": "bx::gemm_kernel (tcgen05 GEMM, all launches of the step: FFN, projections, vocab, dgrad, wgrad)",
                 "achieved": ach, "peak": peaks["tf_sustained"], "unit": "TFLOP/s", "frac": ach / peaks["tf_sustained"],
-                "peak_source": f"{peaks['src']} MEASURED_PEAKS.json bf16_tflops_sustained (kernel timed inside a long step)",
-                "traffic": 188747264,
-                "traffic_note": "dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the kernel (FFN dense0 wgrad, gemm_kernel<1,1,256,1,2>, "
-                                "512x2048x32768) from the committed ncu --set full capture profiles/r01_ncu_full_gemm_instep_backward.txt; "
-                                "algorithmic bytes of that launch = 172.0e6 (A 33.5 MB + B 134.2 MB + D 4.2 MB)",
+                "frac_of_burst_peak": ach / peaks["tf_burst"],
+                "peak_source": f"{peaks['src']} MEASURED_PEAKS.json bf16_tflops_sustained (kernel timed inside a long step); burst = bf16_tflops",
+                "traffic": traffic["bytes"] if traffic else None,
+                "traffic_note": traffic["note"] if traffic else "no per-round ncu capture summary under profiles/ (tools/ncu_traffic.py writes it)",
                 "launches_per_step": gemm_n / rsteps, "share_of_step": gemm_ms / ms_roof,
-                "measured_in": f"eager pass of {rsteps} steps ({ms_roof / rsteps:.3f} ms/step) right after the timed region, events around every launch",
+                "measured_in": f"eager single-stream pass of {rsteps} steps ({ms_roof / rsteps:.3f} ms/step) right after the timed region, events around every launch",
+                "ffn_gemm": {"achieved": ffn_ach, "unit": "TFLOP/s", "frac": ffn_ach / peaks["tf_sustained"], "frac_of_burst_peak": ffn_ach / peaks["tf_burst"],
+                             "launches_per_step": prof[11] / rsteps, "share_of_step": prof[9] / ms_roof,
+                             "what": "point_wise_feed_forward_network GEMMs only (dense0 + dense1: forward, dgrad, wgrad) -- the kernel the north-star target is stated on"},
                 "attention_fwd": {"achieved": prof[4] / (prof[3] * 1e-3) / 1e12 if prof[3] > 0 else 0.0, "unit": "TFLOP/s (dense 4.B.H.Sq.Sk.dk)",
                                   "share_of_step": prof[3] / ms_roof},
                 "attention_bwd": {"achieved": prof[7] / (prof[6] * 1e-3) / 1e12 if prof[6] > 0 else 0.0, "unit": "TFLOP/s (dense)",
                                   "share_of_step": prof[6] / ms_roof},
-                "step_model_flops_tflops": step_flops(L_, d, f, V, Bper, S) / (ms_step * 1e-3) / 1e12}
+                "step_model_flops_tflops": step_flops(L_, d, f, V, Bper, S) / (ms_step * 1e-3) / 1e12,
+                "step_frac_of_sustained_peak": step_flops(L_, d, f, V, Bper, S) / (ms_step * 1e-3) / 1e12 / peaks["tf_sustained"]}
         line = {"metric": "tokens/sec (target positions) of one training step", "value": value, "unit": "tokens/s", "n_gpus": N, "steps": args.steps,
-                "warmup": max(3, args.warmup), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "warmup": max(3, args.warmup), "ms_per_step": ms_step, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
                 "dtype": "bf16 operands / f32 accumulate, f32 master weights", "data": "synthetic", "config": config,
                 "e2e": {"value": e2e_value, "unit": "tokens/s", "ms_per_step": ms_e2e, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
                 "gpu_launches": int(launches), "launch_mode": ("one CUDA-graph replay per step of %d captured kernels" % round(launches_per_step)) if graphed else "eager",
                 "clocks": clocks, "roofline": roof, "loss_per_token": loss_per_tok}
+        if dp is not None:
+            line["dp_check"] = dp
         if N == 1 and not args.no_cpu_baseline:
             base, _ = cpu_reference_run(args.config, 2, 1, sample_batch=2)
             line["cpu_baseline"] = base
         print(json.dumps(line), flush=True)
     if world > 1:
-        # Tear-down: destroy_process_group() can block for minutes once NCCL collectives have been captured into CUDA
-        # graphs.  Everything is measured and printed: synchronise, meet at a barrier, then leave without destructors
-        # (a watchdog bounds even that).
+        # Tear-down: the captured CUDA graphs hold NCCL work, so they are destroyed BEFORE the process group (destroying the
+        # group first blocked for minutes in round 1).  A watchdog still bounds the exit: everything is measured and printed.
         def _bail():
-            time.sleep(60)
+            time.sleep(45)
             os._exit(0)
         threading.Thread(target=_bail, daemon=True).start()
         torch.cuda.synchronize()
         dist.barrier()
+        trainer._graphs.clear()
+        trainer._graph_pool = None
+        torch.cuda.synchronize()
         sys.stdout.flush()
-        os._exit(0)
+        dist.destroy_process_group()
 
 
 if __name__ == "__main__":

@@ -52,15 +52,17 @@ class LazyAttentionWeights(Mapping):
             raise RuntimeError("attention_weights of an earlier forward are no longer available")
         sk = self._T if block == 1 else self._S
         out = torch.empty((self._B, self._H, self._T, sk), dtype=torch.float32, device=self._m.device)
-        L.call("b200xf_model_attention_weights", self._m._handle, layer, block, L.ptr(out), L.stream_ptr())
+        with torch.cuda.device(self._m.device):
+            L.call("b200xf_model_attention_weights", self._m._handle, layer, block, L.ptr(out), L.stream_ptr())
         return out
 
 
 class Variable:
     """A named (possibly strided) fp32 view into the parameter arena -- stands in for a tf.Variable."""
 
-    def __init__(self, name, value, grad):
+    def __init__(self, name, value, grad, model=None):
         self.name, self.value, self.grad = name, value, grad
+        self._model = model                 # assign() must invalidate the model's bf16 operand copy
 
     @property
     def shape(self):
@@ -71,6 +73,8 @@ class Variable:
 
     def assign(self, t):
         self.value.copy_(torch.as_tensor(t).to(self.value.device, self.value.dtype))
+        if self._model is not None:
+            self._model._shadow_dirty = True
 
 
 def _round_up(x, m):
@@ -125,7 +129,7 @@ class Transformer:
                 if cols.value == 0:
                     return arena[off.value:off.value + rows.value]
                 return torch.as_strided(arena, (rows.value, cols.value), (ld.value, 1), off.value)
-            out.append(Variable(name.value.decode(), view(self.params), view(self.grads)))
+            out.append(Variable(name.value.decode(), view(self.params), view(self.grads), self))
             i += 1
         return out
 
@@ -159,7 +163,8 @@ class Transformer:
 
     def sync_shadow(self):
         """refresh the bf16 operand copy after the fp32 weights were written from outside"""
-        L.call("b200xf_model_sync_shadow", self._handle, L.stream_ptr())
+        with torch.cuda.device(self.device):
+            L.call("b200xf_model_sync_shadow", self._handle, L.stream_ptr())
         self._shadow_dirty = False
 
     # ------------------------------------------------------------------ workspace / handle
@@ -197,7 +202,11 @@ class Transformer:
             pass
 
     # ------------------------------------------------------------------ forward
-    def _forward(self, inp, tar, tar_offset, T, training, seed=0, masks=None, want_logits=True, seed_dev=None):
+    def _forward(self, *a, **kw):
+        with torch.cuda.device(self.device):          # library calls launch on the current device's current stream
+            return self._forward_on_device(*a, **kw)
+
+    def _forward_on_device(self, inp, tar, tar_offset, T, training, seed=0, masks=None, want_logits=True, seed_dev=None):
         """inp int64 (B,S); tar int64 (B, >= tar_offset+T) -- the decoder input is tar[:, tar_offset:tar_offset+T].
         ``seed_dev``: optional device uint64 holding the dropout seed (graph-replayable steps); else ``seed``."""
         if inp.dtype != torch.int64 or tar.dtype != torch.int64:
@@ -268,5 +277,6 @@ class Transformer:
         B, S, T = self._last_shape
         rows = B * (S if name.startswith("enc") else T)
         out = torch.empty((rows, self.d_model), dtype=torch.float32, device=self.device)
-        L.call("b200xf_model_tap", self._handle, name.encode(), L.ptr(out), L.stream_ptr())
+        with torch.cuda.device(self.device):
+            L.call("b200xf_model_tap", self._handle, name.encode(), L.ptr(out), L.stream_ptr())
         return out.reshape(B, -1, self.d_model)

@@ -12,6 +12,8 @@
 // the QKV projection GEMM) -- split_heads/transpose (Attention.py:52-57,74-76) never materialise.  TMA 3-D maps
 // {column, token, batch} zero-fill ragged tails.  S = Q.K^T and O = P.V run on tcgen05 (accumulators in TMEM);
 // softmax warps own one query row per thread (tcgen05.ld 32x32b).
+#include <mutex>
+
 #include "common.cuh"
 
 namespace bx {
@@ -858,11 +860,16 @@ static int attn_fwd_launch(const void* Q, long long ld_q, const void* K, long lo
   if ((rc = encode_tmap_3d(&tmV, 0, V, (uint64_t)H * DK, Sk, B, ld_v, (uint64_t)Sk * ld_v, DK, 128, 1, swz))) return rc;
   if ((rc = encode_tmap_3d(&tmO, 0, O, (uint64_t)H * DK, Sq, B, ld_o, (uint64_t)Sq * ld_o, DK, 128, 1, swz))) return rc;
   auto kern = mask.maskf != nullptr ? attn_fwd_kernel<DK, true> : attn_fwd_kernel<DK, false>;
-  static bool attr_done = false;
-  if (!attr_done) {
-    BX_CHECK_CUDA(cudaFuncSetAttribute(attn_fwd_kernel<DK, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::BYTES));
-    BX_CHECK_CUDA(cudaFuncSetAttribute(attn_fwd_kernel<DK, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::BYTES));
-    attr_done = true;
+  {
+    static std::mutex mu;
+    static bool attr_done[kMaxDevices] = {};
+    const int dev = current_device();
+    std::lock_guard<std::mutex> lock(mu);
+    if (!attr_done[dev]) {
+      BX_CHECK_CUDA(cudaFuncSetAttribute(attn_fwd_kernel<DK, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::BYTES));
+      BX_CHECK_CUDA(cudaFuncSetAttribute(attn_fwd_kernel<DK, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::BYTES));
+      attr_done[dev] = true;
+    }
   }
   dim3 grid((Sq + 255) / 256, H, B);
   void* pb = prof_on() ? prof_begin(st) : nullptr;
@@ -891,10 +898,15 @@ static int attn_bwd_launch(const void* Q, long long ld_q, const void* K, long lo
   else rc = encode_tmap_3d(&tmdQ, 1, dq_acc, (uint64_t)H * DK, Sq, B, ld_dq, (uint64_t)Sq * ld_dq, DK / 2, 128, 1, swz);
   if (rc) return rc;
   auto kern = attn_bwd_kernel<DK, kDqBf16>;
-  static bool attr_done = false;
-  if (!attr_done) {
-    BX_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::BYTES));
-    attr_done = true;
+  {
+    static std::mutex mu;
+    static bool attr_done[kMaxDevices] = {};
+    const int dev = current_device();
+    std::lock_guard<std::mutex> lock(mu);
+    if (!attr_done[dev]) {
+      BX_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::BYTES));
+      attr_done[dev] = true;
+    }
   }
   dim3 grid((Sk + 127) / 128, H, B);
   void* pb = prof_on() ? prof_begin(st) : nullptr;

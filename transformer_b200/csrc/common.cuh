@@ -40,6 +40,9 @@ void prof_enable(int on);
 void* prof_begin(cudaStream_t st);
 void prof_end(void* begin, int cat, double work, cudaStream_t st);
 int prof_collect(double* out, int ncat);
+// category the NEXT gemm launches are booked under (0 = GEMM, 3 = FFN GEMM: the kernel the north-star target is stated on)
+void prof_set_gemm_cat(int cat);
+int prof_gemm_cat();
 
 #define BX_REQUIRE(cond, ...)                                                                    \
   do {                                                                                           \
@@ -55,7 +58,9 @@ int encode_tmap_2d(CUtensorMap* tm, int dtype, const void* base, uint64_t inner,
 int encode_tmap_3d(CUtensorMap* tm, int dtype, const void* base, uint64_t d0, uint64_t d1, uint64_t d2,
                    uint64_t stride1_elems, uint64_t stride2_elems, uint32_t b0, uint32_t b1, uint32_t b2,
                    int swizzle_bytes);
-int sm_count();
+int sm_count();                       // of the CURRENT device
+constexpr int kMaxDevices = 64;
+int current_device();                 // cudaGetDevice(), clamped to [0, kMaxDevices)
 
 #ifdef __CUDACC__
 // ------------------------------------------------------------------------------------------------

@@ -10,6 +10,8 @@
 //   dgrad     dx = dy.W^T          reverse-mode of the above (train.py:137)                     (A K-major, B K-major)
 //   wgrad     dW = x^T.dy          ditto, split-K over tokens with TMA reduce-add               (A MN-major, B MN-major)
 // Operand "major": 0 = K-major (K contiguous in memory), 1 = MN-major (M resp. N contiguous).
+#include <mutex>
+
 #include "common.cuh"
 
 namespace bx {
@@ -330,10 +332,16 @@ static int launch_gemm(const void* A, long long lda, const void* B, long long ld
   rc = encode_tmap_2d(&tmD, kOutF32 ? 1 : 0, D, N, M, ldd, kOutF32 ? 32 : 64, GEMM_BM, 128);
   if (rc) return rc;
   auto kern = gemm_kernel<MA, MB, BN, kOutF32, CG>;
-  static bool attr_done = false;
-  if (!attr_done) {
+  // per-device launch state of this instantiation (function attributes and cluster occupancy are per device), under a lock:
+  // several host threads / devices may drive the library
+  static std::mutex mu;
+  static bool attr_done[kMaxDevices] = {};
+  static int max_units_dev[kMaxDevices] = {};
+  const int dev = current_device();
+  std::lock_guard<std::mutex> lock(mu);
+  if (!attr_done[dev]) {
     BX_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
-    attr_done = true;
+    attr_done[dev] = true;
   }
   const long long m_tiles = (M + GEMM_BM * CG - 1) / (GEMM_BM * CG), n_tiles = (N + BN - 1) / BN;
   const long long kblocks = (K + GEMM_BK - 1) / GEMM_BK;
@@ -352,7 +360,7 @@ static int launch_gemm(const void* A, long long lda, const void* B, long long ld
   cfg.numAttrs = 1;
   // The tile schedule is static (tile = unit + i * units), so every unit must be co-resident.  Not every TPC can
   // host a 2-CTA cluster (SMs are yield-harvested individually): ask the runtime how many clusters fit at once.
-  static int max_units = 0;
+  int& max_units = max_units_dev[dev];
   if (max_units == 0) {
     max_units = groups;
     if (CG == 2) {
@@ -372,7 +380,7 @@ static int launch_gemm(const void* A, long long lda, const void* B, long long ld
   void* pb = prof_on() ? prof_begin(stream) : nullptr;
   BX_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, tmA, tmB, tmD, (int)M, (int)N, (int)K, splits, bias, const_cast<void*>(aux), ld_aux,
                                    flags));
-  if (pb) prof_end(pb, 0, 2.0 * (double)M * (double)N * (double)K, stream);
+  if (pb) prof_end(pb, prof_gemm_cat(), 2.0 * (double)M * (double)N * (double)K, stream);
   BX_POST_LAUNCH();
   return 0;
 }

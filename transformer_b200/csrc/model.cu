@@ -322,8 +322,10 @@ int forward_impl(M* m, float* logits_out, int64_t ld_logits, cudaStream_t st) {
     RC(linear_fwd(a.attn_o, d, Sh + p.mha.Wo, d, m->P + p.mha.bo, w.y16, d, false, false, Ms, d, d, st));
     RC(residual_ln(m, w.enc_x16[l], p.ln1g, p.ln1b, a.out1_16, a.ln1, Ms, site_enc(l, 0), st));   // Encoder.py:22-23
     // point_wise_feed_forward_network (point_ffn.py:3-7)
+    bx::prof_set_gemm_cat(3);
     RC(linear_fwd(a.out1_16, d, Sh + p.ffn.W1, f, m->P + p.ffn.b1, a.h, f, false, true, Ms, f, d, st, a.hbits));
     RC(linear_fwd(a.h, f, Sh + p.ffn.W2, d, m->P + p.ffn.b2, w.y16, d, false, false, Ms, d, f, st));
+    bx::prof_set_gemm_cat(0);
     RC(residual_ln(m, a.out1_16, p.ln2g, p.ln2b, w.enc_x16[l + 1], a.ln2, Ms, site_enc(l, 1), st));   // Encoder.py:26-27
   }
   const bf16* enc_out16 = w.enc_x16[L];
@@ -349,8 +351,10 @@ int forward_impl(M* m, float* logits_out, int64_t ld_logits, cudaStream_t st) {
     RC(linear_fwd(a.attn2_o, d, Sh + p.mha2.Wo, d, m->P + p.mha2.bo, w.y16, d, false, false, Mt, d, d, st));
     RC(residual_ln(m, a.out1_16, p.ln2g, p.ln2b, a.out2_16, a.ln2, Mt, site_dec(l, 1), st));
     // ffn (Decoder.py:38-40)
+    bx::prof_set_gemm_cat(3);
     RC(linear_fwd(a.out2_16, d, Sh + p.ffn.W1, f, m->P + p.ffn.b1, a.h, f, false, true, Mt, f, d, st, a.hbits));
     RC(linear_fwd(a.h, f, Sh + p.ffn.W2, d, m->P + p.ffn.b2, w.y16, d, false, false, Mt, d, f, st));
+    bx::prof_set_gemm_cat(0);
     RC(residual_ln(m, a.out2_16, p.ln3g, p.ln3b, w.dec_x16[l + 1], a.ln3, Mt, site_dec(l, 2), st));
   }
   // ---------------- final_layer (Transformer.py:30) ----------------
@@ -382,6 +386,7 @@ int residual_ln_back(M* m, const StreamGrad& g, const LnSave& s, int64_t g_off, 
 int ffn_back(M* m, const Ffn& p, const bf16* x16, const bf16* h, const uint64_t* hbits, const bf16* dy, int64_t rows, cudaStream_t st) {
   const int d = m->lo.d, f = m->lo.f;
   Work& w = m->w;
+  struct CatGuard { CatGuard() { bx::prof_set_gemm_cat(3); } ~CatGuard() { bx::prof_set_gemm_cat(0); } } cat_guard;
   RC(linear_wgrad(h, f, dy, d, m->G + p.W2, d, nullptr, rows, d, f, st));                     // db2: from the LN backward
   RC(linear_dgrad(dy, d, m->Sh + p.W2, d, w.dh, f, false, false, h, f, rows, d, f, st, hbits));         // dh = (dy . W2^T) o [h > 0]
   RC(linear_wgrad(x16, d, w.dh, f, m->G + p.W1, f, m->G + p.b1, rows, f, d, st));

@@ -31,6 +31,9 @@ static bool g_prof_on = false;
 static std::vector<ProfRec> g_prof;
 static std::vector<cudaEvent_t> g_event_pool;
 static std::mutex g_prof_mu;
+static int g_gemm_cat = 0;
+void prof_set_gemm_cat(int cat) { g_gemm_cat = cat; }
+int prof_gemm_cat() { return g_gemm_cat; }
 bool prof_on() { return g_prof_on; }
 void prof_enable(int on) { g_prof_on = on != 0; }
 static cudaEvent_t prof_event() {
@@ -131,14 +134,21 @@ int encode_tmap_3d(CUtensorMap* tm, int dtype, const void* base, uint64_t d0, ui
   return 0;
 }
 
+int current_device() {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0) dev = 0;
+  return dev < kMaxDevices ? dev : kMaxDevices - 1;
+}
+
 int sm_count() {
-  static int n = 0;
-  if (n == 0) {
-    int dev = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess) return 148;
-    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+  static std::atomic<int> n[kMaxDevices];
+  const int dev = current_device();
+  int v = n[dev].load(std::memory_order_relaxed);
+  if (v == 0) {
+    if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || v <= 0) v = 148;
+    n[dev].store(v, std::memory_order_relaxed);
   }
-  return n;
+  return v;
 }
 
 }  // namespace bx

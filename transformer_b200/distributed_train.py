@@ -38,13 +38,17 @@ class MirroredStrategy:
         yield self
 
     def shard(self, src, tar):
-        """make_dataset_iterator semantics (distributed_train.py:151-152): split the global batch evenly over replicas."""
+        """make_dataset_iterator semantics (distributed_train.py:151-152): split the global batch over the replicas.  A full
+        batch splits evenly (the divisibility of ``batch_size`` itself is checked once, distributed_train.py:154-158);
+        the partial LAST batch of an epoch (padded_batch keeps it, utils.py:154-159) is split as evenly as possible --
+        the first ``b % n`` replicas get one more row -- and a replica left without rows gets an EMPTY shard, which
+        ``DistributedTrain`` turns into a zero-gradient step so that every rank still joins the all-reduce."""
         n, r = self.num_replicas_in_sync, self.rank
         b = src.shape[0]
-        if b % n:
-            raise ValueError('Batch size ({}) must be divisible by the number of replicas ({})'.format(b, n))
-        per = b // n
-        return src[r * per:(r + 1) * per], tar[r * per:(r + 1) * per]
+        q, rem = divmod(b, n)
+        lo = r * q + min(r, rem)
+        hi = lo + q + (1 if r < rem else 0)
+        return src[lo:hi], tar[lo:hi]
 
     def experimental_run(self, fn, iterator):
         """strategy.experimental_run(step_fn, iterator) (distributed_train.py:59,62): run fn on this replica's shard."""
@@ -111,6 +115,24 @@ class DistributedTrain(Train):
     def _reduce_gradients(self, stage):
         self.buckets.reduce_stage(self.transformer.grads, stage)
 
+    def _with_rows(self, inputs, step, loss_metric, acc_metric):
+        """run ``step`` on this replica's shard; an EMPTY shard (partial last batch smaller than the replica count) runs on
+        one all-padding row instead: label 0 everywhere => zero loss, zero gradients (train.py:85-87 mask), so the
+        collective still sees every rank; the row's accuracy-counter contribution is taken back out."""
+        src, tar = inputs
+        if src.shape[0] > 0:
+            return step((src, tar))
+        dummy = (torch.zeros((1, max(1, src.shape[1])), dtype=torch.int64), torch.zeros((1, max(2, tar.shape[1])), dtype=torch.int64))
+        step(dummy)
+        loss_metric._acc[1] -= 1                              # Mean(): this step added one (zero) sample
+        acc_metric.add_(-self._stats[1], -self._stats[2])
+
+    def train_step(self, inputs):
+        return self._with_rows(inputs, lambda x: Train.train_step(self, x), self.train_loss, self.train_accuracy)
+
+    def test_step(self, inputs):
+        return self._with_rows(inputs, lambda x: Train.test_step(self, x), self.test_loss, self.test_accuracy)
+
     def _finish_gradients(self):
         self.buckets.wait()
 
@@ -143,13 +165,32 @@ class DistributedTrain(Train):
                         for t in iter(test_iterator):
                             self.test_step(strategy.shard(*t))
                             break                                   # the reference's `if test_steps % 100: break` exits after 1 step
+                        self._print_progress(template, epoch, train_steps, step_timer, strategy)     # distributed_train.py:95-98
                 except StopIteration:
                     break
-            self.reduce_metrics()
+            self._print_progress(template, epoch, train_steps, step_timer, strategy, final=True)     # distributed_train.py:103-106
             if strategy.rank == 0:
-                print(template.format(epoch + 1, train_steps, self.train_loss.result(), self.train_accuracy.result() * 100,
-                                      self.test_loss.result(), self.test_accuracy.result() * 100, time.time() - step_timer))
+                self._write_summaries(epoch, self._epoch_metrics)                                                    # distributed_train.py:108-114
+                if (epoch + 1) % 5 or ((epoch + 1) == self.epochs) == 0:   # the reference's save condition, verbatim (distributed_train.py:116)
+                    if self.ckpt_path:
+                        ckpt_save_path = self.save_checkpoint()             # replicas are mirrored: rank 0's arena is THE model
+                        print('Saving checkpoint for epoch {} at {}'.format(epoch + 1, ckpt_save_path))
                 print('Time taken for {} epoch: {} secs\n'.format(epoch + 1, (time.time() - start_time)))
+
+    def _print_progress(self, template, epoch, train_steps, step_timer, strategy, final=False):
+        """metric read-out across replicas (sync-on-read SUM, every rank takes part) and rank 0's progress line.  The
+        accumulators keep LOCAL sums, so the reduction works on copies."""
+        vals = []
+        for m in (self.train_loss, self.train_accuracy, self.test_loss, self.test_accuracy):
+            acc = m._acc.clone()
+            if dist.is_initialized() and dist.get_world_size() > 1:
+                dist.all_reduce(acc, op=dist.ReduceOp.SUM)
+            s, c = acc.tolist()
+            vals.append(s / c if c else 0.0)
+        if final:
+            self._epoch_metrics = vals
+        if strategy.rank == 0:
+            print(template.format(epoch + 1, train_steps, vals[0], vals[1] * 100, vals[2], vals[3] * 100, time.time() - step_timer))
 
 
 def init_process_group_from_env(backend="nccl"):
@@ -164,3 +205,95 @@ def init_process_group_from_env(backend="nccl"):
         kw = {"device_id": torch.device(f"cuda:{local}")} if backend == "nccl" else {}
         dist.init_process_group(backend=backend, **kw)
     return int(os.environ.get("RANK", "0")), local, world
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# entry point: distributed_train.py:22-23,124-179  (`python -m transformer_b200.distributed_train --num_gpu=N`)
+# ----------------------------------------------------------------------------------------------------------------------
+def _define_num_gpu_flag():
+    from absl import flags
+    if 'num_gpu' not in flags.FLAGS:
+        flags.DEFINE_integer('num_gpu', 4, 'Number of GPUs to use')                     # distributed_train.py:23
+
+
+def run_main(argv):
+    """distributed_train.py:124-128."""
+    del argv
+    from absl import flags
+    from . import utils
+    kwargs = utils.flags_dict()
+    kwargs.update({'num_gpu': flags.FLAGS.num_gpu})
+    main(**kwargs)
+
+
+def _relaunch_one_process_per_gpu(num_gpu):
+    """The reference drives N GPUs from ONE process (MirroredStrategy, distributed_train.py:137-138).  Here each GPU gets its
+    own process: the command line is re-executed under torch.distributed.run with --nproc-per-node=num_gpu on this node
+    (rendezvous on 127.0.0.1); every child then finds WORLD_SIZE in its environment and runs ``main`` as one replica."""
+    import subprocess
+    import sys
+    port = os.environ.get("MASTER_PORT", str(29500 + os.getpid() % 2000))
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={num_gpu}", "--master-addr", "127.0.0.1",
+           "--master-port", port, "-m", "transformer_b200.distributed_train"] + sys.argv[1:]
+    return subprocess.call(cmd)
+
+
+def main(epochs, enable_function, buffer_size, batch_size, d_model, dff, num_heads, src_vocab_file, tgt_vocab_file, dataset_path,
+         dropout_rate, num_layers, sequence_length, per_replica_batch_size, ckpt_path, max_ckpt_keep, num_gpu=1):
+    """distributed_train.py:131-174 on the B200 drop-in."""
+    import datetime
+    from . import utils
+    from .Transformer import Transformer
+    if num_gpu > 1 and "WORLD_SIZE" not in os.environ:
+        if num_gpu > torch.cuda.device_count():
+            raise ValueError('num_gpu ({}) exceeds the visible GPUs ({})'.format(num_gpu, torch.cuda.device_count()))
+        rc = _relaunch_one_process_per_gpu(num_gpu)
+        if rc:
+            raise SystemExit(rc)
+        return None
+    rank, local, world = init_process_group_from_env("nccl")
+    current_time = datetime.datetime.now().strftime("%Y%m%d-%H%M%S")
+    train_log_dir = 'logs/gradient_tape/' + current_time + '/train'
+    test_log_dir = 'logs/gradient_tape/' + current_time + '/test'
+    devices = ['/device:GPU:{}'.format(i) for i in range(world)]
+    strategy = MirroredStrategy(devices)
+    num_replicas = strategy.num_replicas_in_sync
+    with strategy.scope():
+        # every replica reads the same files in the same (seeded) order; rank 0 creates the vocabulary files first
+        if rank == 0:
+            data = utils.load_dataset(dataset_path, sequence_length, src_vocab_file, tgt_vocab_file, batch_size, buffer_size)
+        if world > 1:
+            dist.barrier()
+        if rank != 0:
+            data = utils.load_dataset(dataset_path, sequence_length, src_vocab_file, tgt_vocab_file, batch_size, buffer_size)
+        train_dataset, test_dataset, src_tokenizer, tgt_tokenizer = data
+        input_vocab_size = src_tokenizer.vocab_size + 2
+        target_vocab_size = tgt_tokenizer.vocab_size + 2
+        local_batch_size = split_replica_batch(batch_size, num_replicas)                 # distributed_train.py:154-158
+        longest = max([sequence_length + 2] + [max(s.shape[1], t.shape[1]) for s, t in test_dataset])
+        transformer = Transformer(num_layers, d_model, num_heads, dff, input_vocab_size, target_vocab_size, dropout_rate,
+                                  device=torch.device(f"cuda:{local}"), pos_rows=max(longest, 512), max_batch=local_batch_size + 1,
+                                  max_src_len=longest, max_tgt_len=longest)
+        if rank == 0:
+            print('create training object')
+        train_obj = DistributedTrain(epochs, enable_function, transformer, src_tokenizer, tgt_tokenizer, batch_size, local_batch_size,
+                                     train_log_dir, test_log_dir, max_ckpt_keep, ckpt_path, d_model)
+        if rank == 0:
+            print('Training.....')
+        train_obj.training_loop(train_dataset, test_dataset, strategy)
+        if rank == 0:
+            print(tgt_tokenizer.decode(train_obj.predict(['he goes to school']).tolist()))
+    if world > 1:
+        torch.cuda.synchronize()
+        dist.barrier()
+        train_obj._graphs.clear()                 # captured collectives hold the communicator: drop the graphs first
+        dist.destroy_process_group()
+    return train_obj
+
+
+if __name__ == '__main__':
+    from absl import app
+    from . import utils as _utils
+    _utils.transformer_flags()
+    _define_num_gpu_flag()
+    app.run(run_main)

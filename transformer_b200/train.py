@@ -9,6 +9,7 @@ train.py:134).  No host synchronisation happens inside a step; metrics are read 
 """
 from __future__ import annotations
 
+import collections
 import math
 import os
 import time
@@ -136,9 +137,14 @@ class Train(object):
         if cuda_graph is None:
             cuda_graph = os.environ.get("B200XF_CUDA_GRAPH", "1") != "0"
         self.cuda_graph = bool(cuda_graph) and self.optimizer.schedule_args() is not None
-        self._graphs = {}
+        # one captured graph per batch shape, least-recently-used eviction, ONE memory pool shared by all captures
+        # (replays never overlap), so ragged text batches cannot grow the cache without bound
+        self._graphs = collections.OrderedDict()
+        self._graph_cache_size = int(os.environ.get("B200XF_GRAPH_CACHE", "32"))
+        self._graph_pool = None
         self._shape_seen = {}
         self._graph_handle_generation = None
+        self._summary_writers = {}
 
     # -- train.py:83-88 on materialised predictions (API parity; train_step uses the fused path) ---------------------
     def loss_function(self, real, pred):
@@ -194,6 +200,10 @@ class Train(object):
 
     def train_step(self, inputs):
         """One training step (train.py:124-141).  inputs: (src (B,S) int64, tar (B,T+1) int64)."""
+        with torch.cuda.device(self.transformer.device):        # the library launches on the CURRENT device's stream
+            return self._train_step(inputs)
+
+    def _train_step(self, inputs):
         src, tar = inputs
         tr = self.transformer
         src = src.to(tr.device, torch.int64, non_blocking=True).contiguous()
@@ -210,7 +220,10 @@ class Train(object):
             self._shape_seen[key] = self._shape_seen.get(key, 0) + 1
             self._train_step_body(src, tar)                                    # eager (also the warm-up before a capture)
         else:
+            self._graphs.move_to_end(key)
             graph, g_src, g_tar = entry
+            if tr._shadow_dirty:               # load_ckpt / load_variables / Variable.assign since the last step: the replay
+                tr.sync_shadow()               # does not go through Transformer._forward, so refresh the bf16 operands here
             g_src.copy_(src, non_blocking=True)
             g_tar.copy_(tar, non_blocking=True)
             graph.replay()
@@ -222,9 +235,11 @@ class Train(object):
         self._graph_handle_generation = getattr(tr, "_handle_generation", 0)
         g_src, g_tar = src.clone(), tar.clone()
         graph = torch.cuda.CUDAGraph()
+        if self._graph_pool is None:
+            self._graph_pool = torch.cuda.graph_pool_handle()
         try:
             torch.cuda.synchronize(tr.device)
-            with torch.cuda.graph(graph):
+            with torch.cuda.graph(graph, pool=self._graph_pool):
                 self._train_step_body(g_src, g_tar)
         except Exception as e:                                                 # e.g. a collective that cannot be captured
             import warnings
@@ -233,12 +248,15 @@ class Train(object):
             torch.cuda.synchronize(tr.device)
             return None
         self._graphs[key] = (graph, g_src, g_tar)
+        while len(self._graphs) > max(1, self._graph_cache_size):
+            self._graphs.popitem(last=False)
         return self._graphs[key]
 
     def test_step(self, inputs):
         """One test step (train.py:144-156)."""
         src, tar = inputs
-        self._step_core(src, tar, False)
+        with torch.cuda.device(self.transformer.device):
+            self._step_core(src, tar, False)
         self.test_loss(self._stats[0] * (1.0 / self.batch_size))
         self.test_accuracy.add_(self._stats[1], self._stats[2])
 
@@ -281,6 +299,22 @@ class Train(object):
         print('Latest checkpoint restored!!')
         return True
 
+    def _write_summaries(self, epoch, values=None):
+        """train.py:200-206 / distributed_train.py:108-114: per-epoch 'loss' and 'accuracy' scalars of the train and test
+        metrics, written as TensorBoard event files under train_log_dir / test_log_dir (no-op when the dirs are None)."""
+        if values is None:
+            values = [self.train_loss.result(), self.train_accuracy.result(), self.test_loss.result(), self.test_accuracy.result()]
+        for log_dir, loss, acc in ((self.train_log_dir, values[0], values[1]), (self.test_log_dir, values[2], values[3])):
+            if not log_dir:
+                continue
+            w = self._summary_writers.get(log_dir)
+            if w is None:
+                from torch.utils.tensorboard import SummaryWriter      # event-file writer only; nothing on the hot path
+                w = self._summary_writers[log_dir] = SummaryWriter(log_dir)
+            w.add_scalar('loss', loss, epoch)
+            w.add_scalar('accuracy', acc, epoch)
+            w.flush()
+
     def predict(self, input_sentence, max_steps=10):
         """Greedy inference (train.py:91-121): start token, 10 decode steps, no EOS stop, the whole model re-run per
         step.  (The reference indexes ``input_sentence[0]``, i.e. expects a 1-element batch of strings.)"""
@@ -316,6 +350,7 @@ class Train(object):
                         self.test_step((t_src, t_tgt))
                     print(template.format(epoch + 1, self.train_loss.result(), self.train_accuracy.result() * 100,
                                           self.test_loss.result(), self.test_accuracy.result() * 100))
+            self._write_summaries(epoch)
             if (epoch + 1) % 5 or (epoch + 1 == self.epochs) == 0:      # the reference's save condition, verbatim (train.py:208)
                 if self.ckpt_path:
                     ckpt_save_path = self.save_checkpoint()
@@ -346,8 +381,11 @@ def main(epochs, enable_function, buffer_size, batch_size, d_model, dff, num_hea
         dataset_path, sequence_length, src_vocab_file, tgt_vocab_file, batch_size, buffer_size)
     input_vocab_size = src_tokenizer.vocab_size + 2
     target_vocab_size = tgt_tokenizer.vocab_size + 2
+    # the workspace is sized once for the largest batch the pipeline can emit (no re-creation -- and no stale CUDA graphs --
+    # when a longer batch shows up); test sentences are not length-filtered (utils.py:153 filters train only)
+    longest = max([sequence_length + 2] + [max(s.shape[1], t.shape[1]) for s, t in test_dataset])
     transformer = Transformer(num_layers, d_model, num_heads, dff, input_vocab_size, target_vocab_size, dropout_rate,
-                              pos_rows=max(sequence_length + 2, 512))
+                              pos_rows=max(longest, 512), max_batch=batch_size, max_src_len=longest, max_tgt_len=longest)
     print('create training object')
     train_obj = Train(epochs, enable_function, transformer, src_tokenizer, tgt_tokenizer, batch_size, train_log_dir, test_log_dir,
                       max_ckpt_keep, ckpt_path, d_model)

@@ -166,10 +166,32 @@ def _padded_batches(examples, batch_size):
     return out
 
 
+def make_synthetic_corpus(dataset_path, lines=10000, words=6000, seed=7):
+    """The reference trains on data/src-train.txt -> data/tgt-train.txt (10000 sentence pairs shipped with its repo).  Those
+    files are not part of THIS repo; when ``dataset_path`` has no train files, a synthetic parallel corpus of the same size
+    (Zipf-distributed word ids, 3..40 words per line, the target a deterministic word-by-word 'translation' with a length
+    jitter) is written there so that the default command line runs anywhere."""
+    os.makedirs(dataset_path, exist_ok=True)
+    rng = np.random.default_rng(seed)
+    p = 1.0 / np.arange(1, words + 1)
+    p /= p.sum()
+    with open(os.path.join(dataset_path, 'src-train.txt'), 'w', encoding='utf-8') as fs, \
+            open(os.path.join(dataset_path, 'tgt-train.txt'), 'w', encoding='utf-8') as ft:
+        for _ in range(lines):
+            n = int(rng.integers(3, 41))
+            ids = rng.choice(words, size=n, p=p)
+            fs.write(" ".join(f"s{i}" for i in ids) + "\n")
+            keep = ids[rng.random(n) > 0.08]
+            ft.write(" ".join(f"t{(int(i) * 7 + 3) % words}" for i in keep) + (" t0" if rng.random() < 0.3 else "") + "\n")
+
+
 def load_dataset(dataset_path, sequence_length, src_vocab_file, tgt_vocab_file, batch_size, buffer_size, seed=0,
                  holdout=0.05):
     """utils.py:114-161.  The reference opens src-test.txt / tgt-test.txt, which it does not ship (SURVEY §0 trap 6):
     when they are missing, the last ``holdout`` fraction of the train files is held out as the test set."""
+    if not os.path.exists(os.path.join(dataset_path, 'src-train.txt')):
+        print('{}src-train.txt not found: writing a synthetic parallel corpus there'.format(dataset_path))
+        make_synthetic_corpus(dataset_path)
     pairs = read_data(os.path.join(dataset_path, 'src-train.txt'), os.path.join(dataset_path, 'tgt-train.txt'))
     st, tt = os.path.join(dataset_path, 'src-test.txt'), os.path.join(dataset_path, 'tgt-test.txt')
     if os.path.exists(st) and os.path.exists(tt):
