@@ -56,6 +56,15 @@ int b200xf_gemm_bf16(const void* A, int64_t lda, int a_major, const void* B, int
 int b200xf_attn_fwd(const void* Q, int64_t ld_q, const void* K, int64_t ld_k, const void* V, int64_t ld_v, void* O,
                     int64_t ld_o, float* lse, const uint8_t* kpad, int causal, const float* maskf, int64_t mask_sb,
                     int64_t mask_sq, int B, int H, int Sq, int Sk, int dk, b200xf_stream_t stream);
+/* Training forward: additionally writes O_lo (bf16, same layout / pitch as O) = bf16(O - bf16(O)), the rounding residual of the
+ * attention output.  b200xf_attn_delta_residual then forms delta = rowsum(dO o (O + O_lo)): dS = P o (dP - delta) cancels
+ * catastrophically whenever the value vectors share a common component, and delta from the bf16-rounded O alone then puts
+ * percent-level errors into dQ / dK (tools/attn_precision.py; reverse-mode of Attention.py:29-32). */
+int b200xf_attn_fwd_residual(const void* Q, int64_t ld_q, const void* K, int64_t ld_k, const void* V, int64_t ld_v, void* O,
+                             void* O_lo, int64_t ld_o, float* lse, const uint8_t* kpad, int causal, const float* maskf, int64_t mask_sb,
+                             int64_t mask_sq, int B, int H, int Sq, int Sk, int dk, b200xf_stream_t stream);
+int b200xf_attn_delta_residual(const void* O, const void* O_lo, int64_t ld_o, const void* dO, int64_t ld_do, float* delta, int B, int S,
+                               int H, int dk, b200xf_stream_t stream);
 /*      delta: fp32 [B,H,Sq] = rowsum(dO o O) (b200xf_attn_delta); dq_acc: [B*Sq, ld_dq] ZEROED by the caller, fp32
  *      (every key tile's contribution reduce-added by TMA, cp.reduce.async.bulk.tensor) or, with dq_is_bf16, bf16
  *      (added with red.global.add.v4.bf16x2 directly into the tensor the QKV weight-gradient GEMM reads);
@@ -159,6 +168,11 @@ int b200xf_model_create(const b200xf_model_config* cfg, float* params, float* gr
                         void* shadow, const float* pos_in, const float* pos_tgt, void* workspace,
                         b200xf_model** out);
 void b200xf_model_destroy(b200xf_model* m);
+/* Inside one forward / backward call the library forks work that is off the critical path (weight-gradient GEMMs, bias
+ * column sums, the cross-attention K/V projections) onto a second stream it owns and joins it back before returning, so the
+ * caller still orders everything with ONE stream (and may capture that stream into a CUDA graph).  on = 0 keeps every kernel
+ * on the caller's stream (also: environment B200XF_CONCURRENCY=0 at model creation). */
+void b200xf_model_set_concurrency(b200xf_model* m, int on);
 /* when seed_dev != NULL the dropout seed of forward/backward is read from this device word (b200xf_step_params output)
  * instead of the `seed` argument -- required for CUDA-graph replays */
 void b200xf_model_set_seed_ptr(b200xf_model* m, const uint64_t* seed_dev);

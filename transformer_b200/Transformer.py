@@ -188,7 +188,8 @@ class Transformer:
         shift = (-raw.data_ptr()) % 1024
         self._workspace = raw[shift:shift + int(nbytes)]
         h = C.c_void_p()
-        L.call("b200xf_model_create", C.byref(c), L.ptr(self.params), L.ptr(self.grads), L.ptr(self.adam_m), L.ptr(self.adam_v),
+        with torch.cuda.device(self.device):          # the library creates its second stream / events on the current device
+          L.call("b200xf_model_create", C.byref(c), L.ptr(self.params), L.ptr(self.grads), L.ptr(self.adam_m), L.ptr(self.adam_v),
                L.ptr(self.shadow), L.ptr(self.pos_encoding_in), L.ptr(self.pos_encoding_tgt), L.ptr(self._workspace), C.byref(h))
         self._handle = h
         self._handle_generation = getattr(self, "_handle_generation", 0) + 1      # captured CUDA graphs of older handles are stale

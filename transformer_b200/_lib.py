@@ -40,6 +40,8 @@ _SIGS = {
     "b200xf_attn_bwd": [_P, _I64, _P, _I64, _P, _I64, _P, _I64, _P, _P, _P, _I64, _I, _P, _I64, _P, _I64, _P, _I, _P, _I64,
                         _I64, _I, _I, _I, _I, _I, _P],
     "b200xf_attn_delta": [_P, _I64, _P, _I64, _P, _I, _I, _I, _I, _P],
+    "b200xf_attn_fwd_residual": [_P, _I64, _P, _I64, _P, _I64, _P, _P, _I64, _P, _P, _I, _P, _I64, _I64, _I, _I, _I, _I, _I, _P],
+    "b200xf_attn_delta_residual": [_P, _P, _I64, _P, _I64, _P, _I, _I, _I, _I, _P],
     "b200xf_attn_probs": [_P, _I64, _P, _I64, _P, _P, _P, _I, _P, _I64, _I64, _I, _I, _I, _I, _I, _P],
     "b200xf_embed_fwd": [_P, _I, _I, _P, _P, _P, _P, _I64, _I, _I, _I64, _F, _U64, _U32, _P],
     "b200xf_embed_bwd": [_P, _I, _I, _P, _P, _P, _I64, _I, _I, _I64, _F, _U64, _U32, _P],
@@ -61,6 +63,7 @@ _SIGS = {
                               C.POINTER(_I64), C.POINTER(_I64)],
     "b200xf_model_create": [C.POINTER(ModelConfig), _P, _P, _P, _P, _P, _P, _P, _P, C.POINTER(_P)],
     "b200xf_model_destroy": [_P],
+    "b200xf_model_set_concurrency": [_P, _I],
     "b200xf_model_sync_shadow": [_P, _P],
     "b200xf_model_forward": [_P, _P, _P, _I, _I, _I, _I, _I, _I, _U64, _P, _P, _I64, _P, _P, _I64, _P],
     "b200xf_model_loss": [_P, _P, _I, _I, _F, _P, _I, _P],
@@ -78,7 +81,7 @@ _SIGS = {
 }
 _RESTYPES = {"b200xf_last_error": C.c_char_p, "b200xf_launch_count": C.c_longlong,
              "b200xf_model_param_count": _I64, "b200xf_model_workspace_bytes": _I64,
-             "b200xf_model_destroy": None, "b200xf_model_set_seed_ptr": None, "b200xf_prof_enable": None, "b200xf_gemm_force_cta_group": None}
+             "b200xf_model_destroy": None, "b200xf_model_set_concurrency": None, "b200xf_model_set_seed_ptr": None, "b200xf_prof_enable": None, "b200xf_gemm_force_cta_group": None}
 
 EXPORTED_SYMBOLS = tuple(_SIGS)
 

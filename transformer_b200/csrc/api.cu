@@ -28,6 +28,16 @@ int b200xf_attn_fwd(const void* Q, int64_t ld_q, const void* K, int64_t ld_k, co
   return bx::attn_fwd(Q, ld_q, K, ld_k, V, ld_v, O, ld_o, lse, kpad, causal, maskf, mask_sb, mask_sq, B, H, Sq, Sk, dk,
                       ST(stream));
 }
+int b200xf_attn_fwd_residual(const void* Q, int64_t ld_q, const void* K, int64_t ld_k, const void* V, int64_t ld_v, void* O,
+                             void* O_lo, int64_t ld_o, float* lse, const uint8_t* kpad, int causal, const float* maskf, int64_t mask_sb,
+                             int64_t mask_sq, int B, int H, int Sq, int Sk, int dk, b200xf_stream_t stream) {
+  return bx::attn_fwd(Q, ld_q, K, ld_k, V, ld_v, O, ld_o, lse, kpad, causal, maskf, mask_sb, mask_sq, B, H, Sq, Sk, dk,
+                      ST(stream), O_lo);
+}
+int b200xf_attn_delta_residual(const void* O, const void* O_lo, int64_t ld_o, const void* dO, int64_t ld_do, float* delta, int B, int S,
+                               int H, int dk, b200xf_stream_t stream) {
+  return bx::attn_delta(O, ld_o, dO, ld_do, delta, B, S, H, dk, ST(stream), O_lo);
+}
 int b200xf_attn_bwd(const void* Q, int64_t ld_q, const void* K, int64_t ld_k, const void* V, int64_t ld_v,
                     const void* dO, int64_t ld_do, const float* lse, const float* delta, void* dq_acc, int64_t ld_dq,
                     int dq_is_bf16, void* dK, int64_t ld_dk, void* dV, int64_t ld_dv, const uint8_t* kpad, int causal,

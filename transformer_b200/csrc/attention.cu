@@ -45,19 +45,40 @@ struct AttnMask {
   int causal;             // 1: key index > query index is masked (look-ahead mask)
 };
 
+// A [128 x DK] bf16 tile lives in shared memory as NP = DK / PW PANELS of [128 rows x PW columns] (PW = min(DK, 64): a panel
+// row is at most one 128-byte swizzle span).  Head depth 128 = two 64-column panels, 16 KB apart.
 template <int DK>
 struct AttnCfg {
-  static constexpr uint32_t ROW_BYTES = DK * 2;
-  static constexpr uint32_t TILE_BYTES = 128 * ROW_BYTES;      // a [128 x DK] bf16 tile
-  static constexpr uint32_t SWZ = DK == 64 ? kSwz128 : kSwz64;  // swizzle span == row bytes
+  static_assert(DK == 32 || DK == 64 || DK == 128, "head depth");
+  static constexpr int PW = DK < 64 ? DK : 64;                 // panel width (elements)
+  static constexpr int NP = DK / PW;                           // panels per tile
+  static constexpr uint32_t ROW_BYTES = PW * 2;                // bytes of one panel row
+  static constexpr uint32_t PANEL_BYTES = 128 * ROW_BYTES;
+  static constexpr uint32_t TILE_BYTES = NP * PANEL_BYTES;     // a [128 x DK] bf16 tile
+  static constexpr uint32_t SWZ = PW == 64 ? kSwz128 : kSwz64;  // swizzle span == panel row bytes
   static constexpr uint32_t SBO = 8 * ROW_BYTES;               // 8-row core-matrix group
   static constexpr uint32_t P_BYTES = 128 * 256;               // [128 x 128] bf16 as two 128-byte-wide panels
-  static constexpr uint32_t KSTEP_MN = 16 * ROW_BYTES;         // k16 step of an MN-major [rows x DK] tile
+  static constexpr uint32_t KSTEP_MN = 16 * ROW_BYTES;         // k16 step of an MN-major [rows x DK] tile (16 rows down)
+  // byte offset of the k-th 16-element slice along DK of a K-major tile (rows x DK): panel, then 32 bytes per slice
+  static __device__ __forceinline__ uint32_t kmajor_k16(int k) { return (uint32_t)((k * 16) / PW) * PANEL_BYTES + (uint32_t)((k * 16) % PW) * 2u; }
 };
 
+// byte offset of 16-byte chunk `chunk` of row `row` of a [128 x DK] bf16 tile
 template <int DK>
 __device__ __forceinline__ uint32_t swz_off(uint32_t row, uint32_t chunk) {
-  return DK == 64 ? swz128_off(row, chunk) : swz64_off(row, chunk);
+  if (DK == 32) return swz64_off(row, chunk);
+  return (chunk >> 3) * AttnCfg<DK>::PANEL_BYTES + swz128_off(row, chunk & 7u);
+}
+// TMA load / store of a whole [128 x DK] tile (NP boxes of PW columns); the loads complete on `bar`
+template <int DK>
+__device__ __forceinline__ void tile_load(uint8_t* dst, const CUtensorMap* tm, uint64_t* bar, int col, int row, int b) {
+#pragma unroll
+  for (int p = 0; p < AttnCfg<DK>::NP; ++p) tma_load_3d(dst + p * AttnCfg<DK>::PANEL_BYTES, tm, bar, col + p * AttnCfg<DK>::PW, row, b);
+}
+template <int DK>
+__device__ __forceinline__ void tile_store(const CUtensorMap* tm, const uint8_t* src, int col, int row, int b) {
+#pragma unroll
+  for (int p = 0; p < AttnCfg<DK>::NP; ++p) tma_store_3d(tm, src + p * AttnCfg<DK>::PANEL_BYTES, col + p * AttnCfg<DK>::PW, row, b);
 }
 
 // ================================================================================================
@@ -66,10 +87,11 @@ __device__ __forceinline__ uint32_t swz_off(uint32_t row, uint32_t chunk) {
 template <int DK>
 struct FwdSmem {
   using C = AttnCfg<DK>;
+  static constexpr int KVS = DK <= 64 ? 2 : 1;                          // K/V stages (head depth 128: one, shared memory is full)
   static constexpr uint32_t OFF_Q = 0;                                  // 2 slots
-  static constexpr uint32_t OFF_K = OFF_Q + 2 * C::TILE_BYTES;          // 2 stages
-  static constexpr uint32_t OFF_V = OFF_K + 2 * C::TILE_BYTES;          // 2 stages
-  static constexpr uint32_t OFF_P = OFF_V + 2 * C::TILE_BYTES;          // 2 slots
+  static constexpr uint32_t OFF_K = OFF_Q + 2 * C::TILE_BYTES;          // KVS stages
+  static constexpr uint32_t OFF_V = OFF_K + KVS * C::TILE_BYTES;        // KVS stages
+  static constexpr uint32_t OFF_P = OFF_V + KVS * C::TILE_BYTES;        // 2 slots
   static constexpr uint32_t OFF_BAR = OFF_P + 2 * C::P_BYTES;
   static constexpr uint32_t OFF_PADW = OFF_BAR + 256;                   // key-padding bit words: [2 slots][kMaxPadTiles][4]
   static constexpr uint32_t BYTES = OFF_PADW + 2 * 64 * 4 * 4 + 1024;
@@ -86,9 +108,11 @@ template <int DK, bool kMaskF>
 __global__ void __launch_bounds__(ATTN_FWD_THREADS, 1)
 attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                 const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmO,
+                const __grid_constant__ CUtensorMap tmOlo, int has_lo,
                 float* __restrict__ lse_out, AttnMask mask, int H, int Sq, int Sk, float scale) {
   using C = AttnCfg<DK>;
   using L = FwdSmem<DK>;
+  constexpr int KVS = L::KVS;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L::OFF_BAR);
@@ -154,17 +178,17 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       // ===================================== TMA producer =====================================
       for (int s = 0; s < n_slots; ++s) {
         mbar_arrive_expect_tx(&q_full[s], C::TILE_BYTES);
-        tma_load_3d(smem + L::OFF_Q + s * C::TILE_BYTES, &tmQ, &q_full[s], h * DK, q0 + s * 128, b);
+        tile_load<DK>(smem + L::OFF_Q + s * C::TILE_BYTES, &tmQ, &q_full[s], h * DK, q0 + s * 128, b);
       }
       for (int j = 0; j < ntiles; ++j) {
-        const int st = j & 1;
-        const uint32_t ph = (j >> 1) & 1;
+        const int st = j % KVS;
+        const uint32_t ph = (j / KVS) & 1;
         mbar_wait(&k_empty[st], ph ^ 1);
         mbar_arrive_expect_tx(&k_full[st], C::TILE_BYTES);
-        tma_load_3d(smem + L::OFF_K + st * C::TILE_BYTES, &tmK, &k_full[st], h * DK, j * 128, b);
+        tile_load<DK>(smem + L::OFF_K + st * C::TILE_BYTES, &tmK, &k_full[st], h * DK, j * 128, b);
         mbar_wait(&v_empty[st], ph ^ 1);
         mbar_arrive_expect_tx(&v_full[st], C::TILE_BYTES);
-        tma_load_3d(smem + L::OFF_V + st * C::TILE_BYTES, &tmV, &v_full[st], h * DK, j * 128, b);
+        tile_load<DK>(smem + L::OFF_V + st * C::TILE_BYTES, &tmV, &v_full[st], h * DK, j * 128, b);
       }
     }
   } else if (warp == 1) {
@@ -174,15 +198,15 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     const uint32_t sQ = smem_u32(smem + L::OFF_Q), sK = smem_u32(smem + L::OFF_K), sV = smem_u32(smem + L::OFF_V),
                    sP = smem_u32(smem + L::OFF_P);
     auto issue_S = [&](int s, int j) {
-      const int st = j & 1;
-      mbar_wait(&k_full[st], (j >> 1) & 1);
+      const int st = j % KVS;
+      mbar_wait(&k_full[st], (j / KVS) & 1);
       if (j == 0) mbar_wait(&q_full[s], 0);
       tcgen05_after_thread_sync();
       if (lane == 0) {
 #pragma unroll
         for (int k = 0; k < DK / 16; ++k) {
-          const uint64_t ad = make_smem_desc(sQ + s * C::TILE_BYTES + k * 32, 0, C::SBO, C::SWZ);
-          const uint64_t bd = make_smem_desc(sK + st * C::TILE_BYTES + k * 32, 0, C::SBO, C::SWZ);
+          const uint64_t ad = make_smem_desc(sQ + s * C::TILE_BYTES + C::kmajor_k16(k), 0, C::SBO, C::SWZ);
+          const uint64_t bd = make_smem_desc(sK + st * C::TILE_BYTES + C::kmajor_k16(k), 0, C::SBO, C::SWZ);
           umma_f16(tS[s], ad, bd, idescS, k > 0 ? 1u : 0u);
         }
         umma_commit(&s_full[s]);
@@ -192,15 +216,15 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       __syncwarp();
     };
     auto issue_PV = [&](int s, int j) {
-      const int st = j & 1;
+      const int st = j % KVS;
       mbar_wait(&p_full[s], j & 1);
-      mbar_wait(&v_full[st], (j >> 1) & 1);
+      mbar_wait(&v_full[st], (j / KVS) & 1);
       tcgen05_after_thread_sync();
       if (lane == 0) {
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
           const uint64_t ad = make_smem_desc(sP + s * C::P_BYTES + (k >> 2) * 16384 + (k & 3) * 32, 0, 1024, kSwz128);
-          const uint64_t bd = make_smem_desc(sV + st * C::TILE_BYTES + k * C::KSTEP_MN, C::TILE_BYTES, C::SBO, C::SWZ);
+          const uint64_t bd = make_smem_desc(sV + st * C::TILE_BYTES + k * C::KSTEP_MN, C::PANEL_BYTES, C::SBO, C::SWZ);
           umma_f16(tO[s], ad, bd, idescO, (j > 0 || k > 0) ? 1u : 0u);   // O accumulates in TMEM over the kv tiles
         }
         umma_commit(&o_full[s]);
@@ -385,25 +409,44 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       tcgen05_after_thread_sync();
       if (s == 0 && wg_tid == 0) tl_stamp(2);
       const float inv = 1.f / l_run;
+      // Training also keeps the bf16 ROUNDING RESIDUAL of O (O_lo = bf16(O - bf16(O)), staged in this slot's Q tile, which no
+      // MMA reads any more): the backward's delta = rowsum(dO o O) cancels against dP = dO.V^T in dS = P o (dP - delta), and
+      // any component shared by all value vectors (bias, LayerNorm beta) makes that cancellation amplify the 2^-9 rounding of
+      // O into percent-level errors of dQ / dK (measured: tools/attn_precision.py).  delta is formed from O + O_lo.
+      const uint32_t sLo = smem_u32(smem + L::OFF_Q + s * C::TILE_BYTES);
 #pragma unroll
       for (int c = 0; c < DK / 32; ++c) {
         uint32_t ro[32];
         tmem_ld_x32(tO[s] + lane_sel + c * 32, ro);
         tmem_ld_wait();
 #pragma unroll
-        for (int g = 0; g < 4; ++g)
-          st_shared_v4(sPs + swz_off<DK>(row, c * 4 + g),
-                       pack_bf16x2(__uint_as_float(ro[8 * g]) * inv, __uint_as_float(ro[8 * g + 1]) * inv),
-                       pack_bf16x2(__uint_as_float(ro[8 * g + 2]) * inv, __uint_as_float(ro[8 * g + 3]) * inv),
-                       pack_bf16x2(__uint_as_float(ro[8 * g + 4]) * inv, __uint_as_float(ro[8 * g + 5]) * inv),
-                       pack_bf16x2(__uint_as_float(ro[8 * g + 6]) * inv, __uint_as_float(ro[8 * g + 7]) * inv));
+        for (int g = 0; g < 4; ++g) {
+          uint32_t hi[4], lo[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const float a = __uint_as_float(ro[8 * g + 2 * e]) * inv, c2 = __uint_as_float(ro[8 * g + 2 * e + 1]) * inv;
+            hi[e] = pack_bf16x2(a, c2);
+            const float2 r = unpack_bf16x2(hi[e]);
+            lo[e] = pack_bf16x2(a - r.x, c2 - r.y);
+          }
+          st_shared_v4(sPs + swz_off<DK>(row, c * 4 + g), hi[0], hi[1], hi[2], hi[3]);
+          if (has_lo) st_shared_v4(sLo + swz_off<DK>(row, c * 4 + g), lo[0], lo[1], lo[2], lo[3]);
+        }
       }
-      if (q < Sq) lse_out[((long long)b * H + h) * Sq + q] = (m_used + __log2f(l_run)) * 0.6931471805599453f;   // back to natural log
+      if (q < Sq) {
+        float lse_val = (m_used + __log2f(l_run)) * 0.6931471805599453f;   // back to natural log
+        // a fully-masked row: every logit is the reference's finite -1e9 (times the mask value); fp32 absorbs ln(Sk) there, and
+        // raw * scale only reproduces -1e9 to ~64 ulp-units when scale is not a power of two (head depth 32, 128): snap, so that
+        // the backward / attention_weights recompute exp(-1e9 - lse) = 1 exactly like the reference's own fp32 softmax
+        if (m_used < -1e8f) lse_val = kMaskVal * rintf(lse_val / kMaskVal);
+        lse_out[((long long)b * H + h) * Sq + q] = lse_val;
+      }
       tcgen05_before_thread_sync();
       fence_proxy_async_smem();
       named_bar_sync(1 + s, 128);
       if (wg_tid == 0) {
-        tma_store_3d(&tmO, smem + L::OFF_P + s * C::P_BYTES, h * DK, q0 + s * 128, b);
+        tile_store<DK>(&tmO, smem + L::OFF_P + s * C::P_BYTES, h * DK, q0 + s * 128, b);
+        if (has_lo) tile_store<DK>(&tmOlo, smem + L::OFF_Q + s * C::TILE_BYTES, h * DK, q0 + s * 128, b);
         tma_store_commit();
         tma_store_wait_read<0>();          // smem may be released; the write itself completes before the grid does
         if (s == 0) tl_stamp(3);
@@ -421,17 +464,25 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
 //   S^T = K.Q^T, dP^T = V.dO^T (TMEM)  ->  P^T = exp(S^T*scale - lse), dS^T = P^T o (dP^T - delta) * scale  (smem, bf16)
 //   dV += P^T.dO   dK += dS^T.Q   (TMEM accumulators over all query tiles)    dQ_tile = dS.K  -> added into global dQ (bf16: red.global.v4.bf16x2; fp32: TMA reduce-add)
 // ================================================================================================
+// Head depth 128: the five accumulators S^T, dP^T, dV, dK, dQ (+ P^T) would need 704 tensor-memory columns, so every
+// (kv tile, head, batch) is handled by NH = 2 CTAs; both compute the full S^T / dP^T (contraction over all 128 channels) and
+// each produces ONE 64-column half (DKO) of dV, dK and dQ.  Shared memory then only holds one Q/dO stage (QS = 1) and the fp32
+// dQ staging is dropped (bf16 dQ only).  A slower, correct path for the reference's default configuration (4 heads of 128).
 template <int DK>
 struct BwdSmem {
   using C = AttnCfg<DK>;
+  static constexpr int DKO = DK <= 64 ? DK : 64;                    // output columns per CTA
+  static constexpr int NH = DK / DKO;                               // CTAs per (kv tile, head, batch)
+  static constexpr int QS = DK <= 64 ? 2 : 1;                       // Q / dO stages
   static constexpr uint32_t OFF_K = 0;
   static constexpr uint32_t OFF_V = OFF_K + C::TILE_BYTES;
-  static constexpr uint32_t OFF_Q = OFF_V + C::TILE_BYTES;          // 2 stages
-  static constexpr uint32_t OFF_DO = OFF_Q + 2 * C::TILE_BYTES;     // 2 stages
-  static constexpr uint32_t OFF_DST = OFF_DO + 2 * C::TILE_BYTES;   // dS^T [kv 128][q 128] bf16, two panels, DOUBLE buffered
+  static constexpr uint32_t OFF_Q = OFF_V + C::TILE_BYTES;          // QS stages
+  static constexpr uint32_t OFF_DO = OFF_Q + QS * C::TILE_BYTES;    // QS stages
+  static constexpr uint32_t OFF_DST = OFF_DO + QS * C::TILE_BYTES;  // dS^T [kv 128][q 128] bf16, two panels, DOUBLE buffered
                                                                     // (P^T lives in tensor memory, not in smem)
-  static constexpr uint32_t OFF_DQ = OFF_DST + 2 * C::P_BYTES;      // fp32-dQ variant only: dQ tile fp32 [128 x DK] as two [128 x DK/2] boxes (TMA reduce-add staging)
-  static constexpr uint32_t OFF_ROW = OFF_DQ + 2 * C::TILE_BYTES;   // lse/delta: 2 buffers x (128 + 128) floats
+  static constexpr uint32_t OFF_DQ = OFF_DST + 2 * C::P_BYTES;      // fp32-dQ variant only: dQ tile fp32 [128 x DKO] as two [128 x DKO/2] boxes (TMA reduce-add staging)
+  static constexpr uint32_t DQ_BYTES = DK <= 64 ? 2 * 128 * (DKO / 2) * 4 : 0;
+  static constexpr uint32_t OFF_ROW = OFF_DQ + DQ_BYTES;            // lse/delta: 2 buffers x (128 + 128) floats
   static constexpr uint32_t OFF_BAR = OFF_ROW + 2 * 256 * 4;
   static constexpr uint32_t BYTES = OFF_BAR + 256 + 1024;
 };
@@ -447,6 +498,8 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
                 AttnMask mask, int H, int Sq, int Sk, float scale, __nv_bfloat16* dq16, long long ld_dq16) {
   using C = AttnCfg<DK>;
   using L = BwdSmem<DK>;
+  constexpr int DKO = L::DKO, NH = L::NH, QS = L::QS;
+  static_assert(kDqBf16 || DK <= 64, "head depth 128: bf16 dQ only");
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L::OFF_BAR);
@@ -464,7 +517,9 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   const uint32_t warp = warp_idx(), lane = lane_idx();
   long long* const tlp = tl_begin();
   if (threadIdx.x == 64) tl_stamp(60);
-  const int b = blockIdx.z, h = blockIdx.y, jt = blockIdx.x;
+  const int b = blockIdx.z, h = blockIdx.y, jt = blockIdx.x / NH;
+  const int ho = blockIdx.x % NH;                 // which DKO-column half of dV / dK / dQ this CTA produces (head depth 128)
+  const uint32_t ho_panel = (uint32_t)ho * C::PANEL_BYTES;
   const int kv0 = jt * 128;
   const int nq = (Sq + 127) / 128;
   const bool lead_pad = mask.causal && mask.kpad != nullptr && mask.kpad[(long long)b * Sk] != 0;
@@ -484,46 +539,46 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   tcgen05_after_thread_sync();
   const uint32_t tmem_base = *tmem_ptr;
   // tensor memory (512 columns): S^T 128 | dP^T 128 | dV dk | dK dk | dQ dk | P^T (bf16 pairs) 64
-  const uint32_t tSt = tmem_base, tdPt = tmem_base + 128, tdV = tmem_base + 256, tdK = tmem_base + 256 + DK,
-                 tdQ = tmem_base + 256 + 2 * DK, tPt = tmem_base + 256 + 3 * DK;
+  const uint32_t tSt = tmem_base, tdPt = tmem_base + 128, tdV = tmem_base + 256, tdK = tmem_base + 256 + DKO,
+                 tdQ = tmem_base + 256 + 2 * DKO, tPt = tmem_base + 256 + 3 * DKO;
 
   if (warp == 0) {
     if (lane == 0) {
       // ===================================== TMA producer =====================================
       mbar_arrive_expect_tx(kv_full, 2 * C::TILE_BYTES);
-      tma_load_3d(smem + L::OFF_K, &tmK, kv_full, h * DK, kv0, b);
-      tma_load_3d(smem + L::OFF_V, &tmV, kv_full, h * DK, kv0, b);
+      tile_load<DK>(smem + L::OFF_K, &tmK, kv_full, h * DK, kv0, b);
+      tile_load<DK>(smem + L::OFF_V, &tmV, kv_full, h * DK, kv0, b);
       int n = 0;
       for (int i = i_start; i < nq; ++i, ++n) {
-        const int st = n & 1;
-        mbar_wait(&qdo_empty[st], ((n >> 1) & 1) ^ 1);
+        const int st = n % QS;
+        mbar_wait(&qdo_empty[st], ((n / QS) & 1) ^ 1);
         mbar_arrive_expect_tx(&qdo_full[st], 2 * C::TILE_BYTES);
-        tma_load_3d(smem + L::OFF_Q + st * C::TILE_BYTES, &tmQ, &qdo_full[st], h * DK, i * 128, b);
-        tma_load_3d(smem + L::OFF_DO + st * C::TILE_BYTES, &tmdO, &qdo_full[st], h * DK, i * 128, b);
+        tile_load<DK>(smem + L::OFF_Q + st * C::TILE_BYTES, &tmQ, &qdo_full[st], h * DK, i * 128, b);
+        tile_load<DK>(smem + L::OFF_DO + st * C::TILE_BYTES, &tmdO, &qdo_full[st], h * DK, i * 128, b);
       }
     }
   } else if (warp == 1) {
     // ===================================== MMA issuer =====================================
     constexpr uint32_t idescS = make_idesc_bf16(128, 128, 0, 0);    // [kv, q] = K/V (K-major) . Q/dO^T (K-major)
-    constexpr uint32_t idescKV = make_idesc_bf16(128, DK, 0, 1);    // [kv, dk] = P^T/dS^T (K-major) . dO/Q (MN-major)
-    constexpr uint32_t idescQ = make_idesc_bf16(128, DK, 1, 1);     // [q, dk]  = dS (MN-major view of dS^T) . K (MN-major)
+    constexpr uint32_t idescKV = make_idesc_bf16(128, DKO, 0, 1);   // [kv, dk] = P^T/dS^T (K-major) . dO/Q (MN-major)
+    constexpr uint32_t idescQ = make_idesc_bf16(128, DKO, 1, 1);    // [q, dk]  = dS (MN-major view of dS^T) . K (MN-major)
     const uint32_t sK = smem_u32(smem + L::OFF_K), sV = smem_u32(smem + L::OFF_V), sQ = smem_u32(smem + L::OFF_Q),
                    sdO = smem_u32(smem + L::OFF_DO), sdSt = smem_u32(smem + L::OFF_DST);
     auto issue_sdp = [&](int n) {
-      const int st = n & 1;
-      mbar_wait(&qdo_full[st], (n >> 1) & 1);
+      const int st = n % QS;
+      mbar_wait(&qdo_full[st], (n / QS) & 1);
       tcgen05_after_thread_sync();
       if (lane == 0) {
 #pragma unroll
         for (int k = 0; k < DK / 16; ++k) {
-          const uint64_t ad = make_smem_desc(sK + k * 32, 0, C::SBO, C::SWZ);
-          const uint64_t bd = make_smem_desc(sQ + st * C::TILE_BYTES + k * 32, 0, C::SBO, C::SWZ);
+          const uint64_t ad = make_smem_desc(sK + C::kmajor_k16(k), 0, C::SBO, C::SWZ);
+          const uint64_t bd = make_smem_desc(sQ + st * C::TILE_BYTES + C::kmajor_k16(k), 0, C::SBO, C::SWZ);
           umma_f16(tSt, ad, bd, idescS, k > 0 ? 1u : 0u);
         }
 #pragma unroll
         for (int k = 0; k < DK / 16; ++k) {
-          const uint64_t ad = make_smem_desc(sV + k * 32, 0, C::SBO, C::SWZ);
-          const uint64_t bd = make_smem_desc(sdO + st * C::TILE_BYTES + k * 32, 0, C::SBO, C::SWZ);
+          const uint64_t ad = make_smem_desc(sV + C::kmajor_k16(k), 0, C::SBO, C::SWZ);
+          const uint64_t bd = make_smem_desc(sdO + st * C::TILE_BYTES + C::kmajor_k16(k), 0, C::SBO, C::SWZ);
           umma_f16(tdPt, ad, bd, idescS, k > 0 ? 1u : 0u);
         }
         umma_commit(sdp_full);
@@ -536,25 +591,25 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     // per tile the tensor core runs   dV(n) | S^T,dP^T(n+1) | dK(n), dQ(n)   so the compute warps can start on tile n+1
     // (their S^T/dP^T are ready after the first two groups) while dK/dQ of tile n are still executing
     for (int n = 0; n < ntile; ++n) {
-      const int st = n & 1;
+      const int st = n % QS;
       const uint32_t sdS = sdSt + (n & 1) * C::P_BYTES;
       mbar_wait(pds_full, n & 1);
       tcgen05_after_thread_sync();
       if (lane == 0) {
 #pragma unroll
         for (int k = 0; k < 8; ++k) {   // dV += P^T . dO     (K = 128 queries; A = P^T in tensor memory, 8 columns per k16)
-          const uint64_t bd = make_smem_desc(sdO + st * C::TILE_BYTES + k * C::KSTEP_MN, C::TILE_BYTES, C::SBO, C::SWZ);
+          const uint64_t bd = make_smem_desc(sdO + st * C::TILE_BYTES + ho_panel + k * C::KSTEP_MN, C::PANEL_BYTES, C::SBO, C::SWZ);
           umma_f16_ts(tdV, tPt + k * 8, bd, idescKV, (n > 0 || k > 0) ? 1u : 0u);
         }
         umma_commit(pt_free);
       }
       __syncwarp();
-      if (n + 1 < ntile) issue_sdp(n + 1);
+      if (QS == 2 && n + 1 < ntile) issue_sdp(n + 1);     // (one Q/dO stage: the next tile's operands only arrive after dK/dQ below)
       if (lane == 0) {
 #pragma unroll
         for (int k = 0; k < 8; ++k) {   // dK += dS^T . Q
           const uint64_t ad = make_smem_desc(sdS + (k >> 2) * 16384 + (k & 3) * 32, 0, 1024, kSwz128);
-          const uint64_t bd = make_smem_desc(sQ + st * C::TILE_BYTES + k * C::KSTEP_MN, C::TILE_BYTES, C::SBO, C::SWZ);
+          const uint64_t bd = make_smem_desc(sQ + st * C::TILE_BYTES + ho_panel + k * C::KSTEP_MN, C::PANEL_BYTES, C::SBO, C::SWZ);
           umma_f16(tdK, ad, bd, idescKV, (n > 0 || k > 0) ? 1u : 0u);
         }
       }
@@ -563,13 +618,14 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
 #pragma unroll
         for (int k = 0; k < 8; ++k) {   // dQ = dS . K        (K = 128 keys; A = MN-major view of dS^T)
           const uint64_t ad = make_smem_desc(sdS + k * 2048, 16384, 1024, kSwz128);
-          const uint64_t bd = make_smem_desc(sK + k * C::KSTEP_MN, C::TILE_BYTES, C::SBO, C::SWZ);
+          const uint64_t bd = make_smem_desc(sK + ho_panel + k * C::KSTEP_MN, C::PANEL_BYTES, C::SBO, C::SWZ);
           umma_f16(tdQ, ad, bd, idescQ, k > 0 ? 1u : 0u);
         }
         umma_commit(&qdo_empty[st]);
         umma_commit(dq_full);
       }
       __syncwarp();
+      if (QS == 1 && n + 1 < ntile) issue_sdp(n + 1);
     }
   } else {
     // ===================================== compute warps =====================================
@@ -586,7 +642,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     const float sl2 = scale * kLog2e;
     const float inv_sk = 1.f / (float)Sk;
     const uint32_t sDQ = smem_u32(smem + L::OFF_DQ);
-    constexpr int HC = DK / 2;
+    constexpr int HC = DKO / 2;
     // no padded / out-of-range key among this warp's rows (fixed for the whole CTA)
     const bool rows_clean = !__any_sync(0xffffffffu, kv_pad || !kv_valid);
     // ... and among ALL 128 keys of this CTA's tile (every lane looks at 4 of them)
@@ -640,7 +696,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         mbar_arrive(dq_free);                    // the dQ accumulator may be overwritten by the next tile's MMA
         const int qq = qt0 + (int)row;
         if (qq < Sq) {
-          __nv_bfloat16* dst = dq16 + ((long long)b * Sq + qq) * ld_dq16 + h * DK + half * HC;
+          __nv_bfloat16* dst = dq16 + ((long long)b * Sq + qq) * ld_dq16 + h * DK + ho * DKO + half * HC;
 #pragma unroll
           for (int g = 0; g < HC / 8; ++g)
             asm volatile("red.global.add.noftz.v4.bf16x2 [%0], {%1, %2, %3, %4};" ::"l"(dst + 8 * g), "r"(pack_bf16x2(v[8 * g], v[8 * g + 1])),
@@ -655,7 +711,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       // reduce-add per half (cp.reduce.async.bulk.tensor .add.f32; rows >= Sq are clipped by TMA)
       if (ctid == 0) tma_store_wait_read<0>();   // the previous reduce has drained the staging
       named_bar_sync(2, 256);
-      const uint32_t stg = sDQ + half * C::TILE_BYTES;
+      const uint32_t stg = sDQ + half * (L::DQ_BYTES / 2);
       if (HC == 32) {
         uint32_t r[32];
         tmem_ld_x32(tdQ + lane_sel + half * HC, r);
@@ -675,7 +731,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       named_bar_sync(3, 256);
       if (ctid == 0) {
         tma_reduce_add_3d(&tmdQ, smem + L::OFF_DQ, h * DK, qt0, b);
-        tma_reduce_add_3d(&tmdQ, smem + L::OFF_DQ + C::TILE_BYTES, h * DK + HC, qt0, b);
+        tma_reduce_add_3d(&tmdQ, smem + L::OFF_DQ + L::DQ_BYTES / 2, h * DK + HC, qt0, b);
         tma_store_commit();
         tl_stamp(64 + (n_done & 7) * 8 + 5);
       }
@@ -798,8 +854,8 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       named_bar_sync(1, 256);
       if (ctid == 0) {
         tl_stamp(61);
-        tma_store_3d(&tmdV, smem + L::OFF_DST, h * DK, kv0, b);
-        tma_store_3d(&tmdK, smem + L::OFF_DST + C::P_BYTES, h * DK, kv0, b);
+        tma_store_3d(&tmdV, smem + L::OFF_DST, h * DK + ho * DKO, kv0, b);      // one box: DKO <= the panel width
+        tma_store_3d(&tmdK, smem + L::OFF_DST + C::P_BYTES, h * DK + ho * DKO, kv0, b);
         tma_store_commit();
         tma_store_wait_read<0>();
         tl_stamp(62);
@@ -849,16 +905,19 @@ attn_probs_kernel(const __nv_bfloat16* __restrict__ Q, long long ld_q, const __n
 // ------------------------------------------------------------------------------------------------
 template <int DK>
 static int attn_fwd_launch(const void* Q, long long ld_q, const void* K, long long ld_k, const void* V, long long ld_v,
-                           void* O, long long ld_o, float* lse, const AttnMask& mask, int B, int H, int Sq, int Sk,
+                           void* O, long long ld_o, void* O_lo, float* lse, const AttnMask& mask, int B, int H, int Sq, int Sk,
                            cudaStream_t st) {
   using L = FwdSmem<DK>;
-  const int swz = DK * 2;
+  constexpr int PW = AttnCfg<DK>::PW;      // TMA box = one panel: [128 tokens x PW columns]
+  const int swz = PW * 2;
   CUtensorMap tmQ, tmK, tmV, tmO;
   int rc;
-  if ((rc = encode_tmap_3d(&tmQ, 0, Q, (uint64_t)H * DK, Sq, B, ld_q, (uint64_t)Sq * ld_q, DK, 128, 1, swz))) return rc;
-  if ((rc = encode_tmap_3d(&tmK, 0, K, (uint64_t)H * DK, Sk, B, ld_k, (uint64_t)Sk * ld_k, DK, 128, 1, swz))) return rc;
-  if ((rc = encode_tmap_3d(&tmV, 0, V, (uint64_t)H * DK, Sk, B, ld_v, (uint64_t)Sk * ld_v, DK, 128, 1, swz))) return rc;
-  if ((rc = encode_tmap_3d(&tmO, 0, O, (uint64_t)H * DK, Sq, B, ld_o, (uint64_t)Sq * ld_o, DK, 128, 1, swz))) return rc;
+  if ((rc = encode_tmap_3d(&tmQ, 0, Q, (uint64_t)H * DK, Sq, B, ld_q, (uint64_t)Sq * ld_q, PW, 128, 1, swz))) return rc;
+  if ((rc = encode_tmap_3d(&tmK, 0, K, (uint64_t)H * DK, Sk, B, ld_k, (uint64_t)Sk * ld_k, PW, 128, 1, swz))) return rc;
+  if ((rc = encode_tmap_3d(&tmV, 0, V, (uint64_t)H * DK, Sk, B, ld_v, (uint64_t)Sk * ld_v, PW, 128, 1, swz))) return rc;
+  if ((rc = encode_tmap_3d(&tmO, 0, O, (uint64_t)H * DK, Sq, B, ld_o, (uint64_t)Sq * ld_o, PW, 128, 1, swz))) return rc;
+  CUtensorMap tmOlo = tmO;
+  if (O_lo != nullptr && (rc = encode_tmap_3d(&tmOlo, 0, O_lo, (uint64_t)H * DK, Sq, B, ld_o, (uint64_t)Sq * ld_o, PW, 128, 1, swz))) return rc;
   auto kern = mask.maskf != nullptr ? attn_fwd_kernel<DK, true> : attn_fwd_kernel<DK, false>;
   {
     static std::mutex mu;
@@ -873,7 +932,7 @@ static int attn_fwd_launch(const void* Q, long long ld_q, const void* K, long lo
   }
   dim3 grid((Sq + 255) / 256, H, B);
   void* pb = prof_on() ? prof_begin(st) : nullptr;
-  kern<<<grid, ATTN_FWD_THREADS, L::BYTES, st>>>(tmQ, tmK, tmV, tmO, lse, mask, H, Sq, Sk, 1.f / sqrtf((float)DK));
+  kern<<<grid, ATTN_FWD_THREADS, L::BYTES, st>>>(tmQ, tmK, tmV, tmO, tmOlo, O_lo != nullptr ? 1 : 0, lse, mask, H, Sq, Sk, 1.f / sqrtf((float)DK));
   if (pb) prof_end(pb, 1, 4.0 * B * H * (double)Sq * Sk * DK, st);     // dense count, as the reference computes it
   BX_POST_LAUNCH();
   return 0;
@@ -885,16 +944,17 @@ static int attn_bwd_launch(const void* Q, long long ld_q, const void* K, long lo
                            long long ld_dq, void* dK, long long ld_dk, void* dV, long long ld_dv, const AttnMask& mask,
                            int B, int H, int Sq, int Sk, cudaStream_t st) {
   using L = BwdSmem<DK>;
-  const int swz = DK * 2;
+  constexpr int PW = AttnCfg<DK>::PW;
+  const int swz = PW * 2;
   CUtensorMap tmQ, tmK, tmV, tmdO, tmdK, tmdV, tmdQ;
   int rc;
-  if ((rc = encode_tmap_3d(&tmQ, 0, Q, (uint64_t)H * DK, Sq, B, ld_q, (uint64_t)Sq * ld_q, DK, 128, 1, swz))) return rc;
-  if ((rc = encode_tmap_3d(&tmK, 0, K, (uint64_t)H * DK, Sk, B, ld_k, (uint64_t)Sk * ld_k, DK, 128, 1, swz))) return rc;
-  if ((rc = encode_tmap_3d(&tmV, 0, V, (uint64_t)H * DK, Sk, B, ld_v, (uint64_t)Sk * ld_v, DK, 128, 1, swz))) return rc;
-  if ((rc = encode_tmap_3d(&tmdO, 0, dO, (uint64_t)H * DK, Sq, B, ld_do, (uint64_t)Sq * ld_do, DK, 128, 1, swz))) return rc;
-  if ((rc = encode_tmap_3d(&tmdK, 0, dK, (uint64_t)H * DK, Sk, B, ld_dk, (uint64_t)Sk * ld_dk, DK, 128, 1, swz))) return rc;
-  if ((rc = encode_tmap_3d(&tmdV, 0, dV, (uint64_t)H * DK, Sk, B, ld_dv, (uint64_t)Sk * ld_dv, DK, 128, 1, swz))) return rc;
-  if (kDqBf16) rc = encode_tmap_3d(&tmdQ, 0, dq_acc, (uint64_t)H * DK, Sq, B, ld_dq, (uint64_t)Sq * ld_dq, DK, 128, 1, swz);
+  if ((rc = encode_tmap_3d(&tmQ, 0, Q, (uint64_t)H * DK, Sq, B, ld_q, (uint64_t)Sq * ld_q, PW, 128, 1, swz))) return rc;
+  if ((rc = encode_tmap_3d(&tmK, 0, K, (uint64_t)H * DK, Sk, B, ld_k, (uint64_t)Sk * ld_k, PW, 128, 1, swz))) return rc;
+  if ((rc = encode_tmap_3d(&tmV, 0, V, (uint64_t)H * DK, Sk, B, ld_v, (uint64_t)Sk * ld_v, PW, 128, 1, swz))) return rc;
+  if ((rc = encode_tmap_3d(&tmdO, 0, dO, (uint64_t)H * DK, Sq, B, ld_do, (uint64_t)Sq * ld_do, PW, 128, 1, swz))) return rc;
+  if ((rc = encode_tmap_3d(&tmdK, 0, dK, (uint64_t)H * DK, Sk, B, ld_dk, (uint64_t)Sk * ld_dk, PW, 128, 1, swz))) return rc;
+  if ((rc = encode_tmap_3d(&tmdV, 0, dV, (uint64_t)H * DK, Sk, B, ld_dv, (uint64_t)Sk * ld_dv, PW, 128, 1, swz))) return rc;
+  if (kDqBf16) rc = encode_tmap_3d(&tmdQ, 0, dq_acc, (uint64_t)H * DK, Sq, B, ld_dq, (uint64_t)Sq * ld_dq, PW, 128, 1, swz);   // (unused: red.global)
   else rc = encode_tmap_3d(&tmdQ, 1, dq_acc, (uint64_t)H * DK, Sq, B, ld_dq, (uint64_t)Sq * ld_dq, DK / 2, 128, 1, swz);
   if (rc) return rc;
   auto kern = attn_bwd_kernel<DK, kDqBf16>;
@@ -908,7 +968,7 @@ static int attn_bwd_launch(const void* Q, long long ld_q, const void* K, long lo
       attr_done[dev] = true;
     }
   }
-  dim3 grid((Sk + 127) / 128, H, B);
+  dim3 grid(((Sk + 127) / 128) * L::NH, H, B);
   void* pb = prof_on() ? prof_begin(st) : nullptr;
   kern<<<grid, ATTN_BWD_THREADS, L::BYTES, st>>>(tmQ, tmK, tmV, tmdO, tmdK, tmdV, tmdQ, lse, delta, mask, H, Sq, Sk,
                                                  1.f / sqrtf((float)DK), (__nv_bfloat16*)dq_acc, ld_dq);
@@ -918,7 +978,7 @@ static int attn_bwd_launch(const void* Q, long long ld_q, const void* K, long lo
 }
 
 static int check_attn_args(int B, int H, int Sq, int Sk, int dk, int causal) {
-  BX_REQUIRE(dk == 32 || dk == 64, "attention: head depth %d unsupported (32 or 64)", dk);
+  BX_REQUIRE(dk == 32 || dk == 64 || dk == 128, "attention: head depth %d unsupported (32, 64 or 128)", dk);
   BX_REQUIRE(B > 0 && H > 0 && Sq > 0 && Sk > 0 && B < 65536 && H < 65536, "attention: bad shape");
   BX_REQUIRE(!causal || Sq == Sk, "attention: causal (look-ahead) mask needs Sq == Sk");
   return 0;
@@ -926,11 +986,12 @@ static int check_attn_args(int B, int H, int Sq, int Sk, int dk, int causal) {
 
 int attn_fwd(const void* Q, long long ld_q, const void* K, long long ld_k, const void* V, long long ld_v, void* O,
              long long ld_o, float* lse, const uint8_t* kpad, int causal, const float* maskf, long long mask_sb,
-             long long mask_sq, int B, int H, int Sq, int Sk, int dk, cudaStream_t st) {
+             long long mask_sq, int B, int H, int Sq, int Sk, int dk, cudaStream_t st, void* O_lo) {
   if (int rc = check_attn_args(B, H, Sq, Sk, dk, causal)) return rc;
   AttnMask m{kpad, maskf, mask_sb, mask_sq, causal};
-  return dk == 64 ? attn_fwd_launch<64>(Q, ld_q, K, ld_k, V, ld_v, O, ld_o, lse, m, B, H, Sq, Sk, st)
-                  : attn_fwd_launch<32>(Q, ld_q, K, ld_k, V, ld_v, O, ld_o, lse, m, B, H, Sq, Sk, st);
+  if (dk == 128) return attn_fwd_launch<128>(Q, ld_q, K, ld_k, V, ld_v, O, ld_o, O_lo, lse, m, B, H, Sq, Sk, st);
+  return dk == 64 ? attn_fwd_launch<64>(Q, ld_q, K, ld_k, V, ld_v, O, ld_o, O_lo, lse, m, B, H, Sq, Sk, st)
+                  : attn_fwd_launch<32>(Q, ld_q, K, ld_k, V, ld_v, O, ld_o, O_lo, lse, m, B, H, Sq, Sk, st);
 }
 
 int attn_bwd(const void* Q, long long ld_q, const void* K, long long ld_k, const void* V, long long ld_v, const void* dO,
@@ -942,6 +1003,10 @@ int attn_bwd(const void* Q, long long ld_q, const void* K, long long ld_k, const
   AttnMask m{kpad, maskf, mask_sb, mask_sq, causal};
 #define BX_BWD_GO(D, BF) \
   return attn_bwd_launch<D, BF>(Q, ld_q, K, ld_k, V, ld_v, dO, ld_do, lse, delta, dq_acc, ld_dq, dK, ld_dk, dV, ld_dv, m, B, H, Sq, Sk, st)
+  if (dk == 128) {
+    BX_REQUIRE(dq_bf16, "attention backward at head depth 128 accumulates dQ in bf16 only (dq_is_bf16 = 1)");
+    BX_BWD_GO(128, true);
+  }
   if (dk == 64) { if (dq_bf16) BX_BWD_GO(64, true); else BX_BWD_GO(64, false); }
   if (dq_bf16) BX_BWD_GO(32, true); else BX_BWD_GO(32, false);
 #undef BX_BWD_GO

@@ -603,11 +603,11 @@ __global__ void pad_mask_kernel(const long long* __restrict__ ids, uint8_t* __re
 // attention backward pre-pass: delta[b,h,q] = sum_c dO[b,q,h*dk+c] * O[b,q,h*dk+c]
 //   one thread per (b, h, q), q fastest: coalesced stores; each thread streams its own 2*dk-byte rows (16-byte loads)
 __global__ void __launch_bounds__(256)
-attn_delta_kernel(const __nv_bfloat16* __restrict__ O, long long ld_o, const __nv_bfloat16* __restrict__ dO,
-                  long long ld_do, float* __restrict__ delta, int B, int S, int H, int dk) {
+attn_delta_kernel(const __nv_bfloat16* __restrict__ O, const __nv_bfloat16* __restrict__ O_lo, long long ld_o,
+                  const __nv_bfloat16* __restrict__ dO, long long ld_do, float* __restrict__ delta, int B, int S, int H, int dk) {
   // dk/8 adjacent lanes share one (row, head): every lane reads 16 contiguous bytes of O and dO, so a warp reads
   // 512 contiguous bytes of each; a sub-warp shuffle finishes the dot product
-  const int lph = dk >> 3;                                              // lanes per head: 4 (dk 32) or 8 (dk 64)
+  const int lph = dk >> 3;                                              // lanes per head: 4 (dk 32), 8 (dk 64) or 16 (dk 128)
   const long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   const long long total = (long long)B * S * H * lph;
   const bool live = idx < total;
@@ -617,7 +617,12 @@ attn_delta_kernel(const __nv_bfloat16* __restrict__ O, long long ld_o, const __n
   const long long row = i / ((long long)lph * H);                       // b * S + q
   const uint4 a = __ldg(reinterpret_cast<const uint4*>(O + row * ld_o + h * dk + l * 8));
   const uint4 d = __ldg(reinterpret_cast<const uint4*>(dO + row * ld_do + h * dk + l * 8));
-  const float2 a0 = unpack_bf16x2(a.x), a1 = unpack_bf16x2(a.y), a2 = unpack_bf16x2(a.z), a3 = unpack_bf16x2(a.w);
+  float2 a0 = unpack_bf16x2(a.x), a1 = unpack_bf16x2(a.y), a2 = unpack_bf16x2(a.z), a3 = unpack_bf16x2(a.w);
+  if (O_lo != nullptr) {          // + the rounding residual the forward kept: O to ~16 mantissa bits (see attn_fwd_kernel)
+    const uint4 r = __ldg(reinterpret_cast<const uint4*>(O_lo + row * ld_o + h * dk + l * 8));
+    const float2 r0 = unpack_bf16x2(r.x), r1 = unpack_bf16x2(r.y), r2 = unpack_bf16x2(r.z), r3 = unpack_bf16x2(r.w);
+    a0.x += r0.x; a0.y += r0.y; a1.x += r1.x; a1.y += r1.y; a2.x += r2.x; a2.y += r2.y; a3.x += r3.x; a3.y += r3.y;
+  }
   const float2 d0 = unpack_bf16x2(d.x), d1 = unpack_bf16x2(d.y), d2 = unpack_bf16x2(d.z), d3 = unpack_bf16x2(d.w);
   float s = a0.x * d0.x + a0.y * d0.y + a1.x * d1.x + a1.y * d1.y + a2.x * d2.x + a2.y * d2.y + a3.x * d3.x + a3.y * d3.y;
   for (int o = lph >> 1; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
@@ -777,11 +782,11 @@ int pad_mask(const long long* ids, int id_stride, int id_offset, uint8_t* mask, 
   return 0;
 }
 int attn_delta(const void* O, long long ld_o, const void* dO, long long ld_do, float* delta, int B, int S, int H, int dk,
-               cudaStream_t st) {
-  BX_REQUIRE((dk == 32 || dk == 64) && ld_o % 8 == 0 && ld_do % 8 == 0, "attn_delta: depth must be 32 or 64, leading dimensions multiples of 8");
+               cudaStream_t st, const void* O_lo) {
+  BX_REQUIRE((dk == 32 || dk == 64 || dk == 128) && ld_o % 8 == 0 && ld_do % 8 == 0, "attn_delta: depth must be 32, 64 or 128, leading dimensions multiples of 8");
   const long long n = (long long)B * S * H * (dk / 8);
-  attn_delta_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>((const __nv_bfloat16*)O, ld_o, (const __nv_bfloat16*)dO, ld_do, delta, B,
-                                                                 S, H, dk);
+  attn_delta_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>((const __nv_bfloat16*)O, (const __nv_bfloat16*)O_lo, ld_o,
+                                                                 (const __nv_bfloat16*)dO, ld_do, delta, B, S, H, dk);
   BX_POST_LAUNCH();
   return 0;
 }

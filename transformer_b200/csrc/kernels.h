@@ -15,7 +15,8 @@ int set_timeline(long long* dev_ptr);   // debug: register a device buffer of >=
 
 int attn_fwd(const void* Q, long long ld_q, const void* K, long long ld_k, const void* V, long long ld_v, void* O,
              long long ld_o, float* lse, const uint8_t* kpad, int causal, const float* maskf, long long mask_sb,
-             long long mask_sq, int B, int H, int Sq, int Sk, int dk, cudaStream_t st);
+             long long mask_sq, int B, int H, int Sq, int Sk, int dk, cudaStream_t st,
+             void* O_lo = nullptr);   // O_lo (optional, same layout as O): bf16 rounding residual of O for the backward's delta
 int attn_bwd(const void* Q, long long ld_q, const void* K, long long ld_k, const void* V, long long ld_v, const void* dO,
              long long ld_do, const float* lse, const float* delta, void* dq_acc, long long ld_dq, int dq_bf16, void* dK,
              long long ld_dk, void* dV, long long ld_dv, const uint8_t* kpad, int causal, const float* maskf,
@@ -24,7 +25,7 @@ int attn_probs(const void* Q, long long ld_q, const void* K, long long ld_k, con
                const uint8_t* kpad, int causal, const float* maskf, long long mask_sb, long long mask_sq, int B, int H,
                int Sq, int Sk, int dk, cudaStream_t st);
 int attn_delta(const void* O, long long ld_o, const void* dO, long long ld_do, float* delta, int B, int S, int H, int dk,
-               cudaStream_t st);
+               cudaStream_t st, const void* O_lo = nullptr);   // delta = rowsum(dO o (O + O_lo))
 
 // ids of row r = (b, s) are read at ids[b * id_stride + id_offset + s]  (tar[:, :-1] without a copy)
 int embed_fwd(const long long* ids, int id_stride, int id_offset, const float* table, const float* pos, float* out_f32,

@@ -12,6 +12,7 @@
 //   per decoder layer: Wqkv bqkv Wo bo | Wq [d,d] bq [d] Wkv [d,2d] bkv [2d] Wo2 bo2 | W1 b1 W2 b2 | ln1g ln1b ln2g ln2b ln3g ln3b
 //   Wf [d,Vp] bf [Vp]                 (Vp = target vocab rounded up to 8 columns for 16-byte TMA row pitch)
 // b200xf_model_variable() exposes the keras-order per-variable (strided) views, e.g. wq.kernel = Wqkv[:, 0:d].
+#include <stdlib.h>
 #include <string.h>
 
 #include <string>
@@ -131,10 +132,10 @@ Layout make_layout(const b200xf_model_config& c) {
 
 // ---- workspace (activations kept for backward + gradient scratch), carved from one caller-owned buffer ----
 struct LnSave { bf16* z; float *mean, *rstd; uint8_t* keep; };   // z = x + dropout(y) (bf16) and the row statistics
-struct EncAct { bf16* qkv; bf16* attn_o; float* lse; LnSave ln1; bf16* out1_16; bf16* h; uint64_t* hbits; LnSave ln2; };
+struct EncAct { bf16* qkv; bf16* attn_o; bf16* attn_o_lo; float* lse; LnSave ln1; bf16* out1_16; bf16* h; uint64_t* hbits; LnSave ln2; };
 struct DecAct {
-  bf16* qkv1; bf16* attn1_o; float* lse1; LnSave ln1; bf16* out1_16;
-  bf16* q2; bf16* kv2; bf16* attn2_o; float* lse2; LnSave ln2; bf16* out2_16;
+  bf16* qkv1; bf16* attn1_o; bf16* attn1_o_lo; float* lse1; LnSave ln1; bf16* out1_16;   // *_o_lo: bf16 rounding residual of the attention output
+  bf16* q2; bf16* kv2; bf16* attn2_o; bf16* attn2_o_lo; float* lse2; LnSave ln2; bf16* out2_16;
   bf16* h; uint64_t* hbits; LnSave ln3;
 };
 struct Work {
@@ -148,8 +149,14 @@ struct Work {
   bf16 *gR0, *gR1;                        // [Mmax, d] residual-path gradient (dz of the last LayerNorm backward), ping-pong
   bf16* gD;                               // [Mmax, d] dgrad output of the last sublayer; the stream gradient is gR + gD
   float* d_enc_out;                       // [Ms, d] fp32: accumulates cross-attention K/V gradients of all decoder layers
-  bf16 *dy16, *dO16, *dqkv, *dh;          // [Mmax,d] [Mmax,d] [Mmax,3d] [Mmax,f]
-  bf16* dq16;                             // [Mmax,d] cross-attention dQ (bf16, accumulated by red.global adds)
+  // Buffers the weight-gradient GEMMs (side stream) read while the main stream moves on are RINGS: the main stream waits for
+  // the last side reader of a slot before it overwrites that slot (see BwdCtx)
+  bf16* dy16[3];                          // [Mmax,d] gradient of a sublayer output (one slot per LayerNorm of a decoder layer)
+  bf16* dO16;                             // [Mmax,d] gradient of the attention output (main stream only)
+  bf16* dqkv[2];                          // [Mmax,3d] packed self-attention Q/K/V gradient
+  bf16* dkv2[2];                          // [Ms,2d]  cross-attention K/V gradient
+  bf16* dh[2];                            // [Mmax,f] FFN hidden gradient
+  bf16* dq16[2];                          // [Mmax,d] cross-attention dQ (bf16, accumulated by red.global adds)
   float* delta;                           // [B,H,Smax]
   int64_t bytes;
 };
@@ -180,21 +187,26 @@ Work make_work(const b200xf_model_config& c, const Layout& lo, void* base) {
   w.y16 = b.take<bf16>(Mx * d);
   w.enc.resize(L); w.dec.resize(L);
   for (auto& a : w.enc) {
-    a.qkv = b.take<bf16>(Ms * 3 * d); a.attn_o = b.take<bf16>(Ms * d); a.lse = b.take<float>(c.max_batch * H * c.max_src_len);
+    a.qkv = b.take<bf16>(Ms * 3 * d); a.attn_o = b.take<bf16>(Ms * d); a.attn_o_lo = b.take<bf16>(Ms * d); a.lse = b.take<float>(c.max_batch * H * c.max_src_len);
     a.ln1 = ln(Ms); a.out1_16 = b.take<bf16>(Ms * d); a.h = b.take<bf16>(Ms * f); a.hbits = b.take<uint64_t>(Ms * ((f + 63) / 64)); a.ln2 = ln(Ms);
   }
   for (auto& a : w.dec) {
-    a.qkv1 = b.take<bf16>(Mt * 3 * d); a.attn1_o = b.take<bf16>(Mt * d); a.lse1 = b.take<float>(c.max_batch * H * c.max_tgt_len);
+    a.qkv1 = b.take<bf16>(Mt * 3 * d); a.attn1_o = b.take<bf16>(Mt * d); a.attn1_o_lo = b.take<bf16>(Mt * d); a.lse1 = b.take<float>(c.max_batch * H * c.max_tgt_len);
     a.ln1 = ln(Mt); a.out1_16 = b.take<bf16>(Mt * d);
-    a.q2 = b.take<bf16>(Mt * d); a.kv2 = b.take<bf16>(Ms * 2 * d); a.attn2_o = b.take<bf16>(Mt * d);
+    a.q2 = b.take<bf16>(Mt * d); a.kv2 = b.take<bf16>(Ms * 2 * d); a.attn2_o = b.take<bf16>(Mt * d); a.attn2_o_lo = b.take<bf16>(Mt * d);
     a.lse2 = b.take<float>(c.max_batch * H * c.max_tgt_len);
     a.ln2 = ln(Mt); a.out2_16 = b.take<bf16>(Mt * d); a.h = b.take<bf16>(Mt * f); a.hbits = b.take<uint64_t>(Mt * ((f + 63) / 64)); a.ln3 = ln(Mt);
   }
   w.logits = b.take<bf16>(Mt * lo.Vp);
   w.kpad_in = b.take<uint8_t>(Ms); w.kpad_tar = b.take<uint8_t>(Mt);
   w.gR0 = b.take<bf16>(Mx * d); w.gR1 = b.take<bf16>(Mx * d); w.gD = b.take<bf16>(Mx * d); w.d_enc_out = b.take<float>(Ms * d);
-  w.dy16 = b.take<bf16>(Mx * d); w.dO16 = b.take<bf16>(Mx * d); w.dqkv = b.take<bf16>(Mx * 3 * d); w.dh = b.take<bf16>(Mx * f);
-  w.dq16 = b.take<bf16>(Mx * d); w.delta = b.take<float>(c.max_batch * H * Smax);
+  for (auto& p : w.dy16) p = b.take<bf16>(Mx * d);
+  w.dO16 = b.take<bf16>(Mx * d);
+  for (auto& p : w.dqkv) p = b.take<bf16>(Mx * 3 * d);
+  for (auto& p : w.dkv2) p = b.take<bf16>(Ms * 2 * d);
+  for (auto& p : w.dh) p = b.take<bf16>(Mx * f);
+  for (auto& p : w.dq16) p = b.take<bf16>(Mt * d);
+  w.delta = b.take<float>(c.max_batch * H * Smax);
   w.bytes = b.cur;
   return w;
 }
@@ -203,7 +215,7 @@ int validate(const b200xf_model_config& c) {
   BX_REQUIRE(c.num_layers >= 1 && c.d_model >= 32 && c.num_heads >= 1 && c.dff >= 8, "model: bad sizes");
   BX_REQUIRE(c.d_model % c.num_heads == 0, "model: d_model %% num_heads != 0 (Attention.py:42)");
   const int dk = c.d_model / c.num_heads;
-  BX_REQUIRE(dk == 32 || dk == 64, "model: head depth %d unsupported (d_model/num_heads must be 32 or 64)", dk);
+  BX_REQUIRE(dk == 32 || dk == 64 || dk == 128, "model: head depth %d unsupported (d_model/num_heads must be 32, 64 or 128)", dk);
   BX_REQUIRE(c.d_model % 8 == 0 && c.dff % 8 == 0 && c.d_model <= 1024, "model: d_model, dff must be multiples of 8; d_model <= 1024");
   BX_REQUIRE(c.input_vocab_size >= 2 && c.target_vocab_size >= 2, "model: vocab too small");
   BX_REQUIRE(c.max_batch >= 1 && c.max_src_len >= 1 && c.max_tgt_len >= 1, "model: bad workspace maxima");
@@ -231,6 +243,13 @@ struct b200xf_model {
   int64_t la_bs = 0;
   bool have_loss_grad = false;
   bool logits_valid = false;   // w.logits holds the last forward's bf16 logits (not yet turned into dlogits)
+  // second stream for work off the critical path (weight-gradient GEMMs, bias-gradient column sums, the cross-attention K/V
+  // projections): forked from / joined to the caller's stream with events inside every C call, so the caller still sees ONE
+  // stream -- and a CUDA-graph capture of the caller's stream records the fork as parallel branches
+  cudaStream_t side = nullptr;
+  std::vector<cudaEvent_t> events;
+  int next_event = 0;
+  int concurrency = 1;         // 0: everything on the caller's stream
 };
 
 namespace {
@@ -296,6 +315,58 @@ int residual_ln(M* m, const bf16* x, int64_t g_off, int64_t b_off, bf16* out16, 
                              m->seed, site, st, m->seed_dev);
 }
 
+// ---- fork / join of the side stream ------------------------------------------------------------------------------------
+// Par(m, st): `main` is the caller's stream; `side` is the model's second stream while concurrency is on (and per-launch
+// profiling is off: its events would time overlapped kernels), else `main` itself -- every helper below then degenerates to
+// plain in-order launches.  mark() records "side work so far"; wait(mark) makes the main stream wait for it.
+struct Par {
+  M* m;
+  cudaStream_t main, side;
+  bool forked;
+  Par(M* m_, cudaStream_t st) : m(m_), main(st), side(st), forked(false) {}
+  cudaEvent_t next_event() {
+    cudaEvent_t e = m->events[m->next_event];
+    m->next_event = (m->next_event + 1) % (int)m->events.size();
+    return e;
+  }
+  int fork() {        // side stream joins the main stream's current position
+    if (m->concurrency == 0 || m->side == nullptr || bx::prof_on()) return 0;
+    cudaEvent_t e = next_event();
+    BX_CHECK_CUDA(cudaEventRecord(e, main));
+    BX_CHECK_CUDA(cudaStreamWaitEvent(m->side, e, 0));
+    side = m->side;
+    forked = true;
+    return 0;
+  }
+  // the side stream additionally waits for what the MAIN stream has launched so far (its operands are produced there)
+  int side_after_main() {
+    if (!forked) return 0;
+    cudaEvent_t e = next_event();
+    BX_CHECK_CUDA(cudaEventRecord(e, main));
+    BX_CHECK_CUDA(cudaStreamWaitEvent(side, e, 0));
+    return 0;
+  }
+  cudaEvent_t mark() {                       // completion of the side work launched so far
+    if (!forked) return nullptr;
+    cudaEvent_t e = next_event();
+    if (cudaEventRecord(e, side) != cudaSuccess) return nullptr;
+    return e;
+  }
+  int wait(cudaEvent_t e) {                  // main stream waits for a mark
+    if (forked && e != nullptr) BX_CHECK_CUDA(cudaStreamWaitEvent(main, e, 0));
+    return 0;
+  }
+  int join() {                               // main stream waits for ALL side work; the side stream is released
+    if (!forked) return 0;
+    cudaEvent_t e = next_event();
+    BX_CHECK_CUDA(cudaEventRecord(e, side));
+    BX_CHECK_CUDA(cudaStreamWaitEvent(main, e, 0));
+    forked = false;
+    side = main;
+    return 0;
+  }
+};
+
 int forward_impl(M* m, float* logits_out, int64_t ld_logits, cudaStream_t st) {
   const Layout& lo = m->lo;
   Work& w = m->w;
@@ -318,7 +389,7 @@ int forward_impl(M* m, float* logits_out, int64_t ld_logits, cudaStream_t st) {
     // MultiHeadAttention (Attention.py:59-78): packed QKV projection -> flash attention -> output projection
     RC(linear_fwd(w.enc_x16[l], d, Sh + p.mha.Wqkv, 3 * d, m->P + p.mha.bqkv, a.qkv, 3 * d, false, false, Ms, 3 * d, d, st));
     RC(bx::attn_fwd(a.qkv, 3 * d, a.qkv + d, 3 * d, a.qkv + 2 * d, 3 * d, a.attn_o, d, a.lse, em.kpad, em.causal, em.maskf, em.sb,
-                    em.sq, B, H, S, S, dk, st));
+                    em.sq, B, H, S, S, dk, st, m->training ? a.attn_o_lo : nullptr));
     RC(linear_fwd(a.attn_o, d, Sh + p.mha.Wo, d, m->P + p.mha.bo, w.y16, d, false, false, Ms, d, d, st));
     RC(residual_ln(m, w.enc_x16[l], p.ln1g, p.ln1b, a.out1_16, a.ln1, Ms, site_enc(l, 0), st));   // Encoder.py:22-23
     // point_wise_feed_forward_network (point_ffn.py:3-7)
@@ -331,6 +402,16 @@ int forward_impl(M* m, float* logits_out, int64_t ld_logits, cudaStream_t st) {
   const bf16* enc_out16 = w.enc_x16[L];
 
   // ---------------- decoder (Decoder.py:59-79) ----------------
+  // the cross-attention K/V projections of ALL decoder layers depend only on the encoder output: they run on the side
+  // stream while the main stream works through the decoder (each layer's mha2 waits for its own projection)
+  Par par(m, st);
+  RC(par.fork());
+  std::vector<cudaEvent_t> kv_ready(L, nullptr);
+  for (int l = 0; l < L; ++l) {
+    const DecLayerP& p = lo.dec[l];
+    RC(linear_fwd(enc_out16, d, Sh + p.mha2.Wkv, 2 * d, m->P + p.mha2.bkv, w.dec[l].kv2, 2 * d, false, false, Ms, 2 * d, d, par.side));
+    kv_ready[l] = par.mark();
+  }
   RC(bx::embed_fwd(reinterpret_cast<const long long*>(m->tar), m->tar_stride, m->tar_offset, m->P + lo.dec_emb, m->pos_tgt, nullptr,
                    w.dec_x16[0], Mt, T, d, lo.Vtgt, rate, m->seed, site_dec_embed(), st, m->seed_dev));
   const MaskSpec sm = dec_self_mask(m), cm = dec_cross_mask(m);
@@ -340,14 +421,14 @@ int forward_impl(M* m, float* logits_out, int64_t ld_logits, cudaStream_t st) {
     // mha1: look-ahead-masked self attention (Decoder.py:29-31)
     RC(linear_fwd(w.dec_x16[l], d, Sh + p.mha1.Wqkv, 3 * d, m->P + p.mha1.bqkv, a.qkv1, 3 * d, false, false, Mt, 3 * d, d, st));
     RC(bx::attn_fwd(a.qkv1, 3 * d, a.qkv1 + d, 3 * d, a.qkv1 + 2 * d, 3 * d, a.attn1_o, d, a.lse1, sm.kpad, sm.causal, sm.maskf, sm.sb,
-                    sm.sq, B, H, T, T, dk, st));
+                    sm.sq, B, H, T, T, dk, st, m->training ? a.attn1_o_lo : nullptr));
     RC(linear_fwd(a.attn1_o, d, Sh + p.mha1.Wo, d, m->P + p.mha1.bo, w.y16, d, false, false, Mt, d, d, st));
     RC(residual_ln(m, w.dec_x16[l], p.ln1g, p.ln1b, a.out1_16, a.ln1, Mt, site_dec(l, 0), st));
     // mha2: q from the decoder stream, k = v = enc_output, encoder padding mask (Decoder.py:33-36)
     RC(linear_fwd(a.out1_16, d, Sh + p.mha2.Wq, d, m->P + p.mha2.bq, a.q2, d, false, false, Mt, d, d, st));
-    RC(linear_fwd(enc_out16, d, Sh + p.mha2.Wkv, 2 * d, m->P + p.mha2.bkv, a.kv2, 2 * d, false, false, Ms, 2 * d, d, st));
+    RC(par.wait(kv_ready[l]));
     RC(bx::attn_fwd(a.q2, d, a.kv2, 2 * d, a.kv2 + d, 2 * d, a.attn2_o, d, a.lse2, cm.kpad, cm.causal, cm.maskf, cm.sb, cm.sq, B, H, T, S,
-                    dk, st));
+                    dk, st, m->training ? a.attn2_o_lo : nullptr));
     RC(linear_fwd(a.attn2_o, d, Sh + p.mha2.Wo, d, m->P + p.mha2.bo, w.y16, d, false, false, Mt, d, d, st));
     RC(residual_ln(m, a.out1_16, p.ln2g, p.ln2b, a.out2_16, a.ln2, Mt, site_dec(l, 1), st));
     // ffn (Decoder.py:38-40)
@@ -357,6 +438,7 @@ int forward_impl(M* m, float* logits_out, int64_t ld_logits, cudaStream_t st) {
     bx::prof_set_gemm_cat(0);
     RC(residual_ln(m, a.out2_16, p.ln3g, p.ln3b, w.dec_x16[l + 1], a.ln3, Mt, site_dec(l, 2), st));
   }
+  RC(par.join());
   // ---------------- final_layer (Transformer.py:30) ----------------
   if (logits_out != nullptr)
     RC(linear_fwd(w.dec_x16[L], d, Sh + lo.Wf, lo.Vp, m->P + lo.bf, logits_out, ld_logits, true, false, Mt, lo.Vtgt, d, st));
@@ -365,61 +447,116 @@ int forward_impl(M* m, float* logits_out, int64_t ld_logits, cudaStream_t st) {
   return 0;
 }
 
+// a ring slot: the buffer and the mark of its last side-stream reader
+template <typename T, int N>
+struct Ring {
+  T* buf[N];
+  cudaEvent_t busy[N];
+  int n = 0;
+  void init(T* const* b) { for (int i = 0; i < N; ++i) { buf[i] = b[i]; busy[i] = nullptr; } }
+  // next slot, safe to overwrite on the main stream
+  int acquire(Par& par, T** out) {
+    const int i = n++ % N;
+    RC(par.wait(busy[i]));
+    busy[i] = nullptr;
+    *out = buf[i];
+    return 0;
+  }
+  void read_by_side(const T* p, cudaEvent_t e) {
+    for (int i = 0; i < N; ++i) if (buf[i] == p) busy[i] = e;
+  }
+};
+
 // The gradient of a stream tensor travels as a pair: `r` (residual path: dz of the LayerNorm backward that consumed it,
 // or the fp32 d_enc_out) plus `dg` (dgrad output of the sublayer that consumed it, may be NULL); the next LayerNorm
 // backward (or the embedding backward) sums the two in fp32.
 struct StreamGrad { const void* r; bool r_f32; const bf16* dg; };
 
-// LayerNorm + dropout + residual backward: g (gradient of the LN output) -> dz (gradient of z = of the residual input,
-// bf16) and *dy (gradient of the sublayer output, bf16: w.dy16 under dropout, else dz itself).
-// `bias_off`: bias of the sublayer's last Dense -- its gradient (column sums of dy) falls out of this kernel for free
-int residual_ln_back(M* m, const StreamGrad& g, const LnSave& s, int64_t g_off, int64_t b_off, int64_t bias_off, bf16* dz,
-                     const bf16** dy, int64_t rows, uint32_t site, cudaStream_t st) {
-  const float rate = m->training ? m->cfg.dropout_rate : 0.f;
-  bf16* dy_buf = rate > 0.f ? m->w.dy16 : nullptr;
-  *dy = rate > 0.f ? m->w.dy16 : dz;
-  return bx::residual_ln_bwd(g.r, g.r_f32 ? 1 : 0, g.dg, s.z, s.mean, s.rstd, m->P + g_off, dz, dy_buf, m->G + g_off, m->G + b_off,
-                             m->G + bias_off, s.keep, rows, m->lo.d, rate, m->seed, site, st, m->seed_dev);
-}
+// One backward stage.  Critical path on the main stream: LayerNorm backward -> dgrad GEMMs -> attention backward -> ...;
+// everything that only feeds the gradient arena (wgrad GEMMs, bias column sums) and the cross-attention K/V branch into
+// d_enc_out runs on the side stream, so their CTAs fill the tail waves of the main stream's GEMMs and the HBM-bound kernels
+// of the main stream overlap tensor-bound GEMMs of the side stream.
+struct BwdCtx {
+  M* m;
+  Par par;
+  Ring<bf16, 3> dy;
+  Ring<bf16, 2> dqkv, dkv2, dh, dq16;
+  BwdCtx(M* m_, cudaStream_t st) : m(m_), par(m_, st) {
+    Work& w = m->w;
+    dy.init(w.dy16); dqkv.init(w.dqkv); dkv2.init(w.dkv2); dh.init(w.dh); dq16.init(w.dq16);
+  }
+  cudaStream_t st() const { return par.main; }
 
-// FFN backward: dy = d(ffn output); x16 = ffn input; writes d(input) (sublayer path only) to w.gD
-int ffn_back(M* m, const Ffn& p, const bf16* x16, const bf16* h, const uint64_t* hbits, const bf16* dy, int64_t rows, cudaStream_t st) {
-  const int d = m->lo.d, f = m->lo.f;
-  Work& w = m->w;
-  struct CatGuard { CatGuard() { bx::prof_set_gemm_cat(3); } ~CatGuard() { bx::prof_set_gemm_cat(0); } } cat_guard;
-  RC(linear_wgrad(h, f, dy, d, m->G + p.W2, d, nullptr, rows, d, f, st));                     // db2: from the LN backward
-  RC(linear_dgrad(dy, d, m->Sh + p.W2, d, w.dh, f, false, false, h, f, rows, d, f, st, hbits));         // dh = (dy . W2^T) o [h > 0]
-  RC(linear_wgrad(x16, d, w.dh, f, m->G + p.W1, f, m->G + p.b1, rows, f, d, st));
-  RC(linear_dgrad(w.dh, f, m->Sh + p.W1, f, w.gD, d, false, false, nullptr, 0, rows, f, d, st));
-  return 0;
-}
+  // LayerNorm + dropout + residual backward: g (gradient of the LN output) -> dz (gradient of z = of the residual input,
+  // bf16) and *dy_out (gradient of the sublayer output, bf16, in a dy ring slot).
+  // `bias_off`: bias of the sublayer's last Dense -- its gradient (column sums of dy) falls out of this kernel for free
+  int residual_ln_back(const StreamGrad& g, const LnSave& s, int64_t g_off, int64_t b_off, int64_t bias_off, bf16* dz, const bf16** dy_out,
+                       int64_t rows, uint32_t site) {
+    const float rate = m->training ? m->cfg.dropout_rate : 0.f;
+    bf16* buf = nullptr;
+    RC(dy.acquire(par, &buf));
+    *dy_out = buf;
+    return bx::residual_ln_bwd(g.r, g.r_f32 ? 1 : 0, g.dg, s.z, s.mean, s.rstd, m->P + g_off, dz, buf, m->G + g_off, m->G + b_off,
+                               m->G + bias_off, s.keep, rows, m->lo.d, rate, m->seed, site, st(), m->seed_dev);
+  }
 
-// self-attention block backward (packed QKV).  dy = d(out-projection output); writes d(x) (sublayer path) to w.gD
-int self_attn_back(M* m, const MhaSelf& p, const bf16* x16, const bf16* qkv, const bf16* attn_o, const float* lse, const MaskSpec& mk,
-                   const bf16* dy, int S, cudaStream_t st) {
-  const int d = m->lo.d, H = m->lo.H, dk = d / H, B = m->B;
-  const int64_t rows = (int64_t)B * S;
-  Work& w = m->w;
-  RC(linear_wgrad(attn_o, d, dy, d, m->G + p.Wo, d, nullptr, rows, d, d, st));                 // dbo: from the LN backward
-  RC(linear_dgrad(dy, d, m->Sh + p.Wo, d, w.dO16, d, false, false, nullptr, 0, rows, d, d, st));
-  RC(bx::attn_delta(attn_o, d, w.dO16, d, w.delta, B, S, H, dk, st));
-  // dQ is accumulated (bf16 red.global adds) straight into the first d columns of the packed QKV gradient: zero them first
-  BX_CHECK_CUDA(cudaMemset2DAsync(w.dqkv, (size_t)3 * d * sizeof(bf16), 0, (size_t)d * sizeof(bf16), rows, st));
-  RC(bx::attn_bwd(qkv, 3 * d, qkv + d, 3 * d, qkv + 2 * d, 3 * d, w.dO16, d, lse, w.delta, w.dqkv, 3 * d, 1, w.dqkv + d, 3 * d,
-                  w.dqkv + 2 * d, 3 * d, mk.kpad, mk.causal, mk.maskf, mk.sb, mk.sq, B, H, S, S, dk, st));
-  RC(linear_wgrad(x16, d, w.dqkv, 3 * d, m->G + p.Wqkv, 3 * d, m->G + p.bqkv, rows, 3 * d, d, st));
-  RC(linear_dgrad(w.dqkv, 3 * d, m->Sh + p.Wqkv, 3 * d, w.gD, d, false, false, nullptr, 0, rows, 3 * d, d, st));
-  return 0;
-}
+  // side stream: dW += x^T . dy (+ db += colsum(dy)); x is a saved activation, dy was just produced on the main stream
+  int wgrad_side(const bf16* x, int64_t ldx, const bf16* dyv, int64_t ld_dy, int64_t w_off, int64_t ldw, int64_t b_off, int64_t rows, int64_t N,
+                 int64_t K) {
+    RC(par.side_after_main());
+    return linear_wgrad(x, ldx, dyv, ld_dy, m->G + w_off, ldw, b_off >= 0 ? m->G + b_off : nullptr, rows, N, K, par.side);
+  }
+
+  // FFN backward: dyv = d(ffn output); x16 = ffn input; writes d(input) (sublayer path only) to w.gD
+  int ffn_back(const Ffn& p, const bf16* x16, const bf16* h, const uint64_t* hbits, const bf16* dyv, int64_t rows) {
+    const int d = m->lo.d, f = m->lo.f;
+    Work& w = m->w;
+    struct CatGuard { CatGuard() { bx::prof_set_gemm_cat(3); } ~CatGuard() { bx::prof_set_gemm_cat(0); } } cat_guard;
+    RC(wgrad_side(h, f, dyv, d, p.W2, d, -1, rows, d, f));                                     // db2: from the LN backward
+    dy.read_by_side(dyv, par.mark());
+    bf16* dhb = nullptr;
+    RC(dh.acquire(par, &dhb));
+    RC(linear_dgrad(dyv, d, m->Sh + p.W2, d, dhb, f, false, false, h, f, rows, d, f, st(), hbits));         // dh = (dy . W2^T) o [h > 0]
+    RC(wgrad_side(x16, d, dhb, f, p.W1, f, p.b1, rows, f, d));
+    dh.read_by_side(dhb, par.mark());
+    RC(linear_dgrad(dhb, f, m->Sh + p.W1, f, w.gD, d, false, false, nullptr, 0, rows, f, d, st()));
+    return 0;
+  }
+
+  // self-attention block backward (packed QKV).  dyv = d(out-projection output); writes d(x) (sublayer path) to w.gD
+  int self_attn_back(const MhaSelf& p, const bf16* x16, const bf16* qkv, const bf16* attn_o, const bf16* attn_o_lo, const float* lse,
+                     const MaskSpec& mk, const bf16* dyv, int S) {
+    const int d = m->lo.d, H = m->lo.H, dk = d / H, B = m->B;
+    const int64_t rows = (int64_t)B * S;
+    Work& w = m->w;
+    RC(wgrad_side(attn_o, d, dyv, d, p.Wo, d, -1, rows, d, d));                                 // dbo: from the LN backward
+    dy.read_by_side(dyv, par.mark());
+    RC(linear_dgrad(dyv, d, m->Sh + p.Wo, d, w.dO16, d, false, false, nullptr, 0, rows, d, d, st()));
+    RC(bx::attn_delta(attn_o, d, w.dO16, d, w.delta, B, S, H, dk, st(), m->training ? attn_o_lo : nullptr));
+    bf16* g = nullptr;
+    RC(dqkv.acquire(par, &g));
+    // dQ is accumulated (bf16 red.global adds) straight into the first d columns of the packed QKV gradient: zero them first
+    BX_CHECK_CUDA(cudaMemset2DAsync(g, (size_t)3 * d * sizeof(bf16), 0, (size_t)d * sizeof(bf16), rows, st()));
+    RC(bx::attn_bwd(qkv, 3 * d, qkv + d, 3 * d, qkv + 2 * d, 3 * d, w.dO16, d, lse, w.delta, g, 3 * d, 1, g + d, 3 * d, g + 2 * d, 3 * d,
+                    mk.kpad, mk.causal, mk.maskf, mk.sb, mk.sq, B, H, S, S, dk, st()));
+    RC(wgrad_side(x16, d, g, 3 * d, p.Wqkv, 3 * d, p.bqkv, rows, 3 * d, d));
+    dqkv.read_by_side(g, par.mark());
+    RC(linear_dgrad(g, 3 * d, m->Sh + p.Wqkv, 3 * d, w.gD, d, false, false, nullptr, 0, rows, 3 * d, d, st()));
+    return 0;
+  }
+};
 
 int backward_final(M* m, cudaStream_t st) {
   const Layout& lo = m->lo;
   Work& w = m->w;
   const int d = lo.d, L = lo.L;
   const int64_t Mt = (int64_t)m->B * m->T;
-  // dlogits (bf16, in w.logits) -> final_layer grads and d(dec_output) in gD
-  RC(linear_wgrad(w.dec_x16[L], d, w.logits, lo.Vp, m->G + lo.Wf, lo.Vp, m->G + lo.bf, Mt, lo.Vtgt, d, st));
+  BwdCtx c(m, st);
+  RC(c.par.fork());
+  // dlogits (bf16, in w.logits) -> final_layer grads (side stream) and d(dec_output) in gD (main stream)
+  RC(c.wgrad_side(w.dec_x16[L], d, w.logits, lo.Vp, lo.Wf, lo.Vp, lo.bf, Mt, lo.Vtgt, d));
   RC(linear_dgrad(w.logits, lo.Vp, m->Sh + lo.Wf, lo.Vp, w.gD, d, false, false, nullptr, 0, Mt, lo.Vtgt, d, st));
+  RC(c.par.join());
   return 0;
 }
 
@@ -432,6 +569,8 @@ int backward_decoder(M* m, cudaStream_t st) {
   const float rate = m->training ? m->cfg.dropout_rate : 0.f;
   const MaskSpec sm = dec_self_mask(m), cm = dec_cross_mask(m);
   BX_CHECK_CUDA(cudaMemsetAsync(w.d_enc_out, 0, Ms * d * sizeof(float), st));
+  BwdCtx c(m, st);
+  RC(c.par.fork());
   StreamGrad g{w.gD, false, nullptr};    // gradient of the current layer's output: the vocabulary dgrad wrote it to gD
   bf16* dz = w.gR0;
   bf16* dz_other = w.gR1;
@@ -441,30 +580,41 @@ int backward_decoder(M* m, cudaStream_t st) {
     const DecLayerP& p = lo.dec[l];
     DecAct& a = w.dec[l];
     // out3 = LN3(out2 + drop(ffn(out2)))
-    RC(residual_ln_back(m, g, a.ln3, p.ln3g, p.ln3b, p.ffn.b2, dz, &dy, Mt, site_dec(l, 2), st));
-    RC(ffn_back(m, p.ffn, a.out2_16, a.h, a.hbits, dy, Mt, st));
+    RC(c.residual_ln_back(g, a.ln3, p.ln3g, p.ln3b, p.ffn.b2, dz, &dy, Mt, site_dec(l, 2)));
+    RC(c.ffn_back(p.ffn, a.out2_16, a.h, a.hbits, dy, Mt));
     advance();
     // out2 = LN2(out1 + drop(mha2(enc_out, enc_out, out1)))
-    RC(residual_ln_back(m, g, a.ln2, p.ln2g, p.ln2b, p.mha2.bo, dz, &dy, Mt, site_dec(l, 1), st));
-    RC(linear_wgrad(a.attn2_o, d, dy, d, m->G + p.mha2.Wo, d, nullptr, Mt, d, d, st));
+    RC(c.residual_ln_back(g, a.ln2, p.ln2g, p.ln2b, p.mha2.bo, dz, &dy, Mt, site_dec(l, 1)));
+    RC(c.wgrad_side(a.attn2_o, d, dy, d, p.mha2.Wo, d, -1, Mt, d, d));
+    c.dy.read_by_side(dy, c.par.mark());
     RC(linear_dgrad(dy, d, m->Sh + p.mha2.Wo, d, w.dO16, d, false, false, nullptr, 0, Mt, d, d, st));
-    RC(bx::attn_delta(a.attn2_o, d, w.dO16, d, w.delta, B, T, H, dk, st));
-    BX_CHECK_CUDA(cudaMemsetAsync(w.dq16, 0, Mt * d * sizeof(bf16), st));
-    // dK/dV of the encoder memory go to dqkv[:, 0:2d) viewed as [Ms, 2d]; dQ (bf16 red.global adds) to dq16
-    RC(bx::attn_bwd(a.q2, d, a.kv2, 2 * d, a.kv2 + d, 2 * d, w.dO16, d, a.lse2, w.delta, w.dq16, d, 1, w.dqkv, 2 * d, w.dqkv + d, 2 * d,
+    RC(bx::attn_delta(a.attn2_o, d, w.dO16, d, w.delta, B, T, H, dk, st, m->training ? a.attn2_o_lo : nullptr));
+    bf16 *dq = nullptr, *dkv = nullptr;
+    RC(c.dq16.acquire(c.par, &dq));
+    RC(c.dkv2.acquire(c.par, &dkv));
+    BX_CHECK_CUDA(cudaMemsetAsync(dq, 0, Mt * d * sizeof(bf16), st));
+    // dK/dV of the encoder memory go to dkv [Ms, 2d]; dQ (bf16 red.global adds) to dq
+    RC(bx::attn_bwd(a.q2, d, a.kv2, 2 * d, a.kv2 + d, 2 * d, w.dO16, d, a.lse2, w.delta, dq, d, 1, dkv, 2 * d, dkv + d, 2 * d,
                     cm.kpad, cm.causal, cm.maskf, cm.sb, cm.sq, B, H, T, S, dk, st));
-    RC(linear_wgrad(w.enc_x16[L], d, w.dqkv, 2 * d, m->G + p.mha2.Wkv, 2 * d, m->G + p.mha2.bkv, Ms, 2 * d, d, st));
-    RC(linear_dgrad(w.dqkv, 2 * d, m->Sh + p.mha2.Wkv, 2 * d, w.d_enc_out, d, true, true, nullptr, 0, Ms, 2 * d, d, st));
-    RC(linear_wgrad(a.out1_16, d, w.dq16, d, m->G + p.mha2.Wq, d, m->G + p.mha2.bq, Mt, d, d, st));
-    RC(linear_dgrad(w.dq16, d, m->Sh + p.mha2.Wq, d, w.gD, d, false, false, nullptr, 0, Mt, d, d, st));
+    // the whole K/V branch (weight gradient and the fp32 accumulation into d_enc_out) is off the decoder's critical path
+    RC(c.wgrad_side(w.enc_x16[L], d, dkv, 2 * d, p.mha2.Wkv, 2 * d, p.mha2.bkv, Ms, 2 * d, d));
+    RC(linear_dgrad(dkv, 2 * d, m->Sh + p.mha2.Wkv, 2 * d, w.d_enc_out, d, true, true, nullptr, 0, Ms, 2 * d, d, c.par.side));
+    RC(c.wgrad_side(a.out1_16, d, dq, d, p.mha2.Wq, d, p.mha2.bq, Mt, d, d));
+    {
+      cudaEvent_t e = c.par.mark();
+      c.dkv2.read_by_side(dkv, e);
+      c.dq16.read_by_side(dq, e);
+    }
+    RC(linear_dgrad(dq, d, m->Sh + p.mha2.Wq, d, w.gD, d, false, false, nullptr, 0, Mt, d, d, st));
     advance();
     // out1 = LN1(x + drop(mha1(x, x, x)))
-    RC(residual_ln_back(m, g, a.ln1, p.ln1g, p.ln1b, p.mha1.bo, dz, &dy, Mt, site_dec(l, 0), st));
-    RC(self_attn_back(m, p.mha1, w.dec_x16[l], a.qkv1, a.attn1_o, a.lse1, sm, dy, T, st));
+    RC(c.residual_ln_back(g, a.ln1, p.ln1g, p.ln1b, p.mha1.bo, dz, &dy, Mt, site_dec(l, 0)));
+    RC(c.self_attn_back(p.mha1, w.dec_x16[l], a.qkv1, a.attn1_o, a.attn1_o_lo, a.lse1, sm, dy, T));
     advance();
   }
   RC(bx::embed_bwd(reinterpret_cast<const long long*>(m->tar), m->tar_stride, m->tar_offset, g.r, g.dg, m->G + lo.dec_emb, Mt, T, d,
                    lo.Vtgt, rate, m->seed, site_dec_embed(), st, m->seed_dev));
+  RC(c.par.join());
   return 0;
 }
 
@@ -476,6 +626,8 @@ int backward_encoder(M* m, cudaStream_t st) {
   const int64_t Ms = (int64_t)B * S;
   const float rate = m->training ? m->cfg.dropout_rate : 0.f;
   const MaskSpec em = enc_self_mask(m);
+  BwdCtx c(m, st);
+  RC(c.par.fork());
   StreamGrad g{w.d_enc_out, true, nullptr};   // fp32 sum of the cross-attention K/V gradients of all decoder layers
   bf16* dz = w.gR0;
   bf16* dz_other = w.gR1;
@@ -484,15 +636,16 @@ int backward_encoder(M* m, cudaStream_t st) {
   for (int l = L - 1; l >= 0; --l) {
     const EncLayerP& p = lo.enc[l];
     EncAct& a = w.enc[l];
-    RC(residual_ln_back(m, g, a.ln2, p.ln2g, p.ln2b, p.ffn.b2, dz, &dy, Ms, site_enc(l, 1), st));
-    RC(ffn_back(m, p.ffn, a.out1_16, a.h, a.hbits, dy, Ms, st));
+    RC(c.residual_ln_back(g, a.ln2, p.ln2g, p.ln2b, p.ffn.b2, dz, &dy, Ms, site_enc(l, 1)));
+    RC(c.ffn_back(p.ffn, a.out1_16, a.h, a.hbits, dy, Ms));
     advance();
-    RC(residual_ln_back(m, g, a.ln1, p.ln1g, p.ln1b, p.mha.bo, dz, &dy, Ms, site_enc(l, 0), st));
-    RC(self_attn_back(m, p.mha, w.enc_x16[l], a.qkv, a.attn_o, a.lse, em, dy, S, st));
+    RC(c.residual_ln_back(g, a.ln1, p.ln1g, p.ln1b, p.mha.bo, dz, &dy, Ms, site_enc(l, 0)));
+    RC(c.self_attn_back(p.mha, w.enc_x16[l], a.qkv, a.attn_o, a.attn_o_lo, a.lse, em, dy, S));
     advance();
   }
   RC(bx::embed_bwd(reinterpret_cast<const long long*>(m->inp), S, 0, g.r, g.dg, m->G + lo.enc_emb, Ms, S, d, lo.Vin, rate, m->seed,
                    site_enc_embed(), st, m->seed_dev));
+  RC(c.par.join());
   return 0;
 }
 
@@ -542,10 +695,24 @@ int b200xf_model_create(const b200xf_model_config* cfg, float* params, float* gr
   m->w = make_work(*cfg, m->lo, workspace);
   m->P = params; m->G = grads; m->Am = adam_m; m->Av = adam_v; m->Sh = reinterpret_cast<bf16*>(shadow);
   m->pos_in = pos_in; m->pos_tgt = pos_tgt;
+  // second stream + event pool (host-side objects of the CURRENT device; created here so that nothing is created while a
+  // CUDA-graph capture is in progress)
+  const char* env = getenv("B200XF_CONCURRENCY");
+  m->concurrency = (env != nullptr && env[0] == '0') ? 0 : 1;
+  if (cudaStreamCreateWithFlags(&m->side, cudaStreamNonBlocking) != cudaSuccess) { m->side = nullptr; m->concurrency = 0; (void)cudaGetLastError(); }
+  m->events.resize(1024, nullptr);
+  for (auto& e : m->events)
+    if (cudaEventCreateWithFlags(&e, cudaEventDisableTiming) != cudaSuccess) { m->concurrency = 0; (void)cudaGetLastError(); break; }
   *out = m;
   return 0;
 }
-void b200xf_model_destroy(b200xf_model* m) { delete m; }
+void b200xf_model_destroy(b200xf_model* m) {
+  if (m == nullptr) return;
+  for (auto e : m->events) if (e != nullptr) cudaEventDestroy(e);
+  if (m->side != nullptr) cudaStreamDestroy(m->side);
+  delete m;
+}
+void b200xf_model_set_concurrency(b200xf_model* m, int on) { m->concurrency = (on != 0 && m->side != nullptr) ? 1 : 0; }
 
 void b200xf_model_set_seed_ptr(b200xf_model* m, const uint64_t* seed_dev) {
   m->seed_dev = reinterpret_cast<const unsigned long long*>(seed_dev);
