@@ -82,113 +82,98 @@ __device__ __forceinline__ void tile_store(const CUtensorMap* tm, const uint8_t*
 }
 
 // ================================================================================================
-// forward
+// forward:  one CTA per (128-query tile, head, batch); TWO CTAs are resident per SM (head depth <= 64).
+//   A CTA is a serial chain per kv tile (S ready -> TMEM load -> mask/max -> exponentials -> P to smem -> P.V); with one CTA
+//   per SM and two query tiles per CTA the two chains ran in lockstep and the MUFU unit (16 ex2 / clock / SM, the hard floor
+//   of this kernel at head depth 64) idled through every load/max/store phase, and nothing overlapped the prologue (TMEM
+//   allocation, barrier init, Q load: ~3000 cycles) and the epilogue (O normalise + store: ~2400 cycles) of a 4-tile CTA
+//   (profiles/r02_g_attention_timeline.txt).  Two independent CTAs per SM interleave all of that by themselves.
+//   Budget per CTA: 192 threads x 168 registers, 96 KB shared memory, 256 tensor-memory columns (S 128 | O DK).
 // ================================================================================================
 template <int DK>
 struct FwdSmem {
   using C = AttnCfg<DK>;
-  static constexpr int KVS = DK <= 64 ? 2 : 1;                          // K/V stages (head depth 128: one, shared memory is full)
-  static constexpr uint32_t OFF_Q = 0;                                  // 2 slots
-  static constexpr uint32_t OFF_K = OFF_Q + 2 * C::TILE_BYTES;          // KVS stages
-  static constexpr uint32_t OFF_V = OFF_K + KVS * C::TILE_BYTES;        // KVS stages
-  static constexpr uint32_t OFF_P = OFF_V + KVS * C::TILE_BYTES;        // 2 slots
-  static constexpr uint32_t OFF_BAR = OFF_P + 2 * C::P_BYTES;
-  static constexpr uint32_t OFF_PADW = OFF_BAR + 256;                   // key-padding bit words: [2 slots][kMaxPadTiles][4]
-  static constexpr uint32_t BYTES = OFF_PADW + 2 * 64 * 4 * 4 + 1024;
+  static constexpr int KS = DK <= 64 ? 2 : 1;                           // K stages (head depth 128: one, to stay at 128 KB)
+  static constexpr uint32_t OFF_Q = 0;                                  // 1 tile (re-used as the O_lo staging at the end)
+  static constexpr uint32_t OFF_K = OFF_Q + C::TILE_BYTES;              // KS stages
+  static constexpr uint32_t OFF_V = OFF_K + KS * C::TILE_BYTES;         // 1 stage (V(j+1) is only needed a whole softmax later)
+  static constexpr uint32_t OFF_P = OFF_V + C::TILE_BYTES;              // P tile (re-used as the O staging at the end)
+  static constexpr uint32_t OFF_BAR = OFF_P + C::P_BYTES;
+  static constexpr uint32_t OFF_PADW = OFF_BAR + 128;                   // key-padding bit words: [kMaxPadTiles][4]
+  static constexpr uint32_t BYTES = OFF_PADW + 64 * 4 * 4 + 1024;
 };
 constexpr int kMaxPadTiles = 64;       // kv tiles whose pad bits are preloaded (Sk <= 8192); longer rows load per tile
 
-// warpgroup 0: w0 TMA, w1 MMA (+TMEM alloc), w2-3 idle; warpgroup 1: softmax of q slot 0; warpgroup 2: slot 1.
-// setmaxnreg moves registers from warpgroup 0 (40) to the softmax warpgroups (232; 128*40 + 256*232 = 64512 <= 65536): a thread keeps a whole
-// 128-column S row in registers (single pass over TMEM).
-constexpr int ATTN_FWD_THREADS = 384;
+// w0 TMA, w1 MMA (+TMEM alloc), w2-5 softmax (TMEM lane quadrant = warp & 3): a thread keeps a whole 128-column S row in
+// registers (single pass over TMEM).
+constexpr int ATTN_FWD_THREADS = 192;
 
 // kMaskF: an arbitrary float mask is given (its own instantiation: one more global load per score; every chunk "touched")
 template <int DK, bool kMaskF>
-__global__ void __launch_bounds__(ATTN_FWD_THREADS, 1)
+__global__ void __launch_bounds__(ATTN_FWD_THREADS, DK <= 64 ? 2 : 1)
 attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                 const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmO,
                 const __grid_constant__ CUtensorMap tmOlo, int has_lo,
                 float* __restrict__ lse_out, AttnMask mask, int H, int Sq, int Sk, float scale) {
   using C = AttnCfg<DK>;
   using L = FwdSmem<DK>;
-  constexpr int KVS = L::KVS;
+  constexpr int KS = L::KS;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L::OFF_BAR);
-  uint64_t* q_full = bars;          // [2]
-  uint64_t* k_full = bars + 2;      // [2]
-  uint64_t* v_full = bars + 4;      // [2]
-  uint64_t* k_empty = bars + 6;     // [2]
-  uint64_t* v_empty = bars + 8;     // [2]
-  uint64_t* s_full = bars + 10;     // [2]
-  uint64_t* p_full = bars + 12;     // [2]
-  uint64_t* o_full = bars + 14;     // [2]
-  uint64_t* s_free = bars + 16;     // [2] count 128: the softmax warps hold the S tile in registers, TMEM S may be overwritten
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 18);
+  uint64_t* q_full = bars;          // [1]
+  uint64_t* k_full = bars + 1;      // [2]
+  uint64_t* k_empty = bars + 3;     // [2]
+  uint64_t* v_full = bars + 5;      // [1]
+  uint64_t* v_empty = bars + 6;     // [1]
+  uint64_t* s_full = bars + 7;      // [1]
+  uint64_t* p_full = bars + 8;      // [1] count 128
+  uint64_t* o_full = bars + 9;      // [1]
+  uint64_t* s_free = bars + 10;     // [1] count 128: the softmax warps hold the S tile in registers, TMEM S may be overwritten
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 11);
 
   const uint32_t warp = warp_idx(), lane = lane_idx();
   long long* const tlp = tl_begin();
   if (threadIdx.x == 64) tl_stamp(0);
   const int b = blockIdx.z, h = blockIdx.y;
-  const int q0 = blockIdx.x * 256;
-  const int n_slots = (q0 + 128 < Sq) ? 2 : 1;
+  const int q0 = blockIdx.x * 128;
   const int nkv = (Sk + 127) / 128;
   // key 0 of this batch row (look-ahead mask only): the load is in flight during the prologue below, its value is
-  // first needed for the tile counts after the block-wide sync
+  // first needed for the tile count after the block-wide sync
   const uint8_t lead_byte = (mask.causal && mask.kpad != nullptr) ? mask.kpad[(long long)b * Sk] : (uint8_t)0;
 
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&tmQ); prefetch_tmap(&tmK); prefetch_tmap(&tmV); prefetch_tmap(&tmO);
-    for (int i = 0; i < 2; ++i) {
-      mbar_init(&q_full[i], 1); mbar_init(&k_full[i], 1); mbar_init(&v_full[i], 1);
-      mbar_init(&k_empty[i], 1); mbar_init(&v_empty[i], 1);
-      mbar_init(&s_full[i], 1); mbar_init(&p_full[i], 128); mbar_init(&o_full[i], 1); mbar_init(&s_free[i], 128);
-    }
+    mbar_init(q_full, 1); mbar_init(v_full, 1); mbar_init(v_empty, 1);
+    for (int i = 0; i < 2; ++i) { mbar_init(&k_full[i], 1); mbar_init(&k_empty[i], 1); }
+    mbar_init(s_full, 1); mbar_init(p_full, 128); mbar_init(o_full, 1); mbar_init(s_free, 128);
     fence_barrier_init();
   }
-  if (warp == 1) tmem_alloc<512>(tmem_ptr);
+  if (warp == 1) tmem_alloc<256>(tmem_ptr);
   tcgen05_before_thread_sync();
   __syncthreads();
   tcgen05_after_thread_sync();
   const uint32_t tmem_base = *tmem_ptr;
   if (threadIdx.x == 64) tl_stamp(1);
-  // tiles each slot must visit.  Causal rows only see keys <= query index -- unless key 0 of this batch row is
+  // kv tiles this query tile must visit.  Causal rows only see keys <= query index -- unless key 0 of this batch row is
   // padding, in which case some rows may be fully masked and (reference semantics) attend uniformly to ALL keys.
-  int nt[2];
-  {
-    const bool lead_pad = lead_byte != 0;
-    for (int s = 0; s < 2; ++s) {
-      int n = nkv;
-      if (mask.causal && !lead_pad) {
-        const int last_q = min(q0 + s * 128 + 127, Sq - 1);
-        n = min(nkv, last_q / 128 + 1);
-      }
-      nt[s] = s < n_slots ? n : 0;
-    }
-  }
-  const int ntiles = max(nt[0], nt[1]);
-  const uint32_t tS[2] = {tmem_base, tmem_base + 128};
-  const uint32_t tO[2] = {tmem_base + 256, tmem_base + 256 + DK};
+  int nt = nkv;
+  if (mask.causal && lead_byte == 0) nt = min(nkv, min(q0 + 127, Sq - 1) / 128 + 1);
+  const uint32_t tS = tmem_base, tO = tmem_base + 128;
 
-  if (warp < 4) {
-  setmaxnreg_dec<40>();
   if (warp == 0) {
     if (lane == 0) {
       // ===================================== TMA producer =====================================
-      for (int s = 0; s < n_slots; ++s) {
-        mbar_arrive_expect_tx(&q_full[s], C::TILE_BYTES);
-        tile_load<DK>(smem + L::OFF_Q + s * C::TILE_BYTES, &tmQ, &q_full[s], h * DK, q0 + s * 128, b);
-      }
-      for (int j = 0; j < ntiles; ++j) {
-        const int st = j % KVS;
-        const uint32_t ph = (j / KVS) & 1;
-        mbar_wait(&k_empty[st], ph ^ 1);
+      mbar_arrive_expect_tx(q_full, C::TILE_BYTES);
+      tile_load<DK>(smem + L::OFF_Q, &tmQ, q_full, h * DK, q0, b);
+      for (int j = 0; j < nt; ++j) {
+        const int st = j % KS;
+        mbar_wait(&k_empty[st], ((j / KS) & 1) ^ 1);
         mbar_arrive_expect_tx(&k_full[st], C::TILE_BYTES);
         tile_load<DK>(smem + L::OFF_K + st * C::TILE_BYTES, &tmK, &k_full[st], h * DK, j * 128, b);
-        mbar_wait(&v_empty[st], ph ^ 1);
-        mbar_arrive_expect_tx(&v_full[st], C::TILE_BYTES);
-        tile_load<DK>(smem + L::OFF_V + st * C::TILE_BYTES, &tmV, &v_full[st], h * DK, j * 128, b);
+        mbar_wait(v_empty, (j & 1) ^ 1);
+        mbar_arrive_expect_tx(v_full, C::TILE_BYTES);
+        tile_load<DK>(smem + L::OFF_V, &tmV, v_full, h * DK, j * 128, b);
       }
     }
   } else if (warp == 1) {
@@ -197,266 +182,270 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     constexpr uint32_t idescO = make_idesc_bf16(128, DK, 0, 1);    // O[q,dk] = P (K-major) . V (MN-major)
     const uint32_t sQ = smem_u32(smem + L::OFF_Q), sK = smem_u32(smem + L::OFF_K), sV = smem_u32(smem + L::OFF_V),
                    sP = smem_u32(smem + L::OFF_P);
-    auto issue_S = [&](int s, int j) {
-      const int st = j % KVS;
-      mbar_wait(&k_full[st], (j / KVS) & 1);
-      if (j == 0) mbar_wait(&q_full[s], 0);
+    auto issue_S = [&](int j) {
+      const int st = j % KS;
+      mbar_wait(&k_full[st], (j / KS) & 1);
+      if (j == 0) mbar_wait(q_full, 0);
       tcgen05_after_thread_sync();
       if (lane == 0) {
 #pragma unroll
         for (int k = 0; k < DK / 16; ++k) {
-          const uint64_t ad = make_smem_desc(sQ + s * C::TILE_BYTES + C::kmajor_k16(k), 0, C::SBO, C::SWZ);
+          const uint64_t ad = make_smem_desc(sQ + C::kmajor_k16(k), 0, C::SBO, C::SWZ);
           const uint64_t bd = make_smem_desc(sK + st * C::TILE_BYTES + C::kmajor_k16(k), 0, C::SBO, C::SWZ);
-          umma_f16(tS[s], ad, bd, idescS, k > 0 ? 1u : 0u);
+          umma_f16(tS, ad, bd, idescS, k > 0 ? 1u : 0u);
         }
-        umma_commit(&s_full[s]);
-        const bool last_user = (s == 1) || !(j < nt[1]);
-        if (last_user) umma_commit(&k_empty[st]);
+        umma_commit(s_full);
+        umma_commit(&k_empty[st]);
       }
       __syncwarp();
     };
-    auto issue_PV = [&](int s, int j) {
-      const int st = j % KVS;
-      mbar_wait(&p_full[s], j & 1);
-      mbar_wait(&v_full[st], (j / KVS) & 1);
+    auto issue_PV = [&](int j) {
+      mbar_wait(p_full, j & 1);
+      mbar_wait(v_full, j & 1);
       tcgen05_after_thread_sync();
       if (lane == 0) {
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
-          const uint64_t ad = make_smem_desc(sP + s * C::P_BYTES + (k >> 2) * 16384 + (k & 3) * 32, 0, 1024, kSwz128);
-          const uint64_t bd = make_smem_desc(sV + st * C::TILE_BYTES + k * C::KSTEP_MN, C::PANEL_BYTES, C::SBO, C::SWZ);
-          umma_f16(tO[s], ad, bd, idescO, (j > 0 || k > 0) ? 1u : 0u);   // O accumulates in TMEM over the kv tiles
+          const uint64_t ad = make_smem_desc(sP + (k >> 2) * 16384 + (k & 3) * 32, 0, 1024, kSwz128);
+          const uint64_t bd = make_smem_desc(sV + k * C::KSTEP_MN, C::PANEL_BYTES, C::SBO, C::SWZ);
+          umma_f16(tO, ad, bd, idescO, (j > 0 || k > 0) ? 1u : 0u);   // O accumulates in TMEM over the kv tiles
         }
-        umma_commit(&o_full[s]);
-        const bool last_user = (s == 1) || !(j < nt[1]);
-        if (last_user) umma_commit(&v_empty[st]);
+        umma_commit(o_full);
+        umma_commit(v_empty);
       }
       __syncwarp();
     };
-    for (int s = 0; s < 2; ++s)
-      if (0 < nt[s]) issue_S(s, 0);
+    issue_S(0);
     // S(j+1) is issued as soon as the softmax warps have pulled S(j) into registers (s_free) -- it then runs on the tensor
     // core while they exponentiate tile j -- and P.V(j) once P(j) is in smem.
-    for (int j = 0; j < ntiles; ++j) {
-      for (int s = 0; s < 2; ++s)
-        if (j + 1 < nt[s]) {
-          mbar_wait(&s_free[s], j & 1);
-          tcgen05_after_thread_sync();
-          issue_S(s, j + 1);
-        }
-      for (int s = 0; s < 2; ++s)
-        if (j < nt[s]) issue_PV(s, j);
+    for (int j = 0; j < nt; ++j) {
+      if (j + 1 < nt) {
+        mbar_wait(s_free, j & 1);
+        tcgen05_after_thread_sync();
+        issue_S(j + 1);
+      }
+      issue_PV(j);
     }
-  }
   } else {
-    setmaxnreg_inc<232>();
     // ===================================== softmax warps =====================================
-    const int s = (warp - 4) >> 2;               // q slot
     const uint32_t quad = warp & 3u;             // TMEM lane quadrant
     const uint32_t row = quad * 32u + lane;
-    const int q = q0 + s * 128 + (int)row;       // global query index
-    const int wg_tid = (int)threadIdx.x - 128 - s * 128;
-    if (s < n_slots) {
-      const uint32_t lane_sel = (quad * 32u) << 16;
-      const uint32_t sPs = smem_u32(smem + L::OFF_P + s * C::P_BYTES);
-      const float* mrow = kMaskF ? mask.maskf + (long long)b * mask.sb + (long long)min(q, Sq - 1) * mask.sq : nullptr;
-      const float sl2 = scale * kLog2e;
-      // ---- key-padding bits of every kv tile this slot visits: loaded ONCE into smem (a global load per tile on the
-      //      critical path costs ~1000 cycles); bit e of word 4*tile+c <-> key 128*tile + 32*c + e
-      uint32_t* padw = reinterpret_cast<uint32_t*>(smem + L::OFF_PADW) + s * (kMaxPadTiles * 4);
-      const bool pad_pre = mask.kpad != nullptr && nt[s] <= kMaxPadTiles;
-      if (pad_pre) {
-        const int nwords = nt[s] * 4;
-        for (int w0 = (int)quad; w0 < nwords; w0 += 16) {       // 4 independent loads in flight per warp
-          uint8_t v[4];
+    const int q = q0 + (int)row;                 // global query index
+    const int wg_tid = (int)threadIdx.x - 64;
+    const uint32_t lane_sel = (quad * 32u) << 16;
+    const uint32_t sPs = smem_u32(smem + L::OFF_P);
+    const float* mrow = kMaskF ? mask.maskf + (long long)b * mask.sb + (long long)min(q, Sq - 1) * mask.sq : nullptr;
+    const float sl2 = scale * kLog2e;
+    // ---- key-padding bits of every kv tile this CTA visits: loaded ONCE into smem (a global load per tile on the
+    //      critical path costs ~1000 cycles); bit e of word 4*tile+c <-> key 128*tile + 32*c + e
+    uint32_t* padw = reinterpret_cast<uint32_t*>(smem + L::OFF_PADW);
+    const bool pad_pre = mask.kpad != nullptr && nt <= kMaxPadTiles;
+    if (pad_pre) {
+      const int nwords = nt * 4;
+      const int w_id = (int)warp - 2;                         // 0..3
+      for (int w0 = w_id; w0 < nwords; w0 += 16) {            // 4 independent loads in flight per warp
+        uint8_t v[4];
 #pragma unroll
-          for (int u = 0; u < 4; ++u) {
-            const int kv = (w0 + 4 * u) * 32 + (int)lane;
-            v[u] = (w0 + 4 * u < nwords && kv < Sk) ? mask.kpad[(long long)b * Sk + kv] : (uint8_t)0;
-          }
-#pragma unroll
-          for (int u = 0; u < 4; ++u) {
-            const uint32_t bits = __ballot_sync(0xffffffffu, v[u] != 0);
-            if (lane == 0 && w0 + 4 * u < nwords) padw[w0 + 4 * u] = bits;
-          }
+        for (int u = 0; u < 4; ++u) {
+          const int kv = (w0 + 4 * u) * 32 + (int)lane;
+          v[u] = (w0 + 4 * u < nwords && kv < Sk) ? mask.kpad[(long long)b * Sk + kv] : (uint8_t)0;
         }
-        named_bar_sync(1 + s, 128);
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const uint32_t bits = __ballot_sync(0xffffffffu, v[u] != 0);
+          if (lane == 0 && w0 + 4 * u < nwords) padw[w0 + 4 * u] = bits;
+        }
       }
-      // running state, in the log2 domain (logit * log2 e).  The subtracted maximum `m_used` is STALE by design: it is only
-      // raised (and O, l rescaled) when the tile maximum exceeds it by more than 8 (a factor 2^8), so P stays <= 256 and
-      // the per-tile O correction is rare.
-      float m_used = -INFINITY, l_run = 0.f;
-      // a hidden key holds the RAW score kMaskRaw: times scale it is the reference's finite -1e9 logit (Attention.py:25-26)
-      const float kMaskRaw = kMaskVal / scale;
+      named_bar_sync(1, 128);
+    }
+    // running state, in the log2 domain (logit * log2 e).  The subtracted maximum `m_used` is STALE by design: it is only
+    // raised (and O, l rescaled) when the tile maximum exceeds it by more than 8 (a factor 2^8), so P stays <= 256 and
+    // the per-tile O correction is rare.
+    float m_used = -INFINITY, l_run = 0.f;
+    // a hidden key holds the RAW score kMaskRaw: times scale it is the reference's finite -1e9 logit (Attention.py:25-26)
+    const float kMaskRaw = kMaskVal / scale;
 
-      for (int j = 0; j < nt[s]; ++j) {
-        const int kv0 = j * 128;
-        // ---- per-thread mask words of this tile: bit e of bm[c] = key kv0+32c+e is hidden from this query (padding or
-        //      look-ahead: finite -1e9 logit), of bo[c] = the key does not exist (-inf).  ONE code path serves every mask
-        //      (three unrolled variants of the 128-element passes overflowed the instruction cache: icc hit rate 54 %,
-        //      "no instruction" the top stall); a 32-key chunk with no bit set in the whole warp takes the clean body.
-        uint32_t bm[4], bo[4];
-#pragma unroll
-        for (int c = 0; c < 4; ++c) {
-          const int k0 = kv0 + c * 32;
-          bo[c] = k0 + 32 <= Sk ? 0u : (k0 >= Sk ? 0xffffffffu : (0xffffffffu << (Sk - k0)));
-          uint32_t pb;
-          if (mask.kpad == nullptr) pb = 0u;
-          else if (pad_pre) pb = padw[j * 4 + c];
-          else {
-            const int kv = k0 + (int)lane;
-            pb = __ballot_sync(0xffffffffu, kv < Sk && mask.kpad[(long long)b * Sk + kv] != 0);
-          }
-          if (mask.causal) {                       // keys k0 + e > q are hidden
-            const int dq = q - k0;
-            pb |= dq >= 31 ? 0u : (dq < 0 ? 0xffffffffu : (0xfffffffeu << dq));
-          }
-          bm[c] = pb;
+    for (int j = 0; j < nt; ++j) {
+      const int kv0 = j * 128;
+      // ---- per-thread mask words of a 32-key chunk: bit e of bm = key kv0+32c+e is hidden from this query (padding or
+      //      look-ahead: finite -1e9 logit), of bo = the key does not exist (-inf).  ONE code path serves every mask; a chunk
+      //      with no bit set in the whole warp takes the clean body.
+      auto mask_words = [&](int c, uint32_t& bm, uint32_t& bo) {
+        const int k0 = kv0 + c * 32;
+        bo = k0 + 32 <= Sk ? 0u : (k0 >= Sk ? 0xffffffffu : (0xffffffffu << (Sk - k0)));
+        uint32_t pb;
+        if (mask.kpad == nullptr) pb = 0u;
+        else if (pad_pre) pb = padw[j * 4 + c];
+        else {
+          const int kv = k0 + (int)lane;
+          pb = __ballot_sync(0xffffffffu, kv < Sk && mask.kpad[(long long)b * Sk + kv] != 0);
         }
-        const bool tl = (s == 0 && wg_tid == 0);
-        if (tl) tl_stamp(8 + j * 8 + 0);
-        mbar_wait(&s_full[s], j & 1);
-        tcgen05_after_thread_sync();
-        if (tl) tl_stamp(8 + j * 8 + 1);
-        // ---- the whole 128-column S row of this thread, ONE pass over TMEM
-        uint32_t r[4][32];
-#pragma unroll
-        for (int c = 0; c < 4; ++c) tmem_ld_x32(tS[s] + lane_sel + c * 32, r[c]);
-        tmem_ld_wait();
-        tcgen05_before_thread_sync();
-        mbar_arrive(&s_free[s]);                       // the next tile's S may overwrite tensor memory now
-        // ---- pass 1: apply the mask words to the raw scores (in place), row maximum
-        float mx[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
-        bool hidden[4];                                // the whole chunk is hidden for every row of this warp
-#pragma unroll
-        for (int c = 0; c < 4; ++c) {
-          const bool touched = kMaskF || __any_sync(0xffffffffu, (bm[c] | bo[c]) != 0u);
-          hidden[c] = !kMaskF && __all_sync(0xffffffffu, bm[c] == 0xffffffffu);
-          if (touched) {
-#pragma unroll
-            for (int e = 0; e < 32; ++e) {
-              float t = __uint_as_float(r[c][e]);
-              if (bm[c] & (1u << e)) t = kMaskRaw;
-              if (kMaskF) { const int kv = kv0 + c * 32 + e; if (kv < Sk) t += mrow[kv] * kMaskRaw; }
-              if (bo[c] & (1u << e)) t = -INFINITY;
-              r[c][e] = __float_as_uint(t);
-              mx[e & 3] = fmaxf(mx[e & 3], t);
-            }
-          } else {
-#pragma unroll
-            for (int e = 0; e < 32; ++e) mx[e & 3] = fmaxf(mx[e & 3], __uint_as_float(r[c][e]));
-          }
+        if (mask.causal) {                       // keys k0 + e > q are hidden
+          const int dq = q - k0;
+          pb |= dq >= 31 ? 0u : (dq < 0 ? 0xffffffffu : (0xfffffffeu << dq));
         }
-        const float m_tile = fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3])) * sl2;     // sl2 > 0
-        if (tl) tl_stamp(8 + j * 8 + 2);
-        // ---- lazy rescale
-        const bool need = (j > 0) && (m_tile - m_used > 8.f);
-        if (j == 0) m_used = m_tile;
-        if (__any_sync(0xffffffffu, need)) {
-          const float alpha = need ? fast_exp2(m_used - m_tile) : 1.f;
-          if (need) { m_used = m_tile; l_run *= alpha; }
-          mbar_wait(&o_full[s], (j - 1) & 1);            // P.V of the previous tile has landed in TMEM
-          tcgen05_after_thread_sync();
+        bm = pb;
+      };
+      // raw score -> masked raw score (in place)
+      auto apply_mask = [&](int c, uint32_t bm, uint32_t bo, uint32_t (&rc)[32]) {
 #pragma unroll
-          for (int c = 0; c < DK / 32; ++c) {
-            uint32_t ro[32];
-            tmem_ld_x32(tO[s] + lane_sel + c * 32, ro);
-            tmem_ld_wait();
-#pragma unroll
-            for (int e = 0; e < 32; ++e) ro[e] = __float_as_uint(__uint_as_float(ro[e]) * alpha);
-            tmem_st_x32(tO[s] + lane_sel + c * 32, ro);
-          }
-          tmem_st_wait();
+        for (int e = 0; e < 32; ++e) {
+          float t = __uint_as_float(rc[e]);
+          if (bm & (1u << e)) t = kMaskRaw;
+          if (kMaskF) { const int kv = kv0 + c * 32 + e; if (kv < Sk) t += mrow[kv] * kMaskRaw; }
+          if (bo & (1u << e)) t = -INFINITY;
+          rc[e] = __float_as_uint(t);
         }
-        // ---- p = 2^(raw * scale * log2 e - m_used), row sum (fp32, 4 partial sums), P -> bf16 pairs in registers.
-        //      A chunk hidden for the whole warp contributes exactly 0 (2^(-1.44e9 - m) underflows) unless some row of the
-        //      warp is fully masked so far (m_used is then the -1e9 level itself and those keys count: uniform attention)
-        const bool real_max = __all_sync(0xffffffffu, m_used > -1e8f);
-        float rs4[4] = {0.f, 0.f, 0.f, 0.f};
-        uint32_t pk[4][16];
-#pragma unroll
-        for (int c = 0; c < 4; ++c) {
-          if (hidden[c] && real_max) {
-#pragma unroll
-            for (int g = 0; g < 16; ++g) pk[c][g] = 0u;
-          } else {
-            float p[32];
-#pragma unroll
-            for (int e = 0; e < 32; ++e) { p[e] = fast_exp2(__uint_as_float(r[c][e]) * sl2 - m_used); rs4[e & 3] += p[e]; }
-#pragma unroll
-            for (int g = 0; g < 16; ++g) pk[c][g] = pack_bf16x2(p[2 * g], p[2 * g + 1]);
-          }
-        }
-        // the P smem tile of this slot is still being read by P.V of the previous kv tile until o_full fires
-        // (S(j) was issued BEFORE that P.V, so s_full alone does not order them)
-        if (j > 0) { mbar_wait(&o_full[s], (j - 1) & 1); tcgen05_after_thread_sync(); }
-#pragma unroll
-        for (int c = 0; c < 4; ++c) {
-          const uint32_t panel = sPs + (c >> 1) * 16384;
-#pragma unroll
-          for (int g = 0; g < 4; ++g)
-            st_shared_v4(panel + swz128_off(row, (c & 1) * 4 + g), pk[c][4 * g], pk[c][4 * g + 1], pk[c][4 * g + 2], pk[c][4 * g + 3]);
-        }
-        l_run += (rs4[0] + rs4[1]) + (rs4[2] + rs4[3]);
-        if (tl) tl_stamp(8 + j * 8 + 3);
-        fence_proxy_async_smem();
-        tcgen05_before_thread_sync();
-        mbar_arrive(&p_full[s]);
-        if (tl) tl_stamp(8 + j * 8 + 4);
-      }
-      // finalise: O (TMEM) / l -> bf16 -> smem (reuse this slot's P buffer) -> TMA store ; lse = (m_used + log2 l) ln 2
-      mbar_wait(&o_full[s], (nt[s] - 1) & 1);
+      };
+      const bool tl = (wg_tid == 0);
+      if (tl) tl_stamp(8 + j * 8 + 0);
+      mbar_wait(s_full, j & 1);
       tcgen05_after_thread_sync();
-      if (s == 0 && wg_tid == 0) tl_stamp(2);
-      const float inv = 1.f / l_run;
-      // Training also keeps the bf16 ROUNDING RESIDUAL of O (O_lo = bf16(O - bf16(O)), staged in this slot's Q tile, which no
-      // MMA reads any more): the backward's delta = rowsum(dO o O) cancels against dP = dO.V^T in dS = P o (dP - delta), and
-      // any component shared by all value vectors (bias, LayerNorm beta) makes that cancellation amplify the 2^-9 rounding of
-      // O into percent-level errors of dQ / dK (measured: tools/attn_precision.py).  delta is formed from O + O_lo.
-      const uint32_t sLo = smem_u32(smem + L::OFF_Q + s * C::TILE_BYTES);
-#pragma unroll
-      for (int c = 0; c < DK / 32; ++c) {
-        uint32_t ro[32];
-        tmem_ld_x32(tO[s] + lane_sel + c * 32, ro);
+      if (tl) tl_stamp(8 + j * 8 + 1);
+      // ---- pass 1 over tensor memory: row maximum of the masked scores.  The row is NOT kept in registers (a 128-value row
+      //      + packed P + masks needed more than the 168 registers two resident CTAs leave a thread: ~80 local-memory
+      //      round trips per tile, and a 30 KB unrolled loop body); both passes are ROLLED loops over 32-key chunks that re-read S
+      //      from tensor memory (16 KB per warp and pass, ~100 cycles of latency per chunk, hidden by the other resident CTA).
+      float mx[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+      uint32_t hidden_bits = 0;                      // bit c: chunk c is hidden for every row of this warp
+#pragma unroll 1
+      for (int c = 0; c < 4; ++c) {
+        uint32_t bm, bo;
+        mask_words(c, bm, bo);
+        const bool touched = kMaskF || __any_sync(0xffffffffu, (bm | bo) != 0u);
+        const bool hid = !kMaskF && __all_sync(0xffffffffu, bm == 0xffffffffu);
+        hidden_bits |= (hid ? 1u : 0u) << c;
+        if (hid) { mx[0] = fmaxf(mx[0], kMaskRaw); continue; }     // every existing key of the chunk holds the masked value
+        uint32_t rc[32];
+        tmem_ld_x32(tS + lane_sel + c * 32, rc);
         tmem_ld_wait();
+        if (touched) apply_mask(c, bm, bo, rc);
 #pragma unroll
-        for (int g = 0; g < 4; ++g) {
-          uint32_t hi[4], lo[4];
+        for (int e = 0; e < 32; ++e) mx[e & 3] = fmaxf(mx[e & 3], __uint_as_float(rc[e]));
+      }
+      const float m_tile = fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3])) * sl2;     // sl2 > 0
+      if (tl) tl_stamp(8 + j * 8 + 2);
+      // ---- lazy rescale
+      const bool need = (j > 0) && (m_tile - m_used > 8.f);
+      if (j == 0) m_used = m_tile;
+      if (__any_sync(0xffffffffu, need)) {
+        const float alpha = need ? fast_exp2(m_used - m_tile) : 1.f;
+        if (need) { m_used = m_tile; l_run *= alpha; }
+        mbar_wait(o_full, (j - 1) & 1);                // P.V of the previous tile has landed in TMEM
+        tcgen05_after_thread_sync();
+#pragma unroll 1
+        for (int c = 0; c < DK / 32; ++c) {
+          uint32_t ro[32];
+          tmem_ld_x32(tO + lane_sel + c * 32, ro);
+          tmem_ld_wait();
 #pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            const float a = __uint_as_float(ro[8 * g + 2 * e]) * inv, c2 = __uint_as_float(ro[8 * g + 2 * e + 1]) * inv;
-            hi[e] = pack_bf16x2(a, c2);
-            const float2 r = unpack_bf16x2(hi[e]);
-            lo[e] = pack_bf16x2(a - r.x, c2 - r.y);
-          }
-          st_shared_v4(sPs + swz_off<DK>(row, c * 4 + g), hi[0], hi[1], hi[2], hi[3]);
-          if (has_lo) st_shared_v4(sLo + swz_off<DK>(row, c * 4 + g), lo[0], lo[1], lo[2], lo[3]);
+          for (int e = 0; e < 32; ++e) ro[e] = __float_as_uint(__uint_as_float(ro[e]) * alpha);
+          tmem_st_x32(tO + lane_sel + c * 32, ro);
         }
+        tmem_st_wait();
       }
-      if (q < Sq) {
-        float lse_val = (m_used + __log2f(l_run)) * 0.6931471805599453f;   // back to natural log
-        // a fully-masked row: every logit is the reference's finite -1e9 (times the mask value); fp32 absorbs ln(Sk) there, and
-        // raw * scale only reproduces -1e9 to ~64 ulp-units when scale is not a power of two (head depth 32, 128): snap, so that
-        // the backward / attention_weights recompute exp(-1e9 - lse) = 1 exactly like the reference's own fp32 softmax
-        if (m_used < -1e8f) lse_val = kMaskVal * rintf(lse_val / kMaskVal);
-        lse_out[((long long)b * H + h) * Sq + q] = lse_val;
+      // ---- pass 2: p = 2^(raw * scale * log2 e - m_used), row sum (fp32, 4 partial sums), P -> bf16 -> smem, chunk by chunk.
+      //      A chunk hidden for the whole warp contributes exactly 0 (2^(-1.44e9 - m) underflows) unless some row of the
+      //      warp is fully masked so far (m_used is then the -1e9 level itself and those keys count: uniform attention)
+      const bool real_max = __all_sync(0xffffffffu, m_used > -1e8f);
+      // the P smem tile is still being read by P.V of the previous kv tile until o_full fires (S(j) was issued BEFORE that P.V,
+      // so s_full alone does not order them); it fired long ago
+      if (j > 0) { mbar_wait(o_full, (j - 1) & 1); tcgen05_after_thread_sync(); }
+      float rs4[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll 1
+      for (int c = 0; c < 4; ++c) {
+        uint32_t pk[16];
+        const bool hid = (hidden_bits >> c) & 1u;
+        if (hid && real_max) {
+#pragma unroll
+          for (int g = 0; g < 16; ++g) pk[g] = 0u;
+        } else {
+          uint32_t rc[32];
+          uint32_t bm, bo;
+          mask_words(c, bm, bo);
+          if (hid) {
+#pragma unroll
+            for (int e = 0; e < 32; ++e) rc[e] = __float_as_uint(kMaskRaw);
+            if (__any_sync(0xffffffffu, bo != 0u)) apply_mask(c, bm, bo, rc);
+          } else {
+            tmem_ld_x32(tS + lane_sel + c * 32, rc);
+            tmem_ld_wait();
+            if (kMaskF || __any_sync(0xffffffffu, (bm | bo) != 0u)) apply_mask(c, bm, bo, rc);
+          }
+          float p[32];
+#pragma unroll
+          for (int e = 0; e < 32; ++e) { p[e] = fast_exp2(__uint_as_float(rc[e]) * sl2 - m_used); rs4[e & 3] += p[e]; }
+#pragma unroll
+          for (int g = 0; g < 16; ++g) pk[g] = pack_bf16x2(p[2 * g], p[2 * g + 1]);
+        }
+        if (c == 3) {                                  // every chunk of S has been read: the next tile's S may overwrite it
+          tcgen05_before_thread_sync();
+          mbar_arrive(s_free);
+        }
+        const uint32_t panel = sPs + (c >> 1) * 16384;
+#pragma unroll
+        for (int g = 0; g < 4; ++g)
+          st_shared_v4(panel + swz128_off(row, (c & 1) * 4 + g), pk[4 * g], pk[4 * g + 1], pk[4 * g + 2], pk[4 * g + 3]);
       }
-      tcgen05_before_thread_sync();
+      l_run += (rs4[0] + rs4[1]) + (rs4[2] + rs4[3]);
+      if (tl) tl_stamp(8 + j * 8 + 3);
       fence_proxy_async_smem();
-      named_bar_sync(1 + s, 128);
-      if (wg_tid == 0) {
-        tile_store<DK>(&tmO, smem + L::OFF_P + s * C::P_BYTES, h * DK, q0 + s * 128, b);
-        if (has_lo) tile_store<DK>(&tmOlo, smem + L::OFF_Q + s * C::TILE_BYTES, h * DK, q0 + s * 128, b);
-        tma_store_commit();
-        tma_store_wait_read<0>();          // smem may be released; the write itself completes before the grid does
-        if (s == 0) tl_stamp(3);
+      tcgen05_before_thread_sync();
+      mbar_arrive(p_full);
+      if (tl) tl_stamp(8 + j * 8 + 4);
+    }
+    // finalise: O (TMEM) / l -> bf16 -> smem (the P buffer) -> TMA store ; lse = (m_used + log2 l) ln 2
+    mbar_wait(o_full, (nt - 1) & 1);
+    tcgen05_after_thread_sync();
+    if (wg_tid == 0) tl_stamp(2);
+    const float inv = 1.f / l_run;
+    // Training also keeps the bf16 ROUNDING RESIDUAL of O (O_lo = bf16(O - bf16(O)), staged in the Q tile, which no MMA reads
+    // any more): the backward's delta = rowsum(dO o O) cancels against dP = dO.V^T in dS = P o (dP - delta), and any component
+    // shared by all value vectors (bias, LayerNorm beta) makes that cancellation amplify the 2^-9 rounding of O into
+    // percent-level errors of dQ / dK (measured: tools/attn_precision.py).  delta is formed from O + O_lo.
+    const uint32_t sLo = smem_u32(smem + L::OFF_Q);
+#pragma unroll
+    for (int c = 0; c < DK / 32; ++c) {
+      uint32_t ro[32];
+      tmem_ld_x32(tO + lane_sel + c * 32, ro);
+      tmem_ld_wait();
+#pragma unroll
+      for (int g = 0; g < 4; ++g) {
+        uint32_t hi[4], lo[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const float a = __uint_as_float(ro[8 * g + 2 * e]) * inv, c2 = __uint_as_float(ro[8 * g + 2 * e + 1]) * inv;
+          hi[e] = pack_bf16x2(a, c2);
+          const float2 rr = unpack_bf16x2(hi[e]);
+          lo[e] = pack_bf16x2(a - rr.x, c2 - rr.y);
+        }
+        st_shared_v4(sPs + swz_off<DK>(row, c * 4 + g), hi[0], hi[1], hi[2], hi[3]);
+        if (has_lo) st_shared_v4(sLo + swz_off<DK>(row, c * 4 + g), lo[0], lo[1], lo[2], lo[3]);
       }
+    }
+    if (q < Sq) {
+      float lse_val = (m_used + __log2f(l_run)) * 0.6931471805599453f;   // back to natural log
+      // a fully-masked row: every logit is the reference's finite -1e9 (times the mask value); fp32 absorbs ln(Sk) there, and
+      // raw * scale only reproduces -1e9 to ~64 ulp-units when scale is not a power of two (head depth 32, 128): snap, so that
+      // the backward / attention_weights recompute exp(-1e9 - lse) = 1 exactly like the reference's own fp32 softmax
+      if (m_used < -1e8f) lse_val = kMaskVal * rintf(lse_val / kMaskVal);
+      lse_out[((long long)b * H + h) * Sq + q] = lse_val;
+    }
+    tcgen05_before_thread_sync();
+    fence_proxy_async_smem();
+    named_bar_sync(1, 128);
+    if (wg_tid == 0) {
+      tile_store<DK>(&tmO, smem + L::OFF_P, h * DK, q0, b);
+      if (has_lo) tile_store<DK>(&tmOlo, smem + L::OFF_Q, h * DK, q0, b);
+      tma_store_commit();
+      tma_store_wait_read<0>();          // smem may be released; the write itself completes before the grid does
+      tl_stamp(3);
     }
   }
   tcgen05_before_thread_sync();
   __syncthreads();
   tcgen05_after_thread_sync();
-  if (warp == 1) tmem_dealloc<512>(tmem_base);
+  if (warp == 1) tmem_dealloc<256>(tmem_base);
 }
 
 // ================================================================================================
@@ -927,10 +916,13 @@ static int attn_fwd_launch(const void* Q, long long ld_q, const void* K, long lo
     if (!attr_done[dev]) {
       BX_CHECK_CUDA(cudaFuncSetAttribute(attn_fwd_kernel<DK, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::BYTES));
       BX_CHECK_CUDA(cudaFuncSetAttribute(attn_fwd_kernel<DK, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::BYTES));
+      // two CTAs per SM need the full shared-memory carve-out
+      BX_CHECK_CUDA(cudaFuncSetAttribute(attn_fwd_kernel<DK, true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+      BX_CHECK_CUDA(cudaFuncSetAttribute(attn_fwd_kernel<DK, false>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
       attr_done[dev] = true;
     }
   }
-  dim3 grid((Sq + 255) / 256, H, B);
+  dim3 grid((Sq + 127) / 128, H, B);
   void* pb = prof_on() ? prof_begin(st) : nullptr;
   kern<<<grid, ATTN_FWD_THREADS, L::BYTES, st>>>(tmQ, tmK, tmV, tmO, tmOlo, O_lo != nullptr ? 1 : 0, lse, mask, H, Sq, Sk, 1.f / sqrtf((float)DK));
   if (pb) prof_end(pb, 1, 4.0 * B * H * (double)Sq * Sk * DK, st);     // dense count, as the reference computes it
