@@ -44,6 +44,15 @@ int b200xf_prof_collect(double* out, int ncat);
  *      M > 128 and N > 128, 256 x 256 per CTA PAIR (tcgen05 cta_group::2); b200xf_gemm_force_cta_group(1|2)
  *      overrides the choice (0 restores it) -- used by tests and benchmarks.                                   */
 void b200xf_gemm_force_cta_group(int cg);
+/* K3 / K4 fused (Attention.py:77 + Encoder.py:22-23 / Decoder.py:30-31,35-36 ; point_ffn.py:6 + Encoder.py:26-27 / Decoder.py:39-40):
+ *      z = xres + dropout(A[M,K] . W[K,N] + bias)   out = LayerNorm(z) * gamma + beta        -- ONE kernel, LayerNorm in the epilogue
+ *      A bf16 (row pitch lda), W bf16 keras [in,out] layout (row pitch ldw), N = d_model in {128, 256, 512} (a CTA pair keeps whole
+ *      rows in tensor memory); xres / z / out bf16 [M,N] contiguous, mean / rstd fp32 [M], keep_bits uint8 [M, N/8] (written when
+ *      rate > 0 and non-NULL; identical to b200xf_residual_ln_fwd's mask for the same (seed, site)).                             */
+int b200xf_gemm_bias_dropout_residual_ln(const void* A, int64_t lda, const void* W, int64_t ldw, const float* bias, const void* xres_bf16,
+                                         const float* gamma, const float* beta, void* z_bf16, void* out_bf16, float* mean, float* rstd,
+                                         void* keep_bits, int64_t M, int64_t N, int64_t K, float eps, float rate, uint64_t seed, uint32_t site,
+                                         b200xf_stream_t stream);
 int b200xf_gemm_bf16(const void* A, int64_t lda, int a_major, const void* B, int64_t ldb, int b_major, void* D,
                      int64_t ldd, int d_is_f32, const float* bias, const void* aux, int64_t ld_aux, int flags,
                      int splits, int64_t M, int64_t N, int64_t K, b200xf_stream_t stream);
@@ -170,8 +179,8 @@ int b200xf_model_create(const b200xf_model_config* cfg, float* params, float* gr
 void b200xf_model_destroy(b200xf_model* m);
 /* Inside one forward / backward call the library forks work that is off the critical path (weight-gradient GEMMs, bias
  * column sums, the cross-attention K/V projections) onto a second stream it owns and joins it back before returning, so the
- * caller still orders everything with ONE stream (and may capture that stream into a CUDA graph).  on = 0 keeps every kernel
- * on the caller's stream (also: environment B200XF_CONCURRENCY=0 at model creation). */
+ * caller still orders everything with ONE stream (and may capture that stream into a CUDA graph).  OFF by default (measured: no gain
+ * at transformer-base shapes, see model.cu); on = 1 or environment B200XF_CONCURRENCY=1 at model creation enables it. */
 void b200xf_model_set_concurrency(b200xf_model* m, int on);
 /* when seed_dev != NULL the dropout seed of forward/backward is read from this device word (b200xf_step_params output)
  * instead of the `seed` argument -- required for CUDA-graph replays */

@@ -479,3 +479,44 @@ def test_attention_delta_from_output_residual():
     print(errs)
     assert errs[("residual", "dq")] < 4e-3 and errs[("residual", "dk")] < 4e-3
     assert errs[("rounded", "dk")] > 3 * errs[("residual", "dk")]          # the effect the residual removes
+
+
+@pytest.mark.parametrize("M,N,K,rate", [(512, 512, 512, 0.0), (1000, 512, 2048, 0.1), (300, 256, 384, 0.1), (257, 128, 128, 0.0), (4096, 512, 512, 0.1)])
+def test_gemm_bias_dropout_residual_layernorm_fused(M, N, K, rate):
+    """K3/K4: the LayerNorm-in-the-epilogue GEMM against (a) fp32 torch on the same bf16 operands and (b) the stand-alone
+    GEMM + residual_ln_fwd pair of this library: same dropout mask (bit-identical keep bytes), same z, same statistics."""
+    A = rnd((M, K), 1.0, 1); W = rnd((K, N), K ** -0.5, 2)
+    bias = rnd((N,), 0.2, 3, torch.float32); x = rnd((M, N), 1.0, 4)
+    gamma = 1 + rnd((N,), 0.1, 5, torch.float32); beta = rnd((N,), 0.1, 6, torch.float32)
+    z = torch.full((M, N), float("nan"), dtype=torch.bfloat16, device=dev()); out = torch.full_like(z, float("nan"))
+    mean = torch.full((M,), float("nan"), device=dev()); rstd = torch.full((M,), float("nan"), device=dev())
+    keep = torch.zeros(M, N // 8, dtype=torch.uint8, device=dev())
+    seed, site = 1234, 7
+    L.call("b200xf_gemm_bias_dropout_residual_ln", L.ptr(A), K, L.ptr(W), N, L.ptr(bias), L.ptr(x), L.ptr(gamma), L.ptr(beta), L.ptr(z), L.ptr(out),
+           L.ptr(mean), L.ptr(rstd), L.ptr(keep), M, N, K, 1e-6, rate, seed, site, sp())
+    # the two-kernel path
+    y2 = torch.empty_like(z); z2 = torch.empty_like(z); out2 = torch.empty_like(z)
+    mean2 = torch.empty_like(mean); rstd2 = torch.empty_like(rstd); keep2 = torch.zeros_like(keep)
+    L.call("b200xf_gemm_bf16", L.ptr(A), K, 0, L.ptr(W), N, 1, L.ptr(y2), N, 0, L.ptr(bias), None, 0, 0, 1, M, N, K, sp())
+    L.call("b200xf_residual_ln_fwd", L.ptr(y2), L.ptr(x), L.ptr(gamma), L.ptr(beta), L.ptr(z2), L.ptr(out2), L.ptr(mean2), L.ptr(rstd2), L.ptr(keep2),
+           M, N, 1e-6, rate, seed, site, sp())
+    torch.cuda.synchronize()
+    assert torch.isfinite(out.float()).all() and torch.isfinite(z.float()).all()
+    if rate > 0:
+        assert torch.equal(keep, keep2)                                       # the same Philox mask, bit for bit
+        frac = ((keep[:, :, None].int() >> torch.arange(8, device=dev())) & 1).float().mean().item()
+        assert abs(frac - (1 - rate)) < 0.01
+    # fp32 reference on the same operands (and the mask the kernel reported)
+    y = A.float() @ W.float() + bias
+    if rate > 0:
+        kb = ((keep[:, :, None].int() >> torch.arange(8, device=dev())) & 1).bool().view(M, N)
+        y = torch.where(kb, y / (1 - rate), torch.zeros_like(y))
+    z_ref = x.float() + y
+    out_ref = torch.nn.functional.layer_norm(z_ref, (N,), gamma, beta, 1e-6)
+    assert (z.float() - z_ref).abs().max().item() < 2e-2 * max(1.0, z_ref.abs().max().item())
+    assert (mean - z_ref.mean(-1)).abs().max().item() < 1e-4
+    assert ((rstd - (z_ref.var(-1, unbiased=False) + 1e-6).rsqrt()) / rstd).abs().max().item() < 1e-3
+    assert (out.float() - out_ref).abs().max().item() < 4e-2
+    # the fused kernel normalises the UNROUNDED fp32 GEMM output, the two-kernel path a bf16-rounded y: agreement to bf16 rounding
+    assert (z.float() - z2.float()).abs().max().item() < 4e-2 * max(1.0, z_ref.abs().max().item())
+    assert (out.float() - out2.float()).abs().max().item() < 6e-2

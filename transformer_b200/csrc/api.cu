@@ -22,6 +22,13 @@ int b200xf_gemm_bf16(const void* A, int64_t lda, int a_major, const void* B, int
   return bx::gemm_bf16(A, lda, a_major, B, ldb, b_major, D, ldd, d_is_f32, bias, aux, ld_aux, flags, splits, M, N, K,
                        ST(stream));
 }
+int b200xf_gemm_bias_dropout_residual_ln(const void* A, int64_t lda, const void* W, int64_t ldw, const float* bias, const void* xres_bf16,
+                                         const float* gamma, const float* beta, void* z_bf16, void* out_bf16, float* mean, float* rstd,
+                                         void* keep_bits, int64_t M, int64_t N, int64_t K, float eps, float rate, uint64_t seed, uint32_t site,
+                                         b200xf_stream_t stream) {
+  return bx::gemm_ln(A, lda, W, ldw, bias, xres_bf16, gamma, beta, z_bf16, out_bf16, mean, rstd, keep_bits, M, N, K, eps, rate, seed, site,
+                     ST(stream));
+}
 int b200xf_attn_fwd(const void* Q, int64_t ld_q, const void* K, int64_t ld_k, const void* V, int64_t ld_v, void* O,
                     int64_t ld_o, float* lse, const uint8_t* kpad, int causal, const float* maskf, int64_t mask_sb,
                     int64_t mask_sq, int B, int H, int Sq, int Sk, int dk, b200xf_stream_t stream) {

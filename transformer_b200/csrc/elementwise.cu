@@ -10,18 +10,6 @@ namespace bx {
 // (1 bit per element) in forward and read it back in backward, the embedding kernels regenerate it
 // keras Dropout semantics: keep w.p. 1-rate, scale kept by 1/(1-rate).
 // ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint4 philox4x32_10(uint4 ctr, uint2 key) {
-  constexpr uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
-#pragma unroll
-  for (int i = 0; i < 10; ++i) {
-    const uint32_t hi0 = __umulhi(M0, ctr.x), lo0 = M0 * ctr.x;
-    const uint32_t hi1 = __umulhi(M1, ctr.z), lo1 = M1 * ctr.z;
-    ctr = make_uint4(hi1 ^ ctr.y ^ key.x, lo1, hi0 ^ ctr.w ^ key.y, lo0);
-    key.x += W0;
-    key.y += W1;
-  }
-  return ctr;
-}
 // keep-scale factors for the 4 consecutive elements starting at flat element index `idx4*4`
 __device__ __forceinline__ float4 dropout_scale4(unsigned long long seed, uint32_t site, unsigned long long idx4,
                                                  float rate) {
@@ -58,23 +46,6 @@ __device__ __forceinline__ F8 unpack8(const uint4 u) {
 __device__ __forceinline__ uint4 pack8(const F8& f) {
   return make_uint4(pack_bf16x2(f.v[0], f.v[1]), pack_bf16x2(f.v[2], f.v[3]), pack_bf16x2(f.v[4], f.v[5]), pack_bf16x2(f.v[6], f.v[7]));
 }
-// keep bits (bit e = element e kept) of the 8 consecutive elements starting at flat element index idx8*8: ONE Philox
-// call per 8 elements, 16 random bits each (keep iff u16 >= rate * 65536) -- the RNG was half of the instructions of
-// the LayerNorm kernels when it ran once per 4 elements
-__device__ __forceinline__ uint32_t dropout_keep8(unsigned long long seed, uint32_t site, unsigned long long idx8, float rate) {
-  const uint4 r = philox4x32_10(make_uint4((uint32_t)idx8, (uint32_t)(idx8 >> 32), site, 0x8u),
-                                make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)));
-  const uint32_t thr = (uint32_t)(rate * 65536.f);
-  const uint32_t w[4] = {r.x, r.y, r.z, r.w};
-  uint32_t bits = 0;
-#pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    bits |= ((w[j] & 0xFFFFu) >= thr ? 1u : 0u) << (2 * j);
-    bits |= ((w[j] >> 16) >= thr ? 1u : 0u) << (2 * j + 1);
-  }
-  return bits;
-}
-
 // ------------------------------------------------------------------------------------------------
 // K6  embedding * sqrt(d) + pos_encoding[:, :S] (+ dropout)      Encoder.py:51-55, Decoder.py:65-69
 //   ids int64 [rows] (rows = B*S), table fp32 [V, d], pos fp32 [P, d]  ->  x bf16 [rows, d] (+ optional fp32 copy)

@@ -9,6 +9,12 @@ int gemm_bf16(const void* A, long long lda, int a_major, const void* B, long lon
               long long ldd, int d_is_f32, const float* bias, const void* aux, long long ld_aux, int flags,
               int splits, long long M, long long N, long long K, cudaStream_t stream);
 
+// K3/K4 fused: z = xres + dropout(A.W + bias); out = LayerNorm(z) * gamma + beta, in the GEMM epilogue (gemm_ln.cu); N = 128 / 256 / 512
+bool gemm_ln_supported(long long M, long long N, long long K);
+int gemm_ln(const void* A, long long lda, const void* W, long long ldw, const float* bias, const void* xres, const float* gamma,
+            const float* beta, void* z, void* out, float* mean, float* rstd, void* keep_bits, long long M, long long N, long long K, float eps,
+            float rate, unsigned long long seed, unsigned site, cudaStream_t stream, const unsigned long long* seed_dev = nullptr);
+
 void gemm_force_cta_group(int cg);   // 0 = heuristic, 1 / 2 = force single-CTA / CTA-pair tiles (tests, benchmarks)
 
 int set_timeline(long long* dev_ptr);   // debug: register a device buffer of >= 128 int64 clock stamps (nullptr disables)

@@ -249,7 +249,8 @@ struct b200xf_model {
   cudaStream_t side = nullptr;
   std::vector<cudaEvent_t> events;
   int next_event = 0;
-  int concurrency = 1;         // 0: everything on the caller's stream
+  int concurrency = 0;         // 0: everything on the caller's stream
+  int fuse_ln = 1;             // LayerNorm in the out-projection / FFN dense1 GEMM epilogue (d_model 128 / 256 / 512)
 };
 
 namespace {
@@ -367,6 +368,19 @@ struct Par {
   }
 };
 
+// out = LayerNorm(x + dropout(A . W + b)): ONE kernel (LayerNorm in the GEMM epilogue, gemm_ln.cu) when d_model is 128 / 256 /
+// 512, else the Dense GEMM followed by the stand-alone dropout + residual + LayerNorm kernel
+int dense_residual_ln(M* m, const bf16* A, int64_t lda, int64_t K, int64_t w_off, int64_t bias_off, const bf16* x, int64_t g_off, int64_t b_off,
+                      bf16* out16, const LnSave& s, int64_t rows, uint32_t site, cudaStream_t st) {
+  const int d = m->lo.d;
+  const float rate = m->training ? m->cfg.dropout_rate : 0.f;
+  if (m->fuse_ln && bx::gemm_ln_supported(rows, d, K))
+    return bx::gemm_ln(A, lda, m->Sh + w_off, d, m->P + bias_off, x, m->P + g_off, m->P + b_off, s.z, out16, s.mean, s.rstd, s.keep, rows, d, K,
+                       m->cfg.ln_eps, rate, m->seed, site, st, m->seed_dev);
+  RC(linear_fwd(A, lda, m->Sh + w_off, d, m->P + bias_off, m->w.y16, d, false, false, rows, d, K, st));
+  return residual_ln(m, x, g_off, b_off, out16, s, rows, site, st);
+}
+
 int forward_impl(M* m, float* logits_out, int64_t ld_logits, cudaStream_t st) {
   const Layout& lo = m->lo;
   Work& w = m->w;
@@ -390,14 +404,12 @@ int forward_impl(M* m, float* logits_out, int64_t ld_logits, cudaStream_t st) {
     RC(linear_fwd(w.enc_x16[l], d, Sh + p.mha.Wqkv, 3 * d, m->P + p.mha.bqkv, a.qkv, 3 * d, false, false, Ms, 3 * d, d, st));
     RC(bx::attn_fwd(a.qkv, 3 * d, a.qkv + d, 3 * d, a.qkv + 2 * d, 3 * d, a.attn_o, d, a.lse, em.kpad, em.causal, em.maskf, em.sb,
                     em.sq, B, H, S, S, dk, st, m->training ? a.attn_o_lo : nullptr));
-    RC(linear_fwd(a.attn_o, d, Sh + p.mha.Wo, d, m->P + p.mha.bo, w.y16, d, false, false, Ms, d, d, st));
-    RC(residual_ln(m, w.enc_x16[l], p.ln1g, p.ln1b, a.out1_16, a.ln1, Ms, site_enc(l, 0), st));   // Encoder.py:22-23
+    RC(dense_residual_ln(m, a.attn_o, d, d, p.mha.Wo, p.mha.bo, w.enc_x16[l], p.ln1g, p.ln1b, a.out1_16, a.ln1, Ms, site_enc(l, 0), st));   // Encoder.py:22-23
     // point_wise_feed_forward_network (point_ffn.py:3-7)
     bx::prof_set_gemm_cat(3);
     RC(linear_fwd(a.out1_16, d, Sh + p.ffn.W1, f, m->P + p.ffn.b1, a.h, f, false, true, Ms, f, d, st, a.hbits));
-    RC(linear_fwd(a.h, f, Sh + p.ffn.W2, d, m->P + p.ffn.b2, w.y16, d, false, false, Ms, d, f, st));
+    RC(dense_residual_ln(m, a.h, f, f, p.ffn.W2, p.ffn.b2, a.out1_16, p.ln2g, p.ln2b, w.enc_x16[l + 1], a.ln2, Ms, site_enc(l, 1), st));   // Encoder.py:26-27
     bx::prof_set_gemm_cat(0);
-    RC(residual_ln(m, a.out1_16, p.ln2g, p.ln2b, w.enc_x16[l + 1], a.ln2, Ms, site_enc(l, 1), st));   // Encoder.py:26-27
   }
   const bf16* enc_out16 = w.enc_x16[L];
 
@@ -422,21 +434,18 @@ int forward_impl(M* m, float* logits_out, int64_t ld_logits, cudaStream_t st) {
     RC(linear_fwd(w.dec_x16[l], d, Sh + p.mha1.Wqkv, 3 * d, m->P + p.mha1.bqkv, a.qkv1, 3 * d, false, false, Mt, 3 * d, d, st));
     RC(bx::attn_fwd(a.qkv1, 3 * d, a.qkv1 + d, 3 * d, a.qkv1 + 2 * d, 3 * d, a.attn1_o, d, a.lse1, sm.kpad, sm.causal, sm.maskf, sm.sb,
                     sm.sq, B, H, T, T, dk, st, m->training ? a.attn1_o_lo : nullptr));
-    RC(linear_fwd(a.attn1_o, d, Sh + p.mha1.Wo, d, m->P + p.mha1.bo, w.y16, d, false, false, Mt, d, d, st));
-    RC(residual_ln(m, w.dec_x16[l], p.ln1g, p.ln1b, a.out1_16, a.ln1, Mt, site_dec(l, 0), st));
+    RC(dense_residual_ln(m, a.attn1_o, d, d, p.mha1.Wo, p.mha1.bo, w.dec_x16[l], p.ln1g, p.ln1b, a.out1_16, a.ln1, Mt, site_dec(l, 0), st));
     // mha2: q from the decoder stream, k = v = enc_output, encoder padding mask (Decoder.py:33-36)
     RC(linear_fwd(a.out1_16, d, Sh + p.mha2.Wq, d, m->P + p.mha2.bq, a.q2, d, false, false, Mt, d, d, st));
     RC(par.wait(kv_ready[l]));
     RC(bx::attn_fwd(a.q2, d, a.kv2, 2 * d, a.kv2 + d, 2 * d, a.attn2_o, d, a.lse2, cm.kpad, cm.causal, cm.maskf, cm.sb, cm.sq, B, H, T, S,
                     dk, st, m->training ? a.attn2_o_lo : nullptr));
-    RC(linear_fwd(a.attn2_o, d, Sh + p.mha2.Wo, d, m->P + p.mha2.bo, w.y16, d, false, false, Mt, d, d, st));
-    RC(residual_ln(m, a.out1_16, p.ln2g, p.ln2b, a.out2_16, a.ln2, Mt, site_dec(l, 1), st));
+    RC(dense_residual_ln(m, a.attn2_o, d, d, p.mha2.Wo, p.mha2.bo, a.out1_16, p.ln2g, p.ln2b, a.out2_16, a.ln2, Mt, site_dec(l, 1), st));
     // ffn (Decoder.py:38-40)
     bx::prof_set_gemm_cat(3);
     RC(linear_fwd(a.out2_16, d, Sh + p.ffn.W1, f, m->P + p.ffn.b1, a.h, f, false, true, Mt, f, d, st, a.hbits));
-    RC(linear_fwd(a.h, f, Sh + p.ffn.W2, d, m->P + p.ffn.b2, w.y16, d, false, false, Mt, d, f, st));
+    RC(dense_residual_ln(m, a.h, f, f, p.ffn.W2, p.ffn.b2, a.out2_16, p.ln3g, p.ln3b, w.dec_x16[l + 1], a.ln3, Mt, site_dec(l, 2), st));
     bx::prof_set_gemm_cat(0);
-    RC(residual_ln(m, a.out2_16, p.ln3g, p.ln3b, w.dec_x16[l + 1], a.ln3, Mt, site_dec(l, 2), st));
   }
   RC(par.join());
   // ---------------- final_layer (Transformer.py:30) ----------------
@@ -697,8 +706,14 @@ int b200xf_model_create(const b200xf_model_config* cfg, float* params, float* gr
   m->pos_in = pos_in; m->pos_tgt = pos_tgt;
   // second stream + event pool (host-side objects of the CURRENT device; created here so that nothing is created while a
   // CUDA-graph capture is in progress)
+  // measured on B200 (profiles/r02_*bench_conc*.json): the forked wgrad / K-V branches do NOT pay at transformer-base shapes -- every
+  // GEMM is a persistent kernel that fills all SMs (one CTA per SM, ~210 KB of shared memory), so a second stream's CTAs only ever
+  // enter at the tail of a wave, and the HBM-bound kernels cannot co-reside with a GEMM CTA; the cross-stream dependencies cost
+  // more than the tails return (22.1 vs 21.8 ms/step).  Off by default; B200XF_CONCURRENCY=1 or b200xf_model_set_concurrency.
   const char* env = getenv("B200XF_CONCURRENCY");
-  m->concurrency = (env != nullptr && env[0] == '0') ? 0 : 1;
+  m->concurrency = (env != nullptr && env[0] == '1') ? 1 : 0;
+  env = getenv("B200XF_FUSE_LN");
+  m->fuse_ln = (env != nullptr && env[0] == '0') ? 0 : 1;
   if (cudaStreamCreateWithFlags(&m->side, cudaStreamNonBlocking) != cudaSuccess) { m->side = nullptr; m->concurrency = 0; (void)cudaGetLastError(); }
   m->events.resize(1024, nullptr);
   for (auto& e : m->events)
