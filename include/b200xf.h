@@ -44,6 +44,11 @@ int b200xf_prof_collect(double* out, int ncat);
  *      M > 128 and N > 128, 256 x 256 per CTA PAIR (tcgen05 cta_group::2); b200xf_gemm_force_cta_group(1|2)
  *      overrides the choice (0 restores it) -- used by tests and benchmarks.                                   */
 void b200xf_gemm_force_cta_group(int cg);
+/* GEMM grids are PERSISTENT by default (one CTA or CTA pair per SM, static tile schedule).  While NCCL collectives run on the same GPU
+ * (the data-parallel backward, distributed_train.py:137-166) their CTAs occupy SMs, and a persistent CTA that finds its SM taken starts a
+ * whole wave late; n > 0 launches ~n short-lived units of consecutive tiles per SM instead and lets the hardware block scheduler place
+ * them on whatever SMs are free.  n = 0 restores the persistent schedule.  Process-global, takes effect for subsequent launches. */
+void b200xf_gemm_set_chunks_per_unit(int n);
 /* K3 / K4 fused (Attention.py:77 + Encoder.py:22-23 / Decoder.py:30-31,35-36 ; point_ffn.py:6 + Encoder.py:26-27 / Decoder.py:39-40):
  *      z = xres + dropout(A[M,K] . W[K,N] + bias)   out = LayerNorm(z) * gamma + beta        -- ONE kernel, LayerNorm in the epilogue
  *      A bf16 (row pitch lda), W bf16 keras [in,out] layout (row pitch ldw), N = d_model in {128, 256, 512} (a CTA pair keeps whole
@@ -207,6 +212,12 @@ int b200xf_model_loss(b200xf_model* m, const int64_t* tar, int tar_stride, int l
 int b200xf_model_backward(b200xf_model* m, int stage, b200xf_stream_t stream);
 /* [begin,end) element range of the gradient arena that `stage` finishes */
 int b200xf_model_grad_range(const b200xf_model_config* cfg, int stage, int64_t* begin, int64_t* end);
+/* The same backward in finer PARTS, each finishing one contiguous range of the gradient arena -- the data-parallel gradient buckets
+ * (distributed_train.py:137-166: one SUM all-reduce per bucket, overlapped with the parts that follow).  Order of completion:
+ *   part 0 final layer | part 1 decoder layer `layer` (L-1 down to 0) | part 2 decoder embedding |
+ *   part 3 encoder layer `layer` (L-1 down to 0) | part 4 encoder embedding          (`layer` is ignored by parts 0, 2, 4) */
+int b200xf_model_backward_part(b200xf_model* m, int part, int layer, b200xf_stream_t stream);
+int b200xf_model_grad_range_part(const b200xf_model_config* cfg, int part, int layer, int64_t* begin, int64_t* end);
 /* attention_weights['decoder_layer{layer+1}_block{block}'] of the last forward -> P fp32 [B,H,T,Sk] */
 int b200xf_model_attention_weights(b200xf_model* m, int layer, int block, float* P, b200xf_stream_t stream);
 /* debug/parity taps: copy an internal activation of the last forward (fp32 [rows, d_model]) -- names:

@@ -520,3 +520,28 @@ def test_gemm_bias_dropout_residual_layernorm_fused(M, N, K, rate):
     # the fused kernel normalises the UNROUNDED fp32 GEMM output, the two-kernel path a bf16-rounded y: agreement to bf16 rounding
     assert (z.float() - z2.float()).abs().max().item() < 4e-2 * max(1.0, z_ref.abs().max().item())
     assert (out.float() - out2.float()).abs().max().item() < 6e-2
+
+
+def test_gemm_chunked_schedule_matches_persistent():
+    """b200xf_gemm_set_chunks_per_unit: hardware-scheduled chunks of tiles (data-parallel backward, NCCL sharing the SMs) must
+    produce the persistent grid's results -- bit-identical without split-K, to fp32 reduction order with it."""
+    lib = L.load()
+    M, N, K = 8192 + 96, 1024 + 64, 512
+    A = rnd((M, K), 1.0, 1); B = rnd((K, N), K ** -0.5, 2); bias = rnd((N,), 0.1, 3, torch.float32)
+    outs = []
+    for chunks in (0, 4, 1):
+        lib.b200xf_gemm_set_chunks_per_unit(chunks)
+        D = torch.full((M, N), float("nan"), dtype=torch.bfloat16, device=dev())
+        L.call("b200xf_gemm_bf16", L.ptr(A), K, 0, L.ptr(B), N, 1, L.ptr(D), N, 0, L.ptr(bias), None, 0, 0, 1, M, N, K, sp())
+        # wgrad form: split-K over the tokens with fp32 reduce-add
+        W = torch.zeros(K, N, dtype=torch.float32, device=dev())
+        dY = rnd((M, N), 1.0, 4)
+        L.call("b200xf_gemm_bf16", L.ptr(A), K, 1, L.ptr(dY), N, 1, L.ptr(W), N, 1, None, None, 0, 2, 0, K, N, M, sp())
+        torch.cuda.synchronize()
+        outs.append((D, W))
+    lib.b200xf_gemm_set_chunks_per_unit(0)
+    ref = A.float() @ B.float() + bias
+    assert (outs[0][0].float() - ref).abs().max().item() < 3e-2 * max(1.0, ref.abs().max().item())
+    for D, W in outs[1:]:
+        assert torch.equal(D, outs[0][0])
+        assert (W - outs[0][1]).abs().max().item() < 1e-3 * outs[0][1].abs().max().item()

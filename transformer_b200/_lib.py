@@ -70,6 +70,8 @@ _SIGS = {
     "b200xf_model_loss": [_P, _P, _I, _I, _F, _P, _I, _P],
     "b200xf_model_backward": [_P, _I, _P],
     "b200xf_model_grad_range": [C.POINTER(ModelConfig), _I, C.POINTER(_I64), C.POINTER(_I64)],
+    "b200xf_model_backward_part": [_P, _I, _I, _P],
+    "b200xf_model_grad_range_part": [C.POINTER(ModelConfig), _I, _I, C.POINTER(_I64), C.POINTER(_I64)],
     "b200xf_model_attention_weights": [_P, _I, _I, _P, _P],
     "b200xf_model_tap": [_P, C.c_char_p, _P, _P],
     "b200xf_last_error": [],
@@ -78,11 +80,12 @@ _SIGS = {
     "b200xf_prof_enable": [_I],
     "b200xf_debug_set_timeline": [_P],
     "b200xf_gemm_force_cta_group": [_I],
+    "b200xf_gemm_set_chunks_per_unit": [_I],
     "b200xf_prof_collect": [C.POINTER(C.c_double), _I],
 }
 _RESTYPES = {"b200xf_last_error": C.c_char_p, "b200xf_launch_count": C.c_longlong,
              "b200xf_model_param_count": _I64, "b200xf_model_workspace_bytes": _I64,
-             "b200xf_model_destroy": None, "b200xf_model_set_concurrency": None, "b200xf_model_set_seed_ptr": None, "b200xf_prof_enable": None, "b200xf_gemm_force_cta_group": None}
+             "b200xf_model_destroy": None, "b200xf_model_set_concurrency": None, "b200xf_model_set_seed_ptr": None, "b200xf_prof_enable": None, "b200xf_gemm_force_cta_group": None, "b200xf_gemm_set_chunks_per_unit": None}
 
 EXPORTED_SYMBOLS = tuple(_SIGS)
 

@@ -14,6 +14,7 @@ long long b200xf_launch_count(void) { return bx::launch_count(); }
 void b200xf_prof_enable(int on) { bx::prof_enable(on); }
 int b200xf_debug_set_timeline(long long* dev_ptr) { return bx::set_timeline(dev_ptr); }
 void b200xf_gemm_force_cta_group(int cg) { bx::gemm_force_cta_group(cg); }
+void b200xf_gemm_set_chunks_per_unit(int n) { bx::gemm_set_chunks_per_unit(n); }
 int b200xf_prof_collect(double* out, int ncat) { return bx::prof_collect(out, ncat); }
 
 int b200xf_gemm_bf16(const void* A, int64_t lda, int a_major, const void* B, int64_t ldb, int b_major, void* D,

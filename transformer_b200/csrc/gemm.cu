@@ -45,7 +45,7 @@ template <int MA, int MB, int BN, bool kOutF32, int CG>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
             const __grid_constant__ CUtensorMap tmD, int M, int N, int K, int splits,
-            const float* __restrict__ bias, void* aux_v, long long ld_aux, int flags) {
+            const float* __restrict__ bias, void* aux_v, long long ld_aux, int flags, int chunk) {
   const __nv_bfloat16* aux = reinterpret_cast<const __nv_bfloat16*>(aux_v);
   using Cfg = GemmCfg<BN, CG>;
   constexpr int kStages = Cfg::kStages;
@@ -89,18 +89,25 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   if (CG == 2) cluster_sync_all(); else __syncthreads();
   tcgen05_after_thread_sync();
   const uint32_t tmem_base = *tmem_ptr;
-  const int cta = blockIdx.x / CG, ncta = gridDim.x / CG;    // tile-scheduling unit: a CTA or a CTA pair
+  // Tile schedule of a unit (a CTA, or a CTA pair).  chunk == 0: PERSISTENT -- one unit per SM (pair), tiles unit, unit + units, ...
+  // chunk > 0: unit u works on the `chunk` consecutive tiles from u * chunk and there are more units than SMs, so the hardware
+  // block scheduler hands chunks to whichever SMs are free: used while NCCL collectives share the GPU (data-parallel backward),
+  // where a persistent grid's CTAs that find their SM occupied would start a whole wave late.
+  const int unit_id = blockIdx.x / CG;
+  const int t_begin = chunk > 0 ? unit_id * chunk : unit_id;
+  const int t_step = chunk > 0 ? 1 : (int)(gridDim.x / CG);
 
   const int m_tiles = (M + GEMM_BM * CG - 1) / (GEMM_BM * CG);
   const int n_tiles = (N + BN - 1) / BN;
   const int kblocks = (K + GEMM_BK - 1) / GEMM_BK;
   const int tiles_mn = m_tiles * n_tiles;
   const int total = tiles_mn * splits;
+  const int t_end = chunk > 0 ? min(total, t_begin + chunk) : total;
 
   if (warp == 0 && lane == 0) {
     // ===================================== TMA producer =====================================
     uint32_t stage = 0, phase = 0;
-    for (int t = cta; t < total; t += ncta) {
+    for (int t = t_begin; t < t_end; t += t_step) {
       const int split = t / tiles_mn, rem = t % tiles_mn;
       const int m0 = (rem / n_tiles) * (GEMM_BM * CG) + (int)rank * GEMM_BM;   // this CTA's 128 rows of A
       const int n0 = (rem % n_tiles) * BN + (int)rank * BNC;                     // this CTA's BN/CG columns of B
@@ -149,7 +156,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     // ===================================== MMA issuer (pair: leader CTA only) =====================================
     constexpr uint32_t idesc = make_idesc_bf16(GEMM_BM * CG, BN, MA, MB);
     uint32_t stage = 0, phase = 0, it = 0;
-    for (int t = cta; t < total; t += ncta, ++it) {
+    for (int t = t_begin; t < t_end; t += t_step, ++it) {
       const int split = t / tiles_mn;
       const int kb0 = (int)((long long)split * kblocks / splits), kb1 = (int)((long long)(split + 1) * kblocks / splits);
       const uint32_t acc = it & 1u, acc_phase = (it >> 1) & 1u;
@@ -191,7 +198,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     const uint32_t epi_tid = threadIdx.x - 128u;
     const uint32_t stg_base = smem_u32(smem + Cfg::OFF_D);
     uint32_t it = 0, buf = 0;
-    for (int t = cta; t < total; t += ncta, ++it) {
+    for (int t = t_begin; t < t_end; t += t_step, ++it) {
       const int rem = t % tiles_mn;
       const int m0 = (rem / n_tiles) * (GEMM_BM * CG) + (int)rank * GEMM_BM, n0 = (rem % n_tiles) * BN;
       const uint32_t acc = it & 1u, acc_phase = (it >> 1) & 1u;
@@ -308,6 +315,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
 // ------------------------------------------------------------------------------------------------
 // host launcher
 // ------------------------------------------------------------------------------------------------
+static int g_chunks_per_unit = 0;   // 0 = persistent static schedule; k > 0: ~k chunks of consecutive tiles per SM (pair), handed out by the hardware
+
 // split-K factor for a reduce-add GEMM: aim at ~2 full waves of tile units
 static int auto_splits(long long tiles, long long kblocks, int groups) {
   if (tiles >= 2 * groups) return 1;
@@ -375,11 +384,17 @@ static int launch_gemm(const void* A, long long lda, const void* B, long long ld
     if (splits > kblocks) splits = (int)kblocks;
   }
   const long long total2 = m_tiles * n_tiles * splits;
-  const int grid = (int)(total2 < max_units ? total2 : max_units) * CG;
+  int grid = (int)(total2 < max_units ? total2 : max_units) * CG;
+  int chunk = 0;
+  if (g_chunks_per_unit > 0 && total2 > max_units) {        // more, shorter-lived units than SMs (see the kernel's schedule comment)
+    chunk = (int)((total2 + (long long)g_chunks_per_unit * max_units - 1) / ((long long)g_chunks_per_unit * max_units));
+    if (chunk < 2) chunk = 2;                                  // keep the accumulator double-buffering worth its prologue
+    grid = (int)((total2 + chunk - 1) / chunk) * CG;
+  }
   cfg.gridDim = dim3(grid);
   void* pb = prof_on() ? prof_begin(stream) : nullptr;
   BX_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, tmA, tmB, tmD, (int)M, (int)N, (int)K, splits, bias, const_cast<void*>(aux), ld_aux,
-                                   flags));
+                                   flags, chunk));
   if (pb) prof_end(pb, prof_gemm_cat(), 2.0 * (double)M * (double)N * (double)K, stream);
   BX_POST_LAUNCH();
   return 0;
@@ -387,6 +402,7 @@ static int launch_gemm(const void* A, long long lda, const void* B, long long ld
 
 static int g_force_cg = 0;   // 0 = heuristic, 1 / 2 = force (tests and benchmarks)
 void gemm_force_cta_group(int cg) { g_force_cg = cg; }
+void gemm_set_chunks_per_unit(int n) { g_chunks_per_unit = n < 0 ? 0 : n; }
 
 int gemm_bf16(const void* A, long long lda, int a_major, const void* B, long long ldb, int b_major, void* D,
               long long ldd, int d_is_f32, const float* bias, const void* aux, long long ld_aux, int flags,

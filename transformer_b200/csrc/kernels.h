@@ -15,6 +15,7 @@ int gemm_ln(const void* A, long long lda, const void* W, long long ldw, const fl
             const float* beta, void* z, void* out, float* mean, float* rstd, void* keep_bits, long long M, long long N, long long K, float eps,
             float rate, unsigned long long seed, unsigned site, cudaStream_t stream, const unsigned long long* seed_dev = nullptr);
 
+void gemm_set_chunks_per_unit(int n);   // 0: persistent GEMM grids (default); k > 0: ~k chunks of tiles per SM, scheduled by the hardware
 void gemm_force_cta_group(int cg);   // 0 = heuristic, 1 / 2 = force single-CTA / CTA-pair tiles (tests, benchmarks)
 
 int set_timeline(long long* dev_ptr);   // debug: register a device buffer of >= 128 int64 clock stamps (nullptr disables)

@@ -41,6 +41,8 @@ struct Layout {
   int L, d, H, f, Vin, Vtgt, Vp;
   int64_t enc_emb, dec_emb, Wf, bf, total;
   int64_t stage_begin[3], stage_end[3];   // 0 final layer, 1 decoder (+emb), 2 encoder (+emb)
+  std::vector<std::pair<int64_t, int64_t>> enc_layer_range, dec_layer_range;   // arena range of every layer (gradient buckets)
+  std::pair<int64_t, int64_t> enc_emb_range, dec_emb_range;
   std::vector<EncLayerP> enc;
   std::vector<DecLayerP> dec;
   std::vector<VarView> vars;
@@ -61,21 +63,27 @@ Layout make_layout(const b200xf_model_config& c) {
   auto ffn = [&](Ffn& m) { m.W1 = b.take(d * f); m.b1 = b.take(f); m.W2 = b.take(f * d); m.b2 = b.take(d); };
   lo.stage_begin[2] = b.cur;
   lo.enc_emb = b.take((int64_t)lo.Vin * d);
+  lo.enc_emb_range = {lo.enc_emb, b.cur};
   lo.enc.resize(lo.L);
   for (auto& e : lo.enc) {
+    const int64_t begin = b.cur;
     self(e.mha); ffn(e.ffn);
     e.ln1g = b.take(d); e.ln1b = b.take(d); e.ln2g = b.take(d); e.ln2b = b.take(d);
+    lo.enc_layer_range.push_back({begin, b.cur});
   }
   lo.stage_end[2] = b.cur;
   lo.stage_begin[1] = b.cur;
   lo.dec_emb = b.take((int64_t)lo.Vtgt * d);
+  lo.dec_emb_range = {lo.dec_emb, b.cur};
   lo.dec.resize(lo.L);
   for (auto& e : lo.dec) {
+    const int64_t begin = b.cur;
     self(e.mha1);
     e.mha2.Wq = b.take(d * d); e.mha2.bq = b.take(d); e.mha2.Wkv = b.take(d * 2 * d); e.mha2.bkv = b.take(2 * d);
     e.mha2.Wo = b.take(d * d); e.mha2.bo = b.take(d);
     ffn(e.ffn);
     e.ln1g = b.take(d); e.ln1b = b.take(d); e.ln2g = b.take(d); e.ln2b = b.take(d); e.ln3g = b.take(d); e.ln3b = b.take(d);
+    lo.dec_layer_range.push_back({begin, b.cur});
   }
   lo.stage_end[1] = b.cur;
   lo.stage_begin[0] = b.cur;
@@ -251,6 +259,10 @@ struct b200xf_model {
   int next_event = 0;
   int concurrency = 0;         // 0: everything on the caller's stream
   int fuse_ln = 1;             // LayerNorm in the out-projection / FFN dense1 GEMM epilogue (d_model 128 / 256 / 512)
+  // state carried between the parts of a layer-granular backward (b200xf_model_backward_part): the gradient of the stream
+  // tensor entering the next layer (see StreamGrad) and which of the two dz buffers is written next
+  const void* bw_r = nullptr; bool bw_r_f32 = false; const void* bw_dg = nullptr;
+  int bw_dz = 0;
 };
 
 namespace {
@@ -569,23 +581,28 @@ int backward_final(M* m, cudaStream_t st) {
   return 0;
 }
 
-int backward_decoder(M* m, cudaStream_t st) {
+// Backward in PARTS, each finishing one contiguous range of the gradient arena (data-parallel buckets: the range is
+// all-reduced while the next part runs): the decoder layers l_hi..l_lo (part of the chain that starts at the vocabulary
+// dgrad's output in gD), the decoder embedding, the encoder layers, the encoder embedding.
+int backward_decoder_layers(M* m, int l_hi, int l_lo, cudaStream_t st) {
   const Layout& lo = m->lo;
   Work& w = m->w;
   const int d = lo.d, H = lo.H, L = lo.L, dk = d / H;
   const int B = m->B, S = m->S, T = m->T;
   const int64_t Ms = (int64_t)B * S, Mt = (int64_t)B * T;
-  const float rate = m->training ? m->cfg.dropout_rate : 0.f;
   const MaskSpec sm = dec_self_mask(m), cm = dec_cross_mask(m);
-  BX_CHECK_CUDA(cudaMemsetAsync(w.d_enc_out, 0, Ms * d * sizeof(float), st));
+  if (l_hi == L - 1) {
+    BX_CHECK_CUDA(cudaMemsetAsync(w.d_enc_out, 0, Ms * d * sizeof(float), st));
+    m->bw_r = w.gD; m->bw_r_f32 = false; m->bw_dg = nullptr; m->bw_dz = 0;     // the vocabulary dgrad wrote the stream gradient to gD
+  }
   BwdCtx c(m, st);
   RC(c.par.fork());
-  StreamGrad g{w.gD, false, nullptr};    // gradient of the current layer's output: the vocabulary dgrad wrote it to gD
-  bf16* dz = w.gR0;
-  bf16* dz_other = w.gR1;
+  StreamGrad g{m->bw_r, m->bw_r_f32, reinterpret_cast<const bf16*>(m->bw_dg)};
+  bf16* dz = m->bw_dz == 0 ? w.gR0 : w.gR1;
+  bf16* dz_other = m->bw_dz == 0 ? w.gR1 : w.gR0;
   const bf16* dy = nullptr;
-  auto advance = [&]() { g = StreamGrad{dz, false, w.gD}; std::swap(dz, dz_other); };
-  for (int l = L - 1; l >= 0; --l) {
+  auto advance = [&]() { g = StreamGrad{dz, false, w.gD}; std::swap(dz, dz_other); m->bw_dz ^= 1; };
+  for (int l = l_hi; l >= l_lo; --l) {
     const DecLayerP& p = lo.dec[l];
     DecAct& a = w.dec[l];
     // out3 = LN3(out2 + drop(ffn(out2)))
@@ -621,28 +638,38 @@ int backward_decoder(M* m, cudaStream_t st) {
     RC(c.self_attn_back(p.mha1, w.dec_x16[l], a.qkv1, a.attn1_o, a.attn1_o_lo, a.lse1, sm, dy, T));
     advance();
   }
-  RC(bx::embed_bwd(reinterpret_cast<const long long*>(m->tar), m->tar_stride, m->tar_offset, g.r, g.dg, m->G + lo.dec_emb, Mt, T, d,
-                   lo.Vtgt, rate, m->seed, site_dec_embed(), st, m->seed_dev));
+  m->bw_r = g.r; m->bw_r_f32 = g.r_f32; m->bw_dg = g.dg;
   RC(c.par.join());
   return 0;
 }
 
-int backward_encoder(M* m, cudaStream_t st) {
+int backward_decoder_embed(M* m, cudaStream_t st) {
+  const Layout& lo = m->lo;
+  const int d = lo.d, T = m->T;
+  const int64_t Mt = (int64_t)m->B * T;
+  const float rate = m->training ? m->cfg.dropout_rate : 0.f;
+  return bx::embed_bwd(reinterpret_cast<const long long*>(m->tar), m->tar_stride, m->tar_offset, m->bw_r, m->bw_dg, m->G + lo.dec_emb, Mt, T, d,
+                       lo.Vtgt, rate, m->seed, site_dec_embed(), st, m->seed_dev);
+}
+
+int backward_encoder_layers(M* m, int l_hi, int l_lo, cudaStream_t st) {
   const Layout& lo = m->lo;
   Work& w = m->w;
-  const int d = lo.d, L = lo.L;
+  const int L = lo.L;
   const int B = m->B, S = m->S;
   const int64_t Ms = (int64_t)B * S;
-  const float rate = m->training ? m->cfg.dropout_rate : 0.f;
   const MaskSpec em = enc_self_mask(m);
+  if (l_hi == L - 1) {      // fp32 sum of the cross-attention K/V gradients of all decoder layers
+    m->bw_r = w.d_enc_out; m->bw_r_f32 = true; m->bw_dg = nullptr; m->bw_dz = 0;
+  }
   BwdCtx c(m, st);
   RC(c.par.fork());
-  StreamGrad g{w.d_enc_out, true, nullptr};   // fp32 sum of the cross-attention K/V gradients of all decoder layers
-  bf16* dz = w.gR0;
-  bf16* dz_other = w.gR1;
+  StreamGrad g{m->bw_r, m->bw_r_f32, reinterpret_cast<const bf16*>(m->bw_dg)};
+  bf16* dz = m->bw_dz == 0 ? w.gR0 : w.gR1;
+  bf16* dz_other = m->bw_dz == 0 ? w.gR1 : w.gR0;
   const bf16* dy = nullptr;
-  auto advance = [&]() { g = StreamGrad{dz, false, w.gD}; std::swap(dz, dz_other); };
-  for (int l = L - 1; l >= 0; --l) {
+  auto advance = [&]() { g = StreamGrad{dz, false, w.gD}; std::swap(dz, dz_other); m->bw_dz ^= 1; };
+  for (int l = l_hi; l >= l_lo; --l) {
     const EncLayerP& p = lo.enc[l];
     EncAct& a = w.enc[l];
     RC(c.residual_ln_back(g, a.ln2, p.ln2g, p.ln2b, p.ffn.b2, dz, &dy, Ms, site_enc(l, 1)));
@@ -652,10 +679,27 @@ int backward_encoder(M* m, cudaStream_t st) {
     RC(c.self_attn_back(p.mha, w.enc_x16[l], a.qkv, a.attn_o, a.attn_o_lo, a.lse, em, dy, S));
     advance();
   }
-  RC(bx::embed_bwd(reinterpret_cast<const long long*>(m->inp), S, 0, g.r, g.dg, m->G + lo.enc_emb, Ms, S, d, lo.Vin, rate, m->seed,
-                   site_enc_embed(), st, m->seed_dev));
+  m->bw_r = g.r; m->bw_r_f32 = g.r_f32; m->bw_dg = g.dg;
   RC(c.par.join());
   return 0;
+}
+
+int backward_encoder_embed(M* m, cudaStream_t st) {
+  const Layout& lo = m->lo;
+  const int d = lo.d, S = m->S;
+  const int64_t Ms = (int64_t)m->B * S;
+  const float rate = m->training ? m->cfg.dropout_rate : 0.f;
+  return bx::embed_bwd(reinterpret_cast<const long long*>(m->inp), S, 0, m->bw_r, m->bw_dg, m->G + lo.enc_emb, Ms, S, d, lo.Vin, rate, m->seed,
+                       site_enc_embed(), st, m->seed_dev);
+}
+
+int backward_decoder(M* m, cudaStream_t st) {
+  RC(backward_decoder_layers(m, m->lo.L - 1, 0, st));
+  return backward_decoder_embed(m, st);
+}
+int backward_encoder(M* m, cudaStream_t st) {
+  RC(backward_encoder_layers(m, m->lo.L - 1, 0, st));
+  return backward_encoder_embed(m, st);
 }
 
 }  // namespace
@@ -771,6 +815,36 @@ int b200xf_model_backward(b200xf_model* m, int stage, b200xf_stream_t stream) {
   if (stage == -1 || stage == 0) RC(backward_final(m, st));
   if (stage == -1 || stage == 1) RC(backward_decoder(m, st));
   if (stage == -1 || stage == 2) RC(backward_encoder(m, st));
+  return 0;
+}
+
+/* parts, in backward-completion order: 0 final layer | 1 decoder layer `layer` (L-1 first) | 2 decoder embedding |
+ * 3 encoder layer `layer` (L-1 first) | 4 encoder embedding */
+int b200xf_model_backward_part(b200xf_model* m, int part, int layer, b200xf_stream_t stream) {
+  BX_REQUIRE(m->have_loss_grad, "backward: call b200xf_model_loss(with_grad=1) after a training forward first");
+  BX_REQUIRE(part >= 0 && part <= 4 && layer >= 0 && layer < m->lo.L, "backward_part: bad part %d / layer %d", part, layer);
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  switch (part) {
+    case 0: return backward_final(m, st);
+    case 1: return backward_decoder_layers(m, layer, layer, st);
+    case 2: return backward_decoder_embed(m, st);
+    case 3: return backward_encoder_layers(m, layer, layer, st);
+    default: return backward_encoder_embed(m, st);
+  }
+}
+int b200xf_model_grad_range_part(const b200xf_model_config* cfg, int part, int layer, int64_t* begin, int64_t* end) {
+  RC(validate(*cfg));
+  Layout lo = make_layout(*cfg);
+  BX_REQUIRE(part >= 0 && part <= 4 && layer >= 0 && layer < lo.L, "grad_range_part: bad part %d / layer %d", part, layer);
+  std::pair<int64_t, int64_t> r;
+  switch (part) {
+    case 0: r = {lo.stage_begin[0], lo.stage_end[0]}; break;
+    case 1: r = lo.dec_layer_range[layer]; break;
+    case 2: r = lo.dec_emb_range; break;
+    case 3: r = lo.enc_layer_range[layer]; break;
+    default: r = lo.enc_emb_range; break;
+  }
+  *begin = r.first; *end = r.second;
   return 0;
 }
 

@@ -65,11 +65,12 @@ def split_replica_batch(batch_size, num_replicas):
 
 
 class GradientBuckets:
-    """The three contiguous ranges of the flat gradient arena, in backward-completion order, and their async SUM
-    all-reduce.  Works on any torch.distributed backend (NCCL on GPUs; gloo in the CPU tests of this host logic)."""
+    """Contiguous ranges of the flat gradient arena, in backward-completion order (one per backward part: final layer, every
+    decoder layer, decoder embedding, every encoder layer, encoder embedding), and their async SUM all-reduce.  Works on any
+    torch.distributed backend (NCCL on GPUs; gloo in the CPU tests of this host logic)."""
 
     def __init__(self, ranges, group=None):
-        self.ranges = list(ranges)          # [(begin, end)] for stage 0, 1, 2
+        self.ranges = list(ranges)          # [(begin, end)] per bucket, in the order the backward finishes them
         self.group = group
         self.pending = []
 
@@ -79,18 +80,32 @@ class GradientBuckets:
         b, e = self.ranges[stage]
         self.pending.append(dist.all_reduce(arena[b:e], op=dist.ReduceOp.SUM, group=self.group, async_op=True))
 
-    def wait(self):
-        for w in self.pending:
-            w.wait()              # NCCL: makes the current stream wait on the collective; no host block
-        self.pending = []
+    def wait(self, keep_last=0):
+        """make the current stream wait for the pending collectives, except the newest ``keep_last`` (NCCL: no host block)"""
+        n = len(self.pending) - keep_last
+        for w in self.pending[:max(0, n)]:
+            w.wait()
+        self.pending = self.pending[max(0, n):]
 
 
 def arena_stage_ranges(transformer):
+    """the three coarse ranges (final layer | decoder + embedding | encoder + embedding)"""
     lib = L.load()
     out = []
     for stage in range(3):
         b, e = C.c_int64(), C.c_int64()
         L.check(lib.b200xf_model_grad_range(C.byref(transformer._cfg), stage, C.byref(b), C.byref(e)), "b200xf_model_grad_range")
+        out.append((b.value, e.value))
+    return out
+
+
+def arena_part_ranges(transformer, parts):
+    """arena range finished by each backward part (b200xf_model_grad_range_part)"""
+    lib = L.load()
+    out = []
+    for part, layer in parts:
+        b, e = C.c_int64(), C.c_int64()
+        L.check(lib.b200xf_model_grad_range_part(C.byref(transformer._cfg), part, layer, C.byref(b), C.byref(e)), "b200xf_model_grad_range_part")
         out.append((b.value, e.value))
     return out
 
@@ -104,7 +119,26 @@ class DistributedTrain(Train):
         Train.__init__(self, epochs, enable_function, transformer, src_tokenizer, tgt_tokenizer, batch_size, train_log_dir,
                        test_log_dir, max_ckpt_keep, ckpt_path, d_model, warmup_steps=warmup_steps, seed=seed)
         self.per_replica_batch_size = per_replica_batch_size
-        self.buckets = GradientBuckets(arena_stage_ranges(transformer))
+        # one gradient bucket per backward part: 2L + 3 all-reduces per step, each issued the moment its range is final, so that
+        # only the LAST one (the encoder embedding, 4 x V x d bytes) can still be in flight when the backward ends -- and Adam on
+        # everything else runs underneath it (see _apply_adam_dev)
+        parts = self._backward_parts()
+        ranges = arena_part_ranges(transformer, parts)
+        # Bucket granularity.  Every all-reduce in flight takes SMs away from the persistent GEMMs (whose tile schedule assumes all of
+        # them), so MORE buckets are not better: measured on 2 B200 (profiles/r02_dp_buckets.txt) one bucket per layer costs more than it
+        # hides.  Default "coarse": final layer | decoder layers + decoder embedding | encoder layers | encoder embedding -- the last
+        # one is the only bucket that cannot overlap backward work, and it is the small one.  B200XF_DP_BUCKETS=layer: one per part.
+        mode = os.environ.get("B200XF_DP_BUCKETS", "coarse")
+        if mode == "layer":
+            groups = [[i] for i in range(len(parts))]
+        else:
+            groups = [[i for i, (p, _) in enumerate(parts) if p == 0], [i for i, (p, _) in enumerate(parts) if p in (1, 2)],
+                      [i for i, (p, _) in enumerate(parts) if p == 3], [i for i, (p, _) in enumerate(parts) if p == 4]]
+        self._bucket_after_part = {g[-1]: k for k, g in enumerate(groups)}          # part index that completes bucket k
+        # hardware-scheduled chunks of GEMM tiles while a collective is in flight: measured SLOWER than persistent grids on 2 B200
+        # (23.7-23.9 vs 23.2 ms/step, profiles/r02_dp_buckets.txt), so off unless asked for
+        self._chunks_per_unit = int(os.environ.get("B200XF_DP_GEMM_CHUNKS", "0"))
+        self.buckets = GradientBuckets([(min(ranges[i][0] for i in g), max(ranges[i][1] for i in g)) for g in groups])
         rank = dist.get_rank() if dist.is_initialized() else 0
         self._seed = int(seed) * 1000003 + rank * 7919            # independent dropout streams per replica
         if dist.is_initialized() and dist.get_world_size() > 1:
@@ -112,8 +146,14 @@ class DistributedTrain(Train):
             dist.broadcast(transformer.params, src=0)
             transformer._shadow_dirty = True
 
-    def _reduce_gradients(self, stage):
-        self.buckets.reduce_stage(self.transformer.grads, stage)
+    def _reduce_gradients(self, part_index):
+        k = self._bucket_after_part.get(part_index)
+        if k is not None:
+            self.buckets.reduce_stage(self.transformer.grads, k)
+            if self.buckets.pending and self._chunks_per_unit > 0:
+                # from here to the end of the backward an all-reduce shares the GPU with the GEMMs: hardware-scheduled chunks of tiles
+                # instead of persistent grids (include/b200xf.h: b200xf_gemm_set_chunks_per_unit)
+                L.load().b200xf_gemm_set_chunks_per_unit(self._chunks_per_unit)
 
     def _with_rows(self, inputs, step, loss_metric, acc_metric):
         """run ``step`` on this replica's shard; an EMPTY shard (partial last batch smaller than the replica count) runs on
@@ -135,6 +175,22 @@ class DistributedTrain(Train):
 
     def _finish_gradients(self):
         self.buckets.wait()
+
+    def _apply_adam_dev(self):
+        L.load().b200xf_gemm_set_chunks_per_unit(0)                # the forward of the next step runs alone: persistent grids again
+        return self._apply_adam_split()
+
+    def _apply_adam_split(self):
+        """identical Adam on every replica, split around the last bucket: the ranges whose all-reduce has landed are updated while
+        the encoder-embedding bucket (the one nothing else can overlap) is still on the wire"""
+        tr = self.transformer
+        b_last, e_last = self.buckets.ranges[-1]
+        if len(self.buckets.pending) < 2 or b_last != 0:
+            return Train._apply_adam_dev(self)
+        self.buckets.wait(keep_last=1)
+        self.optimizer.apply_gradients_dev(tr, self._alpha_dev, e_last, tr._n)
+        self.buckets.wait()
+        self.optimizer.apply_gradients_dev(tr, self._alpha_dev, 0, e_last)
 
     def reduce_metrics(self):
         """sync-on-read SUM aggregation of the metric accumulators across replicas (train.py:140-141 under the

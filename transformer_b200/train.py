@@ -82,11 +82,16 @@ class Adam:
             return None                      # arbitrary Python schedule: host-computed alpha only (no graph replay)
         return 1.0, 1.0, float(lr)
 
-    def apply_gradients_dev(self, transformer, alpha_dev):
-        """same update with alpha read from the device (written by b200xf_step_params); graph-replayable."""
-        L.call("b200xf_adam_step_dev", L.ptr(transformer.params), L.ptr(transformer.adam_m), L.ptr(transformer.adam_v),
-               L.ptr(transformer.grads), L.ptr(transformer.shadow), transformer._n, L.ptr(alpha_dev), self.beta_1, self.beta_2,
-               self.epsilon, L.stream_ptr())
+    def apply_gradients_dev(self, transformer, alpha_dev, begin=0, end=None):
+        """same update with alpha read from the device (written by b200xf_step_params); graph-replayable.  ``[begin, end)``:
+        the arena range to update (data parallel: a range is updated as soon as its all-reduce has landed)."""
+        import ctypes as C
+        end = transformer._n if end is None else end
+
+        def at(t):
+            return C.c_void_p(t.data_ptr() + begin * t.element_size())
+        L.call("b200xf_adam_step_dev", at(transformer.params), at(transformer.adam_m), at(transformer.adam_v), at(transformer.grads),
+               at(transformer.shadow), end - begin, L.ptr(alpha_dev), self.beta_1, self.beta_2, self.epsilon, L.stream_ptr())
 
     def apply_gradients(self, transformer):
         t = self.iterations + 1
@@ -160,11 +165,22 @@ class Train(object):
         return stats[0] * (1.0 / self.batch_size)
 
     # -- hooks for DistributedTrain -----------------------------------------------------------------------------------
-    def _reduce_gradients(self, stage):      # called after each backward stage; single device: nothing to do
+    def _reduce_gradients(self, part_index):      # called after each backward part; single device: nothing to do
         pass
 
     def _finish_gradients(self):
         pass
+
+    def _backward_parts(self):
+        """(part, layer) in backward-completion order (include/b200xf.h: b200xf_model_backward_part): final layer, decoder layers
+        L-1..0, decoder embedding, encoder layers L-1..0, encoder embedding -- each finishes one range of the gradient arena."""
+        n = self.transformer.num_layers
+        return ([(0, 0)] + [(1, l) for l in range(n - 1, -1, -1)] + [(2, 0)] + [(3, l) for l in range(n - 1, -1, -1)] + [(4, 0)])
+
+    def _apply_adam_dev(self):
+        """the fused Adam update over the whole arena (DistributedTrain splits it around the last gradient bucket)"""
+        self._finish_gradients()
+        self.optimizer.apply_gradients_dev(self.transformer, self._alpha_dev)
 
     def _step_core(self, src, tar, training, seed_dev=None):
         tr = self.transformer
@@ -186,13 +202,13 @@ class Train(object):
             L.call("b200xf_step_params", L.ptr(self._it_dev), self._seed, sched[0], sched[1], sched[2], self.optimizer.beta_1,
                    self.optimizer.beta_2, L.ptr(self._seed_dev), L.ptr(self._alpha_dev), L.ptr(self._lr_dev), L.stream_ptr())
         self._step_core(src, tar, True, seed_dev=self._seed_dev if sched is not None else None)
-        for stage in (0, 1, 2):                                                # final layer | decoder | encoder
-            L.call("b200xf_model_backward", tr._handle, stage, L.stream_ptr())
-            self._reduce_gradients(stage)
-        self._finish_gradients()
+        for i, (part, layer) in enumerate(self._backward_parts()):             # final layer | decoder layers | ... | encoder embedding
+            L.call("b200xf_model_backward_part", tr._handle, part, layer, L.stream_ptr())
+            self._reduce_gradients(i)
         if sched is not None:
-            self.optimizer.apply_gradients_dev(tr, self._alpha_dev)
+            self._apply_adam_dev()
         else:
+            self._finish_gradients()
             self.optimizer.apply_gradients(tr)
             self.optimizer.iterations -= 1                                     # bookkeeping happens in train_step
         self.train_loss(self._stats[0] * (1.0 / self.batch_size))
