@@ -476,7 +476,8 @@ struct BwdSmem {
   static constexpr uint32_t BYTES = OFF_BAR + 256 + 1024;
 };
 
-constexpr int ATTN_BWD_THREADS = 320;  // w0 TMA, w1 MMA(+TMEM alloc), w2-9 compute (rows x 2 column halves)
+constexpr int ATTN_BWD_THREADS = 576;  // w0 TMA, w1 MMA(+TMEM alloc), w2-17 compute: 4 lane quadrants x 4 groups of 32 query columns
+constexpr int ATTN_BWD_CT = 512;       // compute threads
 
 template <int DK, bool kDqBf16>
 __global__ void __launch_bounds__(ATTN_BWD_THREADS, 1)
@@ -519,7 +520,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     prefetch_tmap(&tmdK); prefetch_tmap(&tmdV); prefetch_tmap(&tmdQ);
     mbar_init(kv_full, 1);
     for (int i = 0; i < 2; ++i) { mbar_init(&qdo_full[i], 1); mbar_init(&qdo_empty[i], 1); }
-    mbar_init(sdp_full, 1); mbar_init(pds_full, 256); mbar_init(dq_full, 1); mbar_init(pt_free, 1); mbar_init(dq_free, 256);
+    mbar_init(sdp_full, 1); mbar_init(pds_full, ATTN_BWD_CT); mbar_init(dq_full, 1); mbar_init(pt_free, 1); mbar_init(dq_free, ATTN_BWD_CT);
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc<512>(tmem_ptr);
@@ -578,7 +579,8 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     const int ntile = nq - i_start;
     issue_sdp(0);
     // per tile the tensor core runs   dV(n) | S^T,dP^T(n+1) | dK(n), dQ(n)   so the compute warps can start on tile n+1
-    // (their S^T/dP^T are ready after the first two groups) while dK/dQ of tile n are still executing
+    // (their S^T/dP^T are ready after the first two groups) while dK/dQ of tile n are still executing.  (Issuing S^T/dP^T(n+1)
+    // even earlier -- as soon as the compute warps hold tile n's values in registers -- measured slower: 250 vs 236 us.)
     for (int n = 0; n < ntile; ++n) {
       const int st = n % QS;
       const uint32_t sdS = sdSt + (n & 1) * C::P_BYTES;
@@ -618,12 +620,15 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     }
   } else {
     // ===================================== compute warps =====================================
-    const int cw = (int)warp - 2;                 // 0..7
+    // 16 warps: warp (quad, grp) owns kv rows 32*quad.. (tensor-memory lane quadrant = warp & 3) and the 32 query columns
+    // 32*grp.. of S^T / dP^T.  (Round 1 used 8 warps x 64 columns: two warps per scheduler left every latency of the
+    // ld -> exp2 -> pack -> st chain exposed: issue-active 26 %, 2750 cycles of compute per tile; profiles/r02_ncu_full_attn_bwd.txt.)
+    const int cw = (int)warp - 2;                 // 0..15
     const uint32_t quad = warp & 3u;
-    const int half = cw >> 2;                     // which 64 query columns / which dk half this warp owns
+    const int grp = cw >> 2;                      // which 32 query columns / which quarter of the dk columns this warp owns
     const uint32_t row = quad * 32u + lane;       // kv row (S^T, dV, dK) or q row (dQ)
     const uint32_t lane_sel = (quad * 32u) << 16;
-    const int ctid = (int)threadIdx.x - 64;       // 0..255
+    const int ctid = (int)threadIdx.x - 64;       // 0..511
     const int kv = kv0 + (int)row;
     const bool kv_valid = kv < Sk;
     const bool kv_pad = kv_valid && mask.kpad != nullptr && mask.kpad[(long long)b * Sk + kv] != 0;
@@ -631,7 +636,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     const float sl2 = scale * kLog2e;
     const float inv_sk = 1.f / (float)Sk;
     const uint32_t sDQ = smem_u32(smem + L::OFF_DQ);
-    constexpr int HC = DKO / 2;
+    constexpr int HC = DKO / 4;                   // dk columns per warp in the dQ / dV / dK epilogues (16 or 8)
     // no padded / out-of-range key among this warp's rows (fixed for the whole CTA)
     const bool rows_clean = !__any_sync(0xffffffffu, kv_pad || !kv_valid);
     // ... and among ALL 128 keys of this CTA's tile (every lane looks at 4 of them)
@@ -641,15 +646,15 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       dirty = (kp[0] | kp[1] | kp[2] | kp[3]) != 0;
     }
     const bool tile_clean = !__any_sync(0xffffffffu, dirty);
-    // lse (x log2 e) / delta of a query tile: thread ctid < 128 fetches lse[q], the others delta[q].  The value for the
-    // NEXT tile is fetched one tile ahead so the global-load latency is off the critical path.
-    // The value for the NEXT tile travels global -> shared memory by cp.async (no register in between: a register copy was
-    // multiplied / spilled right after the load, which made every thread wait out the whole global-load latency --
-    // ~1400 of ~4500 cycles per tile) and is scaled in place once it has landed, one tile later.
+    // lse (x log2 e) / delta of a query tile: thread ctid < 128 fetches lse[q], ctid 128..255 delta[q] (the other compute threads
+    // only wait).  The value for the NEXT tile travels global -> shared memory by cp.async one tile ahead (no register in between)
+    // and is scaled in place once it has landed.
+    const bool row_loader = ctid < 256;
     const float* const row_src = (ctid < 128 ? lse : delta) + ((long long)b * H + h) * Sq;
     const float row_oob = ctid < 128 ? INFINITY : 0.f;                  // +inf lse for out-of-range queries -> p = 0
     const float row_mul = ctid < 128 ? kLog2e : scale;                  // lse in the log2 domain; delta pre-multiplied by 1/sqrt(dk)
     auto prefetch_row = [&](int i, float* buf) {
+      if (!row_loader) return;
       const int qq = i * 128 + (ctid & 127);
       if (qq < Sq) {
         asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" :: "r"(smem_u32(buf + ctid)), "l"(row_src + qq) : "memory");
@@ -658,34 +663,37 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       }
       asm volatile("cp.async.commit_group;" ::: "memory");
     };
-    // dQ tile of query tile `qt`: row = query, this warp's half of the dk columns -> fp32 smem staging -> ONE TMA
-    // reduce-add per half (cp.reduce.async.bulk.tensor .add.f32; rows >= Sq are clipped by TMA)
+    // this warp's HC columns of a [128 x DKO] fp32 accumulator
+    auto load_acc = [&](uint32_t taddr, float (&v)[HC]) {
+      if (HC == 16) {
+        uint32_t r[16];
+        tmem_ld_x16(taddr, r); tmem_ld_wait();
+#pragma unroll
+        for (int e = 0; e < 16; ++e) v[e < HC ? e : 0] = __uint_as_float(r[e]);
+      } else {
+        uint32_t r[8];
+        tmem_ld_x8(taddr, r); tmem_ld_wait();
+#pragma unroll
+        for (int e = 0; e < 8; ++e) v[e < HC ? e : 0] = __uint_as_float(r[e]);
+      }
+    };
+    // dQ tile of query tile `qt`: row = query, this warp's quarter of the dk columns
     auto dq_epilogue = [&](int n_done, int qt0) {
       mbar_wait(dq_full, n_done & 1);
       tcgen05_after_thread_sync();
       if (ctid == 0) tl_stamp(64 + (n_done & 7) * 8 + 4);
+      float v[HC];
       if (kDqBf16) {
-        // bf16 dQ: straight from tensor memory to global memory.  This thread owns query row `row` and HC contiguous columns
-        // (2*HC bytes): red.global.add.noftz.v4.bf16x2 adds 16 bytes per instruction, fire-and-forget -- no smem staging,
-        // no block barrier, no TMA.  (One thread issuing a TMA reduce-add stalled ~1300 cycles at its next memory
-        // instruction, and the loop-top barrier passed that on to all 256 compute threads, every tile.)
-        float v[HC];
-        if (HC == 32) {
-          uint32_t r[32];
-          tmem_ld_x32(tdQ + lane_sel + half * HC, r); tmem_ld_wait();
-#pragma unroll
-          for (int e = 0; e < HC; ++e) v[e] = __uint_as_float(r[e]);
-        } else {
-          uint32_t r[16];
-          tmem_ld_x16(tdQ + lane_sel + half * HC, r); tmem_ld_wait();
-#pragma unroll
-          for (int e = 0; e < HC; ++e) v[e] = __uint_as_float(r[e]);
-        }
+        // bf16 dQ: straight from tensor memory to global memory.  This thread owns query row `row` and HC contiguous columns:
+        // red.global.add.noftz.v4.bf16x2 adds 16 bytes per instruction, fire-and-forget -- no smem staging, no block barrier, no
+        // TMA.  (One thread issuing a TMA reduce-add stalled ~1300 cycles at its next memory instruction, and the loop-top
+        // barrier passed that on to all compute threads, every tile.)
+        load_acc(tdQ + lane_sel + grp * HC, v);
         tcgen05_before_thread_sync();
         mbar_arrive(dq_free);                    // the dQ accumulator may be overwritten by the next tile's MMA
         const int qq = qt0 + (int)row;
         if (qq < Sq) {
-          __nv_bfloat16* dst = dq16 + ((long long)b * Sq + qq) * ld_dq16 + h * DK + ho * DKO + half * HC;
+          __nv_bfloat16* dst = dq16 + ((long long)b * Sq + qq) * ld_dq16 + h * DK + ho * DKO + grp * HC;
 #pragma unroll
           for (int g = 0; g < HC / 8; ++g)
             asm volatile("red.global.add.noftz.v4.bf16x2 [%0], {%1, %2, %3, %4};" ::"l"(dst + 8 * g), "r"(pack_bf16x2(v[8 * g], v[8 * g + 1])),
@@ -696,112 +704,112 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         if (ctid == 0) tl_stamp(64 + (n_done & 7) * 8 + 5);
         return;
       }
-      // fp32 dQ (tests, other callers): row = query, this warp's half of the dk columns -> fp32 smem staging -> one TMA
-      // reduce-add per half (cp.reduce.async.bulk.tensor .add.f32; rows >= Sq are clipped by TMA)
+      // fp32 dQ (tests, other callers): -> fp32 smem staging (two [128 x DKO/2] boxes) -> one TMA reduce-add per box
+      // (cp.reduce.async.bulk.tensor .add.f32; rows >= Sq are clipped by TMA)
       if (ctid == 0) tma_store_wait_read<0>();   // the previous reduce has drained the staging
-      named_bar_sync(2, 256);
-      const uint32_t stg = sDQ + half * (L::DQ_BYTES / 2);
-      if (HC == 32) {
-        uint32_t r[32];
-        tmem_ld_x32(tdQ + lane_sel + half * HC, r);
-        tmem_ld_wait();
+      named_bar_sync(2, ATTN_BWD_CT);
+      const uint32_t stg = sDQ + (grp >> 1) * (L::DQ_BYTES / 2);
+      load_acc(tdQ + lane_sel + grp * HC, v);
 #pragma unroll
-        for (int g = 0; g < 8; ++g) st_shared_v4(stg + swz_off<DK>(row, g), r[4 * g], r[4 * g + 1], r[4 * g + 2], r[4 * g + 3]);
-      } else {
-        uint32_t r[16];
-        tmem_ld_x16(tdQ + lane_sel + half * HC, r);
-        tmem_ld_wait();
-#pragma unroll
-        for (int g = 0; g < 4; ++g) st_shared_v4(stg + swz_off<DK>(row, g), r[4 * g], r[4 * g + 1], r[4 * g + 2], r[4 * g + 3]);
-      }
+      for (int g = 0; g < HC / 4; ++g)
+        st_shared_v4(stg + swz_off<DK>(row, (grp & 1) * (HC / 4) + g), __float_as_uint(v[4 * g]), __float_as_uint(v[4 * g + 1]),
+                     __float_as_uint(v[4 * g + 2]), __float_as_uint(v[4 * g + 3]));
       tcgen05_before_thread_sync();
       mbar_arrive(dq_free);                      // the dQ accumulator may be overwritten by the next tile's MMA
       fence_proxy_async_smem();
-      named_bar_sync(3, 256);
+      named_bar_sync(3, ATTN_BWD_CT);
       if (ctid == 0) {
         tma_reduce_add_3d(&tmdQ, smem + L::OFF_DQ, h * DK, qt0, b);
-        tma_reduce_add_3d(&tmdQ, smem + L::OFF_DQ + L::DQ_BYTES / 2, h * DK + HC, qt0, b);
+        tma_reduce_add_3d(&tmdQ, smem + L::OFF_DQ + L::DQ_BYTES / 2, h * DK + DKO / 2, qt0, b);
         tma_store_commit();
         tl_stamp(64 + (n_done & 7) * 8 + 5);
       }
     };
     prefetch_row(i_start, rowbuf);
     int n = 0;
+    const int col0 = grp * 32;                    // first query column of this warp's chunk
     for (int i = i_start; i < nq; ++i, ++n) {
       const int qt0 = i * 128;
       float* rb = rowbuf + (n & 1) * 256;
-      asm volatile("cp.async.wait_group 0;" ::: "memory");      // this thread's element of tile n has landed ...
-      rb[ctid] *= row_mul;                                      // ... scale it in place (inf / 0 stay what they are)
+      if (row_loader) {
+        asm volatile("cp.async.wait_group 0;" ::: "memory");      // this thread's element of tile n has landed ...
+        rb[ctid] *= row_mul;                                      // ... scale it in place (inf / 0 stay what they are)
+      }
       if (ctid == 0) tl_stamp(64 + (n & 7) * 8 + 0);
-      named_bar_sync(1, 256);                                   // every thread is past tile n-1: its row buffer may be refilled
+      named_bar_sync(1, ATTN_BWD_CT);                             // every thread is past tile n-1: its row buffer may be refilled
       if (i + 1 < nq) prefetch_row(i + 1, rowbuf + ((n + 1) & 1) * 256);
       const bool diag = mask.causal && (qt0 < kv0 + 128);   // tile touches the causal boundary (some q < kv)
       const bool plain = rows_clean && !diag && mask.maskf == nullptr;   // no mask logic needed in this tile
       // aligned diagonal tile of a look-ahead mask, nothing else to mask: query col is hidden from key `row` iff col < row.
-      // Per warp (keys 32w..32w+31) and 32-query chunk cc: cc > w plain, cc < w fully hidden (P = dS = 0: no loads, no
-      // exponentials), cc == w mixed.  With the WHOLE key tile clean every query of the tile sees at least its own key, so
+      // Per warp (keys 32*quad..) and its 32-query chunk grp: grp > quad plain, grp < quad fully hidden (P = dS = 0: no loads, no
+      // exponentials), grp == quad mixed.  With the WHOLE key tile clean every query of the tile sees at least its own key, so
       // no query row here is fully masked (those attend uniformly to all keys, hidden ones included: general path).
       const bool diag_fast = diag && tile_clean && mask.maskf == nullptr && qt0 == kv0;
       const int wk = (int)(row >> 5), lk = (int)(row & 31u);
       mbar_wait(sdp_full, n & 1);
       tcgen05_after_thread_sync();
       if (ctid == 0) tl_stamp(64 + (n & 7) * 8 + 2);
-      const uint32_t sdS = sdSt + (n & 1) * C::P_BYTES + half * 16384;   // this tile's dS^T buffer, this warp's 64-query panel
-      uint32_t pw[32];                                                    // P^T row of this thread, 64 queries as bf16 pairs
+      const uint32_t sdS = sdSt + (n & 1) * C::P_BYTES + (grp >> 1) * 16384;   // this tile's dS^T buffer, this warp's 64-query panel
+      uint32_t pw[16];                                                          // P^T row of this thread, 32 queries as bf16 pairs
+      const bool hidden = diag_fast && grp < wk;
+      // two sub-chunks of 16 query columns: S^T / dP^T values, probabilities and dS of a sub-chunk are the only big live arrays
+      // (the compiler has 96 registers per thread with 18 warps resident)
 #pragma unroll
-      for (int c = 0; c < 2; ++c) {
-        const int col0 = half * 64 + c * 32;
-        uint32_t rs[32], rp[32];
-        const int cc = half * 2 + c;
-        const bool hidden = diag_fast && cc < wk;
-        float p[32], ds[32];
+      for (int sub = 0; sub < 2; ++sub) {
+        const int c16 = col0 + sub * 16;
+        uint32_t rs[16], rp[16];
+        float p[16], ds[16];
         if (!hidden) {
-          tmem_ld_x32(tSt + lane_sel + col0, rs);
-          tmem_ld_x32(tdPt + lane_sel + col0, rp);
+          tmem_ld_x16(tSt + lane_sel + c16, rs);
+          tmem_ld_x16(tdPt + lane_sel + c16, rp);
           tmem_ld_wait();
         }
+        const uint32_t rb_l = smem_u32(rb + c16), rb_d = smem_u32(rb + 128 + c16);       // lse (log2 domain) / delta of the 16 queries
         if (hidden) {
 #pragma unroll
-          for (int e = 0; e < 32; ++e) { p[e] = 0.f; ds[e] = 0.f; }
-        } else if (diag_fast && cc == wk) {
-#pragma unroll
-          for (int e = 0; e < 32; ++e) {
-            p[e] = e >= lk ? fast_exp2(__uint_as_float(rs[e]) * sl2 - rb[col0 + e]) : 0.f;
-            ds[e] = p[e] * (__uint_as_float(rp[e]) * scale - rb[128 + col0 + e]);
-          }
+          for (int e = 0; e < 16; ++e) { p[e] = 0.f; ds[e] = 0.f; }
         } else if (plain || diag_fast) {
+          const bool mixed = diag_fast && grp == wk;          // the chunk on the diagonal: query column e is visible iff e >= lk
 #pragma unroll
-          for (int e = 0; e < 32; ++e) {
-            p[e] = fast_exp2(__uint_as_float(rs[e]) * sl2 - rb[col0 + e]);
-            ds[e] = p[e] * (__uint_as_float(rp[e]) * scale - rb[128 + col0 + e]);      // = p (dP - delta) / sqrt(dk)
+          for (int e4 = 0; e4 < 4; ++e4) {
+            const float4 l4 = ld_shared_f4(rb_l + e4 * 16), d4 = ld_shared_f4(rb_d + e4 * 16);
+            const float ll[4] = {l4.x, l4.y, l4.z, l4.w}, dd[4] = {d4.x, d4.y, d4.z, d4.w};
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              const int e = e4 * 4 + k;
+              float pe = fast_exp2(__uint_as_float(rs[e]) * sl2 - ll[k]);
+              if (mixed && sub * 16 + e < lk) pe = 0.f;
+              p[e] = pe;
+              ds[e] = pe * (__uint_as_float(rp[e]) * scale - dd[k]);      // = p (dP - delta) / sqrt(dk)
+            }
           }
         } else {
 #pragma unroll
-          for (int e = 0; e < 32; ++e) {
-            const int qi = qt0 + col0 + e;
+          for (int e = 0; e < 16; ++e) {
+            const int qi = qt0 + c16 + e;
             float t2 = __uint_as_float(rs[e]) * sl2;                        // logit * log2(e)
             const bool masked = kv_pad || (diag && kv > qi);
             if (masked) t2 = kMaskVal * kLog2e;
             if (mask.maskf != nullptr && kv_valid && qi < Sq)
               t2 += mask.maskf[(long long)b * mask.sb + (long long)qi * mask.sq + kv] * (kMaskVal * kLog2e);
-            const float l2 = rb[col0 + e];
+            const float l2 = rb[c16 + e];
             float pe = fast_exp2(t2 - l2);
             if (l2 < -1e8f) pe *= inv_sk;     // fully-masked query row: lse == -1e9 in fp32 (ln Sk absorbed) -> uniform 1/Sk
             if (!kv_valid) pe = 0.f;
             p[e] = pe;
-            ds[e] = pe * (__uint_as_float(rp[e]) * scale - rb[128 + col0 + e]);
+            ds[e] = pe * (__uint_as_float(rp[e]) * scale - rb[128 + c16 + e]);
           }
         }
 #pragma unroll
-        for (int g = 0; g < 16; ++g) pw[c * 16 + g] = pack_bf16x2(p[2 * g], p[2 * g + 1]);
+        for (int g = 0; g < 8; ++g) pw[sub * 8 + g] = pack_bf16x2(p[2 * g], p[2 * g + 1]);
 #pragma unroll
-        for (int g = 0; g < 4; ++g)
-          st_shared_v4(sdS + swz128_off(row, c * 4 + g), pack_bf16x2(ds[8 * g], ds[8 * g + 1]), pack_bf16x2(ds[8 * g + 2], ds[8 * g + 3]),
+        for (int g = 0; g < 2; ++g)
+          st_shared_v4(sdS + swz128_off(row, (grp & 1) * 4 + sub * 2 + g), pack_bf16x2(ds[8 * g], ds[8 * g + 1]), pack_bf16x2(ds[8 * g + 2], ds[8 * g + 3]),
                        pack_bf16x2(ds[8 * g + 4], ds[8 * g + 5]), pack_bf16x2(ds[8 * g + 6], ds[8 * g + 7]));
       }
       // P^T -> tensor memory (A operand of the dV MMA), once the previous tile's dV MMAs have finished reading it
       if (n > 0) { mbar_wait(pt_free, (n - 1) & 1); tcgen05_after_thread_sync(); }
-      tmem_st_x32(tPt + lane_sel + half * 32, pw);
+      tmem_st_x16(tPt + lane_sel + grp * 16, pw);
       tmem_st_wait();
       if (ctid == 0) tl_stamp(64 + (n & 7) * 8 + 3);
       fence_proxy_async_smem();
@@ -814,33 +822,18 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     // epilogue: dV, dK (TMEM) -> bf16 -> smem (the two dS^T buffers, free once the last dq_full has fired) -> TMA store
     {
       float v[HC], k[HC];
-      if (HC == 32) {
-        uint32_t r[32];
-        tmem_ld_x32(tdV + lane_sel + half * HC, r); tmem_ld_wait();
-#pragma unroll
-        for (int e = 0; e < HC; ++e) v[e] = __uint_as_float(r[e]);
-        tmem_ld_x32(tdK + lane_sel + half * HC, r); tmem_ld_wait();
-#pragma unroll
-        for (int e = 0; e < HC; ++e) k[e] = __uint_as_float(r[e]);
-      } else {
-        uint32_t r[16];
-        tmem_ld_x16(tdV + lane_sel + half * HC, r); tmem_ld_wait();
-#pragma unroll
-        for (int e = 0; e < HC; ++e) v[e] = __uint_as_float(r[e]);
-        tmem_ld_x16(tdK + lane_sel + half * HC, r); tmem_ld_wait();
-#pragma unroll
-        for (int e = 0; e < HC; ++e) k[e] = __uint_as_float(r[e]);
-      }
+      load_acc(tdV + lane_sel + grp * HC, v);
+      load_acc(tdK + lane_sel + grp * HC, k);
 #pragma unroll
       for (int g = 0; g < HC / 8; ++g) {
-        const uint32_t off = swz_off<DK>(row, half * (HC / 8) + g);
+        const uint32_t off = swz_off<DK>(row, grp * (HC / 8) + g);
         st_shared_v4(sdSt + off, pack_bf16x2(v[8 * g], v[8 * g + 1]), pack_bf16x2(v[8 * g + 2], v[8 * g + 3]),
                      pack_bf16x2(v[8 * g + 4], v[8 * g + 5]), pack_bf16x2(v[8 * g + 6], v[8 * g + 7]));
         st_shared_v4(sdSt + C::P_BYTES + off, pack_bf16x2(k[8 * g], k[8 * g + 1]), pack_bf16x2(k[8 * g + 2], k[8 * g + 3]),
                      pack_bf16x2(k[8 * g + 4], k[8 * g + 5]), pack_bf16x2(k[8 * g + 6], k[8 * g + 7]));
       }
       fence_proxy_async_smem();
-      named_bar_sync(1, 256);
+      named_bar_sync(1, ATTN_BWD_CT);
       if (ctid == 0) {
         tl_stamp(61);
         tma_store_3d(&tmdV, smem + L::OFF_DST, h * DK + ho * DKO, kv0, b);      // one box: DKO <= the panel width
