@@ -304,30 +304,24 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       if (tl) tl_stamp(8 + j * 8 + 1);
       // ---- pass 1 over tensor memory: row maximum of the masked scores.  The row is NOT kept in registers (a 128-value row
       //      + packed P + masks needed more than the 168 registers two resident CTAs leave a thread: ~80 local-memory
-      //      round trips per tile, and a 30 KB unrolled loop body); both passes walk the row in 32-key chunks re-read from tensor
-      //      memory.
+      //      round trips per tile, and a 30 KB unrolled loop body); both passes are ROLLED loops over 32-key chunks that re-read S
+      //      from tensor memory (16 KB per warp and pass, ~100 cycles of latency per chunk, hidden by the other resident CTA).
       float mx[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
       uint32_t hidden_bits = 0;                      // bit c: chunk c is hidden for every row of this warp
-      auto pass1_chunk = [&](int c, uint32_t (&rc)[32]) {
+#pragma unroll 1
+      for (int c = 0; c < 4; ++c) {
         uint32_t bm, bo;
         mask_words(c, bm, bo);
         const bool touched = kMaskF || __any_sync(0xffffffffu, (bm | bo) != 0u);
         const bool hid = !kMaskF && __all_sync(0xffffffffu, bm == 0xffffffffu);
         hidden_bits |= (hid ? 1u : 0u) << c;
-        if (hid) { mx[0] = fmaxf(mx[0], kMaskRaw); return; }     // every existing key of the chunk holds the masked value
+        if (hid) { mx[0] = fmaxf(mx[0], kMaskRaw); continue; }     // every existing key of the chunk holds the masked value
+        uint32_t rc[32];
+        tmem_ld_x32(tS + lane_sel + c * 32, rc);
+        tmem_ld_wait();
         if (touched) apply_mask(c, bm, bo, rc);
 #pragma unroll
         for (int e = 0; e < 32; ++e) mx[e & 3] = fmaxf(mx[e & 3], __uint_as_float(rc[e]));
-      };
-      {
-        // ONE tcgen05.wait::ld for the whole row: the wait costs ~100+ cycles by itself (it behaves like a memory barrier), which
-        // dominated a chunk-by-chunk first pass; the 128 values only live until the maximum is known
-        uint32_t r[4][32];
-#pragma unroll
-        for (int c = 0; c < 4; ++c) tmem_ld_x32(tS + lane_sel + c * 32, r[c]);
-        tmem_ld_wait();
-#pragma unroll
-        for (int c = 0; c < 4; ++c) pass1_chunk(c, r[c]);
       }
       const float m_tile = fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3])) * sl2;     // sl2 > 0
       if (tl) tl_stamp(8 + j * 8 + 2);
@@ -358,21 +352,25 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       // so s_full alone does not order them); it fired long ago
       if (j > 0) { mbar_wait(o_full, (j - 1) & 1); tcgen05_after_thread_sync(); }
       float rs4[4] = {0.f, 0.f, 0.f, 0.f};
-      auto pass2_chunk = [&](int c, uint32_t (&rc)[32]) {
+#pragma unroll 1
+      for (int c = 0; c < 4; ++c) {
         uint32_t pk[16];
         const bool hid = (hidden_bits >> c) & 1u;
         if (hid && real_max) {
 #pragma unroll
           for (int g = 0; g < 16; ++g) pk[g] = 0u;
         } else {
+          uint32_t rc[32];
           uint32_t bm, bo;
           mask_words(c, bm, bo);
           if (hid) {
 #pragma unroll
             for (int e = 0; e < 32; ++e) rc[e] = __float_as_uint(kMaskRaw);
             if (__any_sync(0xffffffffu, bo != 0u)) apply_mask(c, bm, bo, rc);
-          } else if (kMaskF || __any_sync(0xffffffffu, (bm | bo) != 0u)) {
-            apply_mask(c, bm, bo, rc);
+          } else {
+            tmem_ld_x32(tS + lane_sel + c * 32, rc);
+            tmem_ld_wait();
+            if (kMaskF || __any_sync(0xffffffffu, (bm | bo) != 0u)) apply_mask(c, bm, bo, rc);
           }
           float p[32];
 #pragma unroll
@@ -380,24 +378,14 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
 #pragma unroll
           for (int g = 0; g < 16; ++g) pk[g] = pack_bf16x2(p[2 * g], p[2 * g + 1]);
         }
+        if (c == 3) {                                  // every chunk of S has been read: the next tile's S may overwrite it
+          tcgen05_before_thread_sync();
+          mbar_arrive(s_free);
+        }
         const uint32_t panel = sPs + (c >> 1) * 16384;
 #pragma unroll
         for (int g = 0; g < 4; ++g)
           st_shared_v4(panel + swz128_off(row, (c & 1) * 4 + g), pk[4 * g], pk[4 * g + 1], pk[4 * g + 2], pk[4 * g + 3]);
-      };
-      // two halves of 64 keys, one tcgen05.wait::ld each
-#pragma unroll 1
-      for (int hh = 0; hh < 2; ++hh) {
-        uint32_t r2[2][32];
-        tmem_ld_x32(tS + lane_sel + hh * 64, r2[0]);
-        tmem_ld_x32(tS + lane_sel + hh * 64 + 32, r2[1]);
-        tmem_ld_wait();
-        if (hh == 1) {                                 // every chunk of S has been read: the next tile's S may overwrite it
-          tcgen05_before_thread_sync();
-          mbar_arrive(s_free);
-        }
-        pass2_chunk(hh * 2, r2[0]);
-        pass2_chunk(hh * 2 + 1, r2[1]);
       }
       l_run += (rs4[0] + rs4[1]) + (rs4[2] + rs4[3]);
       if (tl) tl_stamp(8 + j * 8 + 3);
