@@ -218,6 +218,12 @@ int b200xf_model_grad_range(const b200xf_model_config* cfg, int stage, int64_t* 
  *   part 3 encoder layer `layer` (L-1 down to 0) | part 4 encoder embedding          (`layer` is ignored by parts 0, 2, 4) */
 int b200xf_model_backward_part(b200xf_model* m, int part, int layer, b200xf_stream_t stream);
 int b200xf_model_grad_range_part(const b200xf_model_config* cfg, int part, int layer, int64_t* begin, int64_t* end);
+/* Greedy inference with a key/value cache (train.py:91-121 recomputes encoder and decoder for every generated token):
+ * decode_begin runs the encoder (training = 0) on inp int64 [B,S] and the cross-attention K/V projections of every decoder layer;
+ * each decode_step feeds ONE new decoder-input token per sequence (tokens int64 [B], device), appends its self-attention K/V to
+ * the cache and returns the logits of that position (logits_out fp32 [B, ld_logits]).  At most max_tgt_len steps. */
+int b200xf_model_decode_begin(b200xf_model* m, const int64_t* inp, int B, int S, b200xf_stream_t stream);
+int b200xf_model_decode_step(b200xf_model* m, const int64_t* tokens, float* logits_out, int64_t ld_logits, b200xf_stream_t stream);
 /* attention_weights['decoder_layer{layer+1}_block{block}'] of the last forward -> P fp32 [B,H,T,Sk] */
 int b200xf_model_attention_weights(b200xf_model* m, int layer, int block, float* P, b200xf_stream_t stream);
 /* debug/parity taps: copy an internal activation of the last forward (fp32 [rows, d_model]) -- names:

@@ -268,6 +268,7 @@ def test_checkpoint_roundtrip_and_predict(tmp_path):
     assert not torch.equal(want, model.params)
     out = tr.predict("w1 w2 w3")
     assert out.shape == (11,) and out[0].item() == tok.vocab_size and out.dtype == torch.int64
+    assert torch.equal(out, tr.predict("w1 w2 w3", use_cache=False))      # key/value cache == the reference's full recomputation
     # greedy decode is a fixed point of the model: re-scoring the produced prefix reproduces each next token
     ids = torch.tensor([[tok.vocab_size] + tok.encode("w1 w2 w3") + [tok.vocab_size + 1]], device="cuda")
     logits, _ = model((ids, out[None, :-1]), training=False)
@@ -294,3 +295,19 @@ def test_forward_matches_reference_code_on_numpy_stub(golden_dir):
     tr = make_trainer(model, B)
     lf = tr.loss_function(tar[:, 1:], logits).item()
     assert abs(lf - float(z["loss"])) <= 1e-3 * abs(float(z["loss"]))
+
+
+def test_incremental_decode_matches_full_forward():
+    """KV-cached decoding (b200xf_model_decode_begin/_step) against the full forward on the same prefix, batch of 3 with padding in the
+    source and a pad id inside the target prefix: logits of every position agree to bf16 rounding."""
+    cfg, P, model = make_pair(H=4)
+    src, tar = R.synthetic_batch(3, 29, 14, 1003, 1009, pad_tail=True, seed=21)
+    tar = tar.clone(); tar[1, 4] = 0                                      # a padding id as a decoder input (masked as a key)
+    T = 12
+    full, _ = model((src.cuda(), tar[:, :T].cuda()), training=False)
+    model.decode_begin(src.cuda())
+    for t in range(T):
+        step = model.decode_step(tar[:, t].cuda())
+        torch.cuda.synchronize()
+        err = (step - full[:, t]).abs().max().item()
+        assert err <= 2e-2 * max(1.0, full[:, t].abs().max().item()), (t, err)

@@ -269,6 +269,31 @@ class Transformer:
     def __call__(self, input_, training=False, *extra, **kw):
         return self.call(input_, training, *extra, **kw)
 
+    # ------------------------------------------------------------------ incremental decoding (used by Train.predict)
+    def decode_begin(self, inp):
+        """run the encoder on ``inp`` (B,S) int64 and the cross-attention K/V projections of every decoder layer once"""
+        inp = inp.to(self.device, torch.int64).contiguous()
+        B, S = inp.shape
+        self._ensure_workspace(B, S, self._cfg.max_tgt_len)
+        with torch.cuda.device(self.device):
+            if self._shadow_dirty:
+                self.sync_shadow()
+            self._generation += 1
+            self._keepalive = (inp,)
+            L.call("b200xf_model_decode_begin", self._handle, L.ptr(inp), B, S, L.stream_ptr())
+        self._decode_batch = B
+
+    def decode_step(self, tokens):
+        """feed ONE decoder-input token per sequence (``tokens`` (B,) int64); returns the logits (B, V) fp32 of that position.
+        The self-attention keys/values of all earlier positions come from the cache."""
+        tokens = tokens.to(self.device, torch.int64).contiguous().reshape(-1)
+        assert tokens.numel() == self._decode_batch
+        ld = _round_up(self.target_vocab_size, 4)
+        logits = torch.empty((self._decode_batch, ld), dtype=torch.float32, device=self.device)
+        with torch.cuda.device(self.device):
+            L.call("b200xf_model_decode_step", self._handle, L.ptr(tokens), L.ptr(logits), ld, L.stream_ptr())
+        return logits[:, :self.target_vocab_size]
+
     # ------------------------------------------------------------------ training-step pieces (used by train.Train)
     def zero_grads(self):
         self.grads.zero_()

@@ -72,6 +72,8 @@ _SIGS = {
     "b200xf_model_grad_range": [C.POINTER(ModelConfig), _I, C.POINTER(_I64), C.POINTER(_I64)],
     "b200xf_model_backward_part": [_P, _I, _I, _P],
     "b200xf_model_grad_range_part": [C.POINTER(ModelConfig), _I, _I, C.POINTER(_I64), C.POINTER(_I64)],
+    "b200xf_model_decode_begin": [_P, _P, _I, _I, _P],
+    "b200xf_model_decode_step": [_P, _P, _P, _I64, _P],
     "b200xf_model_attention_weights": [_P, _I, _I, _P, _P],
     "b200xf_model_tap": [_P, C.c_char_p, _P, _P],
     "b200xf_last_error": [],

@@ -888,15 +888,18 @@ attn_probs_kernel(const __nv_bfloat16* __restrict__ Q, long long ld_q, const __n
 template <int DK>
 static int attn_fwd_launch(const void* Q, long long ld_q, const void* K, long long ld_k, const void* V, long long ld_v,
                            void* O, long long ld_o, void* O_lo, float* lse, const AttnMask& mask, int B, int H, int Sq, int Sk,
-                           cudaStream_t st) {
+                           cudaStream_t st, long long bs_q, long long bs_kv) {
   using L = FwdSmem<DK>;
   constexpr int PW = AttnCfg<DK>::PW;      // TMA box = one panel: [128 tokens x PW columns]
   const int swz = PW * 2;
   CUtensorMap tmQ, tmK, tmV, tmO;
   int rc;
-  if ((rc = encode_tmap_3d(&tmQ, 0, Q, (uint64_t)H * DK, Sq, B, ld_q, (uint64_t)Sq * ld_q, PW, 128, 1, swz))) return rc;
-  if ((rc = encode_tmap_3d(&tmK, 0, K, (uint64_t)H * DK, Sk, B, ld_k, (uint64_t)Sk * ld_k, PW, 128, 1, swz))) return rc;
-  if ((rc = encode_tmap_3d(&tmV, 0, V, (uint64_t)H * DK, Sk, B, ld_v, (uint64_t)Sk * ld_v, PW, 128, 1, swz))) return rc;
+  // batch strides (elements) of Q and of K/V: by default the tensors are dense [B, S, ld]; a key/value CACHE has its own pitch
+  const uint64_t sq = bs_q > 0 ? (uint64_t)bs_q : (uint64_t)Sq * ld_q, sk = bs_kv > 0 ? (uint64_t)bs_kv : (uint64_t)Sk * ld_k,
+                 sv = bs_kv > 0 ? (uint64_t)bs_kv : (uint64_t)Sk * ld_v;
+  if ((rc = encode_tmap_3d(&tmQ, 0, Q, (uint64_t)H * DK, Sq, B, ld_q, sq, PW, 128, 1, swz))) return rc;
+  if ((rc = encode_tmap_3d(&tmK, 0, K, (uint64_t)H * DK, Sk, B, ld_k, sk, PW, 128, 1, swz))) return rc;
+  if ((rc = encode_tmap_3d(&tmV, 0, V, (uint64_t)H * DK, Sk, B, ld_v, sv, PW, 128, 1, swz))) return rc;
   if ((rc = encode_tmap_3d(&tmO, 0, O, (uint64_t)H * DK, Sq, B, ld_o, (uint64_t)Sq * ld_o, PW, 128, 1, swz))) return rc;
   CUtensorMap tmOlo = tmO;
   if (O_lo != nullptr && (rc = encode_tmap_3d(&tmOlo, 0, O_lo, (uint64_t)H * DK, Sq, B, ld_o, (uint64_t)Sq * ld_o, PW, 128, 1, swz))) return rc;
@@ -971,12 +974,12 @@ static int check_attn_args(int B, int H, int Sq, int Sk, int dk, int causal) {
 
 int attn_fwd(const void* Q, long long ld_q, const void* K, long long ld_k, const void* V, long long ld_v, void* O,
              long long ld_o, float* lse, const uint8_t* kpad, int causal, const float* maskf, long long mask_sb,
-             long long mask_sq, int B, int H, int Sq, int Sk, int dk, cudaStream_t st, void* O_lo) {
+             long long mask_sq, int B, int H, int Sq, int Sk, int dk, cudaStream_t st, void* O_lo, long long bs_q, long long bs_kv) {
   if (int rc = check_attn_args(B, H, Sq, Sk, dk, causal)) return rc;
   AttnMask m{kpad, maskf, mask_sb, mask_sq, causal};
-  if (dk == 128) return attn_fwd_launch<128>(Q, ld_q, K, ld_k, V, ld_v, O, ld_o, O_lo, lse, m, B, H, Sq, Sk, st);
-  return dk == 64 ? attn_fwd_launch<64>(Q, ld_q, K, ld_k, V, ld_v, O, ld_o, O_lo, lse, m, B, H, Sq, Sk, st)
-                  : attn_fwd_launch<32>(Q, ld_q, K, ld_k, V, ld_v, O, ld_o, O_lo, lse, m, B, H, Sq, Sk, st);
+  if (dk == 128) return attn_fwd_launch<128>(Q, ld_q, K, ld_k, V, ld_v, O, ld_o, O_lo, lse, m, B, H, Sq, Sk, st, bs_q, bs_kv);
+  return dk == 64 ? attn_fwd_launch<64>(Q, ld_q, K, ld_k, V, ld_v, O, ld_o, O_lo, lse, m, B, H, Sq, Sk, st, bs_q, bs_kv)
+                  : attn_fwd_launch<32>(Q, ld_q, K, ld_k, V, ld_v, O, ld_o, O_lo, lse, m, B, H, Sq, Sk, st, bs_q, bs_kv);
 }
 
 int attn_bwd(const void* Q, long long ld_q, const void* K, long long ld_k, const void* V, long long ld_v, const void* dO,

@@ -23,7 +23,8 @@ int set_timeline(long long* dev_ptr);   // debug: register a device buffer of >=
 int attn_fwd(const void* Q, long long ld_q, const void* K, long long ld_k, const void* V, long long ld_v, void* O,
              long long ld_o, float* lse, const uint8_t* kpad, int causal, const float* maskf, long long mask_sb,
              long long mask_sq, int B, int H, int Sq, int Sk, int dk, cudaStream_t st,
-             void* O_lo = nullptr);   // O_lo (optional, same layout as O): bf16 rounding residual of O for the backward's delta
+             void* O_lo = nullptr,    // O_lo (optional, same layout as O): bf16 rounding residual of O for the backward's delta
+             long long bs_q = 0, long long bs_kv = 0);   // batch strides of Q and of K/V in elements (0: dense [B, S, ld]); a K/V cache has its own
 int attn_bwd(const void* Q, long long ld_q, const void* K, long long ld_k, const void* V, long long ld_v, const void* dO,
              long long ld_do, const float* lse, const float* delta, void* dq_acc, long long ld_dq, int dq_bf16, void* dK,
              long long ld_dk, void* dV, long long ld_dv, const uint8_t* kpad, int causal, const float* maskf,

@@ -153,6 +153,8 @@ struct Work {
   std::vector<DecAct> dec;
   bf16* logits;                           // [Mt, Vp] bf16, overwritten in place by dlogits
   uint8_t *kpad_in, *kpad_tar;
+  long long* dec_hist;                    // [max_batch, max_tgt_len] decoder input tokens seen so far (incremental decoding)
+  float* dec_lse;                         // [max_batch, H] scratch lse of a one-query attention
   // backward scratch
   bf16 *gR0, *gR1;                        // [Mmax, d] residual-path gradient (dz of the last LayerNorm backward), ping-pong
   bf16* gD;                               // [Mmax, d] dgrad output of the last sublayer; the stream gradient is gR + gD
@@ -207,6 +209,7 @@ Work make_work(const b200xf_model_config& c, const Layout& lo, void* base) {
   }
   w.logits = b.take<bf16>(Mt * lo.Vp);
   w.kpad_in = b.take<uint8_t>(Ms); w.kpad_tar = b.take<uint8_t>(Mt);
+  w.dec_hist = b.take<long long>(Mt); w.dec_lse = b.take<float>(c.max_batch * H);
   w.gR0 = b.take<bf16>(Mx * d); w.gR1 = b.take<bf16>(Mx * d); w.gD = b.take<bf16>(Mx * d); w.d_enc_out = b.take<float>(Ms * d);
   for (auto& p : w.dy16) p = b.take<bf16>(Mx * d);
   w.dO16 = b.take<bf16>(Mx * d);
@@ -259,6 +262,7 @@ struct b200xf_model {
   int next_event = 0;
   int concurrency = 0;         // 0: everything on the caller's stream
   int fuse_ln = 1;             // LayerNorm in the out-projection / FFN dense1 GEMM epilogue (d_model 128 / 256 / 512)
+  int dec_B = 0, dec_S = 0, dec_len = 0;   // incremental decoding (b200xf_model_decode_begin / _step): batch, source length, tokens cached
   // state carried between the parts of a layer-granular backward (b200xf_model_backward_part): the gradient of the stream
   // tensor entering the next layer (see StreamGrad) and which of the two dz buffers is written next
   const void* bw_r = nullptr; bool bw_r_f32 = false; const void* bw_dg = nullptr;
@@ -702,6 +706,66 @@ int backward_encoder(M* m, cudaStream_t st) {
   return backward_encoder_embed(m, st);
 }
 
+// ---- incremental (KV-cached) decoding: train.py:91-121 re-runs encoder and decoder for every generated token; here the encoder and
+// the cross-attention K/V projections run once (decode_begin) and each step processes ONE new target position per sequence:
+// its Q/K/V row is written straight into the self-attention cache (the layer's qkv1 buffer viewed as [B, max_tgt_len, 3d]: the
+// GEMM's output pitch is the cache's batch pitch), attention reads the cached keys 0..pos through batch-strided TMA maps.
+int decode_begin(M* m, cudaStream_t st) {
+  const Layout& lo = m->lo;
+  Work& w = m->w;
+  const int d = lo.d, H = lo.H, f = lo.f, L = lo.L, dk = d / H;
+  const int B = m->B, S = m->S;
+  const int64_t Ms = (int64_t)B * S;
+  const bf16* Sh = m->Sh;
+  RC(bx::pad_mask(reinterpret_cast<const long long*>(m->inp), S, 0, w.kpad_in, B, S, st));
+  RC(bx::embed_fwd(reinterpret_cast<const long long*>(m->inp), S, 0, m->P + lo.enc_emb, m->pos_in, nullptr, w.enc_x16[0], Ms, S, d, lo.Vin, 0.f, 0, 0, st));
+  for (int l = 0; l < L; ++l) {
+    const EncLayerP& p = lo.enc[l];
+    EncAct& a = w.enc[l];
+    RC(linear_fwd(w.enc_x16[l], d, Sh + p.mha.Wqkv, 3 * d, m->P + p.mha.bqkv, a.qkv, 3 * d, false, false, Ms, 3 * d, d, st));
+    RC(bx::attn_fwd(a.qkv, 3 * d, a.qkv + d, 3 * d, a.qkv + 2 * d, 3 * d, a.attn_o, d, a.lse, w.kpad_in, 0, nullptr, 0, 0, B, H, S, S, dk, st));
+    RC(dense_residual_ln(m, a.attn_o, d, d, p.mha.Wo, p.mha.bo, w.enc_x16[l], p.ln1g, p.ln1b, a.out1_16, a.ln1, Ms, 0, st));
+    RC(linear_fwd(a.out1_16, d, Sh + p.ffn.W1, f, m->P + p.ffn.b1, a.h, f, false, true, Ms, f, d, st));
+    RC(dense_residual_ln(m, a.h, f, f, p.ffn.W2, p.ffn.b2, a.out1_16, p.ln2g, p.ln2b, w.enc_x16[l + 1], a.ln2, Ms, 0, st));
+  }
+  for (int l = 0; l < L; ++l) {
+    const DecLayerP& p = lo.dec[l];
+    RC(linear_fwd(w.enc_x16[L], d, Sh + p.mha2.Wkv, 2 * d, m->P + p.mha2.bkv, w.dec[l].kv2, 2 * d, false, false, Ms, 2 * d, d, st));
+  }
+  return 0;
+}
+
+int decode_step(M* m, const long long* tokens, int pos, float* logits_out, int64_t ld_logits, cudaStream_t st) {
+  const Layout& lo = m->lo;
+  Work& w = m->w;
+  const int d = lo.d, H = lo.H, f = lo.f, L = lo.L, dk = d / H;
+  const int B = m->dec_B, S = m->dec_S;
+  const int64_t Tc = m->cfg.max_tgt_len;              // cache pitch (positions per sequence)
+  const bf16* Sh = m->Sh;
+  // token history -> key-padding bytes of the cached target positions (Decoder.py:29-31: look-ahead mask OR target padding mask;
+  // every cached key is <= the query position, so only the padding part is left)
+  BX_CHECK_CUDA(cudaMemcpy2DAsync(w.dec_hist + pos, (size_t)Tc * sizeof(long long), tokens, sizeof(long long), sizeof(long long), B,
+                                  cudaMemcpyDeviceToDevice, st));
+  RC(bx::pad_mask(w.dec_hist, (int)Tc, 0, w.kpad_tar, B, pos + 1, st));
+  // embedding of the new token at position `pos` (Decoder.py:65-69)
+  RC(bx::embed_fwd(tokens, 1, 0, m->P + lo.dec_emb, m->pos_tgt + (int64_t)pos * d, nullptr, w.dec_x16[0], B, 1, d, lo.Vtgt, 0.f, 0, 0, st));
+  for (int l = 0; l < L; ++l) {
+    const DecLayerP& p = lo.dec[l];
+    DecAct& a = w.dec[l];
+    bf16* cache = a.qkv1;                              // [B, Tc, 3d]
+    RC(linear_fwd(w.dec_x16[l], d, Sh + p.mha1.Wqkv, 3 * d, m->P + p.mha1.bqkv, cache + (int64_t)pos * 3 * d, Tc * 3 * d, false, false, B, 3 * d, d, st));
+    RC(bx::attn_fwd(cache + (int64_t)pos * 3 * d, 3 * d, cache + d, 3 * d, cache + 2 * d, 3 * d, a.attn1_o, d, w.dec_lse, w.kpad_tar, 0, nullptr, 0, 0,
+                    B, H, 1, pos + 1, dk, st, nullptr, Tc * 3 * d, Tc * 3 * d));
+    RC(dense_residual_ln(m, a.attn1_o, d, d, p.mha1.Wo, p.mha1.bo, w.dec_x16[l], p.ln1g, p.ln1b, a.out1_16, a.ln1, B, 0, st));
+    RC(linear_fwd(a.out1_16, d, Sh + p.mha2.Wq, d, m->P + p.mha2.bq, a.q2, d, false, false, B, d, d, st));
+    RC(bx::attn_fwd(a.q2, d, a.kv2, 2 * d, a.kv2 + d, 2 * d, a.attn2_o, d, w.dec_lse, w.kpad_in, 0, nullptr, 0, 0, B, H, 1, S, dk, st));
+    RC(dense_residual_ln(m, a.attn2_o, d, d, p.mha2.Wo, p.mha2.bo, a.out1_16, p.ln2g, p.ln2b, a.out2_16, a.ln2, B, 0, st));
+    RC(linear_fwd(a.out2_16, d, Sh + p.ffn.W1, f, m->P + p.ffn.b1, a.h, f, false, true, B, f, d, st));
+    RC(dense_residual_ln(m, a.h, f, f, p.ffn.W2, p.ffn.b2, a.out2_16, p.ln3g, p.ln3b, w.dec_x16[l + 1], a.ln3, B, 0, st));
+  }
+  return linear_fwd(w.dec_x16[L], d, Sh + lo.Wf, lo.Vp, m->P + lo.bf, logits_out, ld_logits, true, false, B, lo.Vtgt, d, st);
+}
+
 }  // namespace
 
 // ====================================================================================================
@@ -846,6 +910,22 @@ int b200xf_model_grad_range_part(const b200xf_model_config* cfg, int part, int l
   }
   *begin = r.first; *end = r.second;
   return 0;
+}
+
+int b200xf_model_decode_begin(b200xf_model* m, const int64_t* inp, int B, int S, b200xf_stream_t stream) {
+  BX_REQUIRE(B >= 1 && B <= m->cfg.max_batch && S >= 1 && S <= m->cfg.max_src_len, "decode_begin: shape (B %d, S %d) exceeds the workspace", B, S);
+  m->B = B; m->S = S; m->T = 1; m->training = 0; m->seed = 0; m->inp = inp; m->tar = nullptr;
+  m->enc_mask = m->la_mask = m->dec_mask = nullptr;
+  m->have_loss_grad = false; m->logits_valid = false;
+  m->dec_B = B; m->dec_S = S; m->dec_len = 0;
+  return decode_begin(m, reinterpret_cast<cudaStream_t>(stream));
+}
+int b200xf_model_decode_step(b200xf_model* m, const int64_t* tokens, float* logits_out, int64_t ld_logits, b200xf_stream_t stream) {
+  BX_REQUIRE(m->dec_B > 0, "decode_step: call b200xf_model_decode_begin first");
+  BX_REQUIRE(m->dec_len < m->cfg.max_tgt_len, "decode_step: the cache holds max_tgt_len = %d positions", m->cfg.max_tgt_len);
+  BX_REQUIRE(logits_out != nullptr && ld_logits % 4 == 0 && ld_logits >= m->lo.Vtgt, "decode_step: bad logits buffer");
+  const int pos = m->dec_len++;
+  return decode_step(m, reinterpret_cast<const long long*>(tokens), pos, logits_out, ld_logits, reinterpret_cast<cudaStream_t>(stream));
 }
 
 int b200xf_model_attention_weights(b200xf_model* m, int layer, int block, float* P, b200xf_stream_t stream) {

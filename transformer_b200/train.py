@@ -331,9 +331,11 @@ class Train(object):
             w.add_scalar('accuracy', acc, epoch)
             w.flush()
 
-    def predict(self, input_sentence, max_steps=10):
-        """Greedy inference (train.py:91-121): start token, 10 decode steps, no EOS stop, the whole model re-run per
-        step.  (The reference indexes ``input_sentence[0]``, i.e. expects a 1-element batch of strings.)"""
+    def predict(self, input_sentence, max_steps=10, use_cache=True):
+        """Greedy inference (train.py:91-121): start token, 10 decode steps, no EOS stop.  The reference re-runs the whole model
+        (encoder included) for every generated token; with ``use_cache`` the encoder and the cross-attention K/V run once and each
+        step feeds one token through the decoder against a key/value cache (same tokens out; ``use_cache=False`` keeps the
+        reference's full recomputation).  (The reference indexes ``input_sentence[0]``, i.e. expects a 1-element batch of strings.)"""
         if not isinstance(input_sentence, str):
             input_sentence = input_sentence[0]
         tr = self.transformer
@@ -342,6 +344,14 @@ class Train(object):
         ids = start_token + self.src_tokenizer.encode(input_sentence) + end_token
         encoder_input = torch.tensor([ids], dtype=torch.int64, device=tr.device)
         output = torch.tensor([start_token], dtype=torch.int64, device=tr.device)
+        if use_cache:
+            tr._ensure_workspace(1, len(ids), max(max_steps, tr._cfg.max_tgt_len))
+            tr.decode_begin(encoder_input)
+            for i in range(max_steps):
+                logits = tr.decode_step(output[:, i])                          # position i attends to the cached positions 0..i
+                predicted_id = logits.argmax(dim=-1, keepdim=True).to(torch.int64)
+                output = torch.cat([output, predicted_id], dim=-1)
+            return output[0]
         for _ in range(max_steps):
             predictions, _ = tr.call((encoder_input, output), False)
             predicted_id = predictions[:, -1:, :].argmax(dim=-1).to(torch.int64)
