@@ -218,6 +218,12 @@ int b200xf_model_grad_range(const b200xf_model_config* cfg, int stage, int64_t* 
  *   part 3 encoder layer `layer` (L-1 down to 0) | part 4 encoder embedding          (`layer` is ignored by parts 0, 2, 4) */
 int b200xf_model_backward_part(b200xf_model* m, int part, int layer, b200xf_stream_t stream);
 int b200xf_model_grad_range_part(const b200xf_model_config* cfg, int part, int layer, int64_t* begin, int64_t* end);
+/* Shape bucketing: the host may pad a ragged batch (utils.py:154-159 padded_batch) up to a bucket length with pad id 0 so that one
+ * captured CUDA graph serves a range of lengths.  Padded keys are masked and padded target positions carry label 0 (no loss, no
+ * gradient) by the reference's own rules; the one thing that would change is the accuracy metric, which counts ALL positions
+ * (train.py:141): positions t >= *t_valid_dev of b200xf_model_loss are therefore left out of the counters.  The length lives on
+ * the device (a captured graph of the bucket shape is replayed for every real length); NULL = no filler. */
+void b200xf_model_set_valid_target_len_ptr(b200xf_model* m, const int32_t* t_valid_dev);
 /* Greedy inference with a key/value cache (train.py:91-121 recomputes encoder and decoder for every generated token):
  * decode_begin runs the encoder (training = 0) on inp int64 [B,S] and the cross-attention K/V projections of every decoder layer;
  * each decode_step feeds ONE new decoder-input token per sequence (tokens int64 [B], device), appends its self-attention K/V to

@@ -286,3 +286,10 @@ def test_synthetic_corpus_feeds_the_text_pipeline(tmp_path):
     tr, te, st, tt = utils.load_dataset(p, 50, str(tmp_path / "sv"), str(tmp_path / "tv"), 64, 1000)
     assert len(tr) > 100 and len(te) >= 1 and tr[0][0].shape[0] == 64 and tr[0][0].dtype == torch.int64
     assert all(s.shape[1] <= 50 and t.shape[1] <= 50 for s, t in tr)
+
+
+def test_prefetch_to_device_passthrough_on_cpu():
+    from transformer_b200.utils import prefetch_to_device
+    batches = [(torch.arange(6).view(2, 3), torch.arange(8).view(2, 4)) for _ in range(3)]
+    got = list(prefetch_to_device(batches, "cpu"))
+    assert len(got) == 3 and all(torch.equal(a[0], b[0]) and torch.equal(a[1], b[1]) for a, b in zip(got, batches))

@@ -311,3 +311,29 @@ def test_incremental_decode_matches_full_forward():
         torch.cuda.synchronize()
         err = (step - full[:, t]).abs().max().item()
         assert err <= 2e-2 * max(1.0, full[:, t].abs().max().item()), (t, err)
+
+
+def test_shape_bucketing_is_neutral():
+    """Train(shape_bucket=8): ragged batches are padded to bucket lengths (one CUDA graph per bucket); loss, every metric counter and
+    the updated weights must equal the unpadded step's (dropout 0)."""
+    B = 4
+    out = {}
+    for bucket in (0, 8):
+        cfg, P, model = make_pair(H=2)
+        tr = Train(1, True, model, None, None, B, None, None, 5, "ckpt", model.d_model, warmup_steps=20, shape_bucket=bucket)
+        stats = []
+        for i, (S, T1) in enumerate([(21, 18), (19, 23), (21, 18), (22, 17), (21, 18)]):        # (21,18) and (22,17) share the bucket (24, 24)
+            src, tar = R.synthetic_batch(B, S, T1, 1003, 1009, pad_tail=True, seed=30 + i)
+            tr.train_step((src, tar))
+            stats.append(tr._stats.clone())
+        src, tar = R.synthetic_batch(B, 20, 16, 1003, 1009, pad_tail=True, seed=77)
+        tr.test_step((src, tar))
+        torch.cuda.synchronize()
+        out[bucket] = (torch.stack(stats).cpu(), model.params.clone().cpu(), tr.test_accuracy.result(), tr.train_accuracy.result(), len(tr._graphs))
+    s0, p0, ta0, tra0, _ = out[0]
+    s8, p8, ta8, tra8, ng = out[8]
+    assert torch.equal(s0[:, 1:], s8[:, 1:]), (s0, s8)                     # correct / positions / non-pad counters: exact
+    assert torch.allclose(s0[:, 0], s8[:, 0], rtol=2e-3)                   # loss sums (bf16 kernels on a different tile shape)
+    assert abs(ta0 - ta8) < 1e-12 and abs(tra0 - tra8) < 1e-12
+    assert (p0 - p8).norm().item() <= 2e-3 * p0.norm().item()
+    assert ng <= 2                                                          # two buckets seen -> at most two captured graphs

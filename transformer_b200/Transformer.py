@@ -192,6 +192,7 @@ class Transformer:
           L.call("b200xf_model_create", C.byref(c), L.ptr(self.params), L.ptr(self.grads), L.ptr(self.adam_m), L.ptr(self.adam_v),
                L.ptr(self.shadow), L.ptr(self.pos_encoding_in), L.ptr(self.pos_encoding_tgt), L.ptr(self._workspace), C.byref(h))
         self._handle = h
+        self._tvalid_set = False                       # (train.Train: device-side valid target length for shape bucketing)
         self._handle_generation = getattr(self, "_handle_generation", 0) + 1      # captured CUDA graphs of older handles are stale
         self._shadow_dirty = True
 

@@ -72,6 +72,7 @@ _SIGS = {
     "b200xf_model_grad_range": [C.POINTER(ModelConfig), _I, C.POINTER(_I64), C.POINTER(_I64)],
     "b200xf_model_backward_part": [_P, _I, _I, _P],
     "b200xf_model_grad_range_part": [C.POINTER(ModelConfig), _I, _I, C.POINTER(_I64), C.POINTER(_I64)],
+    "b200xf_model_set_valid_target_len_ptr": [_P, _P],
     "b200xf_model_decode_begin": [_P, _P, _I, _I, _P],
     "b200xf_model_decode_step": [_P, _P, _P, _I64, _P],
     "b200xf_model_attention_weights": [_P, _I, _I, _P, _P],
@@ -87,7 +88,7 @@ _SIGS = {
 }
 _RESTYPES = {"b200xf_last_error": C.c_char_p, "b200xf_launch_count": C.c_longlong,
              "b200xf_model_param_count": _I64, "b200xf_model_workspace_bytes": _I64,
-             "b200xf_model_destroy": None, "b200xf_model_set_concurrency": None, "b200xf_model_set_seed_ptr": None, "b200xf_prof_enable": None, "b200xf_gemm_force_cta_group": None, "b200xf_gemm_set_chunks_per_unit": None}
+             "b200xf_model_destroy": None, "b200xf_model_set_concurrency": None, "b200xf_model_set_valid_target_len_ptr": None, "b200xf_model_set_seed_ptr": None, "b200xf_prof_enable": None, "b200xf_gemm_force_cta_group": None, "b200xf_gemm_set_chunks_per_unit": None}
 
 EXPORTED_SYMBOLS = tuple(_SIGS)
 

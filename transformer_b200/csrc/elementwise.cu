@@ -352,7 +352,7 @@ template <typename T>
 __global__ void __launch_bounds__(256)
 xent_kernel(const T* logits, long long ld, const long long* __restrict__ labels, int label_stride,
             int label_offset, int T_len, __nv_bfloat16* dlogits, long long ld_d, float* __restrict__ row_loss,
-            double* __restrict__ stats, int V, float inv_batch) {   // dlogits may alias logits (no __restrict__)
+            double* __restrict__ stats, int V, float inv_batch, const int* __restrict__ t_valid_dev) {   // dlogits may alias logits (no __restrict__)
   // one CTA per row, 16-byte vector loads.  labels for row r = (b, t) live at labels[b*label_stride + label_offset + t]
   constexpr int VEC = LogitVec<T>::N;
   constexpr float L2E = 1.4426950408889634f, LN2 = 0.6931471805599453f;
@@ -421,8 +421,10 @@ xent_kernel(const T* logits, long long ld, const long long* __restrict__ labels,
     const float loss = nonpad ? (lse - s_lab) : 0.f;
     if (row_loss) row_loss[r] = loss;
     if (nonpad) atomicAdd(&stats[0], (double)loss);
-    if ((long long)am == raw_label) atomicAdd(&stats[1], 1.0);
-    atomicAdd(&stats[2], 1.0);
+    if (t_valid_dev == nullptr || t < *t_valid_dev) {   // positions added by shape bucketing (t >= *t_valid_dev) are not part of the batch
+      if ((long long)am == raw_label) atomicAdd(&stats[1], 1.0);
+      atomicAdd(&stats[2], 1.0);
+    }
     if (nonpad) atomicAdd(&stats[3], 1.0);
   }
   if (dlogits == nullptr) return;
@@ -691,15 +693,15 @@ int residual_ln_bwd(const void* g1, int g1_f32, const void* g2, const void* z, c
 
 int xent(const void* logits, int logits_f32, long long ld, const long long* labels, int label_stride, int label_offset,
          int T_len, void* dlogits, long long ld_d, float* row_loss, double* stats, long long rows, int V, float inv_batch,
-         cudaStream_t st) {
+         cudaStream_t st, const int* t_valid) {
   BX_REQUIRE(rows > 0 && rows < (1ll << 31), "xent: bad row count");
   if (logits_f32)
     xent_kernel<float><<<(unsigned)rows, 256, 0, st>>>((const float*)logits, ld, labels, label_stride, label_offset, T_len,
-                                                       (__nv_bfloat16*)dlogits, ld_d, row_loss, stats, V, inv_batch);
+                                                       (__nv_bfloat16*)dlogits, ld_d, row_loss, stats, V, inv_batch, t_valid);
   else
     xent_kernel<__nv_bfloat16><<<(unsigned)rows, 256, 0, st>>>((const __nv_bfloat16*)logits, ld, labels, label_stride,
                                                                label_offset, T_len, (__nv_bfloat16*)dlogits, ld_d, row_loss,
-                                                               stats, V, inv_batch);
+                                                               stats, V, inv_batch, t_valid);
   BX_POST_LAUNCH();
   return 0;
 }

@@ -55,7 +55,7 @@ int residual_ln_bwd(const void* g1, int g1_f32, const void* g2, const void* z, c
                     const unsigned long long* seed_dev = nullptr);
 int xent(const void* logits, int logits_f32, long long ld, const long long* labels, int label_stride, int label_offset,
          int T_len, void* dlogits, long long ld_d, float* row_loss, double* stats, long long rows, int V, float inv_batch,
-         cudaStream_t st);
+         cudaStream_t st, const int* t_valid = nullptr);   // device int (or NULL): positions t >= *t_valid are shape-bucketing filler: no accuracy counters
 int colsum_bf16(const void* X, long long ld, float* out, long long rows, int N, cudaStream_t st);
 int adam_step(float* p, float* m, float* v, const float* g, void* shadow, long long n, float alpha, float b1, float b2,
               float eps, cudaStream_t st, const float* alpha_dev = nullptr);

@@ -262,6 +262,7 @@ struct b200xf_model {
   int next_event = 0;
   int concurrency = 0;         // 0: everything on the caller's stream
   int fuse_ln = 1;             // LayerNorm in the out-projection / FFN dense1 GEMM epilogue (d_model 128 / 256 / 512)
+  const int* t_valid = nullptr;   // device int: target positions >= *t_valid are shape-bucketing filler (NULL: none)
   int dec_B = 0, dec_S = 0, dec_len = 0;   // incremental decoding (b200xf_model_decode_begin / _step): batch, source length, tokens cached
   // state carried between the parts of a layer-granular backward (b200xf_model_backward_part): the gradient of the stream
   // tensor entering the next layer (see StreamGrad) and which of the two dz buffers is written next
@@ -866,7 +867,8 @@ int b200xf_model_loss(b200xf_model* m, const int64_t* tar, int tar_stride, int l
   BX_REQUIRE(m->B > 0 && m->logits_valid, "loss: needs a preceding forward with logits_out == NULL (and no loss-with-grad since)");
   const int64_t Mt = (int64_t)m->B * m->T;
   RC(bx::xent(m->w.logits, 0, m->lo.Vp, reinterpret_cast<const long long*>(tar), tar_stride, label_offset, m->T,
-              with_grad ? m->w.logits : nullptr, m->lo.Vp, nullptr, stats, Mt, m->lo.Vtgt, inv_batch, reinterpret_cast<cudaStream_t>(stream)));
+              with_grad ? m->w.logits : nullptr, m->lo.Vp, nullptr, stats, Mt, m->lo.Vtgt, inv_batch, reinterpret_cast<cudaStream_t>(stream),
+              m->t_valid));
   m->have_loss_grad = with_grad != 0;
   if (with_grad) m->logits_valid = false;
   return 0;
@@ -911,6 +913,8 @@ int b200xf_model_grad_range_part(const b200xf_model_config* cfg, int part, int l
   *begin = r.first; *end = r.second;
   return 0;
 }
+
+void b200xf_model_set_valid_target_len_ptr(b200xf_model* m, const int32_t* t_valid_dev) { m->t_valid = t_valid_dev; }
 
 int b200xf_model_decode_begin(b200xf_model* m, const int64_t* inp, int B, int S, b200xf_stream_t stream) {
   BX_REQUIRE(B >= 1 && B <= m->cfg.max_batch && S >= 1 && S <= m->cfg.max_src_len, "decode_begin: shape (B %d, S %d) exceeds the workspace", B, S);

@@ -115,9 +115,9 @@ class DistributedTrain(Train):
     ``per_replica_batch_size`` is accepted and -- exactly like the reference -- not used by the step."""
 
     def __init__(self, epochs, enable_function, transformer, src_tokenizer, tgt_tokenizer, batch_size, per_replica_batch_size,
-                 train_log_dir, test_log_dir, max_ckpt_keep, ckpt_path, d_model, warmup_steps=60000, seed=0):
+                 train_log_dir, test_log_dir, max_ckpt_keep, ckpt_path, d_model, warmup_steps=60000, seed=0, shape_bucket=0):
         Train.__init__(self, epochs, enable_function, transformer, src_tokenizer, tgt_tokenizer, batch_size, train_log_dir,
-                       test_log_dir, max_ckpt_keep, ckpt_path, d_model, warmup_steps=warmup_steps, seed=seed)
+                       test_log_dir, max_ckpt_keep, ckpt_path, d_model, warmup_steps=warmup_steps, seed=seed, shape_bucket=shape_bucket)
         self.per_replica_batch_size = per_replica_batch_size
         # one gradient bucket per backward part: 2L + 3 all-reduces per step, each issued the moment its range is final, so that
         # only the LAST one (the encoder embedding, 4 x V x d bytes) can still be in flight when the backward ends -- and Adam on
@@ -333,7 +333,7 @@ def main(epochs, enable_function, buffer_size, batch_size, d_model, dff, num_hea
         if rank == 0:
             print('create training object')
         train_obj = DistributedTrain(epochs, enable_function, transformer, src_tokenizer, tgt_tokenizer, batch_size, local_batch_size,
-                                     train_log_dir, test_log_dir, max_ckpt_keep, ckpt_path, d_model)
+                                     train_log_dir, test_log_dir, max_ckpt_keep, ckpt_path, d_model, shape_bucket=8)
         if rank == 0:
             print('Training.....')
         train_obj.training_loop(train_dataset, test_dataset, strategy)

@@ -114,7 +114,7 @@ class Train(object):
     """
 
     def __init__(self, epochs, enable_function, transformer, src_tokenizer, tgt_tokenizer, batch_size, train_log_dir,
-                 test_log_dir, max_ckpt_keep, ckpt_path, d_model, warmup_steps=60000, seed=0, cuda_graph=None):
+                 test_log_dir, max_ckpt_keep, ckpt_path, d_model, warmup_steps=60000, seed=0, cuda_graph=None, shape_bucket=0):
         self.epochs = epochs
         self.enable_function = enable_function
         self.transformer = transformer
@@ -144,6 +144,11 @@ class Train(object):
         self.cuda_graph = bool(cuda_graph) and self.optimizer.schedule_args() is not None
         # one captured graph per batch shape, least-recently-used eviction, ONE memory pool shared by all captures
         # (replays never overlap), so ragged text batches cannot grow the cache without bound
+        # shape bucketing for ragged text batches (padded_batch pads every batch to ITS longest sentence, utils.py:154-159): source and
+        # target lengths are rounded up to a multiple of ``shape_bucket`` with pad id 0, so that a handful of captured graphs serve a
+        # whole epoch; the real target length goes to the device for the accuracy counters (include/b200xf.h)
+        self.shape_bucket = int(shape_bucket)
+        self._tvalid_dev = torch.zeros(1, dtype=torch.int32, device=dev)
         self._graphs = collections.OrderedDict()
         self._graph_cache_size = int(os.environ.get("B200XF_GRAPH_CACHE", "32"))
         self._graph_pool = None
@@ -224,6 +229,7 @@ class Train(object):
         tr = self.transformer
         src = src.to(tr.device, torch.int64, non_blocking=True).contiguous()
         tar = tar.to(tr.device, torch.int64, non_blocking=True).contiguous()
+        src, tar = self._bucket(src, tar)
         self.last_lr = self.optimizer.current_lr()
         key = (tuple(src.shape), tuple(tar.shape))
         if self._graph_handle_generation != getattr(tr, "_handle_generation", 0):
@@ -244,6 +250,28 @@ class Train(object):
             g_tar.copy_(tar, non_blocking=True)
             graph.replay()
         self.optimizer.iterations += 1
+
+    def _bucket(self, src, tar):
+        """pad (B,S) / (B,T+1) up to the bucket lengths with pad id 0 and publish the real target length on the device"""
+        k = self.shape_bucket
+        tr = self.transformer
+        if k <= 1:
+            if tr._tvalid_set:
+                L.load().b200xf_model_set_valid_target_len_ptr(tr._handle, None)
+                tr._tvalid_set = False
+            return src, tar
+        S, T = src.shape[1], tar.shape[1] - 1
+        S2, T2 = min(-(-S // k) * k, max(S, tr._pos_rows)), min(-(-T // k) * k, max(T, tr._pos_rows))
+        if S2 > S:
+            src = torch.nn.functional.pad(src, (0, S2 - S))
+        if T2 > T:
+            tar = torch.nn.functional.pad(tar, (0, T2 - T))
+        tr._ensure_workspace(src.shape[0], S2, T2)     # (a re-created handle forgets the pointer: grow the workspace first)
+        self._tvalid_dev.fill_(T)
+        if not tr._tvalid_set:
+            L.load().b200xf_model_set_valid_target_len_ptr(tr._handle, L.ptr(self._tvalid_dev))
+            tr._tvalid_set = True
+        return src, tar
 
     def _capture(self, key, src, tar):
         tr = self.transformer
@@ -272,6 +300,8 @@ class Train(object):
         """One test step (train.py:144-156)."""
         src, tar = inputs
         with torch.cuda.device(self.transformer.device):
+            if self.transformer._tvalid_set:                   # (shape bucketing active: this batch is not padded, every position counts)
+                self._tvalid_dev.fill_(tar.shape[1] - 1)
             self._step_core(src, tar, False)
         self.test_loss(self._stats[0] * (1.0 / self.batch_size))
         self.test_accuracy.add_(self._stats[1], self._stats[2])
@@ -368,7 +398,8 @@ class Train(object):
             self.test_accuracy.reset_states()
             start = time.time()
             counter = 0
-            for src, tgt in train_dataset:
+            from .utils import prefetch_to_device
+            for src, tgt in prefetch_to_device(train_dataset, self.transformer.device):       # next batch's H2D copy under this step
                 self.train_step((src, tgt))
                 counter += 1
                 if (counter + 1) % 100 == 0:
@@ -414,7 +445,7 @@ def main(epochs, enable_function, buffer_size, batch_size, d_model, dff, num_hea
                               pos_rows=max(longest, 512), max_batch=batch_size, max_src_len=longest, max_tgt_len=longest)
     print('create training object')
     train_obj = Train(epochs, enable_function, transformer, src_tokenizer, tgt_tokenizer, batch_size, train_log_dir, test_log_dir,
-                      max_ckpt_keep, ckpt_path, d_model)
+                      max_ckpt_keep, ckpt_path, d_model, shape_bucket=8)
     train_obj.training_loop(train_dataset, test_dataset)
     train_obj.load_ckpt()
     input_sentence = 'he go to school'

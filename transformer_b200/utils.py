@@ -166,6 +166,37 @@ def _padded_batches(examples, batch_size):
     return out
 
 
+def prefetch_to_device(batches, device):
+    """tf.data's prefetch (utils.py:157-160) on this side of the boundary: yields device-resident (src, tgt) pairs, with the NEXT
+    batch's host -> device copy (from pinned memory, on its own stream) in flight while the current one trains."""
+    dev = torch.device(device)
+    if dev.type != "cuda":
+        yield from batches
+        return
+    copy_stream = torch.cuda.Stream(device=dev)
+
+    def stage(b):
+        with torch.cuda.stream(copy_stream):
+            out = tuple(t if t.is_cuda else (t if t.is_pinned() else t.pin_memory()).to(dev, non_blocking=True) for t in b)
+        ev = torch.cuda.Event()
+        ev.record(copy_stream)
+        return out, ev
+    it = iter(batches)
+    nxt = None
+    for b in it:
+        cur, nxt = nxt, stage(b)
+        if cur is not None:
+            torch.cuda.current_stream(dev).wait_event(cur[1])
+            for t in cur[0]:
+                t.record_stream(torch.cuda.current_stream(dev))
+            yield cur[0]
+    if nxt is not None:
+        torch.cuda.current_stream(dev).wait_event(nxt[1])
+        for t in nxt[0]:
+            t.record_stream(torch.cuda.current_stream(dev))
+        yield nxt[0]
+
+
 def make_synthetic_corpus(dataset_path, lines=10000, words=6000, seed=7):
     """The reference trains on data/src-train.txt -> data/tgt-train.txt (10000 sentence pairs shipped with its repo).  Those
     files are not part of THIS repo; when ``dataset_path`` has no train files, a synthetic parallel corpus of the same size
