@@ -16,6 +16,10 @@
 
 #include "common.cuh"
 
+#ifndef BX_FWD_SINGLE_PASS
+#define BX_FWD_SINGLE_PASS 0
+#endif
+
 namespace bx {
 
 // optional debug timeline: clock64 stamps written by the LAST CTA of the grid (last wave: warm instruction cache; with a
@@ -302,24 +306,98 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       mbar_wait(s_full, j & 1);
       tcgen05_after_thread_sync();
       if (tl) tl_stamp(8 + j * 8 + 1);
+#if BX_FWD_SINGLE_PASS
+      // ---- ONE round trip to tensor memory per tile: the whole 128-column row of this thread is loaded with a single
+      //      tcgen05.wait::ld (a load + wait round trip costs ~250 cycles; the two-pass variant below pays eight per tile) and S is
+      //      handed back at once, so S(j+1) runs under this tile's softmax.  The row is processed IN PLACE (raw score -> masked
+      //      score -> probability) and leaves in groups of 8 (pack, one 16-byte shared-memory store) to stay under 168 registers.
+      uint32_t r[4][32];
+#pragma unroll
+      for (int c = 0; c < 4; ++c) tmem_ld_x32(tS + lane_sel + c * 32, r[c]);
+      tmem_ld_wait();
+      tcgen05_before_thread_sync();
+      mbar_arrive(s_free);
+      float mx[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+      uint32_t hidden_bits = 0;
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        uint32_t bm, bo;
+        mask_words(c, bm, bo);
+        const bool touched = kMaskF || __any_sync(0xffffffffu, (bm | bo) != 0u);
+        if (!kMaskF && __all_sync(0xffffffffu, bm == 0xffffffffu)) hidden_bits |= 1u << c;
+        if (touched) apply_mask(c, bm, bo, r[c]);
+#pragma unroll
+        for (int e = 0; e < 32; ++e) mx[e & 3] = fmaxf(mx[e & 3], __uint_as_float(r[c][e]));
+      }
+      const float m_tile = fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3])) * sl2;     // sl2 > 0
+      if (tl) tl_stamp(8 + j * 8 + 2);
+      const bool need = (j > 0) && (m_tile - m_used > 8.f);
+      if (j == 0) m_used = m_tile;
+      if (__any_sync(0xffffffffu, need)) {
+        const float alpha = need ? fast_exp2(m_used - m_tile) : 1.f;
+        if (need) { m_used = m_tile; l_run *= alpha; }
+        mbar_wait(o_full, (j - 1) & 1);                // P.V of the previous tile has landed in TMEM
+        tcgen05_after_thread_sync();
+#pragma unroll 1
+        for (int c = 0; c < DK / 32; ++c) {
+          uint32_t ro[32];
+          tmem_ld_x32(tO + lane_sel + c * 32, ro);
+          tmem_ld_wait();
+#pragma unroll
+          for (int e = 0; e < 32; ++e) ro[e] = __float_as_uint(__uint_as_float(ro[e]) * alpha);
+          tmem_st_x32(tO + lane_sel + c * 32, ro);
+        }
+        tmem_st_wait();
+      }
+      const bool real_max = __all_sync(0xffffffffu, m_used > -1e8f);
+      if (j > 0) { mbar_wait(o_full, (j - 1) & 1); tcgen05_after_thread_sync(); }
+      float rs4[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        const uint32_t panel = sPs + (c >> 1) * 16384;
+        const bool zero = ((hidden_bits >> c) & 1u) && real_max;
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          uint32_t pk[4];
+#pragma unroll
+          for (int h2 = 0; h2 < 4; ++h2) {
+            const int e = g * 8 + h2 * 2;
+            const float p0 = zero ? 0.f : fast_exp2(__uint_as_float(r[c][e]) * sl2 - m_used);
+            const float p1 = zero ? 0.f : fast_exp2(__uint_as_float(r[c][e + 1]) * sl2 - m_used);
+            rs4[h2] += p0 + p1;
+            pk[h2] = pack_bf16x2(p0, p1);
+          }
+          st_shared_v4(panel + swz128_off(row, (c & 1) * 4 + g), pk[0], pk[1], pk[2], pk[3]);
+        }
+      }
+#else
       // ---- pass 1 over tensor memory: row maximum of the masked scores.  The row is NOT kept in registers (a 128-value row
       //      + packed P + masks needed more than the 168 registers two resident CTAs leave a thread: ~80 local-memory
       //      round trips per tile, and a 30 KB unrolled loop body); both passes are ROLLED loops over 32-key chunks that re-read S
       //      from tensor memory (16 KB per warp and pass, ~100 cycles of latency per chunk, hidden by the other resident CTA).
       float mx[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
-      uint32_t hidden_bits = 0;                      // bit c: chunk c is hidden for every row of this warp
-#pragma unroll 1
+      // the mask words of the tile are classified ONCE (warp-uniform bit sets): the mask words cost more than the 16 FMNMX3 of a
+      // clean chunk (removing them was worth 11 % of the kernel, profiles/r02_attention_fwd_ablation.txt), so clean chunks of both
+      // passes never recompute them
+      uint32_t hidden_bits = 0, touched_bits = 0;    // bit c: chunk c is hidden for every row of this warp / needs the mask applied
+#pragma unroll
       for (int c = 0; c < 4; ++c) {
         uint32_t bm, bo;
         mask_words(c, bm, bo);
-        const bool touched = kMaskF || __any_sync(0xffffffffu, (bm | bo) != 0u);
-        const bool hid = !kMaskF && __all_sync(0xffffffffu, bm == 0xffffffffu);
-        hidden_bits |= (hid ? 1u : 0u) << c;
-        if (hid) { mx[0] = fmaxf(mx[0], kMaskRaw); continue; }     // every existing key of the chunk holds the masked value
+        if (kMaskF || __any_sync(0xffffffffu, (bm | bo) != 0u)) touched_bits |= 1u << c;
+        if (!kMaskF && __all_sync(0xffffffffu, bm == 0xffffffffu)) hidden_bits |= 1u << c;
+      }
+#pragma unroll 1
+      for (int c = 0; c < 4; ++c) {
+        if ((hidden_bits >> c) & 1u) { mx[0] = fmaxf(mx[0], kMaskRaw); continue; }     // every existing key of the chunk holds the masked value
         uint32_t rc[32];
         tmem_ld_x32(tS + lane_sel + c * 32, rc);
         tmem_ld_wait();
-        if (touched) apply_mask(c, bm, bo, rc);
+        if ((touched_bits >> c) & 1u) {
+          uint32_t bm, bo;
+          mask_words(c, bm, bo);
+          apply_mask(c, bm, bo, rc);
+        }
 #pragma unroll
         for (int e = 0; e < 32; ++e) mx[e & 3] = fmaxf(mx[e & 3], __uint_as_float(rc[e]));
       }
@@ -361,16 +439,17 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
           for (int g = 0; g < 16; ++g) pk[g] = 0u;
         } else {
           uint32_t rc[32];
-          uint32_t bm, bo;
-          mask_words(c, bm, bo);
           if (hid) {
 #pragma unroll
             for (int e = 0; e < 32; ++e) rc[e] = __float_as_uint(kMaskRaw);
-            if (__any_sync(0xffffffffu, bo != 0u)) apply_mask(c, bm, bo, rc);
           } else {
             tmem_ld_x32(tS + lane_sel + c * 32, rc);
             tmem_ld_wait();
-            if (kMaskF || __any_sync(0xffffffffu, (bm | bo) != 0u)) apply_mask(c, bm, bo, rc);
+          }
+          if ((touched_bits >> c) & 1u) {
+            uint32_t bm, bo;
+            mask_words(c, bm, bo);
+            apply_mask(c, bm, bo, rc);
           }
           float p[32];
 #pragma unroll
@@ -387,6 +466,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         for (int g = 0; g < 4; ++g)
           st_shared_v4(panel + swz128_off(row, (c & 1) * 4 + g), pk[4 * g], pk[4 * g + 1], pk[4 * g + 2], pk[4 * g + 3]);
       }
+#endif
       l_run += (rs4[0] + rs4[1]) + (rs4[2] + rs4[3]);
       if (tl) tl_stamp(8 + j * 8 + 3);
       fence_proxy_async_smem();
