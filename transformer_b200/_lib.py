@@ -10,7 +10,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libb200xf.so")
+LIB_PATH = os.environ.get("B200XF_LIB_PATH") or os.path.join(_HERE, "libb200xf.so")      # (override: A/B builds in one GPU run)
 
 _lib = None
 
