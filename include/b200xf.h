@@ -61,6 +61,12 @@ int b200xf_gemm_bias_dropout_residual_ln(const void* A, int64_t lda, const void*
 int b200xf_gemm_bf16(const void* A, int64_t lda, int a_major, const void* B, int64_t ldb, int b_major, void* D,
                      int64_t ldd, int d_is_f32, const float* bias, const void* aux, int64_t ld_aux, int flags,
                      int splits, int64_t M, int64_t N, int64_t K, b200xf_stream_t stream);
+/* Same product with a bf16 D, plus  colsum[n] += sum_m D[m,n]  (fp32 atomics, D as rounded to bf16) taken from the epilogue's staging tile.
+ * This is how the backward gets a Dense bias gradient (reverse mode of `+ b`, point_ffn.py:5 under train.py:137) without re-reading
+ * dy from HBM: the dgrad GEMM that PRODUCES dy for the layer below also sums its columns.  colsum is NOT zeroed here.           */
+int b200xf_gemm_bf16_colsum(const void* A, int64_t lda, int a_major, const void* B, int64_t ldb, int b_major, void* D,
+                            int64_t ldd, const float* bias, const void* aux, int64_t ld_aux, int flags, int64_t M, int64_t N,
+                            int64_t K, float* colsum, b200xf_stream_t stream);
 
 /* ---- scaled_dot_product_attention + split_heads/merge (Attention.py:3-34, 52-57, 74-76).
  *      Q/K/V/O: bf16 token-major [B*S, ld], head h = columns [h*dk, (h+1)*dk).  lse: fp32 [B,H,Sq].

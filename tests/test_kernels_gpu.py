@@ -522,6 +522,27 @@ def test_gemm_bias_dropout_residual_layernorm_fused(M, N, K, rate):
     assert (out.float() - out2.float()).abs().max().item() < 6e-2
 
 
+@pytest.mark.parametrize("M,N,K,flags", [(1000, 2048, 512, 16), (4096 + 40, 320, 256, 0), (130, 64, 128, 0)])
+def test_gemm_output_column_sums(M, N, K, flags):
+    """The dgrad GEMM that produces dy for the layer below also accumulates colsum(dy) = that layer's bias gradient from its
+    staging tile (ragged M / N tiles, the ReLU bit-mask epilogue of the FFN backward): must equal the column sums of the bf16
+    D it wrote, added to what the buffer held."""
+    A = rnd((M, K), 1.0, 1); B = rnd((N, K), K ** -0.5, 2)          # dgrad form: both operands K-major
+    D = torch.full((M, N), float("nan"), dtype=torch.bfloat16, device=dev())
+    cs = torch.full((N,), 3.0, device=dev())
+    aux, ld_aux = None, 0
+    if flags & 16:
+        bits = torch.randint(-2 ** 62, 2 ** 62, (M, N // 64), dtype=torch.int64, device=dev())
+        aux, ld_aux = L.ptr(bits), N // 64
+    L.call("b200xf_gemm_bf16_colsum", L.ptr(A), K, 0, L.ptr(B), K, 0, L.ptr(D), N, None, aux, ld_aux, flags, M, N, K, L.ptr(cs), sp())
+    D2 = torch.empty_like(D)
+    L.call("b200xf_gemm_bf16", L.ptr(A), K, 0, L.ptr(B), K, 0, L.ptr(D2), N, 0, None, aux, ld_aux, flags, 1, M, N, K, sp())
+    torch.cuda.synchronize()
+    assert torch.equal(D, D2)                                        # the product itself is untouched
+    ref = 3.0 + D.double().sum(0)
+    assert (cs.double() - ref).abs().max().item() < 1e-3 * max(1.0, ref.abs().max().item())
+
+
 def test_gemm_chunked_schedule_matches_persistent():
     """b200xf_gemm_set_chunks_per_unit: hardware-scheduled chunks of tiles (data-parallel backward, NCCL sharing the SMs) must
     produce the persistent grid's results -- bit-identical without split-K, to fp32 reduction order with it."""

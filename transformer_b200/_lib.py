@@ -36,6 +36,7 @@ _U32 = C.c_uint32
 # name -> argtypes (restype is int unless listed in _RESTYPES)
 _SIGS = {
     "b200xf_gemm_bf16": [_P, _I64, _I, _P, _I64, _I, _P, _I64, _I, _P, _P, _I64, _I, _I, _I64, _I64, _I64, _P],
+    "b200xf_gemm_bf16_colsum": [_P, _I64, _I, _P, _I64, _I, _P, _I64, _P, _P, _I64, _I, _I64, _I64, _I64, _P, _P],
     "b200xf_gemm_bias_dropout_residual_ln": [_P, _I64, _P, _I64, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I64, _I64, _I64, _F, _F, _U64, _U32, _P],
     "b200xf_attn_fwd": [_P, _I64, _P, _I64, _P, _I64, _P, _I64, _P, _P, _I, _P, _I64, _I64, _I, _I, _I, _I, _I, _P],
     "b200xf_attn_bwd": [_P, _I64, _P, _I64, _P, _I64, _P, _I64, _P, _P, _P, _I64, _I, _P, _I64, _P, _I64, _P, _I, _P, _I64,

@@ -23,6 +23,11 @@ int b200xf_gemm_bf16(const void* A, int64_t lda, int a_major, const void* B, int
   return bx::gemm_bf16(A, lda, a_major, B, ldb, b_major, D, ldd, d_is_f32, bias, aux, ld_aux, flags, splits, M, N, K,
                        ST(stream));
 }
+int b200xf_gemm_bf16_colsum(const void* A, int64_t lda, int a_major, const void* B, int64_t ldb, int b_major, void* D,
+                            int64_t ldd, const float* bias, const void* aux, int64_t ld_aux, int flags, int64_t M, int64_t N,
+                            int64_t K, float* colsum, b200xf_stream_t stream) {
+  return bx::gemm_bf16(A, lda, a_major, B, ldb, b_major, D, ldd, 0, bias, aux, ld_aux, flags, 1, M, N, K, ST(stream), colsum);
+}
 int b200xf_gemm_bias_dropout_residual_ln(const void* A, int64_t lda, const void* W, int64_t ldw, const float* bias, const void* xres_bf16,
                                          const float* gamma, const float* beta, void* z_bf16, void* out_bf16, float* mean, float* rstd,
                                          void* keep_bits, int64_t M, int64_t N, int64_t K, float eps, float rate, uint64_t seed, uint32_t site,

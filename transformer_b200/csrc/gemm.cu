@@ -45,7 +45,7 @@ template <int MA, int MB, int BN, bool kOutF32, int CG>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
             const __grid_constant__ CUtensorMap tmD, int M, int N, int K, int splits,
-            const float* __restrict__ bias, void* aux_v, long long ld_aux, int flags, int chunk) {
+            const float* __restrict__ bias, void* aux_v, long long ld_aux, int flags, int chunk, float* __restrict__ colsum) {
   const __nv_bfloat16* aux = reinterpret_cast<const __nv_bfloat16*>(aux_v);
   using Cfg = GemmCfg<BN, CG>;
   constexpr int kStages = Cfg::kStages;
@@ -294,6 +294,26 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           else tma_store_2d(&tmD, smem + Cfg::OFF_D + buf * Cfg::D_BYTES, nc, m0);
           tma_store_commit();
         }
+        if (!kOutF32 && colsum != nullptr) {
+          // colsum[n] += sum over rows of the bf16 tile just staged (the bias gradient of the layer whose dy this GEMM produces):
+          // warp q sums its 32 rows, lane = one bf16 pair of the 128-byte row (conflict-free), one fp32 atomic per column and warp.
+          // The box is next written two chunks from now, behind the next chunk's barrier.
+          const int rows_here = M - m0;
+          float a0 = 0.f, a1 = 0.f;
+#pragma unroll 8
+          for (uint32_t rr = 0; rr < 32u; ++rr) {
+            const uint32_t r2 = q * 32u + rr;
+            if ((int)r2 < rows_here) {
+              uint32_t wv;
+              asm volatile("ld.shared.b32 %0, [%1];" : "=r"(wv) : "r"(stg + swz128_off(r2, lane >> 2) + (lane & 3u) * 4u));
+              const float2 f = unpack_bf16x2(wv);
+              a0 += f.x; a1 += f.y;
+            }
+          }
+          const int col = nc + 2 * (int)lane;
+          if (col < N) atomicAdd(colsum + col, a0);
+          if (col + 1 < N) atomicAdd(colsum + col + 1, a1);
+        }
         buf ^= 1u;
       }
       tcgen05_before_thread_sync();
@@ -328,7 +348,7 @@ static int auto_splits(long long tiles, long long kblocks, int groups) {
 template <int MA, int MB, int BN, bool kOutF32, int CG>
 static int launch_gemm(const void* A, long long lda, const void* B, long long ldb, void* D, long long ldd,
                        const float* bias, const void* aux, long long ld_aux, int flags, int splits, long long M,
-                       long long N, long long K, cudaStream_t stream) {
+                       long long N, long long K, cudaStream_t stream, float* colsum) {
   using Cfg = GemmCfg<BN, CG>;
   CUtensorMap tmA, tmB, tmD;
   int rc;
@@ -394,7 +414,7 @@ static int launch_gemm(const void* A, long long lda, const void* B, long long ld
   cfg.gridDim = dim3(grid);
   void* pb = prof_on() ? prof_begin(stream) : nullptr;
   BX_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, tmA, tmB, tmD, (int)M, (int)N, (int)K, splits, bias, const_cast<void*>(aux), ld_aux,
-                                   flags, chunk));
+                                   flags, chunk, colsum));
   if (pb) prof_end(pb, prof_gemm_cat(), 2.0 * (double)M * (double)N * (double)K, stream);
   BX_POST_LAUNCH();
   return 0;
@@ -406,7 +426,8 @@ void gemm_set_chunks_per_unit(int n) { g_chunks_per_unit = n < 0 ? 0 : n; }
 
 int gemm_bf16(const void* A, long long lda, int a_major, const void* B, long long ldb, int b_major, void* D,
               long long ldd, int d_is_f32, const float* bias, const void* aux, long long ld_aux, int flags,
-              int splits, long long M, long long N, long long K, cudaStream_t stream) {
+              int splits, long long M, long long N, long long K, cudaStream_t stream, float* colsum) {
+  BX_REQUIRE(colsum == nullptr || (!d_is_f32 && splits <= 1), "gemm: column sums come from a bf16 output tile, no split-K");
   BX_REQUIRE(M > 0 && N > 0 && K > 0, "gemm: empty problem %lld x %lld x %lld", M, N, K);
   BX_REQUIRE(M < (1ll << 31) && N < (1ll << 31) && K < (1ll << 31), "gemm: dimension too large");
   BX_REQUIRE(splits <= 1 || ((flags & GEMM_FLAG_ACCUM) && d_is_f32), "gemm: split-K needs fp32 D with ACCUM");
@@ -422,7 +443,7 @@ int gemm_bf16(const void* A, long long lda, int a_major, const void* B, long lon
   const bool wide = N > 128;
   const bool pair = g_force_cg ? g_force_cg == 2 : (M > 128 && wide);   // CTA pairs need >= 2 row tiles; 256-wide N tile only
 #define BX_GEMM_GO(ma, mb, bn, f32, cg) \
-  return launch_gemm<ma, mb, bn, f32, cg>(A, lda, B, ldb, D, ldd, bias, aux, ld_aux, flags, splits, M, N, K, stream)
+  return launch_gemm<ma, mb, bn, f32, cg>(A, lda, B, ldb, D, ldd, bias, aux, ld_aux, flags, splits, M, N, K, stream, colsum)
 #define BX_GEMM_CASE(ma, mb)                                              \
   if (a_major == ma && b_major == mb) {                                   \
     if (wide && pair) { if (d_is_f32) BX_GEMM_GO(ma, mb, 256, true, 2); else BX_GEMM_GO(ma, mb, 256, false, 2); } \

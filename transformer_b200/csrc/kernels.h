@@ -7,7 +7,7 @@ namespace bx {
 
 int gemm_bf16(const void* A, long long lda, int a_major, const void* B, long long ldb, int b_major, void* D,
               long long ldd, int d_is_f32, const float* bias, const void* aux, long long ld_aux, int flags,
-              int splits, long long M, long long N, long long K, cudaStream_t stream);
+              int splits, long long M, long long N, long long K, cudaStream_t stream, float* colsum = nullptr);
 
 // K3/K4 fused: z = xres + dropout(A.W + bias); out = LayerNorm(z) * gamma + beta, in the GEMM epilogue (gemm_ln.cu); N = 128 / 256 / 512
 bool gemm_ln_supported(long long M, long long N, long long K);

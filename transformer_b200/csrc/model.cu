@@ -296,11 +296,12 @@ int linear_fwd(const bf16* x, int64_t ldx, const bf16* W, int64_t ldw, const flo
 // dx[M,K] (+)= dy[M,N] . W^T          (W [K,N] row-major is exactly the K-major B operand of this product)
 int linear_dgrad(const bf16* dy, int64_t ld_dy, const bf16* W, int64_t ldw, void* dx, int64_t ld_dx, bool dx_f32, bool accum,
                  const bf16* relu_aux, int64_t ld_aux, int64_t Mr, int64_t N, int64_t K, cudaStream_t st,
-                 const uint64_t* relu_bits = nullptr) {
+                 const uint64_t* relu_bits = nullptr, float* dx_colsum = nullptr) {
+  // dx_colsum: += column sums of the (bf16) dx this call writes = the bias gradient of the layer below, from the epilogue's staging tile
   if (relu_bits != nullptr && !dx_f32 && K % 64 == 0)     // ReLU gate from the compact mask the forward epilogue stored
-    return bx::gemm_bf16(dy, ld_dy, 0, W, ldw, 0, dx, ld_dx, 0, nullptr, relu_bits, K / 64, (accum ? 2 : 0) | 16, 1, Mr, K, N, st);
+    return bx::gemm_bf16(dy, ld_dy, 0, W, ldw, 0, dx, ld_dx, 0, nullptr, relu_bits, K / 64, (accum ? 2 : 0) | 16, 1, Mr, K, N, st, dx_colsum);
   const int flags = (accum ? 2 : 0) | (relu_aux ? 4 : 0);
-  return bx::gemm_bf16(dy, ld_dy, 0, W, ldw, 0, dx, ld_dx, dx_f32 ? 1 : 0, nullptr, relu_aux, ld_aux, flags, 1, Mr, K, N, st);
+  return bx::gemm_bf16(dy, ld_dy, 0, W, ldw, 0, dx, ld_dx, dx_f32 ? 1 : 0, nullptr, relu_aux, ld_aux, flags, 1, Mr, K, N, st, dx_colsum);
 }
 // dW[K,N] += x[M,K]^T . dy[M,N] ; db[N] += colsum(dy)     (split-K over the token dimension, TMA reduce-add)
 int linear_wgrad(const bf16* x, int64_t ldx, const bf16* dy, int64_t ld_dy, float* dW, int64_t ldw, float* db, int64_t Mr,
@@ -542,8 +543,9 @@ struct BwdCtx {
     dy.read_by_side(dyv, par.mark());
     bf16* dhb = nullptr;
     RC(dh.acquire(par, &dhb));
-    RC(linear_dgrad(dyv, d, m->Sh + p.W2, d, dhb, f, false, false, h, f, rows, d, f, st(), hbits));         // dh = (dy . W2^T) o [h > 0]
-    RC(wgrad_side(x16, d, dhb, f, p.W1, f, p.b1, rows, f, d));
+    static const bool fuse_db = [] { const char* e = getenv("B200XF_FUSE_COLSUM"); return !(e && e[0] == '0'); }();
+    RC(linear_dgrad(dyv, d, m->Sh + p.W2, d, dhb, f, false, false, h, f, rows, d, f, st(), hbits, fuse_db ? m->G + p.b1 : nullptr));   // dh = (dy . W2^T) o [h > 0]; db1 += colsum(dh)
+    RC(wgrad_side(x16, d, dhb, f, p.W1, f, fuse_db ? -1 : p.b1, rows, f, d));                  // db1: from the GEMM above
     dh.read_by_side(dhb, par.mark());
     RC(linear_dgrad(dhb, f, m->Sh + p.W1, f, w.gD, d, false, false, nullptr, 0, rows, f, d, st()));
     return 0;
