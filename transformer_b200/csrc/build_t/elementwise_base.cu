@@ -1,8 +1,6 @@
 // HBM-bound kernels of the training step: embedding (+pos-enc, dropout), dropout+residual+LayerNorm fwd/bwd,
 // softmax-cross-entropy (+ its gradient, accuracy counters), column sums (bias grads), fused Adam (+bf16 shadow),
 // casts and masks.  All vectorised 16-byte accesses, fp32 math.  Reference call sites are cited per kernel.
-#include <mutex>
-
 #include "common.cuh"
 
 namespace bx {
@@ -191,16 +189,6 @@ residual_ln_fwd_kernel(const __nv_bfloat16* __restrict__ y, const __nv_bfloat16*
   }
 }
 
-constexpr int kLnBwdStages = 3;
-__device__ __forceinline__ void cp_async16(uint32_t saddr, const void* gptr) {
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(saddr), "l"(gptr) : "memory");
-}
-__device__ __forceinline__ uint4 lds_u4(uint32_t saddr) {
-  uint4 v;
-  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(saddr));
-  return v;
-}
-
 // backward of out = LN(z), z = x + dropout(y); the incoming gradient is g1 (+ g2): the residual-path gradient and the
 // previous sublayer's dgrad output arrive as separate streams and are summed here in fp32 (no read-modify-write
 // accumulation in a GEMM epilogue, no intermediate bf16 rounding of the sum):
@@ -209,7 +197,7 @@ __device__ __forceinline__ uint4 lds_u4(uint32_t saddr) {
 //                                                                         NULL when rate == 0: it equals dz)
 //   dgamma += sum_rows dy*xhat ; dbeta += sum_rows dy ; dbias += sum_rows dy_sub   (block partials -> atomicAdd)
 // kRegen: the dropout mask is regenerated with Philox (no stored bits); that variant needs the registers of a 256-thread block
-template <int NV, bool kG1F32, bool kRegen, bool kFull>
+template <int NV, bool kG1F32, bool kRegen>
 __global__ void __launch_bounds__((NV <= 2 && !kRegen) ? 512 : 256, 1)
 residual_ln_bwd_kernel(const void* __restrict__ g1v, const __nv_bfloat16* __restrict__ g2, const __nv_bfloat16* __restrict__ z,
                        const float* __restrict__ mean_in, const float* __restrict__ rstd_in, const float* __restrict__ gamma,
@@ -217,106 +205,85 @@ residual_ln_bwd_kernel(const void* __restrict__ g1v, const __nv_bfloat16* __rest
                        float* __restrict__ dbeta, float* __restrict__ dbias, const uint8_t* __restrict__ keep_in, long long rows, int d, float rate,
                        unsigned long long seed, uint32_t site, const unsigned long long* __restrict__ seed_dev) {
   if (seed_dev != nullptr) seed = *seed_dev;
-  extern __shared__ float red[];  // the input ring; at the end the warps' dgamma / dbeta / dbias partials [nw][3][d]
+  extern __shared__ float red[];  // [3][d]: dgamma, dbeta, dbias partials of this block (shared-memory atomics)
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, nw = blockDim.x >> 5;
   const long long warp_global = (long long)blockIdx.x * nw + wib;
   const long long nwarps = (long long)gridDim.x * nw;
   const int d8 = d >> 3;
+  for (int c = threadIdx.x; c < 3 * d; c += blockDim.x) red[c] = 0.f;
+  __syncthreads();
   F8 ag[NV], ab[NV], ac[NV];      // gamma is re-read per row (L1-resident) instead of living in 8*NV registers
 #pragma unroll
   for (int i = 0; i < NV; ++i) {
 #pragma unroll
     for (int e = 0; e < 8; ++e) { ag[i].v[e] = 0.f; ab[i].v[e] = 0.f; ac[i].v[e] = 0.f; }
   }
-  // Input pipeline: every warp owns a ring of kLnBwdStages row slots in shared memory, filled by cp.async (16 bytes per lane and vector)
-  // two rows ahead of the one being reduced -- a lane reads back exactly the bytes it copied, so no barrier is involved.  With the
-  // prefetch in REGISTERS (one row ahead, 26 registers) a 512-thread block kept ~49 KB in flight per SM and the kernel ran at ~0.6 of
-  // the HBM copy rate; the ring holds 16 warps x 2 rows x 3 KB.
-  constexpr int G1B = kG1F32 ? 4 : 2;                       // bytes per element of g1
-  const int g1_bytes = d * G1B, slot_bytes = g1_bytes + 4 * d;     // g1 | g2 | z
-  uint8_t* const ring = reinterpret_cast<uint8_t*>(red) + (size_t)wib * kLnBwdStages * slot_bytes;
-  const uint32_t ring_s = smem_u32(ring);
-  auto issue = [&](long long r, int slot) {
-    if (r < rows) {
-      const uint32_t sbase = ring_s + slot * slot_bytes;
-#pragma unroll
-      for (int i = 0; i < NV; ++i) {
-        const int c8 = lane + 32 * i;
-        if (c8 < d8) {
-          const long long idx = r * d8 + c8;
-          if (kG1F32) {
-            cp_async16(sbase + c8 * 32, reinterpret_cast<const uint4*>(g1v) + 2 * idx);
-            cp_async16(sbase + c8 * 32 + 16, reinterpret_cast<const uint4*>(g1v) + 2 * idx + 1);
-          } else {
-            cp_async16(sbase + c8 * 16, reinterpret_cast<const uint4*>(g1v) + idx);
-          }
-          if (g2 != nullptr) cp_async16(sbase + g1_bytes + c8 * 16, reinterpret_cast<const uint4*>(g2) + idx);
-          cp_async16(sbase + g1_bytes + 2 * d + c8 * 16, reinterpret_cast<const uint4*>(z) + idx);
-        }
-      }
-    }
-    asm volatile("cp.async.commit_group;" ::: "memory");    // (an empty group past the last row keeps the wait count uniform)
-  };
-  const float inv_keep = 1.f / (1.f - rate);
+  // software pipeline: the NEXT row's gradient / z vectors are in flight while the current row is reduced and written
+  constexpr int G1V = kG1F32 ? 2 : 1;
+  uint4 n1[NV][G1V], n2[NV], nz[NV];
   uint32_t nkeep[NV], nk[NV];
+  const float inv_keep = 1.f / (1.f - rate);
   float nmean = 0.f, nrstd = 0.f;
-  auto fetch_small = [&](long long r) {                     // one row ahead in registers: keep byte(s), mean, rstd
+  auto fetch = [&](long long r) {
 #pragma unroll
     for (int i = 0; i < NV; ++i) {
       const int c8 = lane + 32 * i;
-      nkeep[i] = (!kRegen && keep_in != nullptr && c8 < d8) ? keep_in[r * d8 + c8] : 0u;
+      if (c8 < d8) {
+        const long long idx = r * d8 + c8;
+        if (kG1F32) {
+          n1[i][0] = reinterpret_cast<const uint4*>(g1v)[2 * idx];
+          n1[i][G1V - 1] = reinterpret_cast<const uint4*>(g1v)[2 * idx + 1];
+        } else {
+          n1[i][0] = reinterpret_cast<const uint4*>(g1v)[idx];
+        }
+        n2[i] = g2 != nullptr ? reinterpret_cast<const uint4*>(g2)[idx] : make_uint4(0, 0, 0, 0);
+        nz[i] = reinterpret_cast<const uint4*>(z)[idx];
+        nkeep[i] = (!kRegen && keep_in != nullptr) ? keep_in[idx] : 0u;
+      } else {
+#pragma unroll
+        for (int k = 0; k < G1V; ++k) n1[i][k] = make_uint4(0, 0, 0, 0);
+        n2[i] = make_uint4(0, 0, 0, 0); nz[i] = make_uint4(0, 0, 0, 0); nkeep[i] = 0u;
+      }
     }
     nmean = mean_in[r]; nrstd = rstd_in[r];
   };
-  issue(warp_global, 0);
-  issue(warp_global + nwarps, 1);
-  if (warp_global < rows) fetch_small(warp_global);
-  int slot = 0;
+  if (warp_global < rows) fetch(warp_global);
   for (long long r = warp_global; r < rows; r += nwarps) {
-    issue(r + 2 * nwarps, slot == 0 ? 2 : slot - 1);        // (the slot read in the previous iteration)
-    asm volatile("cp.async.wait_group 2;" ::: "memory");    // this row's group has landed
     F8 gd[NV], xh[NV];              // gamma * dy and xhat of this row
-    const float rstd = nrstd, nmr = -nmean * nrstd;
+    const float mean = nmean, rstd = nrstd;
     float s1 = 0.f, s2 = 0.f;
-    const uint32_t sbase = ring_s + slot * slot_bytes;
 #pragma unroll
     for (int i = 0; i < NV; ++i) {
-      const int c8 = lane + 32 * i;
-      const bool live = kFull || c8 < d8;      // kFull: d = 256 NV, every lane vector is inside the row (no per-element selects)
-      const int cg = live ? c8 : 0;
       F8 dy;
       if (kG1F32) {
-        const float4 lo = ld_shared_f4(sbase + cg * 32), hi = ld_shared_f4(sbase + cg * 32 + 16);
-        dy.v[0] = lo.x; dy.v[1] = lo.y; dy.v[2] = lo.z; dy.v[3] = lo.w; dy.v[4] = hi.x; dy.v[5] = hi.y; dy.v[6] = hi.z; dy.v[7] = hi.w;
+        dy.v[0] = __uint_as_float(n1[i][0].x); dy.v[1] = __uint_as_float(n1[i][0].y);
+        dy.v[2] = __uint_as_float(n1[i][0].z); dy.v[3] = __uint_as_float(n1[i][0].w);
+        dy.v[4] = __uint_as_float(n1[i][G1V - 1].x); dy.v[5] = __uint_as_float(n1[i][G1V - 1].y);
+        dy.v[6] = __uint_as_float(n1[i][G1V - 1].z); dy.v[7] = __uint_as_float(n1[i][G1V - 1].w);
       } else {
-        dy = unpack8(lds_u4(sbase + cg * 16));
+        dy = unpack8(n1[i][0]);
       }
-      F8 b;
-      if (g2 != nullptr) {
-        b = unpack8(lds_u4(sbase + g1_bytes + cg * 16));
-      } else {
-#pragma unroll
-        for (int e = 0; e < 8; ++e) b.v[e] = 0.f;
-      }
-      const F8 zv = unpack8(lds_u4(sbase + g1_bytes + 2 * d + cg * 16));
+      const F8 b = unpack8(n2[i]);
+      const F8 zv = unpack8(nz[i]);
+      const int c8 = lane + 32 * i;
+      const bool live = c8 < d8;
+      const int cg = live ? c8 : 0;
       const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma) + 2 * cg), g1 = __ldg(reinterpret_cast<const float4*>(gamma) + 2 * cg + 1);
       const float gm[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
       nk[i] = nkeep[i];
 #pragma unroll
       for (int e = 0; e < 8; ++e) {
         const float dv = dy.v[e] + b.v[e];
-        xh[i].v[e] = live ? fmaf(zv.v[e], rstd, nmr) : 0.f;
+        xh[i].v[e] = live ? (zv.v[e] - mean) * rstd : 0.f;
         gd[i].v[e] = live ? gm[e] * dv : 0.f;
         s1 += gd[i].v[e];
         s2 += gd[i].v[e] * xh[i].v[e];
-        ag[i].v[e] += live ? dv * xh[i].v[e] : 0.f;
-        ab[i].v[e] += live ? dv : 0.f;
+        ag[i].v[e] += dv * xh[i].v[e];
+        ab[i].v[e] += dv;
       }
     }
-    slot = slot == 2 ? 0 : slot + 1;
-    if (r + nwarps < rows) fetch_small(r + nwarps);
-    const float inv_d = 1.f / (float)d;
-    const float nrm1 = -rstd * warp_sum(s1) * inv_d, nrm2 = -rstd * warp_sum(s2) * inv_d;     // dz = rstd gd - rstd m1 - xhat rstd m2
+    if (r + nwarps < rows) fetch(r + nwarps);
+    const float m1 = warp_sum(s1) / d, m2 = warp_sum(s2) / d;
 #pragma unroll
     for (int i = 0; i < NV; ++i) {
       const int c8 = lane + 32 * i;
@@ -324,7 +291,7 @@ residual_ln_bwd_kernel(const void* __restrict__ g1v, const __nv_bfloat16* __rest
         const long long idx = r * d8 + c8;
         F8 o;
 #pragma unroll
-        for (int e = 0; e < 8; ++e) o.v[e] = fmaf(gd[i].v[e], rstd, fmaf(xh[i].v[e], nrm2, nrm1));
+        for (int e = 0; e < 8; ++e) o.v[e] = rstd * (gd[i].v[e] - m1 - xh[i].v[e] * m2);
         reinterpret_cast<uint4*>(dz)[idx] = pack8(o);
         if (rate > 0.f) {
           const uint32_t keep = kRegen ? dropout_keep8(seed, site, (unsigned long long)idx, rate) : nk[i];
@@ -337,30 +304,23 @@ residual_ln_bwd_kernel(const void* __restrict__ g1v, const __nv_bfloat16* __rest
       }
     }
   }
-  // column partials: every warp parks its 3 x d sums in shared memory (the ring is dead now), then each thread adds up one column over
-  // the warps and issues ONE global atomic per column and block (shared-memory atomics here cost 1/6 of the kernel: 16 warps, same addresses)
-  asm volatile("cp.async.wait_all;" ::: "memory");
-  __syncthreads();
-  float* const part = red + (size_t)wib * 3 * d;
 #pragma unroll
   for (int i = 0; i < NV; ++i) {
     const int c = (lane + 32 * i) * 8;
     if (c < d) {
-      *reinterpret_cast<float4*>(part + c) = make_float4(ag[i].v[0], ag[i].v[1], ag[i].v[2], ag[i].v[3]);
-      *reinterpret_cast<float4*>(part + c + 4) = make_float4(ag[i].v[4], ag[i].v[5], ag[i].v[6], ag[i].v[7]);
-      *reinterpret_cast<float4*>(part + d + c) = make_float4(ab[i].v[0], ab[i].v[1], ab[i].v[2], ab[i].v[3]);
-      *reinterpret_cast<float4*>(part + d + c + 4) = make_float4(ab[i].v[4], ab[i].v[5], ab[i].v[6], ab[i].v[7]);
-      *reinterpret_cast<float4*>(part + 2 * d + c) = make_float4(ac[i].v[0], ac[i].v[1], ac[i].v[2], ac[i].v[3]);
-      *reinterpret_cast<float4*>(part + 2 * d + c + 4) = make_float4(ac[i].v[4], ac[i].v[5], ac[i].v[6], ac[i].v[7]);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        atomicAdd(red + c + e, ag[i].v[e]);
+        atomicAdd(red + d + c + e, ab[i].v[e]);
+        if (dbias != nullptr) atomicAdd(red + 2 * d + c + e, ac[i].v[e]);
+      }
     }
   }
   __syncthreads();
-  for (int c = threadIdx.x; c < 3 * d; c += blockDim.x) {
-    float v = 0.f;
-    for (int w = 0; w < nw; ++w) v += red[(size_t)w * 3 * d + c];
-    if (c < d) atomicAdd(dgamma + c, v);
-    else if (c < 2 * d) atomicAdd(dbeta + c - d, v);
-    else if (dbias != nullptr) atomicAdd(dbias + c - 2 * d, v);
+  for (int c = threadIdx.x; c < d; c += blockDim.x) {
+    atomicAdd(dgamma + c, red[c]);
+    atomicAdd(dbeta + c, red[d + c]);
+    if (dbias != nullptr) atomicAdd(dbias + c, red[2 * d + c]);
   }
 }
 
@@ -695,26 +655,6 @@ int residual_ln_fwd(const void* y, const void* x, const float* gamma, const floa
   BX_POST_LAUNCH();
   return 0;
 }
-template <int NV, bool F32, bool REGEN, bool FULL>
-static int ln_bwd_go(const void* g1, const void* g2, const void* z, const float* mean, const float* rstd, const float* gamma, void* dz, void* dy_sub,
-                     float* dgamma, float* dbeta, float* dbias, const void* keep_bits, long long rows, int d, float rate, unsigned long long seed,
-                     unsigned site, cudaStream_t st, const unsigned long long* seed_dev, int grid, int threads, size_t smem) {
-  auto kern = residual_ln_bwd_kernel<NV, F32, REGEN, FULL>;
-  static std::mutex mu;
-  static bool attr_done[kMaxDevices] = {};
-  {
-    std::lock_guard<std::mutex> lock(mu);
-    const int dev = current_device();
-    if (!attr_done[dev]) {
-      BX_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-      attr_done[dev] = true;
-    }
-  }
-  kern<<<grid, threads, smem, st>>>(g1, (const __nv_bfloat16*)g2, (const __nv_bfloat16*)z, mean, rstd, gamma, (__nv_bfloat16*)dz,
-                                    (__nv_bfloat16*)dy_sub, dgamma, dbeta, dbias, (const uint8_t*)keep_bits, rows, d, rate, seed, site, seed_dev);
-  return 0;
-}
-
 int residual_ln_bwd(const void* g1, int g1_f32, const void* g2, const void* z, const float* mean, const float* rstd,
                     const float* gamma, void* dz, void* dy_sub, float* dgamma, float* dbeta, float* dbias, const void* keep_bits,
                     long long rows, int d, float rate, unsigned long long seed, unsigned site, cudaStream_t st,
@@ -723,21 +663,30 @@ int residual_ln_bwd(const void* g1, int g1_f32, const void* g2, const void* z, c
   const bool regen = rate > 0.f && keep_bits == nullptr;
   const int threads = (d <= 512 && !regen) ? 512 : 256;
   const int grid = grid_for(rows * 32, threads, 1);
-  const size_t smem = (size_t)(threads / 32) * kLnBwdStages * ((size_t)d * (g1_f32 ? 4 : 2) + 4 * (size_t)d);      // >= [warps][3][d] floats
-  BX_REQUIRE(smem <= 227 * 1024, "layernorm backward: input ring of %zu bytes does not fit", smem);
-#define BX_LN_BWD_GO(NV, F32, REGEN) \
-  rc = (d == 256 * NV) ? ln_bwd_go<NV, F32, REGEN, true>(g1, g2, z, mean, rstd, gamma, dz, dy_sub, dgamma, dbeta, dbias, keep_bits, rows, d, rate, seed, site, st, seed_dev, grid, threads, smem) \
-                       : ln_bwd_go<NV, F32, REGEN, false>(g1, g2, z, mean, rstd, gamma, dz, dy_sub, dgamma, dbeta, dbias, keep_bits, rows, d, rate, seed, site, st, seed_dev, grid, threads, smem)
-#define BX_LN_BWD_NV(F32, REGEN) \
-  do { if (d <= 256) BX_LN_BWD_GO(1, F32, REGEN); else if (d <= 512) BX_LN_BWD_GO(2, F32, REGEN); else BX_LN_BWD_GO(4, F32, REGEN); } while (0)
-  int rc = 0;
-  if (g1_f32 && regen) BX_LN_BWD_NV(true, true);
-  else if (g1_f32) BX_LN_BWD_NV(true, false);
-  else if (regen) BX_LN_BWD_NV(false, true);
-  else BX_LN_BWD_NV(false, false);
-#undef BX_LN_BWD_NV
+  const size_t smem = (size_t)3 * d * sizeof(float);
+#define BX_LN_BWD_GO(F32, REGEN)                                                                                                   \
+  BX_LN_DISPATCH(residual_ln_bwd_kernel, <<<grid, threads, smem, st>>>(g1, (const __nv_bfloat16*)g2, (const __nv_bfloat16*)z, mean, \
+                                                                      rstd, gamma, (__nv_bfloat16*)dz, (__nv_bfloat16*)dy_sub,      \
+                                                                      dgamma, dbeta, dbias, (const uint8_t*)keep_bits, rows, d,     \
+                                                                      rate, seed, site, seed_dev))
+  if (g1_f32 && regen) {
+#define BX_LN_EXTRA , true, true
+    BX_LN_BWD_GO(true, true)
+#undef BX_LN_EXTRA
+  } else if (g1_f32) {
+#define BX_LN_EXTRA , true, false
+    BX_LN_BWD_GO(true, false)
+#undef BX_LN_EXTRA
+  } else if (regen) {
+#define BX_LN_EXTRA , false, true
+    BX_LN_BWD_GO(false, true)
+#undef BX_LN_EXTRA
+  } else {
+#define BX_LN_EXTRA , false, false
+    BX_LN_BWD_GO(false, false)
+#undef BX_LN_EXTRA
+  }
 #undef BX_LN_BWD_GO
-  if (rc) return rc;
   BX_POST_LAUNCH();
   return 0;
 }
