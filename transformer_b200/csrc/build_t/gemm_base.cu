@@ -10,8 +10,6 @@
 //   dgrad     dx = dy.W^T          reverse-mode of the above (train.py:137)                     (A K-major, B K-major)
 //   wgrad     dW = x^T.dy          ditto, split-K over tokens with TMA reduce-add               (A MN-major, B MN-major)
 // Operand "major": 0 = K-major (K contiguous in memory), 1 = MN-major (M resp. N contiguous).
-#include <stdlib.h>
-
 #include <mutex>
 
 #include "common.cuh"
@@ -20,8 +18,7 @@ namespace bx {
 
 constexpr int GEMM_BM = 128;
 constexpr int GEMM_BK = 64;
-// w0 TMA, w1 MMA, w2 TMEM alloc, w3 idle, then EW epilogue warpgroups: w4-7 (EW = 1) or w4-7 / w8-11 taking alternate 128-byte chunks of a tile (EW = 2)
-constexpr int gemm_threads(int ew) { return 128 + 128 * ew; }
+constexpr int GEMM_THREADS = 256;  // w0 TMA, w1 MMA, w2 TMEM alloc, w3 idle, w4-7 epilogue
 
 constexpr int GEMM_FLAG_RELU = 1;       // out = max(out, 0)
 constexpr int GEMM_FLAG_ACCUM = 2;      // D += out (TMA reduce-add; fp32 D only)
@@ -35,7 +32,6 @@ template <int BN, int CG>
 struct GemmCfg {
   static constexpr uint32_t A_BYTES = GEMM_BM * GEMM_BK * 2;
   static constexpr uint32_t B_BYTES = (BN / CG) * GEMM_BK * 2;
-  // one staging box per epilogue warpgroup (the other warpgroup's chunk covers the time its TMA store needs to read it out)
   static constexpr int kStages = (A_BYTES + B_BYTES) == 49152 ? 4 : ((A_BYTES + B_BYTES) == 32768 ? 6 : 8);
   static constexpr uint32_t STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr uint32_t D_BYTES = GEMM_BM * 128;  // one 128-byte-wide staging box
@@ -45,8 +41,8 @@ struct GemmCfg {
   static constexpr uint32_t TMEM_COLS = 2 * BN;
 };
 
-template <int MA, int MB, int BN, bool kOutF32, int CG, int EW>
-__global__ void __launch_bounds__(gemm_threads(EW), 1)
+template <int MA, int MB, int BN, bool kOutF32, int CG>
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
             const __grid_constant__ CUtensorMap tmD, int M, int N, int K, int splits,
             const float* __restrict__ bias, void* aux_v, long long ld_aux, int flags, int chunk, float* __restrict__ colsum) {
@@ -81,7 +77,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tmem_full[i], 1);
-      mbar_init(&tmem_empty[i], 128 * EW * CG);   // every epilogue thread (pair: of both CTAs, on the leader's barrier)
+      mbar_init(&tmem_empty[i], 128 * CG);   // pair: the leader's barrier collects both CTAs' epilogue threads
     }
     fence_barrier_init();
   }
@@ -199,14 +195,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     // ===================================== epilogue =====================================
     const uint32_t q = warp & 3u;                // TMEM lane quadrant this warp may access
     const uint32_t row = q * 32u + lane;         // accumulator row owned by this thread
-    // EW = 2 (launcher: short K with a bias epilogue): one warpgroup reads tensor memory at ~55 B/cycle and pays a fence + barrier +
-    // store per chunk, which makes the epilogue of a K = 512 tile (128 KB of accumulators per CTA) longer than its mainloop; two
-    // warpgroups take alternate chunks, each with ONE staging box (the other warpgroup's chunk covers its store's read-out).
-    // EW = 1: one warpgroup, the two boxes double-buffered.
-    const uint32_t eg = (warp - 4u) >> 2;        // epilogue warpgroup
-    const uint32_t epi_tid = (threadIdx.x - 128u) & 127u;
-    const uint32_t stg_base = smem_u32(smem + Cfg::OFF_D) + (EW == 2 ? eg * Cfg::D_BYTES : 0u);
-    uint8_t* const stg_ptr0 = smem + Cfg::OFF_D + (EW == 2 ? eg * Cfg::D_BYTES : 0u);
+    const uint32_t epi_tid = threadIdx.x - 128u;
+    const uint32_t stg_base = smem_u32(smem + Cfg::OFF_D);
     uint32_t it = 0, buf = 0;
     for (int t = t_begin; t < t_end; t += t_step, ++it) {
       const int rem = t % tiles_mn;
@@ -217,7 +207,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       const uint32_t t_row = tmem_base + ((q * 32u) << 16) + acc * BN;
       const long long grow = (long long)m0 + row;
 #pragma unroll 1
-      for (int c = (int)eg; c < BN / OUT_COLS; c += EW) {
+      for (int c = 0; c < BN / OUT_COLS; ++c) {
         const int nc = n0 + c * OUT_COLS;
         if (nc >= N) break;
         float v[OUT_COLS];
@@ -281,14 +271,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
               if (nc + j < N && !(__bfloat162float(ap[j]) > 0.f)) v[j] = 0.f;
           }
         }
-        uint32_t stg;
-        if (EW == 2) {     // this warpgroup's only staging box: free once the store of its previous chunk has read it out
-          if (epi_tid == 0) tma_store_wait_read<0>();
-          named_bar_sync(1 + eg, 128);
-          stg = stg_base;
-        } else {           // box `buf` is free: the barrier of the previous chunk was passed only after thread 0 had seen the TMA store
-          stg = stg_base + buf * Cfg::D_BYTES;      // that last read it complete (two boxes, ONE named barrier per chunk)
-        }
+        // staging buffer `buf` is free: the barrier of the previous chunk was passed only after thread 0 had seen
+        // the TMA store that last read it complete (two buffers, ONE named barrier per chunk).
+        const uint32_t stg = stg_base + buf * Cfg::D_BYTES;
         if (kOutF32) {
 #pragma unroll
           for (int j = 0; j < 8; ++j)
@@ -302,12 +287,11 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                          pack_bf16x2(v[8 * j + 6], v[8 * j + 7]));
         }
         fence_proxy_async_smem();
-        if (EW == 1 && epi_tid == 0) tma_store_wait_read<0>();   // the previous chunk's store has drained the OTHER box
-        named_bar_sync(1 + eg, 128);
+        if (epi_tid == 0) tma_store_wait_read<0>();   // the previous chunk's store has drained the OTHER buffer
+        named_bar_sync(1, 128);
         if (epi_tid == 0) {
-          uint8_t* const src = stg_ptr0 + (EW == 1 ? buf * Cfg::D_BYTES : 0u);
-          if (flags & GEMM_FLAG_ACCUM) tma_reduce_add_2d(&tmD, src, nc, m0);
-          else tma_store_2d(&tmD, src, nc, m0);
+          if (flags & GEMM_FLAG_ACCUM) tma_reduce_add_2d(&tmD, smem + Cfg::OFF_D + buf * Cfg::D_BYTES, nc, m0);
+          else tma_store_2d(&tmD, smem + Cfg::OFF_D + buf * Cfg::D_BYTES, nc, m0);
           tma_store_commit();
         }
         if (!kOutF32 && colsum != nullptr) {
@@ -361,7 +345,7 @@ static int auto_splits(long long tiles, long long kblocks, int groups) {
   return (int)(s < 1 ? 1 : s);
 }
 
-template <int MA, int MB, int BN, bool kOutF32, int CG, int EW>
+template <int MA, int MB, int BN, bool kOutF32, int CG>
 static int launch_gemm(const void* A, long long lda, const void* B, long long ldb, void* D, long long ldd,
                        const float* bias, const void* aux, long long ld_aux, int flags, int splits, long long M,
                        long long N, long long K, cudaStream_t stream, float* colsum) {
@@ -376,7 +360,7 @@ static int launch_gemm(const void* A, long long lda, const void* B, long long ld
   if (rc) return rc;
   rc = encode_tmap_2d(&tmD, kOutF32 ? 1 : 0, D, N, M, ldd, kOutF32 ? 32 : 64, GEMM_BM, 128);
   if (rc) return rc;
-  auto kern = gemm_kernel<MA, MB, BN, kOutF32, CG, EW>;
+  auto kern = gemm_kernel<MA, MB, BN, kOutF32, CG>;
   // per-device launch state of this instantiation (function attributes and cluster occupancy are per device), under a lock:
   // several host threads / devices may drive the library
   static std::mutex mu;
@@ -395,7 +379,7 @@ static int launch_gemm(const void* A, long long lda, const void* B, long long ld
   if (splits <= 0) splits = (flags & GEMM_FLAG_ACCUM) ? auto_splits(m_tiles * n_tiles, kblocks, groups) : 1;
   if (splits > kblocks) splits = (int)kblocks;
   cudaLaunchConfig_t cfg = {};
-  cfg.blockDim = dim3(gemm_threads(EW));
+  cfg.blockDim = dim3(GEMM_THREADS);
   cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
   cfg.stream = stream;
   cudaLaunchAttribute attr[1];
@@ -437,7 +421,6 @@ static int launch_gemm(const void* A, long long lda, const void* B, long long ld
 }
 
 static int g_force_cg = 0;   // 0 = heuristic, 1 / 2 = force (tests and benchmarks)
-static int g_force_ew = [] { const char* e = getenv("B200XF_GEMM_EPI_WG"); return e ? atoi(e) : 0; }();   // 0 = heuristic, 1 / 2 = force the number of epilogue warpgroups
 void gemm_force_cta_group(int cg) { g_force_cg = cg; }
 void gemm_set_chunks_per_unit(int n) { g_chunks_per_unit = n < 0 ? 0 : n; }
 
@@ -459,12 +442,8 @@ int gemm_bf16(const void* A, long long lda, int a_major, const void* B, long lon
   BX_REQUIRE(a_major >= 0 && a_major <= 1 && b_major >= 0 && b_major <= 1, "gemm: bad majors %d/%d", a_major, b_major);
   const bool wide = N > 128;
   const bool pair = g_force_cg ? g_force_cg == 2 : (M > 128 && wide);   // CTA pairs need >= 2 row tiles; 256-wide N tile only
-  // two epilogue warpgroups where the epilogue outlasts the mainloop: short K with a bias (+ ReLU) epilogue -- the forward projections
-  // (+4..13 % measured, profiles/r02_gemm_two_epilogue_warpgroups.txt); elsewhere the extra warps cost 1-2 %
-  const bool ew2 = g_force_ew ? g_force_ew == 2 : (K <= 512 && bias != nullptr && N > 128);
 #define BX_GEMM_GO(ma, mb, bn, f32, cg) \
-  do { if (ew2) return launch_gemm<ma, mb, bn, f32, cg, 2>(A, lda, B, ldb, D, ldd, bias, aux, ld_aux, flags, splits, M, N, K, stream, colsum); \
-       return launch_gemm<ma, mb, bn, f32, cg, 1>(A, lda, B, ldb, D, ldd, bias, aux, ld_aux, flags, splits, M, N, K, stream, colsum); } while (0)
+  return launch_gemm<ma, mb, bn, f32, cg>(A, lda, B, ldb, D, ldd, bias, aux, ld_aux, flags, splits, M, N, K, stream, colsum)
 #define BX_GEMM_CASE(ma, mb)                                              \
   if (a_major == ma && b_major == mb) {                                   \
     if (wide && pair) { if (d_is_f32) BX_GEMM_GO(ma, mb, 256, true, 2); else BX_GEMM_GO(ma, mb, 256, false, 2); } \
