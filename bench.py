@@ -413,7 +413,7 @@ def main():
                              "what": "point_wise_feed_forward_network GEMMs only (dense0 + dense1: forward, dgrad, wgrad) -- the kernel the north-star target is stated on"},
                 "dense_layernorm_fused": {"achieved": prof[13] / (prof[12] * 1e-3) / 1e12 if prof[12] > 0 else 0.0, "unit": "TFLOP/s", "launches_per_step": prof[14] / rsteps,
                                           "share_of_step": prof[12] / ms_roof,
-                                          "what": "bx::gemm_ln_kernel: out-projection / FFN dense1 GEMM with bias + dropout + residual + LayerNorm in the epilogue "
+                                          "what": "bx::gemm_ln2_kernel (d_model 256 / 512; gemm_ln_kernel for 128): out-projection / FFN dense1 GEMM with bias + dropout + residual + LayerNorm in the epilogue "
                                                   "(its time contains the LayerNorm that used to be a separate HBM-bound kernel; not part of the gemm_kernel figure above)"},
                 "attention_fwd": {"achieved": prof[4] / (prof[3] * 1e-3) / 1e12 if prof[3] > 0 else 0.0, "unit": "TFLOP/s (dense 4.B.H.Sq.Sk.dk)",
                                   "share_of_step": prof[3] / ms_roof},
