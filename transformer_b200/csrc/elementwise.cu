@@ -393,7 +393,11 @@ __global__ void __launch_bounds__(256)
 xent_kernel(const T* logits, long long ld, const long long* __restrict__ labels, int label_stride,
             int label_offset, int T_len, __nv_bfloat16* dlogits, long long ld_d, float* __restrict__ row_loss,
             double* __restrict__ stats, int V, float inv_batch, const int* __restrict__ t_valid_dev) {   // dlogits may alias logits (no __restrict__)
-  // one CTA per row, 16-byte vector loads.  labels for row r = (b, t) live at labels[b*label_stride + label_offset + t]
+  // one CTA per row, 16-byte vector loads.  labels for row r = (b, t) live at labels[b*label_stride + label_offset + t].
+  // The kernel is instruction-issue bound (ncu: 23 instructions per logit before this version, issue slots 73 % busy next to 59 % MUFU
+  // and 62 % DRAM), so the inner loops carry nothing per ELEMENT beyond unpack / max / exp / add: the ragged last vector is peeled, the
+  // running maximum is updated branch-free, the arg-max is tracked per VECTOR (its element is looked up once, after the reduction), the
+  // label's logit is fetched by one thread up front and the label's gradient correction is a per-vector test.
   constexpr int VEC = LogitVec<T>::N;
   constexpr float L2E = 1.4426950408889634f, LN2 = 0.6931471805599453f;
   const long long r = blockIdx.x;
@@ -402,63 +406,68 @@ xent_kernel(const T* logits, long long ld, const long long* __restrict__ labels,
   const long long raw_label = labels[b * label_stride + label_offset + t];
   const bool nonpad = raw_label != 0;
   const int label = (raw_label < 0 || raw_label >= V) ? 0 : (int)raw_label;
-  __shared__ float s_m[8], s_s[8], s_lab;
+  __shared__ float s_m[8], s_s[8];
   __shared__ int s_i[8];
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-  const int nvec = (V + VEC - 1) / VEC;          // ld is a multiple of VEC, so every vector lies inside the row
-  // pass 1: online max / sum-exp / argmax (first index attaining the max, like tf.argmax)
+  const int nfull = V / VEC;                        // vectors entirely inside the row
+  const int nvec = (V + VEC - 1) / VEC;             // ld is a multiple of VEC, so every vector lies inside the allocation
+  float lab_logit = 0.f;
+  if (threadIdx.x == 0) lab_logit = (float)row[label];        // before pass 2 may overwrite the (aliased) row in place
+  // ---- pass 1: online max / sum-exp, and the first VECTOR attaining the maximum
   float m = -INFINITY, s = 0.f;
-  int am = 0x7fffffff;
-  for (int i = threadIdx.x; i < nvec; i += blockDim.x) {
-    float x[8];
-    LogitVec<T>::load(row + (long long)i * VEC, x);
-    const int c0 = i * VEC;
-    if (c0 + VEC > V) {                       // ragged last vector only: columns >= V are not logits
-#pragma unroll
-      for (int e = 0; e < VEC; ++e) if (c0 + e >= V) x[e] = -INFINITY;
-    }
-    if ((unsigned)(label - c0) < (unsigned)VEC) {       // captured now: pass 2 may overwrite the (aliased) row in place
-#pragma unroll
-      for (int e = 0; e < VEC; ++e) if (c0 + e == label) s_lab = x[e];
-    }
+  int bi = 0x7fffffff;
+  auto fold = [&](const float (&x)[8], int i) {
     float vmax = x[0];
 #pragma unroll
     for (int e = 1; e < VEC; ++e) vmax = fmaxf(vmax, x[e]);
-    if (vmax > m) {
-      int first = 0;
+    bi = vmax > m ? i : bi;
+    const float mn = fmaxf(m, vmax), mb = mn * L2E;
+    float acc = s * fast_exp2((m - mn) * L2E);       // (m = -inf, s = 0 at the start: 0 * 2^-inf = 0)
 #pragma unroll
-      for (int e = VEC - 1; e >= 0; --e) if (x[e] == vmax) first = e;
-      am = c0 + first;
-      s *= fast_exp2((m - vmax) * L2E);
-      m = vmax;
-    }
-    const float mb = m * L2E;
+    for (int e = 0; e < VEC; ++e) acc += fast_exp2(fmaf(x[e], L2E, -mb));
+    s = acc; m = mn;
+  };
+  for (int i = threadIdx.x; i < nfull; i += blockDim.x) {
+    float x[8];
+    LogitVec<T>::load(row + (long long)i * VEC, x);
+    fold(x, i);
+  }
+  if (nfull < nvec && (nfull % (int)blockDim.x) == (int)threadIdx.x) {        // the ragged last vector: columns >= V are not logits
+    float x[8];
+    LogitVec<T>::load(row + (long long)nfull * VEC, x);
 #pragma unroll
-    for (int e = 0; e < VEC; ++e) s += fast_exp2(x[e] * L2E - mb);
+    for (int e = 0; e < VEC; ++e) if (nfull * VEC + e >= V) x[e] = -INFINITY;
+    fold(x, nfull);
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
     const float m2 = __shfl_xor_sync(0xffffffffu, m, o), s2 = __shfl_xor_sync(0xffffffffu, s, o);
-    const int a2 = __shfl_xor_sync(0xffffffffu, am, o);
+    const int a2 = __shfl_xor_sync(0xffffffffu, bi, o);
     const float mn = fmaxf(m, m2);
     s = (m == -INFINITY ? 0.f : s * fast_exp2((m - mn) * L2E)) + (m2 == -INFINITY ? 0.f : s2 * fast_exp2((m2 - mn) * L2E));
-    am = (m2 > m || (m2 == m && a2 < am)) ? a2 : am;
+    bi = (m2 > m || (m2 == m && a2 < bi)) ? a2 : bi;
     m = mn;
   }
-  if (lane == 0) { s_m[wib] = m; s_s[wib] = s; s_i[wib] = am; }
+  if (lane == 0) { s_m[wib] = m; s_s[wib] = s; s_i[wib] = bi; }
   __syncthreads();
-  m = s_m[0]; s = s_s[0]; am = s_i[0];
+  m = s_m[0]; s = s_s[0]; bi = s_i[0];
   for (int w = 1; w < (int)(blockDim.x >> 5); ++w) {
     const float m2 = s_m[w], s2 = s_s[w];
     const int a2 = s_i[w];
     const float mn = fmaxf(m, m2);
     s = (m == -INFINITY ? 0.f : s * fast_exp2((m - mn) * L2E)) + (m2 == -INFINITY ? 0.f : s2 * fast_exp2((m2 - mn) * L2E));
-    am = (m2 > m || (m2 == m && a2 < am)) ? a2 : am;
+    bi = (m2 > m || (m2 == m && a2 < bi)) ? a2 : bi;
     m = mn;
   }
   const float lse = m + __log2f(s) * LN2;
   if (threadIdx.x == 0) {
-    const float loss = nonpad ? (lse - s_lab) : 0.f;
+    // arg-max = first element of the first vector that attains the maximum (tf.argmax); the row is still intact here
+    float x[8];
+    LogitVec<T>::load(row + (long long)bi * VEC, x);
+    int am = bi * VEC;
+#pragma unroll
+    for (int e = VEC - 1; e >= 0; --e) if (x[e] == m && bi * VEC + e < V) am = bi * VEC + e;
+    const float loss = nonpad ? (lse - lab_logit) : 0.f;
     if (row_loss) row_loss[r] = loss;
     if (nonpad) atomicAdd(&stats[0], (double)loss);
     if (t_valid_dev == nullptr || t < *t_valid_dev) {   // positions added by shape bucketing (t >= *t_valid_dev) are not part of the batch
@@ -468,31 +477,43 @@ xent_kernel(const T* logits, long long ld, const long long* __restrict__ labels,
     if (nonpad) atomicAdd(&stats[3], 1.0);
   }
   if (dlogits == nullptr) return;
-  // pass 2: gradient (row re-read hits L1/L2); padded columns [V, ld_d) are zeroed
+  __syncthreads();                                   // thread 0 has read its arg-max vector: the row may now be overwritten in place
+  // ---- pass 2: gradient (row re-read hits L1/L2); padded columns [V, ld_d) are zeroed
   const float gscale = nonpad ? inv_batch : 0.f;
   const float lb = lse * L2E;
+  const int lab_vec = label / VEC, lab_e = label % VEC;
   __nv_bfloat16* drow = dlogits + r * ld_d;
-  for (int i = threadIdx.x; i < nvec; i += blockDim.x) {
-    float x[8];
-    LogitVec<T>::load(row + (long long)i * VEC, x);
-    const int c0 = i * VEC;
-    float g[8];
-#pragma unroll
-    for (int e = 0; e < VEC; ++e) g[e] = fast_exp2(x[e] * L2E - lb) * gscale;
-    if ((unsigned)(label - c0) < (unsigned)VEC) {
-#pragma unroll
-      for (int e = 0; e < VEC; ++e) if (c0 + e == label) g[e] -= gscale;
-    }
-    if (c0 + VEC > V) {
-#pragma unroll
-      for (int e = 0; e < VEC; ++e) if (c0 + e >= V) g[e] = 0.f;
-    }
+  auto store = [&](const float (&g)[8], int c0) {
     if (VEC == 8) {
       *reinterpret_cast<uint4*>(drow + c0) = make_uint4(pack_bf16x2(g[0], g[1]), pack_bf16x2(g[2], g[3]), pack_bf16x2(g[4], g[5]),
                                                         pack_bf16x2(g[6], g[7]));
     } else {
       *reinterpret_cast<uint2*>(drow + c0) = make_uint2(pack_bf16x2(g[0], g[1]), pack_bf16x2(g[2], g[3]));
     }
+  };
+  for (int i = threadIdx.x; i < nfull; i += blockDim.x) {
+    float x[8];
+    LogitVec<T>::load(row + (long long)i * VEC, x);
+    float g[8];
+#pragma unroll
+    for (int e = 0; e < VEC; ++e) g[e] = fast_exp2(fmaf(x[e], L2E, -lb)) * gscale;
+    if (i == lab_vec) {
+#pragma unroll
+      for (int e = 0; e < VEC; ++e) if (e == lab_e) g[e] -= gscale;
+    }
+    store(g, i * VEC);
+  }
+  if (nfull < nvec && (nfull % (int)blockDim.x) == (int)threadIdx.x) {
+    float x[8];
+    LogitVec<T>::load(row + (long long)nfull * VEC, x);
+    float g[8];
+#pragma unroll
+    for (int e = 0; e < VEC; ++e) {
+      g[e] = fast_exp2(fmaf(x[e], L2E, -lb)) * gscale;
+      if (nfull * VEC + e == label) g[e] -= gscale;
+      if (nfull * VEC + e >= V) g[e] = 0.f;
+    }
+    store(g, nfull * VEC);
   }
   for (long long c = (long long)nvec * VEC + threadIdx.x; c < ld_d; c += blockDim.x) drow[c] = __float2bfloat16(0.f);
 }
