@@ -8,14 +8,14 @@
 namespace bx {
 
 // ------------------------------------------------------------------------------------------------
-// counter-based dropout RNG (Philox-4x32-10) keyed by (seed, site, element); the LayerNorm kernels store the keep mask
+// counter-based dropout RNG (Philox-4x32, 7 rounds) keyed by (seed, site, element); the LayerNorm kernels store the keep mask
 // (1 bit per element) in forward and read it back in backward, the embedding kernels regenerate it
 // keras Dropout semantics: keep w.p. 1-rate, scale kept by 1/(1-rate).
 // ------------------------------------------------------------------------------------------------
 // keep-scale factors for the 4 consecutive elements starting at flat element index `idx4*4`
 __device__ __forceinline__ float4 dropout_scale4(unsigned long long seed, uint32_t site, unsigned long long idx4,
                                                  float rate) {
-  const uint4 r = philox4x32_10(make_uint4((uint32_t)idx4, (uint32_t)(idx4 >> 32), site, 0u),
+  const uint4 r = philox4x32(make_uint4((uint32_t)idx4, (uint32_t)(idx4 >> 32), site, 0u),
                                 make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)));
   const float inv = 1.f / (1.f - rate);
   const float s = 2.3283064365386963e-10f;  // 2^-32
