@@ -236,14 +236,16 @@ residual_ln_bwd_kernel(const void* __restrict__ g1v, const __nv_bfloat16* __rest
   const int g1_bytes = d * G1B, slot_bytes = g1_bytes + 4 * d;     // g1 | g2 | z
   uint8_t* const ring = reinterpret_cast<uint8_t*>(red) + (size_t)wib * kLnBwdStages * slot_bytes;
   const uint32_t ring_s = smem_u32(ring);
-  auto issue = [&](long long r, int slot) {
+  // running 16-byte-vector offsets of the rows in flight (row * d8 + lane): one 64-bit add per row instead of a 64-bit multiply per access
+  const long long vstride = nwarps * d8;
+  auto issue = [&](long long r, long long voff, int slot) {
     if (r < rows) {
       const uint32_t sbase = ring_s + slot * slot_bytes;
 #pragma unroll
       for (int i = 0; i < NV; ++i) {
         const int c8 = lane + 32 * i;
         if (c8 < d8) {
-          const long long idx = r * d8 + c8;
+          const long long idx = voff + 32 * i;
           if (kG1F32) {
             cp_async16(sbase + c8 * 32, reinterpret_cast<const uint4*>(g1v) + 2 * idx);
             cp_async16(sbase + c8 * 32 + 16, reinterpret_cast<const uint4*>(g1v) + 2 * idx + 1);
@@ -260,20 +262,21 @@ residual_ln_bwd_kernel(const void* __restrict__ g1v, const __nv_bfloat16* __rest
   const float inv_keep = 1.f / (1.f - rate);
   uint32_t nkeep[NV], nk[NV];
   float nmean = 0.f, nrstd = 0.f;
-  auto fetch_small = [&](long long r) {                     // one row ahead in registers: keep byte(s), mean, rstd
+  auto fetch_small = [&](long long r, long long voff) {     // one row ahead in registers: keep byte(s), mean, rstd
 #pragma unroll
     for (int i = 0; i < NV; ++i) {
       const int c8 = lane + 32 * i;
-      nkeep[i] = (!kRegen && keep_in != nullptr && c8 < d8) ? keep_in[r * d8 + c8] : 0u;
+      nkeep[i] = (!kRegen && keep_in != nullptr && c8 < d8) ? keep_in[voff + 32 * i] : 0u;
     }
     nmean = mean_in[r]; nrstd = rstd_in[r];
   };
-  issue(warp_global, 0);
-  issue(warp_global + nwarps, 1);
-  if (warp_global < rows) fetch_small(warp_global);
+  long long voff = warp_global * d8 + lane;                 // of the row being reduced
+  issue(warp_global, voff, 0);
+  issue(warp_global + nwarps, voff + vstride, 1);
+  if (warp_global < rows) fetch_small(warp_global, voff);
   int slot = 0;
-  for (long long r = warp_global; r < rows; r += nwarps) {
-    issue(r + 2 * nwarps, slot == 0 ? 2 : slot - 1);        // (the slot read in the previous iteration)
+  for (long long r = warp_global; r < rows; r += nwarps, voff += vstride) {
+    issue(r + 2 * nwarps, voff + 2 * vstride, slot == 0 ? 2 : slot - 1);        // (the slot read in the previous iteration)
     asm volatile("cp.async.wait_group 2;" ::: "memory");    // this row's group has landed
     F8 gd[NV], xh[NV];              // gamma * dy and xhat of this row
     const float rstd = nrstd, nmr = -nmean * nrstd;
@@ -314,14 +317,14 @@ residual_ln_bwd_kernel(const void* __restrict__ g1v, const __nv_bfloat16* __rest
       }
     }
     slot = slot == 2 ? 0 : slot + 1;
-    if (r + nwarps < rows) fetch_small(r + nwarps);
+    if (r + nwarps < rows) fetch_small(r + nwarps, voff + vstride);
     const float inv_d = 1.f / (float)d;
     const float nrm1 = -rstd * warp_sum(s1) * inv_d, nrm2 = -rstd * warp_sum(s2) * inv_d;     // dz = rstd gd - rstd m1 - xhat rstd m2
 #pragma unroll
     for (int i = 0; i < NV; ++i) {
       const int c8 = lane + 32 * i;
       if (c8 < d8) {
-        const long long idx = r * d8 + c8;
+        const long long idx = voff + 32 * i;
         F8 o;
 #pragma unroll
         for (int e = 0; e < 8; ++e) o.v[e] = fmaf(gd[i].v[e], rstd, fmaf(xh[i].v[e], nrm2, nrm1));
