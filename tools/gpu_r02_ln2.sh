@@ -1,5 +1,6 @@
 #!/bin/bash
-# gemm_ln v2 against v1 and the GEMM + LayerNorm pair; then the per-warp trace
+# gemm_ln v2 against v1 and the GEMM + LayerNorm pair; then the per-warp clock trace (needs transformer_b200/libb200xf_trace.so:
+# gemm_ln.cu compiled with -DBX_LN2_TRACE and linked with the other objects of csrc/build, see tools/ln_trace.py)
 mkdir -p gpurun_out
 timeout 600 python -m pytest tests/test_kernels_gpu.py -x -q -m gpu -k "layernorm_fused" > gpurun_out/r02_ln2_test.txt 2>&1
 tail -3 gpurun_out/r02_ln2_test.txt
